@@ -1,0 +1,112 @@
+/*
+ * simclr_b200 -- C ABI of the B200-native contrastive-objective hot path.
+ *
+ * Drop-in target: the two callables of the reference's objective.py
+ *     contrastive_loss(x_batch1, x_batch2, temperature, normalize, weight)   objective.py:6-55
+ *     modified_contrastive_loss(x_batch1, x_batch2, **kwargs)                objective.py:58-98
+ * as called from utils/model_utils.py:30 (eval, forward only) and :115,:120 (train, forward+backward).
+ * The reference has no FFI of its own (pure PyTorch); these entry points are what a ctypes binding in a
+ * replacement objective.py binds.  Plain pointers and sizes only; every pointer is
+ * a BORROWED device pointer that must stay valid until the stream reaches the end of the call.  Nothing
+ * here synchronises the host.  All functions are re-entrant for distinct streams/workspaces.
+ *
+ * Layout convention ("view-padded"): B images, two views.  Per-row arrays are float[2 * Bpad] and
+ * operand matrices are bf16[2 * Bpad][Dpad], Bpad = simclr_pad_rows(B) (multiple of 128), Dpad =
+ * simclr_pad_dim(d) (64, 128 or 256).  Slot (v, i) lives at index v * Bpad + i; padding slots are zero.
+ *
+ * Return value: 0 on success; a negative SIMCLR_ERR_* for rejected arguments; a positive value is a
+ * cudaError_t reported by the CUDA runtime.  There is no CPU fallback.
+ */
+#ifndef SIMCLR_B200_H_
+#define SIMCLR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIMCLR_ABI_VERSION 1
+
+/* loss kinds */
+#define SIMCLR_LOSS_NTXENT 0   /* objective.py:6-55  */
+#define SIMCLR_LOSS_MODIFIED 1 /* objective.py:58-98 */
+
+/* input element types of x_batch1 / x_batch2 (and of the returned gradients) */
+#define SIMCLR_DTYPE_F32 0
+#define SIMCLR_DTYPE_BF16 1
+
+/* error codes */
+#define SIMCLR_OK 0
+#define SIMCLR_ERR_NULL_POINTER (-1)
+#define SIMCLR_ERR_BAD_SHAPE (-2)       /* B < 1, d < 1, shard outside the global batch */
+#define SIMCLR_ERR_UNSUPPORTED_DIM (-3) /* d > 256 */
+#define SIMCLR_ERR_BAD_DTYPE (-4)
+#define SIMCLR_ERR_WORKSPACE_TOO_SMALL (-5)
+#define SIMCLR_ERR_MISALIGNED (-6)      /* operand / vector pointers must be 16-byte aligned */
+#define SIMCLR_ERR_BAD_TEMPERATURE (-7)
+#define SIMCLR_ERR_NOT_SM100 (-8)       /* device is not compute capability 10.x */
+#define SIMCLR_ERR_DRIVER_ENTRY (-9)    /* cuTensorMapEncodeTiled unavailable */
+#define SIMCLR_ERR_TENSOR_MAP (-10)
+#define SIMCLR_ERR_BAD_LOSS (-11)
+
+int simclr_abi_version(void);
+const char* simclr_error_string(int code);
+
+/* Bpad / Dpad helpers (pure host arithmetic). simclr_pad_dim returns 0 when d is unsupported. */
+int64_t simclr_pad_rows(int64_t b);
+int64_t simclr_pad_dim(int64_t d);
+
+/* Bytes of scratch each stage needs.  b_local == b_global on a single GPU. */
+size_t simclr_forward_workspace_bytes(int loss, int64_t b_local, int64_t b_global, int64_t d);
+size_t simclr_backward_workspace_bytes(int loss, int64_t b_local, int64_t b_global, int64_t d);
+
+/*
+ * Stage 1 -- prologue (objective.py:25-30 L2 normalise, or :70-78 softplus + L1 normalise).
+ * Reads x_batch1 / x_batch2 ([b_local][d], row-major contiguous, `in_dtype`), writes
+ *   operand  bf16 [2*Blpad][Dpad]  round-to-nearest operands for the tensor cores (padding zeroed)
+ *   inv_norm f32  [2*Blpad]        1 / max(||z||, 1e-12)   (1 when normalize == 0)
+ *   pos_dot  f32  [2*Blpad]        exact fp32 <op_r, op_pos(r)> of the positive pair
+ */
+int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
+                   int normalize, void* operand, float* inv_norm, float* pos_dot, void* stream);
+
+/*
+ * Stage 2 -- forward over this rank's rows against the global batch's columns
+ * (objective.py:35-53 / :87-97).  `operand_cols` is the [2*Bgpad][Dpad] operand of the global batch in
+ * view-padded order (== operand_rows on one GPU).  Outputs:
+ *   lse2     f32 [2*Blpad]  log2-domain log-sum-exp of every local row (saved for backward)
+ *   row_loss f32 [2*Blpad]  per-row loss L_r (natural log)
+ *   stats    f32 [4]        { sum_r w_r L_r, sum_r w_r, #rows whose first-argmax is the positive,
+ *                             stats[0] / stats[1] }   -- local to this rank
+ *   loss_out f32 [1]        optional separate copy of stats[3] (so a caller can hand out a tensor it may
+ *                           modify in place, as utils/model_utils.py:31,116 does); may be NULL
+ * `row_weight` is the reference's `weight` argument restricted to this rank: f32 [2*b_local] in the
+ * reference's compact order (view-1 rows then view-2 rows), or NULL.
+ */
+int simclr_forward(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
+                   int64_t row_offset, int64_t d, float temperature, const float* pos_dot, const float* row_weight,
+                   float* lse2, float* row_loss, float* stats, float* loss_out, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/*
+ * Stage 3 -- backward: gradients of  grad_out * loss  with respect to x_batch1 / x_batch2 of this rank.
+ *   lse2_cols  f32 [2*Bgpad]  lse2 of the global batch (== lse2 on one GPU)
+ *   col_scale  f32 [2*Bgpad]  w_c / sum(w) in view-padded order, or NULL for the unweighted 1/(2B)
+ *   grad_out   f32 [1] on the device, or NULL for 1.0
+ *   grad1/2    [b_local][d] in `in_dtype`
+ */
+int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t b_global,
+                    int64_t row_offset, int64_t d, int in_dtype, int normalize, float temperature,
+                    const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,
+                    const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Diagnostics: UMMA/TMA primitive self-test (tests/test_primitives.py). out_f32 receives 3*128*128 floats. */
+int simclr_selftest_umma(const void* a_bf16_128x128, const void* b_bf16_128x128, float* out_f32, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMCLR_B200_H_ */

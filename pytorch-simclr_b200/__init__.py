@@ -1,0 +1,11 @@
+"""B200-native contrastive objective for SimCLR (NT-Xent + the probabilistic "modified" loss).
+
+Import name: ``pytorch_simclr_b200`` (the directory is ``pytorch-simclr_b200/``; the root-level
+``pytorch_simclr_b200.py`` shim points Python at it).
+"""
+from .objective import contrastive_loss, modified_contrastive_loss  # noqa: F401
+from .functional import (ContrastiveLossFunction, contrastive_forward_backward, LOSS_NTXENT,  # noqa: F401
+                         LOSS_MODIFIED)
+
+__all__ = ["contrastive_loss", "modified_contrastive_loss", "ContrastiveLossFunction",
+           "contrastive_forward_backward", "LOSS_NTXENT", "LOSS_MODIFIED"]

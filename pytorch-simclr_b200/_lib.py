@@ -1,0 +1,77 @@
+"""ctypes binding of include/simclr_b200.h.  There is no CPU fallback: a missing library is an error."""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsimclr_b200.so")
+
+LOSS_NTXENT = 0
+LOSS_MODIFIED = 1
+DTYPE_F32 = 0
+DTYPE_BF16 = 1
+ABI_VERSION = 1
+
+_lock = threading.Lock()
+_lib = None
+
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+_f32 = ctypes.c_float
+_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/simclr_b200.h declares
+SIGNATURES = {
+    "simclr_abi_version": (_int, []),
+    "simclr_error_string": (ctypes.c_char_p, [_int]),
+    "simclr_pad_rows": (_i64, [_i64]),
+    "simclr_pad_dim": (_i64, [_i64]),
+    "simclr_forward_workspace_bytes": (_sz, [_int, _i64, _i64, _i64]),
+    "simclr_backward_workspace_bytes": (_sz, [_int, _i64, _i64, _i64]),
+    "simclr_prepare": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _vp, _vp, _vp, _vp]),
+    "simclr_forward": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                              _vp]),
+    "simclr_backward": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp,
+                               _vp, _vp, _vp, _vp, _sz, _vp]),
+    "simclr_selftest_umma": (_int, [_vp, _vp, _vp, _vp]),
+}
+
+
+class SimclrLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libsimclr_b200.so (built by build.py / __graft_entry__.build()); raise loudly when absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise SimclrLibraryError(
+                f"{LIB_PATH} is missing: build the sm_100a extension first (python pytorch-simclr_b200/build.py). "
+                "This package has no CPU or eager fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)      # AttributeError -> the library is stale
+            fn.restype = res
+            fn.argtypes = args
+        if lib.simclr_abi_version() != ABI_VERSION:
+            raise SimclrLibraryError(f"ABI mismatch: library {lib.simclr_abi_version()} vs binding {ABI_VERSION}")
+        _lib = lib
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    """Translate a C-ABI return code (include/simclr_b200.h error convention) into an exception."""
+    if code == 0:
+        return
+    msg = load().simclr_error_string(code).decode()
+    if code < 0:
+        raise ValueError(f"{what}: {msg} (code {code})")
+    raise RuntimeError(f"{what}: CUDA error {code}: {msg}")

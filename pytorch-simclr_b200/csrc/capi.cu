@@ -1,0 +1,423 @@
+// Host side of the C ABI declared in include/simclr_b200.h: argument validation, workspace carving,
+// TMA tensor-map encoding and kernel launches.  No host synchronisation, no allocation.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/simclr_b200.h"
+#include "aux_kernels.cuh"
+#include "selftest.cuh"
+
+using namespace simclr;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+// bf16 [rows][d_pad] row-major, box = 128 rows x 64 elements (128 B), 128-byte swizzle
+int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, int64_t d_pad) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return SIMCLR_ERR_DRIVER_ENTRY;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d_pad), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(d_pad) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kAtomK), static_cast<cuuint32_t>(kBlockM)};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? SIMCLR_OK : SIMCLR_ERR_TENSOR_MAP;
+}
+
+struct DeviceInfo {
+    int sm_count = 148;
+    int cc_major = 0;
+    bool valid = false;
+};
+
+const DeviceInfo& device_info() {
+    static DeviceInfo info[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        static DeviceInfo fallback;
+        return fallback;
+    }
+    if (!info[dev].valid) {
+        cudaDeviceGetAttribute(&info[dev].sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&info[dev].cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+        info[dev].valid = true;
+    }
+    return info[dev];
+}
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct Geometry {
+    int64_t bl_pad, bg_pad, d_pad;
+    int n_row_blocks, n_col_tiles, grid, max_segs;
+    long long total_tiles;
+};
+
+int make_geometry(int loss, int64_t b_local, int64_t b_global, int64_t row_offset, int64_t d, Geometry* g) {
+    if (loss != SIMCLR_LOSS_NTXENT && loss != SIMCLR_LOSS_MODIFIED) return SIMCLR_ERR_BAD_LOSS;
+    if (b_local < 1 || b_global < b_local || d < 1 || row_offset < 0 || row_offset + b_local > b_global)
+        return SIMCLR_ERR_BAD_SHAPE;
+    if (b_global > (int64_t(1) << 29)) return SIMCLR_ERR_BAD_SHAPE;
+    g->d_pad = simclr_pad_dim(d);
+    if (g->d_pad == 0) return SIMCLR_ERR_UNSUPPORTED_DIM;
+    g->bl_pad = round_up(b_local, kBlockM);
+    g->bg_pad = round_up(b_global, kBlockM);
+    g->n_row_blocks = static_cast<int>(2 * g->bl_pad / kBlockM);
+    g->n_col_tiles = static_cast<int>((loss == SIMCLR_LOSS_NTXENT ? 2 : 1) * g->bg_pad / kBlockN);
+    g->total_tiles = static_cast<long long>(g->n_row_blocks) * g->n_col_tiles;
+    const int sms = device_info().sm_count;
+    g->grid = static_cast<int>(g->total_tiles < sms ? g->total_tiles : sms);
+    const long long per_cta = (g->total_tiles + g->grid - 1) / g->grid;
+    g->max_segs = static_cast<int>((per_cta + g->n_col_tiles - 2) / g->n_col_tiles + 1);
+    return SIMCLR_OK;
+}
+
+struct FwdWorkspace {
+    float* part;
+    float* block_part;
+    unsigned int* ticket;
+    size_t bytes;
+};
+FwdWorkspace carve_forward(const Geometry& g, void* base) {
+    FwdWorkspace w;
+    size_t off = 0;
+    w.ticket = reinterpret_cast<unsigned int*>(static_cast<char*>(base) + off);
+    off += 256;
+    w.block_part = reinterpret_cast<float*>(static_cast<char*>(base) + off);
+    off += align256(static_cast<size_t>(g.n_row_blocks) * 4 * sizeof(float));
+    w.part = reinterpret_cast<float*>(static_cast<char*>(base) + off);
+    off += align256(static_cast<size_t>(g.grid) * g.max_segs * 2 * kFwdFields * kBlockM * sizeof(float));
+    w.bytes = off;
+    return w;
+}
+struct BwdWorkspace {
+    float* colvec;
+    float* dacc;
+    size_t dacc_floats;
+    size_t bytes;
+};
+BwdWorkspace carve_backward(const Geometry& g, void* base) {
+    BwdWorkspace w;
+    size_t off = 0;
+    w.colvec = reinterpret_cast<float*>(static_cast<char*>(base) + off);
+    off += align256(static_cast<size_t>(4) * g.bg_pad * sizeof(float));
+    w.dacc = reinterpret_cast<float*>(static_cast<char*>(base) + off);
+    w.dacc_floats = static_cast<size_t>(2) * g.bl_pad * g.d_pad;
+    off += align256(w.dacc_floats * sizeof(float));
+    w.bytes = off;
+    return w;
+}
+
+// log2-domain constants shared by forward and backward
+struct Scales {
+    float k2, inv_tau, m2, qscale;
+    int const_shift;
+};
+Scales make_scales(int loss, float temperature, int normalize, int64_t b_global) {
+    Scales s;
+    s.inv_tau = 1.0f / temperature;
+    s.qscale = static_cast<float>(b_global);
+    if (loss == SIMCLR_LOSS_NTXENT) {
+        s.k2 = 1.4426950408889634f * s.inv_tau;
+        // |S| <= 1 (+ bf16 rounding) when rows are normalised: exp2(S*k2 - m2) <= 1 and a_r <= 2^(2*k2)
+        s.m2 = s.k2 * 1.0078125f;
+        s.const_shift = (normalize && 2.0f * s.k2 <= 80.0f) ? 1 : 0;
+    } else {
+        s.k2 = s.inv_tau;
+        // y = log2(q) * (1/tau - 1) with q in [1e-4, B]
+        const float lo = std::log2(kClampMin) * (s.k2 - 1.0f), hi = std::log2(s.qscale) * (s.k2 - 1.0f);
+        s.m2 = std::fmax(lo, hi);
+        // a_r = g 2^(m2 - lse2_r) with lse2_r >= log2(1e-4)/tau
+        const float worst = s.m2 - std::log2(kClampMin) * s.k2;
+        s.const_shift = (worst <= 80.0f) ? 1 : 0;
+    }
+    return s;
+}
+
+template <int D, int kLoss, bool kBackward>
+int launch_tile(const CUtensorMap& rows, const CUtensorMap& cols, const TileParams& p, int grid, cudaStream_t st) {
+    auto kern = contrastive_tile_kernel<D, kLoss, kBackward>;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             SmemLayout<D>::kDynamicBytes);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        configured[dev & 63] = true;
+    }
+    kern<<<grid, kNumThreads, SmemLayout<D>::kDynamicBytes, st>>>(rows, cols, p);
+    return static_cast<int>(cudaGetLastError());
+}
+
+template <bool kBackward>
+int dispatch_tile(int loss, int64_t d_pad, const CUtensorMap& rows, const CUtensorMap& cols, const TileParams& p,
+                  int grid, cudaStream_t st) {
+#define SIMCLR_CASE(DV)                                                                          \
+    case DV:                                                                                     \
+        return loss == SIMCLR_LOSS_NTXENT ? launch_tile<DV, kNtXent, kBackward>(rows, cols, p, grid, st) \
+                                          : launch_tile<DV, kModified, kBackward>(rows, cols, p, grid, st);
+    switch (d_pad) {
+        SIMCLR_CASE(64)
+        SIMCLR_CASE(128)
+        SIMCLR_CASE(256)
+    }
+#undef SIMCLR_CASE
+    return SIMCLR_ERR_UNSUPPORTED_DIM;
+}
+
+AuxParams make_aux(const Geometry& g, const Scales& s, int64_t b_local, int64_t b_global, int64_t row_offset,
+                   int64_t d, int normalize) {
+    AuxParams a;
+    a.b_loc = static_cast<int>(b_local);
+    a.b_glob = static_cast<int>(b_global);
+    a.row_off = static_cast<int>(row_offset);
+    a.bl_pad = static_cast<int>(g.bl_pad);
+    a.bg_pad = static_cast<int>(g.bg_pad);
+    a.d = static_cast<int>(d);
+    a.d_pad = static_cast<int>(g.d_pad);
+    a.normalize = normalize;
+    a.k2 = s.k2;
+    a.inv_tau = s.inv_tau;
+    a.m2 = s.m2;
+    a.const_shift = s.const_shift;
+    a.qscale = s.qscale;
+    return a;
+}
+
+TileParams make_tile_params(const Geometry& g, const Scales& s, int64_t b_local, int64_t b_global, int64_t row_offset) {
+    TileParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.b_loc = static_cast<int>(b_local);
+    p.b_glob = static_cast<int>(b_global);
+    p.row_off = static_cast<int>(row_offset);
+    p.bl_pad = static_cast<int>(g.bl_pad);
+    p.bg_pad = static_cast<int>(g.bg_pad);
+    p.n_row_blocks = g.n_row_blocks;
+    p.n_col_tiles = g.n_col_tiles;
+    p.max_segs = g.max_segs;
+    p.total_tiles = g.total_tiles;
+    p.k2 = s.k2;
+    p.m2 = s.m2;
+    p.const_shift = s.const_shift;
+    p.qscale = s.qscale;
+    return p;
+}
+
+inline bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
+
+int check_device() {
+    const DeviceInfo& di = device_info();
+    if (!di.valid) return static_cast<int>(cudaErrorNoDevice);
+    if (di.cc_major != 10) return SIMCLR_ERR_NOT_SM100;
+    return SIMCLR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int simclr_abi_version(void) { return SIMCLR_ABI_VERSION; }
+
+const char* simclr_error_string(int code) {
+    switch (code) {
+        case SIMCLR_OK: return "ok";
+        case SIMCLR_ERR_NULL_POINTER: return "null pointer argument";
+        case SIMCLR_ERR_BAD_SHAPE: return "bad shape (need 1 <= b_local <= b_global, d >= 1, shard inside the batch)";
+        case SIMCLR_ERR_UNSUPPORTED_DIM: return "embedding dimension above 256 is not supported";
+        case SIMCLR_ERR_BAD_DTYPE: return "unsupported element type (f32 or bf16)";
+        case SIMCLR_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
+        case SIMCLR_ERR_MISALIGNED: return "pointer not 16-byte aligned";
+        case SIMCLR_ERR_BAD_TEMPERATURE: return "temperature must be finite and > 0";
+        case SIMCLR_ERR_NOT_SM100: return "device is not compute capability 10.x (B200)";
+        case SIMCLR_ERR_DRIVER_ENTRY: return "cuTensorMapEncodeTiled not available from the driver";
+        case SIMCLR_ERR_TENSOR_MAP: return "cuTensorMapEncodeTiled failed";
+        case SIMCLR_ERR_BAD_LOSS: return "unknown loss kind";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+    return "unknown error";
+}
+
+int64_t simclr_pad_rows(int64_t b) { return b < 1 ? 0 : round_up(b, kBlockM); }
+
+int64_t simclr_pad_dim(int64_t d) {
+    if (d < 1 || d > 256) return 0;
+    return d <= 64 ? 64 : (d <= 128 ? 128 : 256);
+}
+
+size_t simclr_forward_workspace_bytes(int loss, int64_t b_local, int64_t b_global, int64_t d) {
+    Geometry g;
+    if (make_geometry(loss, b_local, b_global, 0, d, &g) != SIMCLR_OK) return 0;
+    return carve_forward(g, nullptr).bytes;
+}
+
+size_t simclr_backward_workspace_bytes(int loss, int64_t b_local, int64_t b_global, int64_t d) {
+    Geometry g;
+    if (make_geometry(loss, b_local, b_global, 0, d, &g) != SIMCLR_OK) return 0;
+    return carve_backward(g, nullptr).bytes;
+}
+
+int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
+                   int normalize, void* operand, float* inv_norm, float* pos_dot, void* stream) {
+    if (!x_batch1 || !x_batch2 || !operand || !inv_norm || !pos_dot) return SIMCLR_ERR_NULL_POINTER;
+    if (in_dtype != SIMCLR_DTYPE_F32 && in_dtype != SIMCLR_DTYPE_BF16) return SIMCLR_ERR_BAD_DTYPE;
+    Geometry g;
+    int rc = make_geometry(loss, b_local, b_local, 0, d, &g);
+    if (rc) return rc;
+    if (misaligned(operand)) return SIMCLR_ERR_MISALIGNED;
+    if ((rc = check_device())) return rc;
+    Scales s = make_scales(loss, 1.0f, normalize, b_local);
+    AuxParams a = make_aux(g, s, b_local, b_local, 0, d, normalize);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int warps = 8;
+    const int blocks = static_cast<int>((g.bl_pad + warps - 1) / warps);
+    auto* op = static_cast<__nv_bfloat16*>(operand);
+#define SIMCLR_PREP(T, LOSS) \
+    prepare_kernel<T, LOSS><<<blocks, warps * 32, 0, st>>>(static_cast<const T*>(x_batch1), static_cast<const T*>(x_batch2), a, op, inv_norm, pos_dot)
+    if (loss == SIMCLR_LOSS_NTXENT) {
+        if (in_dtype == SIMCLR_DTYPE_F32) SIMCLR_PREP(float, kNtXent);
+        else SIMCLR_PREP(__nv_bfloat16, kNtXent);
+    } else {
+        if (in_dtype == SIMCLR_DTYPE_F32) SIMCLR_PREP(float, kModified);
+        else SIMCLR_PREP(__nv_bfloat16, kModified);
+    }
+#undef SIMCLR_PREP
+    return static_cast<int>(cudaGetLastError());
+}
+
+int simclr_forward(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
+                   int64_t row_offset, int64_t d, float temperature, const float* pos_dot, const float* row_weight,
+                   float* lse2, float* row_loss, float* stats, float* loss_out, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+    if (!operand_rows || !operand_cols || !pos_dot || !lse2 || !row_loss || !stats || !workspace)
+        return SIMCLR_ERR_NULL_POINTER;
+    if (!(temperature > 0.f) || !std::isfinite(temperature)) return SIMCLR_ERR_BAD_TEMPERATURE;
+    Geometry g;
+    int rc = make_geometry(loss, b_local, b_global, row_offset, d, &g);
+    if (rc) return rc;
+    if (misaligned(operand_rows) || misaligned(operand_cols) || misaligned(workspace)) return SIMCLR_ERR_MISALIGNED;
+    FwdWorkspace w = carve_forward(g, workspace);
+    if (workspace_bytes < w.bytes) return SIMCLR_ERR_WORKSPACE_TOO_SMALL;
+    if ((rc = check_device())) return rc;
+
+    CUtensorMap map_rows, map_cols;
+    if ((rc = make_operand_map(&map_rows, operand_rows, 2 * g.bl_pad, g.d_pad))) return rc;
+    if ((rc = make_operand_map(&map_cols, operand_cols, 2 * g.bg_pad, g.d_pad))) return rc;
+
+    // the forward never needs the bounded-score shortcut: normalize=1 only affects backward's const_shift
+    Scales s = make_scales(loss, temperature, 1, b_global);
+    TileParams p = make_tile_params(g, s, b_local, b_global, row_offset);
+    p.part = w.part;
+    p.ticket = w.ticket;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = dispatch_tile<false>(loss, g.d_pad, map_rows, map_cols, p, g.grid, st))) return rc;
+
+    AuxParams a = make_aux(g, s, b_local, b_global, row_offset, d, 1);
+    if (loss == SIMCLR_LOSS_NTXENT)
+        forward_finalize_kernel<kNtXent><<<g.n_row_blocks, kBlockM, 0, st>>>(
+            a, w.part, g.grid, g.max_segs, g.n_col_tiles, g.total_tiles, pos_dot, row_weight, lse2, row_loss,
+            w.block_part, w.ticket, stats, loss_out);
+    else
+        forward_finalize_kernel<kModified><<<g.n_row_blocks, kBlockM, 0, st>>>(
+            a, w.part, g.grid, g.max_segs, g.n_col_tiles, g.total_tiles, pos_dot, row_weight, lse2, row_loss,
+            w.block_part, w.ticket, stats, loss_out);
+    return static_cast<int>(cudaGetLastError());
+}
+
+int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t b_global,
+                    int64_t row_offset, int64_t d, int in_dtype, int normalize, float temperature,
+                    const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,
+                    const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+    if (!x_batch1 || !x_batch2 || !operand_rows || !operand_cols || !inv_norm || !pos_dot || !lse2_cols || !grad1 ||
+        !grad2 || !workspace)
+        return SIMCLR_ERR_NULL_POINTER;
+    if (in_dtype != SIMCLR_DTYPE_F32 && in_dtype != SIMCLR_DTYPE_BF16) return SIMCLR_ERR_BAD_DTYPE;
+    if (!(temperature > 0.f) || !std::isfinite(temperature)) return SIMCLR_ERR_BAD_TEMPERATURE;
+    Geometry g;
+    int rc = make_geometry(loss, b_local, b_global, row_offset, d, &g);
+    if (rc) return rc;
+    if (misaligned(operand_rows) || misaligned(operand_cols) || misaligned(workspace)) return SIMCLR_ERR_MISALIGNED;
+    BwdWorkspace w = carve_backward(g, workspace);
+    if (workspace_bytes < w.bytes) return SIMCLR_ERR_WORKSPACE_TOO_SMALL;
+    if ((rc = check_device())) return rc;
+
+    CUtensorMap map_rows, map_cols;
+    if ((rc = make_operand_map(&map_rows, operand_rows, 2 * g.bl_pad, g.d_pad))) return rc;
+    if ((rc = make_operand_map(&map_cols, operand_cols, 2 * g.bg_pad, g.d_pad))) return rc;
+
+    Scales s = make_scales(loss, temperature, normalize, b_global);
+    AuxParams a = make_aux(g, s, b_local, b_global, row_offset, d, normalize);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    backward_prepare_kernel<<<device_info().sm_count * 2, 256, 0, st>>>(
+        a, lse2_cols, col_scale, w.colvec, reinterpret_cast<float4*>(w.dacc), w.dacc_floats / 4);
+    if ((rc = static_cast<int>(cudaGetLastError()))) return rc;
+
+    TileParams p = make_tile_params(g, s, b_local, b_global, row_offset);
+    p.colvec = w.colvec;
+    p.dacc = w.dacc;
+    p.ticket = nullptr;
+    if ((rc = dispatch_tile<true>(loss, g.d_pad, map_rows, map_cols, p, g.grid, st))) return rc;
+
+    const int warps = 8;
+    const int blocks = static_cast<int>((b_local + warps - 1) / warps);
+#define SIMCLR_FIN(T, LOSS)                                                                                        \
+    backward_finalize_kernel<T, LOSS><<<blocks, warps * 32, 0, st>>>(                                              \
+        static_cast<const T*>(x_batch1), static_cast<const T*>(x_batch2), a, inv_norm, pos_dot, lse2_cols, col_scale, \
+        grad_out, w.dacc, static_cast<T*>(grad1), static_cast<T*>(grad2))
+    if (loss == SIMCLR_LOSS_NTXENT) {
+        if (in_dtype == SIMCLR_DTYPE_F32) SIMCLR_FIN(float, kNtXent);
+        else SIMCLR_FIN(__nv_bfloat16, kNtXent);
+    } else {
+        if (in_dtype == SIMCLR_DTYPE_F32) SIMCLR_FIN(float, kModified);
+        else SIMCLR_FIN(__nv_bfloat16, kModified);
+    }
+#undef SIMCLR_FIN
+    return static_cast<int>(cudaGetLastError());
+}
+
+int simclr_selftest_umma(const void* a_bf16, const void* b_bf16, float* out_f32, void* stream) {
+    if (!a_bf16 || !b_bf16 || !out_f32) return SIMCLR_ERR_NULL_POINTER;
+    int rc = check_device();
+    if (rc) return rc;
+    CUtensorMap map_a, map_b;
+    if ((rc = make_operand_map(&map_a, a_bf16, 128, 128))) return rc;
+    if ((rc = make_operand_map(&map_b, b_bf16, 128, 128))) return rc;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kSelftestSmemBytes);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        configured = true;
+    }
+    selftest_umma_kernel<<<1, 128, kSelftestSmemBytes, static_cast<cudaStream_t>(stream)>>>(map_a, map_b, out_f32);
+    return static_cast<int>(cudaGetLastError());
+}
+
+}  // extern "C"

@@ -1,0 +1,509 @@
+// NT-Xent and "modified" (probabilistic) contrastive losses for sm_100a -- the tile kernel.
+//
+// Reference semantics: objective.py:6-55 (contrastive_loss) and :58-98 (modified_contrastive_loss);
+// closed forms in DESIGN.md section 3.
+//
+// Geometry ("view-padded" layout).  B images, two views.  Every per-row array and every operand matrix
+// is laid out as [2][Bpad] with Bpad = ceil(B/128)*128 and zero padding, so that a 128-row block never
+// mixes views.  Rows are this rank's shard (b_loc images, padded bl_pad), columns are the global batch
+// (b_glob images, padded bg_pad).  Column index c in [0, 2*bg_pad): view vc = c / bg_pad, image
+// ic = c % bg_pad, valid iff ic < b_glob.  For row (vr, image g):
+//     NT-Xent : all columns of both views except itself (vr, g); positive = (1-vr, g)
+//     modified: the columns of the other view only;              positive = (1-vr, g)
+//
+//   S[r,c]   = <op_r, op_c>              tcgen05.mma kind::f16, bf16 operands, fp32 accumulate in TMEM
+//   forward  : online max / sum of exp2(score) over the valid negatives; the positive pair is excluded
+//              here and added in exact fp32 by the finalize kernel; first-argmax bookkeeping
+//   backward : W[r,c] (symmetric form) written as bf16 into TMEM over the consumed score
+//              tile and used as the A operand of a second tcgen05.mma:  dacc[r,:] += W[r,:] * op[c,:]
+// The 2N x 2N matrix never exists outside one 128 x 128 TMEM tile.
+//
+// Warp roles (384 threads, 1 CTA / SM, each CTA owns a contiguous range of (row block, column tile)):
+//   warp 0      TMA producer (row-block tile once per segment, column tiles through an mbarrier ring)
+//   warp 1      UMMA issuer (one lane)
+//   warp 2      TMEM allocator / deallocator
+//   warp 3      idle
+//   warps 4-7   softmax warpgroup 0  (even CTA iterations, TMEM score buffer 0)
+//   warps 8-11  softmax warpgroup 1  (odd  CTA iterations, TMEM score buffer 1)
+#pragma once
+
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "sm100_ptx.cuh"
+
+namespace simclr {
+
+constexpr int kBlockM = 128;          // rows per row block (= UMMA M = TMEM lanes)
+constexpr int kBlockN = 128;          // columns per tile   (= UMMA N of the score MMA)
+constexpr int kAtomK = 64;            // bf16 elements per 128-byte swizzle row
+constexpr int kAtomBytes = kBlockM * kAtomK * 2;   // one TMA box: 128 rows x 128 B = 16 KB
+constexpr int kNumThreads = 384;
+constexpr int kSoftmaxWarp0 = 4;
+constexpr int kTmemCols = 512;
+constexpr int kFwdFields = 5;         // per-row partial: sum, run-max, max-preceding, max-following, pos(mma)
+constexpr float kNegBig = -3.0e38f;   // finite stand-in for -inf
+constexpr float kClampMin = 1e-4f;    // reference objective.py:87-88
+
+enum LossKind : int { kNtXent = 0, kModified = 1 };
+
+struct TileParams {
+    int b_loc;         // images held by this rank
+    int b_glob;        // images in the global batch
+    int row_off;       // global index of this rank's first image
+    int bl_pad;        // b_loc rounded up to 128
+    int bg_pad;        // b_glob rounded up to 128
+    int n_row_blocks;  // 2 * bl_pad / 128
+    int n_col_tiles;   // column tiles per row block (NT-Xent: 2*bg_pad/128, modified: bg_pad/128)
+    int max_segs;      // max number of row blocks one CTA touches
+    long long total_tiles;
+    float k2;          // NT-Xent: log2(e)/tau.  modified: 1/tau (scores are already log2)
+    float m2;          // constant log2-domain shift of the one-exp backward form
+    int const_shift;   // backward: 1 -> one exp per element (bounded scores), 0 -> general two-exp form
+    float qscale;      // modified loss: (float) b_glob, the factor inside the clamp
+    float* part;       // forward : [grid][max_segs][2 warpgroups][kFwdFields][128]
+    const float* colvec;   // backward: [2 planes][2*bg_pad]; plane 0 = a_c (or g_c), plane 1 = lse2_c
+    float* dacc;           // backward: [2*bl_pad][D] fp32, zero on entry, accumulated with red.global.add
+    unsigned int* ticket;  // zeroed by CTA 0 for the finalize kernel's last-block reduction
+};
+
+template <int D>
+struct SmemLayout {
+    static constexpr int kAtoms = D / kAtomK;
+    static constexpr int kTileBytes = kAtoms * kAtomBytes;          // 128 x D bf16
+    static constexpr int kStages = (D <= 64) ? 6 : (D <= 128 ? 4 : 2);
+    static constexpr int kColvecBytes = 2 * kBlockN * 4;             // two planes of 128 floats
+    static constexpr int kOffA = 0;
+    static constexpr int kOffB = kTileBytes;
+    static constexpr int kOffCv = kOffB + kStages * kTileBytes;
+    static constexpr int kOffBar = kOffCv + kStages * kColvecBytes;
+    // barriers: a_full, a_empty, acc_full, acc_empty, b_full[S], b_empty[S], s_full[2], s_free[2], w_full[2]
+    static constexpr int kNumBars = 4 + 2 * kStages + 6;
+    static constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
+    static constexpr int kBytes = kOffTmemPtr + 16;
+    static constexpr int kDynamicBytes = kBytes + 1024;              // slack for manual 1024 B alignment
+};
+
+// First global column of tile j for a row block of view vr.
+template <int kLoss>
+SIMCLR_DEVICE int tile_col0(const TileParams& p, int vr, int j) {
+    if constexpr (kLoss == kNtXent) return j * kBlockN;
+    else return (1 - vr) * p.bg_pad + j * kBlockN;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-element maths.  "v" is the tracked raw value (monotone in the logit):
+//   NT-Xent : v = S              logit2 = v * k2                     (k2 = log2(e)/tau)
+//   modified: v = max(B*S, 1e-4) logit2 = log2(v) * k2               (k2 = 1/tau)
+// ---------------------------------------------------------------------------------------------
+template <int kLoss>
+SIMCLR_DEVICE float raw_value(const TileParams& p, float s) {
+    if constexpr (kLoss == kNtXent) return s;
+    else return fmaxf(s * p.qscale, kClampMin);
+}
+template <int kLoss>
+SIMCLR_DEVICE float logit2(const TileParams& p, float v) {
+    if constexpr (kLoss == kNtXent) return v * p.k2;
+    else return lg2_approx(v) * p.k2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The tile kernel
+// ---------------------------------------------------------------------------------------------
+template <int D, int kLoss, bool kBackward>
+__global__ void __launch_bounds__(kNumThreads, 1)
+contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
+                        const TileParams p) {
+    using L = SmemLayout<D>;
+    constexpr int S = L::kStages;
+    constexpr uint32_t kIdescScore = make_idesc_bf16(kBlockM, kBlockN, 0, 0);
+    constexpr uint32_t kIdescGrad = make_idesc_bf16(kBlockM, D, 0, 1);
+    constexpr uint32_t kTmemAcc = 2 * kBlockN;       // accumulator columns start after the two score buffers
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem + L::kOffA;
+    uint8_t* smem_b = smem + L::kOffB;
+    float* smem_cv = reinterpret_cast<float*>(smem + L::kOffCv);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+    uint64_t* a_full = bars + 0;
+    uint64_t* a_empty = bars + 1;
+    uint64_t* acc_full = bars + 2;
+    uint64_t* acc_empty = bars + 3;
+    uint64_t* b_full = bars + 4;
+    uint64_t* b_empty = b_full + S;
+    uint64_t* s_full = b_empty + S;      // [2] score tile ready in TMEM
+    uint64_t* s_free = s_full + 2;       // [2] forward only: softmax finished reading the score tile
+    uint64_t* w_full = s_free + 2;       // [2] backward only: W written to TMEM
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + L::kOffTmemPtr);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // contiguous tile range of this CTA
+    const long long t_begin = (p.total_tiles * blockIdx.x) / gridDim.x;
+    const long long t_end = (p.total_tiles * (blockIdx.x + 1)) / gridDim.x;
+    const int nct = p.n_col_tiles;
+    const int blocks_per_view = p.bl_pad / kBlockM;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_rows);
+        tma_prefetch_desc(&tmap_cols);
+        if (blockIdx.x == 0 && p.ticket != nullptr) *p.ticket = 0u;
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 256);
+        for (int i = 0; i < S; ++i) {
+            mbar_init(b_full + i, 1);
+            mbar_init(b_empty + i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(s_full + i, 1);
+            mbar_init(s_free + i, 128);
+            mbar_init(w_full + i, 128);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_smem, kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int it = 0, seg = 0;
+            for (long long t = t_begin; t < t_end; ++t, ++it) {
+                const int rb = static_cast<int>(t / nct);
+                const int j = static_cast<int>(t % nct);
+                if (t == t_begin || j == 0) {
+                    if (seg > 0) mbar_wait(a_empty, (seg - 1) & 1, 100);
+                    mbar_arrive_expect_tx(a_full, L::kTileBytes);
+#pragma unroll
+                    for (int ka = 0; ka < L::kAtoms; ++ka)
+                        tma_load_2d(smem_a + ka * kAtomBytes, &tmap_rows, a_full, ka * kAtomK, rb * kBlockM);
+                    ++seg;
+                }
+                const int stage = it % S;
+                const int use = it / S;
+                if (use > 0) mbar_wait(b_empty + stage, (use - 1) & 1, 101);
+                const int c0 = tile_col0<kLoss>(p, rb / blocks_per_view, j);
+                mbar_arrive_expect_tx(b_full + stage, L::kTileBytes + (kBackward ? L::kColvecBytes : 0));
+#pragma unroll
+                for (int ka = 0; ka < L::kAtoms; ++ka)
+                    tma_load_2d(smem_b + stage * L::kTileBytes + ka * kAtomBytes, &tmap_cols, b_full + stage,
+                                ka * kAtomK, c0);
+                if constexpr (kBackward) {
+                    float* cv = smem_cv + stage * 2 * kBlockN;
+                    bulk_load_1d(cv, p.colvec + c0, kBlockN * 4, b_full + stage);
+                    bulk_load_1d(cv + kBlockN, p.colvec + 2 * p.bg_pad + c0, kBlockN * 4, b_full + stage);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ UMMA issuer ================================
+        if (lane == 0) {
+            const uint32_t a_addr = smem_u32(smem_a);
+            const uint32_t b_addr0 = smem_u32(smem_b);
+            const int n = static_cast<int>(t_end - t_begin);
+
+            // score MMA for CTA iteration `idx`:  S[buf] = A * B_stage^T   (both operands K-major)
+            auto issue_score = [&](int idx, int& seg_seen) {
+                const long long t = t_begin + idx;
+                const int j = static_cast<int>(t % nct);
+                const bool seg_first = (idx == 0) || (j == 0);
+                const bool seg_last = (idx == n - 1) || (j == nct - 1);
+                if (seg_first) {
+                    mbar_wait(a_full, seg_seen & 1, 200);
+                    ++seg_seen;
+                }
+                const int stage = idx % S;
+                mbar_wait(b_full + stage, (idx / S) & 1, 201);
+                const int buf = idx & 1;
+                if constexpr (!kBackward) {
+                    if (idx >= 2) mbar_wait(s_free + buf, ((idx >> 1) - 1) & 1, 202);
+                }
+                tc_fence_after_sync();
+                const uint32_t b_addr = b_addr0 + stage * L::kTileBytes;
+#pragma unroll
+                for (int ka = 0; ka < L::kAtoms; ++ka) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t off = ka * kAtomBytes + kk * 32;
+                        umma_ss(tmem_base + buf * kBlockN, make_smem_desc(a_addr + off, 0, 1024),
+                                make_smem_desc(b_addr + off, 0, 1024), kIdescScore, (ka | kk) != 0);
+                    }
+                }
+                // s_full is committed last so that, when the softmax sees it, the other arrivals have landed
+                if constexpr (!kBackward) umma_commit(b_empty + stage);
+                if (seg_last) umma_commit(a_empty);
+                umma_commit(s_full + buf);
+            };
+
+            int seg_seen = 0;
+            if constexpr (!kBackward) {
+                for (int idx = 0; idx < n; ++idx) issue_score(idx, seg_seen);
+            } else {
+                int seg_done = 0;     // segments whose accumulator has been handed to the flush
+                if (n > 0) issue_score(0, seg_seen);
+                for (int idx = 0; idx < n; ++idx) {
+                    if (idx + 1 < n) issue_score(idx + 1, seg_seen);      // keep the tensor pipe one tile ahead
+                    const long long t = t_begin + idx;
+                    const int j = static_cast<int>(t % nct);
+                    const bool seg_first = (idx == 0) || (j == 0);
+                    const bool seg_last = (idx == n - 1) || (j == nct - 1);
+                    const int buf = idx & 1;
+                    const int stage = idx % S;
+                    if (seg_first && seg_done > 0) mbar_wait(acc_empty, (seg_done - 1) & 1, 203);
+                    mbar_wait(w_full + buf, (idx >> 1) & 1, 204);
+                    tc_fence_after_sync();
+                    // gradient MMA: acc += W[buf] (TMEM, 128 x 128 bf16) * B_stage (MN-major: K = column index)
+                    const uint32_t b_addr = b_addr0 + stage * L::kTileBytes;
+#pragma unroll
+                    for (int kc = 0; kc < kBlockN / 16; ++kc) {
+                        umma_ts(tmem_base + kTmemAcc, tmem_base + buf * kBlockN + kc * 8,
+                                make_smem_desc(b_addr + kc * 2048, kAtomBytes, 1024), kIdescGrad,
+                                !(seg_first && kc == 0));
+                    }
+                    umma_commit(b_empty + stage);
+                    if (seg_last) {
+                        umma_commit(acc_full);
+                        ++seg_done;
+                    }
+                }
+            }
+        }
+    } else if (warp >= kSoftmaxWarp0) {
+        // ================================ softmax warpgroups ================================
+        const int wg = (warp - kSoftmaxWarp0) >> 2;          // 0 / 1
+        const int quarter = warp & 3;                         // TMEM lane quarter this warp may touch
+        const int row_in_block = quarter * 32 + lane;
+        const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+        const int n = static_cast<int>(t_end - t_begin);
+
+        int idx = 0;
+        int seg = 0;
+        while (idx < n) {
+            // ---- segment = run of tiles sharing one row block ----
+            const long long t0 = t_begin + idx;
+            const int rb = static_cast<int>(t0 / nct);
+            const int j0 = static_cast<int>(t0 % nct);
+            const int seg_len = min(n - idx, nct - j0);
+
+            const int vr = rb / blocks_per_view;                                  // view of this row block
+            const int img = (rb - vr * blocks_per_view) * kBlockM + row_in_block; // local image index
+            const bool row_ok = img < p.b_loc;
+            const int g = p.row_off + img;                                        // global image index
+            const int diag_col = (kLoss == kNtXent && row_ok) ? vr * p.bg_pad + g : -1;
+            const int pos_col = row_ok ? (1 - vr) * p.bg_pad + g : -1;
+            // warp-uniform description of this warp's 32 rows
+            const int img_lo = (rb - vr * blocks_per_view) * kBlockM + quarter * 32;
+            const bool warp_rows_ok = img_lo + 31 < p.b_loc;
+            const int g_lo = p.row_off + img_lo, g_hi = g_lo + 31;
+
+            float run_max = kNegBig, sum = 0.f, max_prec = kNegBig, max_foll = kNegBig, pos_mma = kNegBig;
+            float row_a = 0.f, row_l2 = 0.f;
+            if constexpr (kBackward) {
+                if (row_ok) {
+                    row_a = __ldg(p.colvec + vr * p.bg_pad + g);
+                    row_l2 = __ldg(p.colvec + 2 * p.bg_pad + vr * p.bg_pad + g);
+                }
+            }
+
+            for (int s = 0; s < seg_len; ++s) {
+                const int it = idx + s;
+                if ((it & 1) != wg) continue;
+                const int c0 = tile_col0<kLoss>(p, vr, j0 + s);
+                const int vc = c0 >= p.bg_pad ? 1 : 0;            // a tile never mixes views
+                const int ic0 = c0 - vc * p.bg_pad;               // image index of the tile's first column
+                const int buf = wg;
+                const int stage = it % S;
+
+                mbar_wait(s_full + buf, (it >> 1) & 1, 300);
+                if constexpr (kBackward) mbar_wait(b_full + stage, (it / S) & 1, 301);   // colvec visibility
+                tc_fence_after_sync();
+                const float* cv = smem_cv + stage * 2 * kBlockN;
+
+                // ---- warp-uniform tile classification ----
+                const bool overlaps_rows = !(ic0 > g_hi || ic0 + kBlockN - 1 < g_lo);
+                bool special = !warp_rows_ok || overlaps_rows;    // diagonal or positive may be inside
+                bool tile_prec = false;
+                if constexpr (!kBackward) {
+                    special = special || (ic0 + kBlockN - 1 >= p.b_glob);        // padded columns inside
+                    // first-argmax rule: does the tile precede the positive in the reference's column order?
+                    // NT-Xent rows see [view-2 block | view-1 block] (objective.py:48-49); modified rows see
+                    // the other view in natural order (objective.py:93).
+                    const bool before = ic0 + kBlockN - 1 < g_lo;
+                    if constexpr (kLoss == kNtXent) tile_prec = (vr == 0) ? (vc == 1 && before) : (vc == 1 || before);
+                    else tile_prec = before;
+                }
+
+#pragma unroll 1
+                for (int q = 0; q < kBlockN / 32; ++q) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + lane_addr + buf * kBlockN + q * 32, r);
+                    tmem_ld_wait();
+                    const int cq = c0 + q * 32;
+                    if constexpr (!kBackward) {
+                        // ------------------------- forward -------------------------
+                        float v[32];
+                        float cm = kNegBig;
+                        if (!special) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                v[i] = raw_value<kLoss>(p, __uint_as_float(r[i]));
+                                cm = fmaxf(cm, v[i]);
+                            }
+                            if (tile_prec) max_prec = fmaxf(max_prec, cm); else max_foll = fmaxf(max_foll, cm);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const int c = cq + i;
+                                const int ic = c - vc * p.bg_pad;
+                                const float x = raw_value<kLoss>(p, __uint_as_float(r[i]));
+                                if (c == pos_col) pos_mma = x;
+                                const bool valid = row_ok && ic < p.b_glob && c != diag_col && c != pos_col;
+                                v[i] = valid ? x : kNegBig;
+                                if (valid) {
+                                    cm = fmaxf(cm, x);
+                                    bool prec;
+                                    if constexpr (kLoss == kNtXent) prec = (vr == 0) ? (vc == 1 && ic < g) : (vc == 1 || ic < g);
+                                    else prec = ic < g;
+                                    if (prec) max_prec = fmaxf(max_prec, x); else max_foll = fmaxf(max_foll, x);
+                                }
+                            }
+                        }
+                        if (cm > run_max) {
+                            // rescale the running sum to the new maximum (0 * 0 when run_max is still the sentinel)
+                            sum *= (run_max == kNegBig) ? 0.f : ex2_approx(logit2<kLoss>(p, run_max) - logit2<kLoss>(p, cm));
+                            run_max = cm;
+                        }
+                        if (run_max != kNegBig) {
+                            const float shift = logit2<kLoss>(p, run_max);
+                            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 2) {
+                                float e0, e1;
+                                if constexpr (kLoss == kNtXent) {
+                                    e0 = ex2_approx(fmaf(v[i], p.k2, -shift));
+                                    e1 = ex2_approx(fmaf(v[i + 1], p.k2, -shift));
+                                } else {
+                                    e0 = ex2_approx(fmaf(lg2_approx(v[i]), p.k2, -shift));
+                                    e1 = ex2_approx(fmaf(lg2_approx(v[i + 1]), p.k2, -shift));
+                                }
+                                if (special) {               // masked entries carry the sentinel
+                                    e0 = (v[i] == kNegBig) ? 0.f : e0;
+                                    e1 = (v[i + 1] == kNegBig) ? 0.f : e1;
+                                }
+                                acc0 += e0;
+                                acc1 += e1;
+                            }
+                            sum += acc0 + acc1;
+                        }
+                    } else {
+                        // ------------------------- backward -------------------------
+                        uint32_t w[16];
+                        const float4* cva = reinterpret_cast<const float4*>(cv + q * 32);
+                        const float4* cvl = reinterpret_cast<const float4*>(cv + kBlockN + q * 32);
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 ac = cva[i >> 2];
+                            float4 lc = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (!p.const_shift) lc = cvl[i >> 2];
+                            const float acs[4] = {ac.x, ac.y, ac.z, ac.w};
+                            const float lcs[4] = {lc.x, lc.y, lc.z, lc.w};
+                            float wv[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float sraw = __uint_as_float(r[i + u]);
+                                float y;       // log2-domain exponent argument shared by both softmax terms
+                                bool live = true;
+                                if constexpr (kLoss == kNtXent) {
+                                    y = sraw * p.k2;
+                                } else {
+                                    // d/dP of log(max(B P,1e-4))/tau = 1/(tau P) where live; folded: e^{A}/P = B q^{1/tau - 1}
+                                    const float qv = sraw * p.qscale;
+                                    live = qv >= kClampMin;
+                                    y = lg2_approx(fmaxf(qv, kClampMin)) * (p.k2 - 1.0f);
+                                }
+                                float wval;
+                                if (p.const_shift) wval = ex2_approx(y - p.m2) * (row_a + acs[u]);
+                                else wval = row_a * ex2_approx(y - row_l2) + acs[u] * ex2_approx(y - lcs[u]);
+                                if (special) {
+                                    const int c = cq + i + u;
+                                    if (c == diag_col || c == pos_col) wval = 0.f;
+                                }
+                                if constexpr (kLoss == kModified) wval = live ? wval : 0.f;
+                                wv[u] = wval;
+                            }
+                            w[(i >> 1) + 0] = pack_bf16x2(wv[0], wv[1]);
+                            w[(i >> 1) + 1] = pack_bf16x2(wv[2], wv[3]);
+                        }
+                        // bf16 W overwrites the (already consumed) low columns of this score buffer
+                        tmem_st16(tmem_base + lane_addr + buf * kBlockN + q * 16, w);
+                    }
+                }
+                if constexpr (kBackward) {
+                    tmem_st_wait();
+                    tc_fence_before_sync();
+                    mbar_arrive(w_full + buf);
+                } else {
+                    tc_fence_before_sync();
+                    mbar_arrive(s_free + buf);
+                }
+            }
+
+            // ---- end of segment ----
+            if constexpr (!kBackward) {
+                float* dst = p.part + ((static_cast<size_t>(blockIdx.x) * p.max_segs + seg) * 2 + wg) *
+                                          (kFwdFields * kBlockM) + row_in_block;
+                dst[0 * kBlockM] = sum;
+                dst[1 * kBlockM] = run_max;
+                dst[2 * kBlockM] = max_prec;
+                dst[3 * kBlockM] = max_foll;
+                dst[4 * kBlockM] = pos_mma;
+            } else {
+                // flush the gradient accumulator: warpgroup g takes columns [g*D/2, (g+1)*D/2)
+                mbar_wait(acc_full, seg & 1, 302);
+                tc_fence_after_sync();
+#pragma unroll 1
+                for (int q = 0; q < D / 64; ++q) {
+                    uint32_t r[32];
+                    const int col = wg * (D / 2) + q * 32;
+                    tmem_ld32(tmem_base + lane_addr + kTmemAcc + col, r);
+                    tmem_ld_wait();
+                    if (row_ok) {
+                        float* dst = p.dacc + static_cast<size_t>(rb * kBlockM + row_in_block) * D + col;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            red_add_v4(dst + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                       __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                    }
+                }
+                tc_fence_before_sync();
+                mbar_arrive(acc_empty);
+            }
+            idx += seg_len;
+            ++seg;
+        }
+    }
+
+    // ================================ teardown ================================
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+}  // namespace simclr

@@ -1,0 +1,179 @@
+"""torch.autograd.Function wrappers around the C ABI (single GPU and row-sharded global batch).
+
+The tensors handed to the library are allocated by PyTorch's caching allocator and kept alive by the
+autograd context; launches go to ``torch.cuda.current_stream()``.  Nothing here computes the loss in
+PyTorch: if the extension is missing or the tensors are not on a B200 the call raises.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import DTYPE_BF16, DTYPE_F32, LOSS_MODIFIED, LOSS_NTXENT, check
+
+__all__ = ["contrastive_forward_backward", "ContrastiveLossFunction", "LOSS_NTXENT", "LOSS_MODIFIED", "pad_rows",
+           "pad_dim", "compact_to_padded", "padded_to_compact"]
+
+BLOCK = 128
+
+
+def pad_rows(b: int) -> int:
+    return (b + BLOCK - 1) // BLOCK * BLOCK
+
+
+def pad_dim(d: int) -> int:
+    if d < 1 or d > 256:
+        raise ValueError(f"embedding dimension {d} is not supported (1..256)")
+    return 64 if d <= 64 else (128 if d <= 128 else 256)
+
+
+def compact_to_padded(x: torch.Tensor, b: int) -> torch.Tensor:
+    """[2b] in the reference's order (view 1 rows, view 2 rows) -> [2*pad_rows(b)] view-padded, zero filled."""
+    bp = pad_rows(b)
+    out = x.new_zeros(2 * bp)
+    out[:b] = x[:b]
+    out[bp:bp + b] = x[b:]
+    return out
+
+
+def padded_to_compact(x: torch.Tensor, b: int) -> torch.Tensor:
+    bp = x.shape[0] // 2
+    return torch.cat((x[:b], x[bp:bp + b]))
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return DTYPE_F32
+    if t.dtype == torch.bfloat16:
+        return DTYPE_BF16
+    raise ValueError(f"unsupported dtype {t.dtype}: pass float32 or bfloat16 embeddings")
+
+
+def _validate(x1: torch.Tensor, x2: torch.Tensor) -> Tuple[int, int]:
+    if x1.dim() != 2 or x1.shape != x2.shape:
+        raise ValueError(f"x_batch1 / x_batch2 must both be [batch, dim]; got {tuple(x1.shape)} and {tuple(x2.shape)}")
+    if x1.dtype != x2.dtype:
+        raise ValueError("x_batch1 and x_batch2 must share a dtype")
+    if not (x1.is_cuda and x2.is_cuda) or x1.device != x2.device:
+        raise ValueError("simclr_b200 runs on a B200 only: both batches must live on the same CUDA device "
+                         "(there is no CPU fallback; the CPU oracle lives in oracle/ for tests)")
+    b, d = x1.shape
+    if b < 1 or d < 1:
+        raise ValueError("empty batch")
+    return b, d
+
+
+class _Saved:
+    """State a forward leaves for its backward (device buffers only)."""
+    __slots__ = ("operand_rows", "operand_cols", "inv_norm", "pos_dot", "lse2_cols", "col_scale", "b_local",
+                 "b_global", "row_offset", "d", "loss", "temperature", "normalize", "dtype_code")
+
+
+def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature: float, normalize: bool,
+                weight: Optional[torch.Tensor], gather=None):
+    """prepare + forward through the C ABI.  ``gather`` (distributed.py) turns the local operand / lse2 into
+    their global-batch counterparts and returns (operand_cols, b_global, row_offset, reducer)."""
+    lib = _lib.load()
+    b, d = _validate(x1, x2)
+    x1 = x1.contiguous()
+    x2 = x2.contiguous()
+    dev = x1.device
+    bp, dp = pad_rows(b), pad_dim(d)
+    code = _dtype_code(x1)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        operand = torch.empty((2 * bp, dp), dtype=torch.bfloat16, device=dev)
+        rowvec = torch.empty((4, 2 * bp), dtype=torch.float32, device=dev)   # inv_norm, pos_dot, lse2, row_loss
+        stats = torch.empty(4, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        check(lib.simclr_prepare(loss_kind, x1.data_ptr(), x2.data_ptr(), b, d, code, int(bool(normalize)),
+                                 operand.data_ptr(), rowvec[0].data_ptr(), rowvec[1].data_ptr(), stream),
+              "simclr_prepare")
+        if gather is None:
+            operand_cols, b_global, row_offset = operand, b, 0
+        else:
+            operand_cols, b_global, row_offset = gather.operand(operand, b)
+        w_local = None
+        if weight is not None:
+            w_local = weight.to(device=dev, dtype=torch.float32).contiguous()
+            if w_local.numel() != 2 * b:
+                raise ValueError(f"weight must have {2 * b} entries, got {w_local.numel()}")
+        ws_bytes = lib.simclr_forward_workspace_bytes(loss_kind, b, b_global, d)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib.simclr_forward(loss_kind, operand.data_ptr(), operand_cols.data_ptr(), b, b_global, row_offset, d,
+                                 float(temperature), rowvec[1].data_ptr(), _ptr(w_local), rowvec[2].data_ptr(),
+                                 rowvec[3].data_ptr(), stats.data_ptr(), loss.data_ptr(), ws.data_ptr(), ws_bytes,
+                                 stream), "simclr_forward")
+    saved = _Saved()
+    saved.operand_rows, saved.operand_cols = operand, operand_cols
+    saved.inv_norm, saved.pos_dot = rowvec[0], rowvec[1]
+    saved.lse2_cols = rowvec[2]
+    saved.col_scale = None
+    saved.b_local, saved.b_global, saved.row_offset, saved.d = b, b_global, row_offset, d
+    saved.loss, saved.temperature, saved.normalize, saved.dtype_code = loss_kind, float(temperature), bool(normalize), code
+    if gather is not None:
+        loss, stats = gather.reduce(stats, loss)
+        saved.lse2_cols = gather.rowvec(rowvec[2], b)
+        if weight is not None:
+            saved.col_scale = gather.col_scale(w_local, stats, b)
+    elif weight is not None:
+        saved.col_scale = compact_to_padded(w_local / w_local.sum(), b)
+    return loss, stats, rowvec, saved
+
+
+def run_backward(saved: "_Saved", x1: torch.Tensor, x2: torch.Tensor, grad_out: Optional[torch.Tensor]):
+    lib = _lib.load()
+    dev = x1.device
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        g1 = torch.empty_like(x1)
+        g2 = torch.empty_like(x2)
+        go = None
+        if grad_out is not None:
+            go = grad_out.to(device=dev, dtype=torch.float32).contiguous()
+        ws_bytes = lib.simclr_backward_workspace_bytes(saved.loss, saved.b_local, saved.b_global, saved.d)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib.simclr_backward(saved.loss, x1.data_ptr(), x2.data_ptr(), saved.b_local, saved.b_global,
+                                  saved.row_offset, saved.d, saved.dtype_code, int(saved.normalize), saved.temperature,
+                                  saved.operand_rows.data_ptr(), saved.operand_cols.data_ptr(),
+                                  saved.inv_norm.data_ptr(), saved.pos_dot.data_ptr(), saved.lse2_cols.data_ptr(),
+                                  _ptr(saved.col_scale), _ptr(go), g1.data_ptr(), g2.data_ptr(), ws.data_ptr(),
+                                  ws_bytes, stream), "simclr_backward")
+    return g1, g2
+
+
+class ContrastiveLossFunction(torch.autograd.Function):
+    """(x_batch1, x_batch2) -> (loss, stats).  stats = [sum w L, sum w, #correct, loss] is not differentiable.
+
+    The returned ``loss`` is its own 0-d tensor (not a view, not saved), so the caller may divide it in place
+    (reference utils/model_utils.py:31,116); backward honours the resulting ``grad_output``.
+    """
+
+    @staticmethod
+    def forward(ctx, x1, x2, loss_kind, temperature, normalize, weight, gather):
+        loss, stats, _rowvec, saved = run_forward(loss_kind, x1, x2, temperature, normalize, weight, gather)
+        ctx.saved_state = saved
+        ctx.save_for_backward(x1, x2)
+        ctx.mark_non_differentiable(stats)
+        return loss, stats
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_stats):
+        x1, x2 = ctx.saved_tensors
+        g1, g2 = run_backward(ctx.saved_state, x1.contiguous(), x2.contiguous(), grad_loss)
+        return g1, g2, None, None, None, None, None
+
+
+def contrastive_forward_backward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature: float,
+                                 normalize: bool = True, weight: Optional[torch.Tensor] = None,
+                                 grad_out: Optional[torch.Tensor] = None):
+    """Autograd-free fused call used by bench.py: returns (loss, stats, grad1, grad2), all on the device."""
+    loss, stats, _rowvec, saved = run_forward(loss_kind, x1, x2, temperature, normalize, weight)
+    g1, g2 = run_backward(saved, x1.contiguous(), x2.contiguous(), grad_out)
+    return loss, stats, g1, g2

@@ -1,0 +1,40 @@
+"""Drop-in mirror of the reference's ``objective.py`` (same names, signatures and return conventions).
+
+    contrastive_loss(x_batch1, x_batch2, temperature=1.0, normalize=True, weight=None) -> (loss, acc)
+        reference objective.py:6-55
+    modified_contrastive_loss(x_batch1, x_batch2, **kwargs) -> (loss, top1_acc)
+        reference objective.py:58-98  (only ``temperature`` is read from kwargs, :68)
+
+``loss`` is a 0-d float32 tensor on the inputs' device, connected to autograd; ``acc`` is a python float in
+[0, 100] (this forces the same device->host sync the reference performs at objective.py:52 / :96).
+The arithmetic runs in the sm_100a extension; CPU tensors raise ``ValueError``.
+"""
+from __future__ import annotations
+
+import torch
+
+from .functional import LOSS_MODIFIED, LOSS_NTXENT, ContrastiveLossFunction
+
+__all__ = ["contrastive_loss", "modified_contrastive_loss"]
+
+
+def _as_supported(x: torch.Tensor) -> torch.Tensor:
+    # fp16 / fp64 inputs are computed in fp32 (autograd casts the gradients back)
+    return x if x.dtype in (torch.float32, torch.bfloat16) else x.float()
+
+
+def contrastive_loss(x_batch1, x_batch2, temperature=1.0, normalize=True, weight=None):
+    """NT-Xent loss and auxiliary-task top-1 accuracy (reference objective.py:6-55)."""
+    x1, x2 = _as_supported(x_batch1), _as_supported(x_batch2)
+    loss, stats = ContrastiveLossFunction.apply(x1, x2, LOSS_NTXENT, float(temperature), bool(normalize), weight, None)
+    correct = stats[2].item()                    # host sync, as reference objective.py:52
+    return loss, 100.0 * correct / (2 * x1.shape[0])
+
+
+def modified_contrastive_loss(x_batch1, x_batch2, **kwargs):
+    """Probabilistic ("--new_loss" / --modified_loss) variant (reference objective.py:58-98)."""
+    temperature = kwargs.get("temperature", 1.0)   # objective.py:68: every other kwarg is ignored
+    x1, x2 = _as_supported(x_batch1), _as_supported(x_batch2)
+    loss, stats = ContrastiveLossFunction.apply(x1, x2, LOSS_MODIFIED, float(temperature), True, None, None)
+    correct = stats[2].item()                    # host sync, as reference objective.py:96
+    return loss, 100.0 * correct / (2 * x1.shape[0])
