@@ -1,0 +1,72 @@
+"""Allocation-free forward(+backward) runner over the staged C ABI with pre-allocated buffers.
+
+``ContrastiveStep`` is what a training loop that wants CUDA-graph capture (or bench.py) uses: all scratch,
+saved state and outputs are allocated once; ``forward()`` / ``backward()`` only enqueue kernels on the
+current stream, so a whole step can be captured into a ``torch.cuda.CUDAGraph`` and replayed.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import check
+from .functional import _dtype_code, pad_dim, pad_rows
+
+__all__ = ["ContrastiveStep"]
+
+
+class ContrastiveStep:
+    KERNELS_FORWARD = 3     # prepare, tile kernel, finalize
+    KERNELS_BACKWARD = 3    # prepare (+zero accumulator), tile kernel, finalize
+
+    def __init__(self, loss_kind: int, batch: int, dim: int, temperature: float, normalize: bool = True,
+                 dtype: torch.dtype = torch.float32, device="cuda"):
+        self.lib = _lib.load()
+        self.kind, self.b, self.d = int(loss_kind), int(batch), int(dim)
+        self.temperature, self.normalize = float(temperature), bool(normalize)
+        self.device = torch.device(device)
+        bp, dp = pad_rows(batch), pad_dim(dim)
+        dev = self.device
+        self.x1 = torch.zeros((batch, dim), dtype=dtype, device=dev)
+        self.x2 = torch.zeros((batch, dim), dtype=dtype, device=dev)
+        self.code = _dtype_code(self.x1)
+        self.operand = torch.empty((2 * bp, dp), dtype=torch.bfloat16, device=dev)
+        self.rowvec = torch.empty((4, 2 * bp), dtype=torch.float32, device=dev)   # inv_norm, pos_dot, lse2, row_loss
+        self.stats = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.grad1 = torch.empty_like(self.x1)
+        self.grad2 = torch.empty_like(self.x2)
+        self.fwd_ws_bytes = self.lib.simclr_forward_workspace_bytes(self.kind, batch, batch, dim)
+        self.bwd_ws_bytes = self.lib.simclr_backward_workspace_bytes(self.kind, batch, batch, dim)
+        if not self.fwd_ws_bytes or not self.bwd_ws_bytes:
+            raise ValueError("unsupported shape")
+        self.fwd_ws = torch.empty(self.fwd_ws_bytes, dtype=torch.uint8, device=dev)
+        self.bwd_ws = torch.empty(self.bwd_ws_bytes, dtype=torch.uint8, device=dev)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def forward(self) -> None:
+        lib, st = self.lib, self._stream()
+        check(lib.simclr_prepare(self.kind, self.x1.data_ptr(), self.x2.data_ptr(), self.b, self.d, self.code,
+                                 int(self.normalize), self.operand.data_ptr(), self.rowvec[0].data_ptr(),
+                                 self.rowvec[1].data_ptr(), st), "simclr_prepare")
+        check(lib.simclr_forward(self.kind, self.operand.data_ptr(), self.operand.data_ptr(), self.b, self.b, 0, self.d,
+                                 self.temperature, self.rowvec[1].data_ptr(), None, self.rowvec[2].data_ptr(),
+                                 self.rowvec[3].data_ptr(), self.stats.data_ptr(), self.loss.data_ptr(),
+                                 self.fwd_ws.data_ptr(), self.fwd_ws_bytes, st), "simclr_forward")
+
+    def backward(self, grad_out: Optional[torch.Tensor] = None) -> None:
+        lib, st = self.lib, self._stream()
+        check(lib.simclr_backward(self.kind, self.x1.data_ptr(), self.x2.data_ptr(), self.b, self.b, 0, self.d,
+                                  self.code, int(self.normalize), self.temperature, self.operand.data_ptr(),
+                                  self.operand.data_ptr(), self.rowvec[0].data_ptr(), self.rowvec[1].data_ptr(),
+                                  self.rowvec[2].data_ptr(), None, None if grad_out is None else grad_out.data_ptr(),
+                                  self.grad1.data_ptr(), self.grad2.data_ptr(), self.bwd_ws.data_ptr(),
+                                  self.bwd_ws_bytes, st), "simclr_backward")
+
+    def step(self) -> None:
+        self.forward()
+        self.backward()

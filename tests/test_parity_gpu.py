@@ -1,0 +1,224 @@
+"""GPU parity tests: the CUDA path (through the public objective API -> C ABI) against
+
+  * the committed golden fixtures produced by the unmodified reference (tests/golden, oracle/make_golden.py),
+  * the fp64 closed-form oracle on seeded inputs at sizes it finishes in seconds,
+  * size-independent properties at the full BASELINE size (2N = 8192).
+
+Tolerances are the bf16-input / fp32-accumulate contract of BASELINE.json's north_star: loss within 2e-3
+relative, gradients within 1e-2 of max|reference gradient|; accuracy (an integer count) exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import contrastive_oracle as oracle
+import pytorch_simclr_b200 as sb
+from conftest import golden_files, load_golden
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 2e-3
+GRAD_TOL = 1e-2
+
+
+def _grad_err(g, ref):
+    scale = max(float(np.abs(ref).max()), 1e-30)
+    return float(np.abs(g.astype(np.float64) - ref).max() / scale)
+
+
+def _run(fn, z1, z2, grad_output=1.0, dtype=torch.float32, **kw):
+    a = z1.to(device="cuda", dtype=dtype).requires_grad_(True)
+    b = z2.to(device="cuda", dtype=dtype).requires_grad_(True)
+    loss, acc = fn(a, b, **kw)
+    assert loss.dim() == 0 and loss.dtype == torch.float32 and loss.is_cuda and isinstance(acc, float)
+    if grad_output != 1.0:
+        loss = loss * grad_output
+    loss.backward()
+    torch.cuda.synchronize()
+    return float(loss.detach()) / grad_output, acc, a.grad.float().cpu().numpy(), b.grad.float().cpu().numpy()
+
+
+@pytest.mark.parametrize("path", golden_files("ntxent"), ids=os.path.basename)
+def test_ntxent_matches_reference_fixture(path):
+    g = load_golden(path)
+    kw = dict(temperature=float(g["temperature"]), normalize=bool(g["normalize"]))
+    if g["weight"].size:
+        kw["weight"] = torch.from_numpy(g["weight"]).cuda()
+    dtype = torch.bfloat16 if bool(g["bf16"]) else torch.float32
+    loss, acc, g1, g2 = _run(sb.contrastive_loss, torch.from_numpy(g["z1"]), torch.from_numpy(g["z2"]),
+                             float(g["grad_output"]), dtype, **kw)
+    assert loss == pytest.approx(float(g["loss"]), rel=LOSS_RTOL, abs=2e-6)
+    if "ties" in path:
+        # duplicated rows: the tie rule of objective.py:51 decides; bf16 rounding keeps exact ties exact
+        assert acc == float(g["acc"])
+    else:
+        assert acc == float(g["acc"])
+    if float(np.abs(g["grad1"]).max()) > 0:
+        tol = GRAD_TOL if bool(g["normalize"]) else 2 * GRAD_TOL   # unnormalised logits reach +-100
+        assert _grad_err(g1, g["grad1"]) < tol
+        assert _grad_err(g2, g["grad2"]) < tol
+    else:
+        assert np.abs(g1).max() < 1e-6 and np.abs(g2).max() < 1e-6
+
+
+@pytest.mark.parametrize("path", golden_files("modified"), ids=os.path.basename)
+def test_modified_matches_reference_fixture(path):
+    g = load_golden(path)
+    kw = {} if bool(g["default_tau"]) else dict(temperature=float(g["temperature"]))
+    dtype = torch.bfloat16 if bool(g["bf16"]) else torch.float32
+    loss, acc, g1, g2 = _run(sb.modified_contrastive_loss, torch.from_numpy(g["z1"]), torch.from_numpy(g["z2"]),
+                             float(g["grad_output"]), dtype, **kw)
+    assert loss == pytest.approx(float(g["loss"]), rel=LOSS_RTOL, abs=2e-6)
+    assert acc == float(g["acc"])
+    if float(np.abs(g["grad1"]).max()) > 0:
+        assert _grad_err(g1, g["grad1"]) < GRAD_TOL
+        assert _grad_err(g2, g["grad2"]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("b,d,tau,kind,dtype", [
+    (512, 128, 0.5, "iid", torch.float32),            # BASELINE configs[0] shape
+    (1000, 256, 0.5, "iid", torch.float32),
+    (777, 100, 0.1, "correlated", torch.float32),     # ragged rows and ragged feature dim
+    (2048, 64, 0.5, "correlated", torch.bfloat16),
+    (4096, 128, 0.5, "iid", torch.bfloat16),          # BASELINE metric shape, bf16 in
+    (4096, 128, 0.1, "correlated", torch.float32),
+])
+def test_ntxent_against_fp64_oracle(b, d, tau, kind, dtype):
+    z1, z2 = oracle.make_embeddings(b, d, seed=b + d, kind=kind, bf16_representable=(dtype == torch.bfloat16))
+    ref = oracle.ntxent_closed_form(z1, z2, temperature=tau)
+    loss, acc, g1, g2 = _run(sb.contrastive_loss, z1, z2, 1.0, dtype, temperature=tau)
+    assert loss == pytest.approx(ref.loss, rel=LOSS_RTOL)
+    assert acc == ref.acc
+    assert _grad_err(g1, ref.grad1) < GRAD_TOL and _grad_err(g2, ref.grad2) < GRAD_TOL
+
+
+@pytest.mark.parametrize("b,d,tau,kind,dtype", [
+    (512, 128, 0.5, "iid", torch.float32),
+    (777, 100, 1.0, "correlated", torch.float32),
+    (4096, 128, 0.5, "iid", torch.bfloat16),          # BASELINE configs[2]
+    (4096, 128, 0.1, "correlated", torch.bfloat16),   # general pow path
+])
+def test_modified_against_fp64_oracle(b, d, tau, kind, dtype):
+    z1, z2 = oracle.make_embeddings(b, d, seed=b + d + 1, kind=kind, bf16_representable=(dtype == torch.bfloat16))
+    ref = oracle.modified_closed_form(z1, z2, temperature=tau)
+    loss, acc, g1, g2 = _run(sb.modified_contrastive_loss, z1, z2, 1.0, dtype, temperature=tau)
+    assert loss == pytest.approx(ref.loss, rel=LOSS_RTOL)
+    assert acc == ref.acc
+    assert _grad_err(g1, ref.grad1) < GRAD_TOL and _grad_err(g2, ref.grad2) < GRAD_TOL
+
+
+def test_general_two_exp_backward_path_small_temperature():
+    """tau = 0.02 makes 2*log2(e)/tau > 80, which disables the one-exp (bounded score) backward form."""
+    z1, z2 = oracle.make_embeddings(300, 128, seed=4, kind="correlated", noise=1.0)
+    ref = oracle.ntxent_closed_form(z1, z2, temperature=0.02)
+    loss, acc, g1, g2 = _run(sb.contrastive_loss, z1, z2, temperature=0.02)
+    assert loss == pytest.approx(ref.loss, rel=LOSS_RTOL, abs=1e-5)
+    assert acc == ref.acc
+    assert _grad_err(g1, ref.grad1) < 3 * GRAD_TOL      # logits span +-50: bf16 operands, documented in DESIGN.md
+
+
+def test_drop_in_behaviours_the_callers_rely_on():
+    """reference utils/model_utils.py:24-36 (eval under no_grad) and :115-120 (in-place division, backward)."""
+    z1, z2 = oracle.make_embeddings(64, 128, seed=2)
+    a = z1.cuda().requires_grad_(True)
+    b = z2.cuda().requires_grad_(True)
+    with torch.no_grad():
+        loss, acc = sb.contrastive_loss(a, b, temperature=0.5)
+        assert not loss.requires_grad
+        loss /= 8
+    loss, acc = sb.contrastive_loss(a, b, temperature=0.5)
+    assert loss.requires_grad and loss.grad_fn is not None
+    full = float(loss.detach())
+    loss /= 8                                   # model_utils.py:116, in place on the returned tensor
+    assert float(loss.detach()) == pytest.approx(full / 8, rel=1e-6)
+    loss.backward()
+    ref = oracle.ntxent_closed_form(z1, z2, temperature=0.5, grad_output=1.0 / 8)
+    assert _grad_err(a.grad.cpu().numpy(), ref.grad1) < GRAD_TOL
+    # positional call exactly like the reference's callers, modified loss ignores unknown kwargs (:68)
+    l2, acc2 = sb.modified_contrastive_loss(a, b, temperature=0.5, normalize=False, bogus=1)
+    assert torch.isfinite(l2) and 0.0 <= acc2 <= 100.0
+
+
+def test_fp16_and_fp64_inputs_are_computed_in_fp32():
+    z1, z2 = oracle.make_embeddings(96, 64, seed=8, kind="correlated")
+    ref = oracle.ntxent_closed_form(z1, z2, temperature=0.5)
+    for dt in (torch.float64, torch.float16):
+        a = z1.to("cuda", dt).requires_grad_(True)
+        b = z2.to("cuda", dt).requires_grad_(True)
+        loss, acc = sb.contrastive_loss(a, b, temperature=0.5)
+        loss.backward()
+        assert a.grad.dtype == dt
+        assert float(loss.detach()) == pytest.approx(ref.loss, rel=5e-3)
+
+
+def test_full_size_properties_2n8192():
+    """Size-independent properties at the BASELINE metric shape (2N = 8192, d = 128)."""
+    b, d, tau = 4096, 128, 0.5
+    z1, z2 = oracle.make_embeddings(b, d, seed=21, kind="correlated", noise=1.0)
+    loss, acc, g1, g2 = _run(sb.contrastive_loss, z1, z2, temperature=tau)
+    # (1) loss(z1,z2) == loss(z2,z1) and the gradients swap
+    loss_s, acc_s, h1, h2 = _run(sb.contrastive_loss, z2, z1, temperature=tau)
+    assert loss_s == pytest.approx(loss, rel=1e-6)
+    assert np.abs(h2 - g1).max() <= 1e-3 * np.abs(g1).max()
+    # (2) scale invariance under normalisation (exact power-of-two scales)
+    loss_k, _, k1, _ = _run(sb.contrastive_loss, 4.0 * z1, 0.25 * z2, temperature=tau)
+    assert loss_k == pytest.approx(loss, rel=1e-6)
+    assert np.abs(4.0 * k1 - g1).max() <= 1e-3 * np.abs(g1).max()
+    # (3) the gradient of a normalised row is orthogonal to the row:  z_r . dz_r = 0
+    ortho = np.abs((z1.numpy() * g1).sum(1)) / (np.linalg.norm(z1.numpy(), axis=1) * np.linalg.norm(g1, axis=1) + 1e-30)
+    assert ortho.max() < 1e-3
+    # (4) consistent relabelling of the images leaves the loss unchanged and permutes the gradients
+    perm = torch.from_numpy(np.random.default_rng(0).permutation(b))
+    loss_p, acc_p, p1, _ = _run(sb.contrastive_loss, z1[perm], z2[perm], temperature=tau)
+    assert loss_p == pytest.approx(loss, rel=1e-6)
+    assert acc_p == acc
+    assert np.abs(p1 - g1[perm.numpy()]).max() <= 1e-3 * np.abs(g1).max()
+    # (5) gradients sum: sum_r dL/dz_r . z_r == 0 was (3); total loss bounded by log(2N-1) + 2/tau
+    assert 0.0 < loss < np.log(2 * b - 1) + 2.0 / tau
+    # (6) the oracle agrees at this size too (blockwise fp64, a few seconds)
+    ref = oracle.ntxent_closed_form(z1, z2, temperature=tau)
+    assert loss == pytest.approx(ref.loss, rel=LOSS_RTOL)
+    assert acc == ref.acc
+    assert _grad_err(g1, ref.grad1) < GRAD_TOL
+
+
+def test_row_sharded_kernels_equal_single_shot():
+    """Emulate R = 4 ranks on one GPU through the staged C ABI (row_offset / b_global), no collectives:
+    per-rank stats must add up to, and per-rank gradients must equal, the single-shot result."""
+    from pytorch_simclr_b200 import functional as F
+
+    class FakeGather:
+        def __init__(self, full_operand, full_lse2, b_glob, row_off):
+            self.full_operand, self.full_lse2, self.b_glob, self.row_off = full_operand, full_lse2, b_glob, row_off
+
+        def operand(self, operand_local, b):
+            return self.full_operand, self.b_glob, self.row_off
+
+        def reduce(self, stats, loss):
+            return loss, stats
+
+        def rowvec(self, vec, b):
+            return self.full_lse2
+
+        def col_scale(self, *a):
+            raise AssertionError
+
+    b, d, tau, ranks = 1024, 128, 0.5, 4
+    z1, z2 = oracle.make_embeddings(b, d, seed=5, kind="correlated", noise=1.0)
+    x1, x2 = z1.cuda(), z2.cuda()
+    loss, stats, rowvec, saved = F.run_forward(F.LOSS_NTXENT, x1, x2, tau, True, None)
+    g1, g2 = F.run_backward(saved, x1, x2, None)
+    bl = b // ranks
+    tot = torch.zeros(3, device="cuda")
+    for r in range(ranks):
+        sl = slice(r * bl, (r + 1) * bl)
+        gather = FakeGather(saved.operand_cols, rowvec[2], b, r * bl)
+        l_r, st_r, _, sv_r = F.run_forward(F.LOSS_NTXENT, x1[sl].contiguous(), x2[sl].contiguous(), tau, True, None, gather)
+        tot += st_r[:3]
+        h1, h2 = F.run_backward(sv_r, x1[sl].contiguous(), x2[sl].contiguous(), None)
+        assert torch.allclose(h1, g1[sl], rtol=1e-4, atol=1e-7 * float(g1.abs().max()) + 1e-12)
+        assert torch.allclose(h2, g2[sl], rtol=1e-4, atol=1e-7 * float(g1.abs().max()) + 1e-12)
+    assert float(tot[0] / tot[1]) == pytest.approx(float(loss), rel=1e-6)
+    assert float(tot[2]) == float(stats[2])
