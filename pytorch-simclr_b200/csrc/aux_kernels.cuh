@@ -152,17 +152,19 @@ forward_finalize_kernel(AuxParams a, const float* __restrict__ part, int grid_ti
     float v_pos = pos_dot[slot];
     if constexpr (kLoss == kModified) v_pos = fmaxf(v_pos * a.qscale, kClampMin);
 
-    // pass 1: maxima
-    float vmax = v_pos, max_prec = kNegBig, max_foll = kNegBig, pos_mma = kNegBig;
+    // CTAs whose contiguous tile range [T*k/G, T*(k+1)/G) overlaps this row block: owner(t) = ((t+1)*G - 1) / T
     const long long t_lo = static_cast<long long>(rb) * n_col_tiles;
     const long long t_hi = t_lo + n_col_tiles;
-    for (int k = 0; k < grid_tiles; ++k) {
+    const int k_first = static_cast<int>(((t_lo + 1) * grid_tiles - 1) / total_tiles);
+    const int k_last = static_cast<int>((t_hi * grid_tiles - 1) / total_tiles);
+
+    // pass 1: maxima
+    float vmax = v_pos, max_prec = kNegBig, max_foll = kNegBig, pos_mma = kNegBig;
+    for (int k = k_first; k <= k_last; ++k) {
         const long long c0 = (total_tiles * k) / grid_tiles;
-        const long long c1 = (total_tiles * (k + 1)) / grid_tiles;
-        if (c0 >= t_hi || c1 <= t_lo) continue;
         const int seg = rb - static_cast<int>(c0 / n_col_tiles);
-        for (int wg = 0; wg < 2; ++wg) {
-            const float* src = part + ((static_cast<size_t>(k) * max_segs + seg) * 2 + wg) * (kFwdFields * kBlockM) + tid;
+        for (int wg = 0; wg < kNumSoftmaxWG; ++wg) {
+            const float* src = part + ((static_cast<size_t>(k) * max_segs + seg) * kNumSoftmaxWG + wg) * (kFwdFields * kBlockM) + tid;
             vmax = fmaxf(vmax, src[1 * kBlockM]);
             max_prec = fmaxf(max_prec, src[2 * kBlockM]);
             max_foll = fmaxf(max_foll, src[3 * kBlockM]);
@@ -172,13 +174,11 @@ forward_finalize_kernel(AuxParams a, const float* __restrict__ part, int grid_ti
     // pass 2: rescaled sums
     const float top = exact_logit2<kLoss>(a, vmax);
     float total = exp2f(exact_logit2<kLoss>(a, v_pos) - top);
-    for (int k = 0; k < grid_tiles; ++k) {
+    for (int k = k_first; k <= k_last; ++k) {
         const long long c0 = (total_tiles * k) / grid_tiles;
-        const long long c1 = (total_tiles * (k + 1)) / grid_tiles;
-        if (c0 >= t_hi || c1 <= t_lo) continue;
         const int seg = rb - static_cast<int>(c0 / n_col_tiles);
-        for (int wg = 0; wg < 2; ++wg) {
-            const float* src = part + ((static_cast<size_t>(k) * max_segs + seg) * 2 + wg) * (kFwdFields * kBlockM) + tid;
+        for (int wg = 0; wg < kNumSoftmaxWG; ++wg) {
+            const float* src = part + ((static_cast<size_t>(k) * max_segs + seg) * kNumSoftmaxWG + wg) * (kFwdFields * kBlockM) + tid;
             const float s = src[0];
             const float m = src[1 * kBlockM];
             if (m > kNegBig) total += s * exp2f(exact_logit2<kLoss>(a, m) - top);

@@ -110,7 +110,7 @@ FwdWorkspace carve_forward(const Geometry& g, void* base) {
     w.block_part = reinterpret_cast<float*>(static_cast<char*>(base) + off);
     off += align256(static_cast<size_t>(g.n_row_blocks) * 4 * sizeof(float));
     w.part = reinterpret_cast<float*>(static_cast<char*>(base) + off);
-    off += align256(static_cast<size_t>(g.grid) * g.max_segs * 2 * kFwdFields * kBlockM * sizeof(float));
+    off += align256(static_cast<size_t>(g.grid) * g.max_segs * kNumSoftmaxWG * kFwdFields * kBlockM * sizeof(float));
     w.bytes = off;
     return w;
 }

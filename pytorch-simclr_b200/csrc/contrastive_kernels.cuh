@@ -18,13 +18,13 @@
 //              tile and used as the A operand of a second tcgen05.mma:  dacc[r,:] += W[r,:] * op[c,:]
 // The 2N x 2N matrix never exists outside one 128 x 128 TMEM tile.
 //
-// Warp roles (384 threads, 1 CTA / SM, each CTA owns a contiguous range of (row block, column tile)):
+// Warp roles (640 threads, 1 CTA / SM, each CTA owns a contiguous range of (row block, column tile)):
 //   warp 0      TMA producer (row-block tile once per segment, column tiles through an mbarrier ring)
 //   warp 1      UMMA issuer (one lane)
 //   warp 2      TMEM allocator / deallocator
 //   warp 3      idle
-//   warps 4-7   softmax warpgroup 0  (even CTA iterations, TMEM score buffer 0)
-//   warps 8-11  softmax warpgroup 1  (odd  CTA iterations, TMEM score buffer 1)
+//   warps 4-19  four softmax warpgroups; CTA iteration `it` is handled by warpgroup it % 4 and lives in
+//               TMEM score buffer it % NB (NB = 4 forward, (512 - D) / 128 backward) so the MMA runs ahead
 #pragma once
 
 #include <cstdint>
@@ -40,8 +40,11 @@ constexpr int kBlockM = 128;          // rows per row block (= UMMA M = TMEM lan
 constexpr int kBlockN = 128;          // columns per tile   (= UMMA N of the score MMA)
 constexpr int kAtomK = 64;            // bf16 elements per 128-byte swizzle row
 constexpr int kAtomBytes = kBlockM * kAtomK * 2;   // one TMA box: 128 rows x 128 B = 16 KB
-constexpr int kNumThreads = 384;
+constexpr int kNumSoftmaxWG = 4;      // softmax warpgroups (4 warps each: one per TMEM lane quarter)
 constexpr int kSoftmaxWarp0 = 4;
+constexpr int kNumThreads = 32 * (kSoftmaxWarp0 + 4 * kNumSoftmaxWG);   // 640
+constexpr int kMaxScoreBufs = 4;
+constexpr int kMaxSlots = kMaxScoreBufs * kNumSoftmaxWG;   // barrier slots for the score / W hand-off
 constexpr int kTmemCols = 512;
 constexpr int kFwdFields = 5;         // per-row partial: sum, run-max, max-preceding, max-following, pos(mma)
 constexpr float kNegBig = -3.0e38f;   // finite stand-in for -inf
@@ -63,7 +66,7 @@ struct TileParams {
     float m2;          // constant log2-domain shift of the one-exp backward form
     int const_shift;   // backward: 1 -> one exp per element (bounded scores), 0 -> general two-exp form
     float qscale;      // modified loss: (float) b_glob, the factor inside the clamp
-    float* part;       // forward : [grid][max_segs][2 warpgroups][kFwdFields][128]
+    float* part;       // forward : [grid][max_segs][kNumSoftmaxWG][kFwdFields][128]
     const float* colvec;   // backward: [2 planes][2*bg_pad]; plane 0 = a_c (or g_c), plane 1 = lse2_c
     float* dacc;           // backward: [2*bl_pad][D] fp32, zero on entry, accumulated with red.global.add
     unsigned int* ticket;  // zeroed by CTA 0 for the finalize kernel's last-block reduction
@@ -79,8 +82,8 @@ struct SmemLayout {
     static constexpr int kOffB = kTileBytes;
     static constexpr int kOffCv = kOffB + kStages * kTileBytes;
     static constexpr int kOffBar = kOffCv + kStages * kColvecBytes;
-    // barriers: a_full, a_empty, acc_full, acc_empty, b_full[S], b_empty[S], s_full[2], s_free[2], w_full[2]
-    static constexpr int kNumBars = 4 + 2 * kStages + 6;
+    // barriers: a_full, a_empty, acc_full, acc_empty, b_full[S], b_empty[S], s_full[16], s_free[16], w_full[16]
+    static constexpr int kNumBars = 4 + 2 * kStages + 3 * kMaxSlots;
     static constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
     static constexpr int kBytes = kOffTmemPtr + 16;
     static constexpr int kDynamicBytes = kBytes + 1024;              // slack for manual 1024 B alignment
@@ -110,6 +113,160 @@ SIMCLR_DEVICE float logit2(const TileParams& p, float v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Softmax-warp helpers.  One thread owns one row (TMEM lane); a tile is consumed in four 32-column
+// chunks with the TMEM load of chunk q+1 in flight while chunk q is processed.
+// ---------------------------------------------------------------------------------------------
+struct RowCtx {
+    int vr;         // view of the row block
+    int g;          // global image index of this thread's row
+    int diag_col;   // global column of the row itself (NT-Xent only, -1 if none)
+    int pos_col;    // global column of the positive (-1 for padding rows)
+    bool row_ok;
+};
+
+struct FwdState {
+    float run_max = kNegBig, sum = 0.f, max_prec = kNegBig, max_foll = kNegBig, pos_mma = kNegBig;
+};
+
+struct BwdRow {
+    float row_a, row_l2;
+};
+
+SIMCLR_DEVICE float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// ---- forward: one 32-column chunk ----
+template <int kLoss, bool kSpecial>
+SIMCLR_DEVICE void fwd_chunk(const TileParams& p, const uint32_t (&r)[32], int cq, int vc, const RowCtx& rc,
+                             bool tile_prec, FwdState& st) {
+    float v[32];
+    float cm = kNegBig;
+    if constexpr (!kSpecial) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = raw_value<kLoss>(p, __uint_as_float(r[i]));
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) cm = fmaxf(cm, fmaxf(v[i], v[i + 1]));     // FMNMX3
+        st.max_prec = fmaxf(st.max_prec, tile_prec ? cm : kNegBig);
+        st.max_foll = fmaxf(st.max_foll, tile_prec ? kNegBig : cm);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int c = cq + i;
+            const int ic = c - vc * p.bg_pad;
+            const float x = raw_value<kLoss>(p, __uint_as_float(r[i]));
+            if (c == rc.pos_col) st.pos_mma = x;
+            const bool valid = rc.row_ok && ic < p.b_glob && c != rc.diag_col && c != rc.pos_col;
+            v[i] = valid ? x : kNegBig;
+            if (valid) {
+                cm = fmaxf(cm, x);
+                bool prec;
+                if constexpr (kLoss == kNtXent) prec = (rc.vr == 0) ? (vc == 1 && ic < rc.g) : (vc == 1 || ic < rc.g);
+                else prec = ic < rc.g;
+                if (prec) st.max_prec = fmaxf(st.max_prec, x); else st.max_foll = fmaxf(st.max_foll, x);
+            }
+        }
+    }
+    // online max without a data-dependent branch in the fast path: rescale the running sum by
+    // exp2(old_shift - new_shift) (== 1 when the maximum did not move)
+    const float new_max = fmaxf(st.run_max, cm);
+    if (!kSpecial || new_max != kNegBig) {                 // special tiles may have seen nothing valid yet
+        const float shift = logit2<kLoss>(p, new_max);
+        const float old_shift = (st.run_max == kNegBig) ? shift : logit2<kLoss>(p, st.run_max);
+        st.sum *= ex2_approx(old_shift - shift);
+        st.run_max = new_max;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            float e[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if constexpr (kLoss == kNtXent) e[u] = ex2_approx(fmaf(v[i + u], p.k2, -shift));
+                else e[u] = ex2_approx(fmaf(lg2_approx(v[i + u]), p.k2, -shift));
+                if constexpr (kSpecial) e[u] = (v[i + u] == kNegBig) ? 0.f : e[u];
+            }
+            a0 += e[0];
+            a1 += e[1];
+            a2 += e[2];
+            a3 += e[3];
+        }
+        st.sum += (a0 + a1) + (a2 + a3);
+    }
+}
+
+template <int kLoss, bool kSpecial>
+SIMCLR_DEVICE void fwd_tile(const TileParams& p, uint32_t tmem_tile, int c0, int vc, const RowCtx& rc, bool tile_prec,
+                            FwdState& st) {
+#pragma unroll 1
+    for (int q = 0; q < kBlockN / 32; ++q) {
+        uint32_t r[32];
+        tmem_ld32(tmem_tile + q * 32, r);
+        tmem_ld_wait();
+        fwd_chunk<kLoss, kSpecial>(p, r, c0 + q * 32, vc, rc, tile_prec, st);
+    }
+}
+
+// ---- backward: one 32-column chunk -> 16 packed bf16x2 words of W ----
+template <int kLoss, bool kConst, bool kSpecial>
+SIMCLR_DEVICE void bwd_chunk(const TileParams& p, const uint32_t (&r)[32], uint32_t cv_addr, int cq, const RowCtx& rc,
+                             const BwdRow& br, uint32_t (&w)[16]) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        const float4 ac = lds_f4(cv_addr + i * 4);
+        float4 lc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (!kConst) lc = lds_f4(cv_addr + kBlockN * 4 + i * 4);
+        const float acs[4] = {ac.x, ac.y, ac.z, ac.w};
+        const float lcs[4] = {lc.x, lc.y, lc.z, lc.w};
+        float wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float sraw = __uint_as_float(r[i + u]);
+            float wval;
+            if constexpr (kLoss == kNtXent) {
+                if constexpr (kConst) {
+                    // one exp per element: W = exp2(S*k2 - m2) * (a_r + a_c)
+                    wval = ex2_approx(fmaf(sraw, p.k2, -p.m2)) * (br.row_a + acs[u]);
+                } else {
+                    // general form: W = g_r exp2(S*k2 - lse2_r) + g_c exp2(S*k2 - lse2_c)
+                    wval = br.row_a * ex2_approx(fmaf(sraw, p.k2, -br.row_l2)) +
+                           acs[u] * ex2_approx(fmaf(sraw, p.k2, -lcs[u]));
+                }
+            } else {
+                // d/dP of log(max(B P,1e-4))/tau = 1/(tau P) where live; folded: e^{A}/P = B q^{1/tau - 1}
+                const float qv = sraw * p.qscale;
+                const float y = lg2_approx(fmaxf(qv, kClampMin)) * (p.k2 - 1.0f);
+                if constexpr (kConst) wval = ex2_approx(y - p.m2) * (br.row_a + acs[u]);
+                else wval = br.row_a * ex2_approx(y - br.row_l2) + acs[u] * ex2_approx(y - lcs[u]);
+                wval = (qv >= kClampMin) ? wval : 0.f;
+            }
+            if constexpr (kSpecial) {
+                const int c = cq + i + u;
+                if (c == rc.diag_col || c == rc.pos_col) wval = 0.f;
+            }
+            wv[u] = wval;
+        }
+        w[(i >> 1) + 0] = pack_bf16x2(wv[0], wv[1]);
+        w[(i >> 1) + 1] = pack_bf16x2(wv[2], wv[3]);
+    }
+}
+
+template <int kLoss, bool kConst, bool kSpecial>
+SIMCLR_DEVICE void bwd_tile(const TileParams& p, uint32_t tmem_tile, uint32_t cv_addr, int c0, const RowCtx& rc,
+                            const BwdRow& br) {
+    // bf16 W chunk q overwrites columns [16q, 16q+16) of the score buffer: columns this thread has already read.
+#pragma unroll 1
+    for (int q = 0; q < kBlockN / 32; ++q) {
+        uint32_t r[32], w[16];
+        tmem_ld32(tmem_tile + q * 32, r);
+        tmem_ld_wait();
+        bwd_chunk<kLoss, kConst, kSpecial>(p, r, cv_addr + q * 128, c0 + q * 32, rc, br, w);
+        tmem_st16(tmem_tile + q * 16, w);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // The tile kernel
 // ---------------------------------------------------------------------------------------------
 template <int D, int kLoss, bool kBackward>
@@ -120,7 +277,11 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
     constexpr int S = L::kStages;
     constexpr uint32_t kIdescScore = make_idesc_bf16(kBlockM, kBlockN, 0, 0);
     constexpr uint32_t kIdescGrad = make_idesc_bf16(kBlockM, D, 0, 1);
-    constexpr uint32_t kTmemAcc = 2 * kBlockN;       // accumulator columns start after the two score buffers
+    // TMEM: NB score buffers of 128 columns, then (backward) the D-column gradient accumulator
+    constexpr int NB = kBackward ? ((kTmemCols - D) / kBlockN > kMaxScoreBufs ? kMaxScoreBufs : (kTmemCols - D) / kBlockN)
+                                 : kMaxScoreBufs;
+    constexpr uint32_t kTmemAcc = NB * kBlockN;
+    constexpr int kSlots = NB * kNumSoftmaxWG;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -134,9 +295,9 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
     uint64_t* acc_empty = bars + 3;
     uint64_t* b_full = bars + 4;
     uint64_t* b_empty = b_full + S;
-    uint64_t* s_full = b_empty + S;      // [2] score tile ready in TMEM
-    uint64_t* s_free = s_full + 2;       // [2] forward only: softmax finished reading the score tile
-    uint64_t* w_full = s_free + 2;       // [2] backward only: W written to TMEM
+    uint64_t* s_full = b_empty + S;               // [kSlots] score tile ready in TMEM
+    uint64_t* s_free = s_full + kMaxSlots;        // [kSlots] forward only: softmax finished reading the score tile
+    uint64_t* w_full = s_free + kMaxSlots;        // [kSlots] backward only: W written to TMEM
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + L::kOffTmemPtr);
 
     const int warp = threadIdx.x >> 5;
@@ -157,12 +318,12 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
         mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 256);
+        mbar_init(acc_empty, 128 * kNumSoftmaxWG);
         for (int i = 0; i < S; ++i) {
             mbar_init(b_full + i, 1);
             mbar_init(b_empty + i, 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kMaxSlots; ++i) {
             mbar_init(s_full + i, 1);
             mbar_init(s_free + i, 128);
             mbar_init(w_full + i, 128);
@@ -228,9 +389,10 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 }
                 const int stage = idx % S;
                 mbar_wait(b_full + stage, (idx / S) & 1, 201);
-                const int buf = idx & 1;
+                const int buf = idx % NB;
                 if constexpr (!kBackward) {
-                    if (idx >= 2) mbar_wait(s_free + buf, ((idx >> 1) - 1) & 1, 202);
+                    // the buffer's previous tenant (tile idx-NB) must have been read completely
+                    if (idx >= NB) mbar_wait(s_free + (idx - NB) % kSlots, ((idx - NB) / kSlots) & 1, 202);
                 }
                 tc_fence_after_sync();
                 const uint32_t b_addr = b_addr0 + stage * L::kTileBytes;
@@ -246,7 +408,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 // s_full is committed last so that, when the softmax sees it, the other arrivals have landed
                 if constexpr (!kBackward) umma_commit(b_empty + stage);
                 if (seg_last) umma_commit(a_empty);
-                umma_commit(s_full + buf);
+                umma_commit(s_full + idx % kSlots);
             };
 
             int seg_seen = 0;
@@ -254,17 +416,20 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 for (int idx = 0; idx < n; ++idx) issue_score(idx, seg_seen);
             } else {
                 int seg_done = 0;     // segments whose accumulator has been handed to the flush
-                if (n > 0) issue_score(0, seg_seen);
+                // The score MMAs run NB-1 tiles ahead of the gradient MMAs.  Buffer (idx+NB-1) % NB was last used by
+                // tile idx-1, whose gradient MMA has already been issued: tcgen05 ops of one thread execute in order.
+                constexpr int kAhead = NB - 1;
+                for (int i = 0; i < kAhead && i < n; ++i) issue_score(i, seg_seen);
                 for (int idx = 0; idx < n; ++idx) {
-                    if (idx + 1 < n) issue_score(idx + 1, seg_seen);      // keep the tensor pipe one tile ahead
+                    if (idx + kAhead < n) issue_score(idx + kAhead, seg_seen);
                     const long long t = t_begin + idx;
                     const int j = static_cast<int>(t % nct);
                     const bool seg_first = (idx == 0) || (j == 0);
                     const bool seg_last = (idx == n - 1) || (j == nct - 1);
-                    const int buf = idx & 1;
+                    const int buf = idx % NB;
                     const int stage = idx % S;
                     if (seg_first && seg_done > 0) mbar_wait(acc_empty, (seg_done - 1) & 1, 203);
-                    mbar_wait(w_full + buf, (idx >> 1) & 1, 204);
+                    mbar_wait(w_full + idx % kSlots, (idx / kSlots) & 1, 204);
                     tc_fence_after_sync();
                     // gradient MMA: acc += W[buf] (TMEM, 128 x 128 bf16) * B_stage (MN-major: K = column index)
                     const uint32_t b_addr = b_addr0 + stage * L::kTileBytes;
@@ -284,11 +449,12 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         }
     } else if (warp >= kSoftmaxWarp0) {
         // ================================ softmax warpgroups ================================
-        const int wg = (warp - kSoftmaxWarp0) >> 2;          // 0 / 1
+        const int wg = (warp - kSoftmaxWarp0) >> 2;          // 0 .. kNumSoftmaxWG-1
         const int quarter = warp & 3;                         // TMEM lane quarter this warp may touch
         const int row_in_block = quarter * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
         const int n = static_cast<int>(t_end - t_begin);
+        const uint32_t cv_base = smem_u32(smem_cv);
 
         int idx = 0;
         int seg = 0;
@@ -299,43 +465,42 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             const int j0 = static_cast<int>(t0 % nct);
             const int seg_len = min(n - idx, nct - j0);
 
-            const int vr = rb / blocks_per_view;                                  // view of this row block
-            const int img = (rb - vr * blocks_per_view) * kBlockM + row_in_block; // local image index
-            const bool row_ok = img < p.b_loc;
-            const int g = p.row_off + img;                                        // global image index
-            const int diag_col = (kLoss == kNtXent && row_ok) ? vr * p.bg_pad + g : -1;
-            const int pos_col = row_ok ? (1 - vr) * p.bg_pad + g : -1;
+            RowCtx rc;
+            rc.vr = rb / blocks_per_view;                                            // view of this row block
+            const int img = (rb - rc.vr * blocks_per_view) * kBlockM + row_in_block; // local image index
+            rc.row_ok = img < p.b_loc;
+            rc.g = p.row_off + img;                                                  // global image index
+            rc.diag_col = (kLoss == kNtXent && rc.row_ok) ? rc.vr * p.bg_pad + rc.g : -1;
+            rc.pos_col = rc.row_ok ? (1 - rc.vr) * p.bg_pad + rc.g : -1;
             // warp-uniform description of this warp's 32 rows
-            const int img_lo = (rb - vr * blocks_per_view) * kBlockM + quarter * 32;
+            const int img_lo = (rb - rc.vr * blocks_per_view) * kBlockM + quarter * 32;
             const bool warp_rows_ok = img_lo + 31 < p.b_loc;
             const int g_lo = p.row_off + img_lo, g_hi = g_lo + 31;
 
-            float run_max = kNegBig, sum = 0.f, max_prec = kNegBig, max_foll = kNegBig, pos_mma = kNegBig;
-            float row_a = 0.f, row_l2 = 0.f;
+            FwdState fs;
+            BwdRow br;
+            br.row_a = 0.f;
+            br.row_l2 = 0.f;
             if constexpr (kBackward) {
-                if (row_ok) {
-                    row_a = __ldg(p.colvec + vr * p.bg_pad + g);
-                    row_l2 = __ldg(p.colvec + 2 * p.bg_pad + vr * p.bg_pad + g);
+                if (rc.row_ok) {
+                    br.row_a = __ldg(p.colvec + rc.vr * p.bg_pad + rc.g);
+                    br.row_l2 = __ldg(p.colvec + 2 * p.bg_pad + rc.vr * p.bg_pad + rc.g);
                 }
             }
 
             for (int s = 0; s < seg_len; ++s) {
                 const int it = idx + s;
-                if ((it & 1) != wg) continue;
-                const int c0 = tile_col0<kLoss>(p, vr, j0 + s);
+                if ((it % kNumSoftmaxWG) != wg) continue;
+                const int c0 = tile_col0<kLoss>(p, rc.vr, j0 + s);
                 const int vc = c0 >= p.bg_pad ? 1 : 0;            // a tile never mixes views
                 const int ic0 = c0 - vc * p.bg_pad;               // image index of the tile's first column
-                const int buf = wg;
+                const int buf = it % NB;
                 const int stage = it % S;
-
-                mbar_wait(s_full + buf, (it >> 1) & 1, 300);
-                if constexpr (kBackward) mbar_wait(b_full + stage, (it / S) & 1, 301);   // colvec visibility
-                tc_fence_after_sync();
-                const float* cv = smem_cv + stage * 2 * kBlockN;
+                const uint32_t tmem_tile = tmem_base + lane_addr + buf * kBlockN;
 
                 // ---- warp-uniform tile classification ----
                 const bool overlaps_rows = !(ic0 > g_hi || ic0 + kBlockN - 1 < g_lo);
-                bool special = !warp_rows_ok || overlaps_rows;    // diagonal or positive may be inside
+                bool special = !warp_rows_ok || overlaps_rows;    // the diagonal or the positive may be inside
                 bool tile_prec = false;
                 if constexpr (!kBackward) {
                     special = special || (ic0 + kBlockN - 1 >= p.b_glob);        // padded columns inside
@@ -343,145 +508,58 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                     // NT-Xent rows see [view-2 block | view-1 block] (objective.py:48-49); modified rows see
                     // the other view in natural order (objective.py:93).
                     const bool before = ic0 + kBlockN - 1 < g_lo;
-                    if constexpr (kLoss == kNtXent) tile_prec = (vr == 0) ? (vc == 1 && before) : (vc == 1 || before);
+                    if constexpr (kLoss == kNtXent) tile_prec = (rc.vr == 0) ? (vc == 1 && before) : (vc == 1 || before);
                     else tile_prec = before;
                 }
 
-#pragma unroll 1
-                for (int q = 0; q < kBlockN / 32; ++q) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + lane_addr + buf * kBlockN + q * 32, r);
-                    tmem_ld_wait();
-                    const int cq = c0 + q * 32;
-                    if constexpr (!kBackward) {
-                        // ------------------------- forward -------------------------
-                        float v[32];
-                        float cm = kNegBig;
-                        if (!special) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                v[i] = raw_value<kLoss>(p, __uint_as_float(r[i]));
-                                cm = fmaxf(cm, v[i]);
-                            }
-                            if (tile_prec) max_prec = fmaxf(max_prec, cm); else max_foll = fmaxf(max_foll, cm);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const int c = cq + i;
-                                const int ic = c - vc * p.bg_pad;
-                                const float x = raw_value<kLoss>(p, __uint_as_float(r[i]));
-                                if (c == pos_col) pos_mma = x;
-                                const bool valid = row_ok && ic < p.b_glob && c != diag_col && c != pos_col;
-                                v[i] = valid ? x : kNegBig;
-                                if (valid) {
-                                    cm = fmaxf(cm, x);
-                                    bool prec;
-                                    if constexpr (kLoss == kNtXent) prec = (vr == 0) ? (vc == 1 && ic < g) : (vc == 1 || ic < g);
-                                    else prec = ic < g;
-                                    if (prec) max_prec = fmaxf(max_prec, x); else max_foll = fmaxf(max_foll, x);
-                                }
-                            }
-                        }
-                        if (cm > run_max) {
-                            // rescale the running sum to the new maximum (0 * 0 when run_max is still the sentinel)
-                            sum *= (run_max == kNegBig) ? 0.f : ex2_approx(logit2<kLoss>(p, run_max) - logit2<kLoss>(p, cm));
-                            run_max = cm;
-                        }
-                        if (run_max != kNegBig) {
-                            const float shift = logit2<kLoss>(p, run_max);
-                            float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-                            for (int i = 0; i < 32; i += 2) {
-                                float e0, e1;
-                                if constexpr (kLoss == kNtXent) {
-                                    e0 = ex2_approx(fmaf(v[i], p.k2, -shift));
-                                    e1 = ex2_approx(fmaf(v[i + 1], p.k2, -shift));
-                                } else {
-                                    e0 = ex2_approx(fmaf(lg2_approx(v[i]), p.k2, -shift));
-                                    e1 = ex2_approx(fmaf(lg2_approx(v[i + 1]), p.k2, -shift));
-                                }
-                                if (special) {               // masked entries carry the sentinel
-                                    e0 = (v[i] == kNegBig) ? 0.f : e0;
-                                    e1 = (v[i + 1] == kNegBig) ? 0.f : e1;
-                                }
-                                acc0 += e0;
-                                acc1 += e1;
-                            }
-                            sum += acc0 + acc1;
-                        }
+                // One barrier per slot = it % (NB * #warpgroups): a slot always maps to the same warpgroup and the
+                // same TMEM buffer, so every barrier has a single waiter that observes all of its phases in order
+                // (a parity wait is only meaningful when the waiter is at most one phase away from the barrier).
+                const int slot = it % kSlots;
+                mbar_wait(s_full + slot, (it / kSlots) & 1, 300);
+                if constexpr (kBackward) mbar_wait(b_full + stage, (it / S) & 1, 301);   // colvec visibility
+                tc_fence_after_sync();
+
+                if constexpr (!kBackward) {
+                    if (special) fwd_tile<kLoss, true>(p, tmem_tile, c0, vc, rc, tile_prec, fs);
+                    else fwd_tile<kLoss, false>(p, tmem_tile, c0, vc, rc, tile_prec, fs);
+                    tc_fence_before_sync();
+                    mbar_arrive(s_free + slot);
+                } else {
+                    const uint32_t cv_addr = cv_base + stage * (2 * kBlockN * 4);
+                    if (p.const_shift) {
+                        if (special) bwd_tile<kLoss, true, true>(p, tmem_tile, cv_addr, c0, rc, br);
+                        else bwd_tile<kLoss, true, false>(p, tmem_tile, cv_addr, c0, rc, br);
                     } else {
-                        // ------------------------- backward -------------------------
-                        uint32_t w[16];
-                        const float4* cva = reinterpret_cast<const float4*>(cv + q * 32);
-                        const float4* cvl = reinterpret_cast<const float4*>(cv + kBlockN + q * 32);
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            const float4 ac = cva[i >> 2];
-                            float4 lc = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (!p.const_shift) lc = cvl[i >> 2];
-                            const float acs[4] = {ac.x, ac.y, ac.z, ac.w};
-                            const float lcs[4] = {lc.x, lc.y, lc.z, lc.w};
-                            float wv[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const float sraw = __uint_as_float(r[i + u]);
-                                float y;       // log2-domain exponent argument shared by both softmax terms
-                                bool live = true;
-                                if constexpr (kLoss == kNtXent) {
-                                    y = sraw * p.k2;
-                                } else {
-                                    // d/dP of log(max(B P,1e-4))/tau = 1/(tau P) where live; folded: e^{A}/P = B q^{1/tau - 1}
-                                    const float qv = sraw * p.qscale;
-                                    live = qv >= kClampMin;
-                                    y = lg2_approx(fmaxf(qv, kClampMin)) * (p.k2 - 1.0f);
-                                }
-                                float wval;
-                                if (p.const_shift) wval = ex2_approx(y - p.m2) * (row_a + acs[u]);
-                                else wval = row_a * ex2_approx(y - row_l2) + acs[u] * ex2_approx(y - lcs[u]);
-                                if (special) {
-                                    const int c = cq + i + u;
-                                    if (c == diag_col || c == pos_col) wval = 0.f;
-                                }
-                                if constexpr (kLoss == kModified) wval = live ? wval : 0.f;
-                                wv[u] = wval;
-                            }
-                            w[(i >> 1) + 0] = pack_bf16x2(wv[0], wv[1]);
-                            w[(i >> 1) + 1] = pack_bf16x2(wv[2], wv[3]);
-                        }
-                        // bf16 W overwrites the (already consumed) low columns of this score buffer
-                        tmem_st16(tmem_base + lane_addr + buf * kBlockN + q * 16, w);
+                        if (special) bwd_tile<kLoss, false, true>(p, tmem_tile, cv_addr, c0, rc, br);
+                        else bwd_tile<kLoss, false, false>(p, tmem_tile, cv_addr, c0, rc, br);
                     }
-                }
-                if constexpr (kBackward) {
                     tmem_st_wait();
                     tc_fence_before_sync();
-                    mbar_arrive(w_full + buf);
-                } else {
-                    tc_fence_before_sync();
-                    mbar_arrive(s_free + buf);
+                    mbar_arrive(w_full + slot);
                 }
             }
 
             // ---- end of segment ----
             if constexpr (!kBackward) {
-                float* dst = p.part + ((static_cast<size_t>(blockIdx.x) * p.max_segs + seg) * 2 + wg) *
+                float* dst = p.part + ((static_cast<size_t>(blockIdx.x) * p.max_segs + seg) * kNumSoftmaxWG + wg) *
                                           (kFwdFields * kBlockM) + row_in_block;
-                dst[0 * kBlockM] = sum;
-                dst[1 * kBlockM] = run_max;
-                dst[2 * kBlockM] = max_prec;
-                dst[3 * kBlockM] = max_foll;
-                dst[4 * kBlockM] = pos_mma;
+                dst[0 * kBlockM] = fs.sum;
+                dst[1 * kBlockM] = fs.run_max;
+                dst[2 * kBlockM] = fs.max_prec;
+                dst[3 * kBlockM] = fs.max_foll;
+                dst[4 * kBlockM] = fs.pos_mma;
             } else {
-                // flush the gradient accumulator: warpgroup g takes columns [g*D/2, (g+1)*D/2)
+                // flush the gradient accumulator: the D columns are split in 32-column chunks over the warpgroups
                 mbar_wait(acc_full, seg & 1, 302);
                 tc_fence_after_sync();
 #pragma unroll 1
-                for (int q = 0; q < D / 64; ++q) {
+                for (int q = wg; q < D / 32; q += kNumSoftmaxWG) {
                     uint32_t r[32];
-                    const int col = wg * (D / 2) + q * 32;
+                    const int col = q * 32;
                     tmem_ld32(tmem_base + lane_addr + kTmemAcc + col, r);
                     tmem_ld_wait();
-                    if (row_ok) {
+                    if (rc.row_ok) {
                         float* dst = p.dacc + static_cast<size_t>(rb * kBlockM + row_in_block) * D + col;
 #pragma unroll
                         for (int i = 0; i < 32; i += 4)
