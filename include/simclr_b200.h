@@ -103,6 +103,14 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
                     const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* Diagnostics: per-role clock64() timeline of one CTA of the tile kernels (tools/trace_timeline.py).
+ * device_buffer: int64[6 roles][64 iterations][4] or NULL to switch tracing off. */
+int simclr_debug_set_trace(void* device_buffer, int cta);
+
+/* Diagnostics: tcgen05.mma issue / execution rate probe under contention (tools/mma_rate.py).
+ * out: int64[4 configs][4]; mode 0 idle, 1 tcgen05.ld, 2 MUFU, 3 FFMA, 4 all; sink: float[640] scratch. */
+int simclr_debug_mma_rate(long long* out_device, int batches, int grid, int mode, float* sink, void* stream);
+
 /* Diagnostics: UMMA/TMA primitive self-test (tests/test_primitives.py). out_f32 receives 3*128*128 floats. */
 int simclr_selftest_umma(const void* a_bf16_128x128, const void* b_bf16_128x128, float* out_f32, void* stream);
 

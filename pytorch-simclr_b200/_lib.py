@@ -37,6 +37,8 @@ SIGNATURES = {
     "simclr_backward": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp,
                                _vp, _vp, _vp, _vp, _sz, _vp]),
     "simclr_selftest_umma": (_int, [_vp, _vp, _vp, _vp]),
+    "simclr_debug_set_trace": (_int, [_vp, _int]),
+    "simclr_debug_mma_rate": (_int, [_vp, _int, _int, _int, _vp, _vp]),
 }
 
 

@@ -13,6 +13,10 @@ using namespace simclr;
 
 namespace {
 
+// debug timeline target (simclr_debug_set_trace); applies to subsequent launches of this process
+long long* g_trace_ptr = nullptr;
+int g_trace_cta = 0;
+
 // ------------------------------------------------------------------------------------------
 // cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
 // ------------------------------------------------------------------------------------------
@@ -225,6 +229,8 @@ TileParams make_tile_params(const Geometry& g, const Scales& s, int64_t b_local,
     p.m2 = s.m2;
     p.const_shift = s.const_shift;
     p.qscale = s.qscale;
+    p.trace = g_trace_ptr;
+    p.trace_cta = g_trace_cta;
     return p;
 }
 
@@ -399,6 +405,22 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
         else SIMCLR_FIN(__nv_bfloat16, kModified);
     }
 #undef SIMCLR_FIN
+    return static_cast<int>(cudaGetLastError());
+}
+
+int simclr_debug_set_trace(void* device_buffer, int cta) {
+    g_trace_ptr = static_cast<long long*>(device_buffer);
+    g_trace_cta = cta;
+    return SIMCLR_OK;
+}
+
+int simclr_debug_mma_rate(long long* out_device, int batches, int grid, int mode, float* sink, void* stream) {
+    if (!out_device || !sink) return SIMCLR_ERR_NULL_POINTER;
+    int rc = check_device();
+    if (rc) return rc;
+    cudaError_t e = cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRateSmemBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    mma_rate_kernel<<<grid, 640, kRateSmemBytes, static_cast<cudaStream_t>(stream)>>>(out_device, batches, mode, sink);
     return static_cast<int>(cudaGetLastError());
 }
 
