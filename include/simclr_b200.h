@@ -68,9 +68,13 @@ size_t simclr_backward_workspace_bytes(int loss, int64_t b_local, int64_t b_glob
  *   operand  bf16 [2*Blpad][Dpad]  round-to-nearest operands for the tensor cores (padding zeroed)
  *   inv_norm f32  [2*Blpad]        1 / max(||z||, 1e-12)   (1 when normalize == 0)
  *   pos_dot  f32  [2*Blpad]        exact fp32 <op_r, op_pos(r)> of the positive pair
+ * `forward_workspace` (may be NULL) is the workspace the following simclr_forward call will use; its counter
+ * header is zeroed here so that no separate memset is needed.  simclr_forward requires that header (the first
+ * 4 * (2*Blpad/128 + 4) bytes) to be zero on entry and leaves it zero on exit.
  */
 int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
-                   int normalize, void* operand, float* inv_norm, float* pos_dot, void* stream);
+                   int normalize, void* operand, float* inv_norm, float* pos_dot, void* forward_workspace,
+                   void* stream);
 
 /*
  * Stage 2 -- forward over this rank's rows against the global batch's columns
@@ -106,6 +110,11 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
 /* Diagnostics: per-role clock64() timeline of one CTA of the tile kernels (tools/trace_timeline.py).
  * device_buffer: int64[6 roles][64 iterations][4] or NULL to switch tracing off. */
 int simclr_debug_set_trace(void* device_buffer, int cta);
+
+/* Diagnostics: kernel-level %globaltimer timeline (tools/kernel_timeline.py).  device_buffer: uint64[8][2]
+ * (min start / max end in ns per kernel id: 0 prepare, 1 forward tile, 2 backward prepare, 3 backward tile),
+ * start slots initialised to ~0, end slots to 0; NULL switches it off.  Captured into graphs at capture time. */
+int simclr_debug_set_kernel_trace(void* device_buffer);
 
 /* Diagnostics: tcgen05.mma issue / execution rate probe under contention (tools/mma_rate.py).
  * out: int64[4 configs][4]; mode 0 idle, 1 tcgen05.ld, 2 MUFU, 3 FFMA, 4 all; sink: float[640] scratch. */

@@ -16,6 +16,7 @@ namespace {
 // debug timeline target (simclr_debug_set_trace); applies to subsequent launches of this process
 long long* g_trace_ptr = nullptr;
 int g_trace_cta = 0;
+unsigned long long* g_ktrace_ptr = nullptr;
 
 // ------------------------------------------------------------------------------------------
 // cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
@@ -100,21 +101,25 @@ int make_geometry(int loss, int64_t b_local, int64_t b_global, int64_t row_offse
     return SIMCLR_OK;
 }
 
+// The forward workspace starts with a 256-byte header holding the ticket of the finalize kernel's last-block
+// reduction.  It must be zero when simclr_forward starts and is left zero; simclr_prepare zeroes it as well.
+inline size_t header_bytes(const Geometry&) { return 256; }
+
 struct FwdWorkspace {
+    unsigned int* ticket;
     float* part;
     float* block_part;
-    unsigned int* ticket;
     size_t bytes;
 };
 FwdWorkspace carve_forward(const Geometry& g, void* base) {
     FwdWorkspace w;
     size_t off = 0;
     w.ticket = reinterpret_cast<unsigned int*>(static_cast<char*>(base) + off);
-    off += 256;
+    off += header_bytes(g);
     w.block_part = reinterpret_cast<float*>(static_cast<char*>(base) + off);
     off += align256(static_cast<size_t>(g.n_row_blocks) * 4 * sizeof(float));
     w.part = reinterpret_cast<float*>(static_cast<char*>(base) + off);
-    off += align256(static_cast<size_t>(g.grid) * g.max_segs * kNumSoftmaxWG * kFwdFields * kBlockM * sizeof(float));
+    off += align256(static_cast<size_t>(g.grid) * g.max_segs * kFwdFields * kBlockM * sizeof(float));
     w.bytes = off;
     return w;
 }
@@ -229,8 +234,11 @@ TileParams make_tile_params(const Geometry& g, const Scales& s, int64_t b_local,
     p.m2 = s.m2;
     p.const_shift = s.const_shift;
     p.qscale = s.qscale;
+    p.inv_tau = s.inv_tau;
     p.trace = g_trace_ptr;
     p.trace_cta = g_trace_cta;
+    p.ktrace = g_ktrace_ptr;
+    p.tile_grid = g.grid;
     return p;
 }
 
@@ -289,22 +297,25 @@ size_t simclr_backward_workspace_bytes(int loss, int64_t b_local, int64_t b_glob
 }
 
 int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
-                   int normalize, void* operand, float* inv_norm, float* pos_dot, void* stream) {
+                   int normalize, void* operand, float* inv_norm, float* pos_dot, void* forward_workspace,
+                   void* stream) {
     if (!x_batch1 || !x_batch2 || !operand || !inv_norm || !pos_dot) return SIMCLR_ERR_NULL_POINTER;
     if (in_dtype != SIMCLR_DTYPE_F32 && in_dtype != SIMCLR_DTYPE_BF16) return SIMCLR_ERR_BAD_DTYPE;
     Geometry g;
     int rc = make_geometry(loss, b_local, b_local, 0, d, &g);
     if (rc) return rc;
-    if (misaligned(operand)) return SIMCLR_ERR_MISALIGNED;
+    if (misaligned(operand) || misaligned(forward_workspace)) return SIMCLR_ERR_MISALIGNED;
     if ((rc = check_device())) return rc;
     Scales s = make_scales(loss, 1.0f, normalize, b_local);
+    unsigned int* zero_ptr = static_cast<unsigned int*>(forward_workspace);
+    const int zero_words = static_cast<int>(header_bytes(g) / 4);
     AuxParams a = make_aux(g, s, b_local, b_local, 0, d, normalize);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int warps = 8;
     const int blocks = static_cast<int>((g.bl_pad + warps - 1) / warps);
     auto* op = static_cast<__nv_bfloat16*>(operand);
 #define SIMCLR_PREP(T, LOSS) \
-    prepare_kernel<T, LOSS><<<blocks, warps * 32, 0, st>>>(static_cast<const T*>(x_batch1), static_cast<const T*>(x_batch2), a, op, inv_norm, pos_dot)
+    prepare_kernel<T, LOSS><<<blocks, warps * 32, 0, st>>>(static_cast<const T*>(x_batch1), static_cast<const T*>(x_batch2), a, op, inv_norm, pos_dot, zero_ptr, zero_words, g_ktrace_ptr)
     if (loss == SIMCLR_LOSS_NTXENT) {
         if (in_dtype == SIMCLR_DTYPE_F32) SIMCLR_PREP(float, kNtXent);
         else SIMCLR_PREP(__nv_bfloat16, kNtXent);
@@ -338,20 +349,20 @@ int simclr_forward(int loss, const void* operand_rows, const void* operand_cols,
     // the forward never needs the bounded-score shortcut: normalize=1 only affects backward's const_shift
     Scales s = make_scales(loss, temperature, 1, b_global);
     TileParams p = make_tile_params(g, s, b_local, b_global, row_offset);
-    p.part = w.part;
+    p.d = static_cast<int>(d);
     p.ticket = w.ticket;
+    p.part = w.part;
+    p.pos_dot = pos_dot;
+    p.row_weight = row_weight;
+    p.lse2 = lse2;
+    p.row_loss = row_loss;
+    p.block_part = w.block_part;
+    p.stats = stats;
+    p.loss_out = loss_out;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if ((rc = dispatch_tile<false>(loss, g.d_pad, map_rows, map_cols, p, g.grid, st))) return rc;
-
-    AuxParams a = make_aux(g, s, b_local, b_global, row_offset, d, 1);
-    if (loss == SIMCLR_LOSS_NTXENT)
-        forward_finalize_kernel<kNtXent><<<g.n_row_blocks, kBlockM, 0, st>>>(
-            a, w.part, g.grid, g.max_segs, g.n_col_tiles, g.total_tiles, pos_dot, row_weight, lse2, row_loss,
-            w.block_part, w.ticket, stats, loss_out);
-    else
-        forward_finalize_kernel<kModified><<<g.n_row_blocks, kBlockM, 0, st>>>(
-            a, w.part, g.grid, g.max_segs, g.n_col_tiles, g.total_tiles, pos_dot, row_weight, lse2, row_loss,
-            w.block_part, w.ticket, stats, loss_out);
+    if (loss == SIMCLR_LOSS_NTXENT) forward_finalize_kernel<kNtXent><<<g.n_row_blocks, kBlockM, 0, st>>>(p);
+    else forward_finalize_kernel<kModified><<<g.n_row_blocks, kBlockM, 0, st>>>(p);
     return static_cast<int>(cudaGetLastError());
 }
 
@@ -382,35 +393,46 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     backward_prepare_kernel<<<device_info().sm_count * 2, 256, 0, st>>>(
-        a, lse2_cols, col_scale, w.colvec, reinterpret_cast<float4*>(w.dacc), w.dacc_floats / 4);
+        a, lse2_cols, col_scale, w.colvec, reinterpret_cast<float4*>(w.dacc), w.dacc_floats / 4, g_ktrace_ptr);
     if ((rc = static_cast<int>(cudaGetLastError()))) return rc;
 
     TileParams p = make_tile_params(g, s, b_local, b_global, row_offset);
+    p.d = static_cast<int>(d);
+    p.in_bf16 = in_dtype == SIMCLR_DTYPE_BF16 ? 1 : 0;
+    p.normalize = normalize;
     p.colvec = w.colvec;
     p.dacc = w.dacc;
-    p.ticket = nullptr;
+    p.x1 = x_batch1;
+    p.x2 = x_batch2;
+    p.g1 = grad1;
+    p.g2 = grad2;
+    p.inv_norm = inv_norm;
+    p.pos_dot = pos_dot;
+    p.col_scale = col_scale;
+    p.grad_out = grad_out;
     if ((rc = dispatch_tile<true>(loss, g.d_pad, map_rows, map_cols, p, g.grid, st))) return rc;
-
-    const int warps = 8;
-    const int blocks = static_cast<int>((b_local + warps - 1) / warps);
-#define SIMCLR_FIN(T, LOSS)                                                                                        \
-    backward_finalize_kernel<T, LOSS><<<blocks, warps * 32, 0, st>>>(                                              \
-        static_cast<const T*>(x_batch1), static_cast<const T*>(x_batch2), a, inv_norm, pos_dot, lse2_cols, col_scale, \
-        grad_out, w.dacc, static_cast<T*>(grad1), static_cast<T*>(grad2))
-    if (loss == SIMCLR_LOSS_NTXENT) {
-        if (in_dtype == SIMCLR_DTYPE_F32) SIMCLR_FIN(float, kNtXent);
-        else SIMCLR_FIN(__nv_bfloat16, kNtXent);
-    } else {
-        if (in_dtype == SIMCLR_DTYPE_F32) SIMCLR_FIN(float, kModified);
-        else SIMCLR_FIN(__nv_bfloat16, kModified);
+#define SIMCLR_BFIN(DV)                                                                                  \
+    case DV:                                                                                             \
+        if (loss == SIMCLR_LOSS_NTXENT) backward_finalize_kernel<DV, kNtXent><<<g.n_row_blocks * kBwdFinBlocksPerRowBlock, 512, 0, st>>>(p); \
+        else backward_finalize_kernel<DV, kModified><<<g.n_row_blocks * kBwdFinBlocksPerRowBlock, 512, 0, st>>>(p); \
+        break;
+    switch (g.d_pad) {
+        SIMCLR_BFIN(64)
+        SIMCLR_BFIN(128)
+        SIMCLR_BFIN(256)
     }
-#undef SIMCLR_FIN
+#undef SIMCLR_BFIN
     return static_cast<int>(cudaGetLastError());
 }
 
 int simclr_debug_set_trace(void* device_buffer, int cta) {
     g_trace_ptr = static_cast<long long*>(device_buffer);
     g_trace_cta = cta;
+    return SIMCLR_OK;
+}
+
+int simclr_debug_set_kernel_trace(void* device_buffer) {
+    g_ktrace_ptr = static_cast<unsigned long long*>(device_buffer);
     return SIMCLR_OK;
 }
 

@@ -35,6 +35,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include "row_math.cuh"
 #include "sm100_ptx.cuh"
 
 namespace simclr {
@@ -78,12 +79,34 @@ struct TileParams {
     float m2;          // constant log2-domain shift of the one-exp backward form
     int const_shift;   // backward: 1 -> one exp per element (bounded scores), 0 -> general two-exp form
     float qscale;      // modified loss: (float) b_glob, the factor inside the clamp
-    float* part;       // forward : [grid][max_segs][kNumSoftmaxWG][kFwdFields][128]
-    const float* colvec;   // backward: [2 planes][2*bg_pad]; plane 0 = a_c (or g_c), plane 1 = lse2_c
-    float* dacc;           // backward: [2*bl_pad][D] fp32, zero on entry, accumulated with red.global.add
-    unsigned int* ticket;  // zeroed by CTA 0 for the finalize kernel's last-block reduction
+    float inv_tau;
+    int d;             // true embedding dimension (<= D)
+    int in_bf16;       // element type of x_batch / grad: 0 = f32, 1 = bf16
+    int normalize;
+    unsigned int* ticket;      // forward finalize: row blocks finished so far (zero on entry, left zero on exit)
+    // forward
+    float* part;               // [grid][max_segs][kFwdFields][128] per-CTA partials (warpgroups merged in smem)
+    const float* pos_dot;      // [2*bl_pad] exact fp32 positive-pair dot products
+    const float* row_weight;   // [2*b_loc] compact order, or nullptr
+    float* lse2;               // [2*bl_pad]
+    float* row_loss;           // [2*bl_pad]
+    float* block_part;         // [n_row_blocks][4]
+    float* stats;              // [4]
+    float* loss_out;           // [1] or nullptr
+    // backward
+    const float* colvec;       // [2 planes][2*bg_pad]; plane 0 = a_c (or g_c), plane 1 = lse2_c
+    float* dacc;               // [2*bl_pad][D] fp32, zero on entry, accumulated with red.global.add
+    const void* x1;            // inputs [b_loc][d]
+    const void* x2;
+    void* g1;                  // gradients [b_loc][d]
+    void* g2;
+    const float* inv_norm;     // [2*bl_pad]
+    const float* col_scale;    // [2*bg_pad] w_c / sum(w) or nullptr
+    const float* grad_out;     // [1] or nullptr
     long long* trace;      // optional (debug): per-role clock64() timestamps of CTA `trace_cta`
     int trace_cta;
+    int tile_grid;         // grid size of the tile kernel (the finalize kernels need it to locate partials)
+    unsigned long long* ktrace;   // optional (debug): kernel-level %globaltimer stamps
 };
 
 // Debug timeline: trace[(role * kTraceIters + it) * 4 + k].  Roles: 0 TMA producer, 1 MMA issuer,
@@ -108,7 +131,10 @@ struct SmemLayout {
     // barriers: a_full, a_empty, acc_full, acc_empty, b_full[S], b_empty[S], s_full[8], s_free[8], w_full[8], w_done[8]
     static constexpr int kNumBars = 4 + 2 * kStages + 4 * kMaxSlots;   // kMaxSlots = 8
     static constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
-    static constexpr int kBytes = kOffTmemPtr + 16;
+    static constexpr int kOffFlags = kOffTmemPtr + 16;                 // 16 ints of CTA-wide scratch
+    static constexpr int kOffMerge = kOffFlags + 64;                   // forward: [2][4 WG][5][128] floats
+    static constexpr int kMergeBytes = 2 * kNumSoftmaxWG * kFwdFields * kBlockM * 4;
+    static constexpr int kBytes = kOffMerge + kMergeBytes;
     static constexpr int kDynamicBytes = kBytes + 1024;              // slack for manual 1024 B alignment
 };
 
@@ -263,6 +289,229 @@ SIMCLR_DEVICE void bwd_chunk(const TileParams& p, const uint32_t (&r)[32], uint3
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused finalize steps.  A row block's tiles are spread over a few CTAs (contiguous tile ranges); the CTA that
+// completes its share last (atomic ticket per row block) finishes the block's 128 rows from L2-resident data.
+// ---------------------------------------------------------------------------------------------
+// CTAs whose range [T*k/G, T*(k+1)/G) overlaps row block rb: owner(t) = ((t+1)*G - 1) / T
+SIMCLR_DEVICE void contributing_ctas(const TileParams& p, int rb, int& k_first, int& k_last) {
+    const long long g = p.tile_grid;
+    const long long t_lo = static_cast<long long>(rb) * p.n_col_tiles;
+    const long long t_hi = t_lo + p.n_col_tiles;
+    k_first = static_cast<int>(((t_lo + 1) * g - 1) / p.total_tiles);
+    k_last = static_cast<int>((t_hi * g - 1) / p.total_tiles);
+}
+
+template <int kLoss>
+SIMCLR_DEVICE float exact_logit2(const TileParams& p, float v) {
+    if constexpr (kLoss == kNtXent) return v * p.k2;
+    else return log2f(v) * p.k2;
+}
+
+// Forward: merge the per-CTA partials of row block rb, add the exact positive term, emit lse2 / row_loss and the
+// block's contribution to the loss statistics.  Called by the 128 threads of softmax warpgroup 0 (tid = row).
+template <int kLoss>
+SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int tid, float* red /*smem, 16 floats*/,
+                                             int* flags /*smem*/) {
+    const int blocks_per_view = p.bl_pad / kBlockM;
+    const int vr = rb / blocks_per_view;
+    const int img = (rb - vr * blocks_per_view) * kBlockM + tid;
+    const bool row_ok = img < p.b_loc;
+    const int slot = rb * kBlockM + tid;
+    int k_first, k_last;
+    contributing_ctas(p, rb, k_first, k_last);
+
+    float v_pos = __ldg(p.pos_dot + slot);
+    if constexpr (kLoss == kModified) v_pos = fmaxf(v_pos * p.qscale, kClampMin);
+    // Partials of CTA k live at part[(k * max_segs + seg_k)]: the first contributing CTA may have started in an
+    // earlier row block (seg_k = rb - its first row block); every later one starts inside this row block (seg 0).
+    const long long c_first = (p.total_tiles * k_first) / p.tile_grid;
+    const int seg_first = rb - static_cast<int>(c_first / p.n_col_tiles);
+    const size_t stride_k = static_cast<size_t>(p.max_segs) * (kFwdFields * kBlockM);
+    const float* base = p.part + static_cast<size_t>(k_first) * stride_k + tid;
+    const int nk = k_last - k_first + 1;
+    float vmax = v_pos, max_prec = kNegBig, max_foll = kNegBig, pos_mma = kNegBig, total;
+    constexpr int kFast = 6;
+    if (nk <= kFast) {
+        // common case: issue every load up front (one L2 round trip), then merge from registers
+        float sv[kFast], mv[kFast];
+#pragma unroll
+        for (int i = 0; i < kFast; ++i) {
+            sv[i] = 0.f;
+            mv[i] = kNegBig;
+            if (i < nk) {
+                const float* src = base + i * stride_k + (i == 0 ? seg_first * (kFwdFields * kBlockM) : 0);
+                sv[i] = __ldcg(src + 0 * kBlockM);
+                mv[i] = __ldcg(src + 1 * kBlockM);
+                max_prec = fmaxf(max_prec, __ldcg(src + 2 * kBlockM));
+                max_foll = fmaxf(max_foll, __ldcg(src + 3 * kBlockM));
+                pos_mma = fmaxf(pos_mma, __ldcg(src + 4 * kBlockM));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kFast; ++i) vmax = fmaxf(vmax, mv[i]);
+        const float top = exact_logit2<kLoss>(p, vmax);
+        total = exp2f(exact_logit2<kLoss>(p, v_pos) - top);
+#pragma unroll
+        for (int i = 0; i < kFast; ++i)
+            if (mv[i] > kNegBig) total += sv[i] * exp2f(exact_logit2<kLoss>(p, mv[i]) - top);
+    } else {
+        // many small CTAs per row block (tiny problems): two passes
+        for (int i = 0; i < nk; ++i) {
+            const float* src = base + i * stride_k + (i == 0 ? seg_first * (kFwdFields * kBlockM) : 0);
+            vmax = fmaxf(vmax, __ldcg(src + 1 * kBlockM));
+            max_prec = fmaxf(max_prec, __ldcg(src + 2 * kBlockM));
+            max_foll = fmaxf(max_foll, __ldcg(src + 3 * kBlockM));
+            pos_mma = fmaxf(pos_mma, __ldcg(src + 4 * kBlockM));
+        }
+        const float top = exact_logit2<kLoss>(p, vmax);
+        total = exp2f(exact_logit2<kLoss>(p, v_pos) - top);
+        for (int i = 0; i < nk; ++i) {
+            const float* src = base + i * stride_k + (i == 0 ? seg_first * (kFwdFields * kBlockM) : 0);
+            const float mk = __ldcg(src + 1 * kBlockM);
+            if (mk > kNegBig) total += __ldcg(src + 0 * kBlockM) * exp2f(exact_logit2<kLoss>(p, mk) - top);
+        }
+    }
+    const float top = exact_logit2<kLoss>(p, vmax);
+    float l2 = 0.f, loss_r = 0.f, w = 0.f, hit = 0.f;
+    if (row_ok) {
+        l2 = top + log2f(total);
+        loss_r = (l2 - exact_logit2<kLoss>(p, v_pos)) * kLn2;
+        w = p.row_weight ? __ldg(p.row_weight + vr * p.b_loc + img) : 1.f;
+        // reference objective.py:51 -- Tensor.max returns the first maximal index
+        hit = (max_prec < pos_mma && max_foll <= pos_mma) ? 1.f : 0.f;
+    }
+    p.lse2[slot] = l2;
+    p.row_loss[slot] = loss_r;
+
+    // block sums in a fixed order (deterministic)
+    const float r0 = warp_sum(w * loss_r), r1 = warp_sum(w), r2 = warp_sum(hit);
+    if ((tid & 31) == 0) {
+        red[0 * 4 + (tid >> 5)] = r0;
+        red[1 * 4 + (tid >> 5)] = r1;
+        red[2 * 4 + (tid >> 5)] = r2;
+    }
+    named_bar_sync(2, kBlockM);
+    if (tid == 0) {
+        p.block_part[rb * 4 + 0] = (red[0] + red[1]) + (red[2] + red[3]);
+        p.block_part[rb * 4 + 1] = (red[4] + red[5]) + (red[6] + red[7]);
+        p.block_part[rb * 4 + 2] = (red[8] + red[9]) + (red[10] + red[11]);
+        __threadfence();
+        const unsigned int prev = atomicAdd(p.ticket, 1u);
+        flags[1] = (prev == static_cast<unsigned int>(p.n_row_blocks) - 1u) ? 1 : 0;
+    }
+    named_bar_sync(2, kBlockM);
+    if (flags[1] && tid < 32) {
+        __threadfence();
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int i = tid; i < p.n_row_blocks; i += 32) {
+            s0 += __ldcg(p.block_part + i * 4 + 0);
+            s1 += __ldcg(p.block_part + i * 4 + 1);
+            s2 += __ldcg(p.block_part + i * 4 + 2);
+        }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (tid == 0) {
+            p.stats[0] = s0;
+            p.stats[1] = s1;
+            p.stats[2] = s2;
+            p.stats[3] = s0 / s1;
+            if (p.loss_out) *p.loss_out = s0 / s1;
+            *p.ticket = 0u;                        // leave the workspace header clean for the next call
+        }
+    }
+}
+
+// Backward: rows of row block rb are complete in dacc.  Adds the exact positive-pair term and applies the
+// backward of the row normalisation (NT-Xent: L2, objective.py:26-27; modified: softplus + L1, :70-78).
+// Body of backward_finalize_kernel: one block per row block, warp w handles rows w, w+nwarps, ...
+template <int D, int kLoss>
+SIMCLR_DEVICE void backward_finalize_rowblock(const TileParams& p, int rb, int warp, int lane, int nwarps) {
+    const int blocks_per_view = p.bl_pad / kBlockM;
+    const int vr = rb / blocks_per_view;
+    const int img0 = (rb - vr * blocks_per_view) * kBlockM;
+    const float go = p.grad_out ? __ldg(p.grad_out) : 1.f;
+    const void* x_self = vr == 0 ? p.x1 : p.x2;
+    const void* x_other = vr == 0 ? p.x2 : p.x1;
+    void* g_self = vr == 0 ? p.g1 : p.g2;
+    constexpr int kPerLane = D / 32;
+    for (int r = warp; r < kBlockM; r += nwarps) {
+        const int img = img0 + r;
+        if (img >= p.b_loc) break;
+        const int slot_self = rb * kBlockM + r;
+        const int slot_other = (1 - vr) * p.bl_pad + img;
+        const int c_self = vr * p.bg_pad + p.row_off + img;
+        const int c_other = (1 - vr) * p.bg_pad + p.row_off + img;
+        const float inv_s = __ldg(p.inv_norm + slot_self), inv_o = __ldg(p.inv_norm + slot_other);
+        const float sc_s = p.col_scale ? __ldg(p.col_scale + c_self) : 0.5f / static_cast<float>(p.b_glob);
+        const float sc_o = p.col_scale ? __ldg(p.col_scale + c_other) : 0.5f / static_cast<float>(p.b_glob);
+        const float l2_s = __ldg(p.colvec + 2 * p.bg_pad + c_self), l2_o = __ldg(p.colvec + 2 * p.bg_pad + c_other);
+        const float pd = __ldg(p.pos_dot + slot_self);
+        float coef, outer;
+        if constexpr (kLoss == kNtXent) {
+            // (g_r P[r,pos] + g_pos P[pos,r] - g_r - g_pos) * zhat_pos in exact fp32
+            const float y = pd * p.k2;
+            coef = sc_s * (exp2f(y - l2_s) - 1.f) + sc_o * (exp2f(y - l2_o) - 1.f);
+            outer = p.inv_tau * go;
+        } else {
+            const float qv = pd * p.qscale;
+            const float lq = log2f(fmaxf(qv, kClampMin));
+            const float y = lq * (p.k2 - 1.f);
+            coef = (qv >= kClampMin) ? (sc_s * exp2f(y - l2_s) + sc_o * exp2f(y - l2_o) - (sc_s + sc_o) * exp2f(-lq)) : 0.f;
+            outer = p.inv_tau * p.qscale * go;
+        }
+        const bool scaled = (kLoss == kModified) || p.normalize;
+        const float mul_s = scaled ? (inv_s == kInvNormClamped ? 1.f / kNormEps : inv_s) : 1.f;
+        const float mul_o = scaled ? (inv_o == kInvNormClamped ? 1.f / kNormEps : inv_o) : 1.f;
+        float raw[kPerLane], hs[kPerLane], dv[kPerLane];
+        float t = 0.f;
+#pragma unroll
+        for (int u = 0; u < kPerLane; ++u) {
+            const int k = lane + 32 * u;
+            const bool in = k < p.d;
+            float es = 0.f, eo = 0.f;
+            if (in) {
+                es = load_elem(x_self, static_cast<size_t>(img) * p.d + k, p.in_bf16);
+                eo = load_elem(x_other, static_cast<size_t>(img) * p.d + k, p.in_bf16);
+            }
+            raw[u] = es;
+            if constexpr (kLoss == kModified) {
+                es = in ? softplus_beta(es) : 0.f;
+                eo = in ? softplus_beta(eo) : 0.f;
+            }
+            hs[u] = es * mul_s;
+            const float ho = eo * mul_o;
+            const float acc = __ldcg(p.dacc + static_cast<size_t>(slot_self) * D + k);
+            dv[u] = (acc + coef * ho) * outer;
+            t = fmaf(dv[u], hs[u], t);
+        }
+        t = warp_sum(t);
+#pragma unroll
+        for (int u = 0; u < kPerLane; ++u) {
+            const int k = lane + 32 * u;
+            if (k < p.d) {
+                float o = dv[u];
+                if constexpr (kLoss == kNtXent) {
+                    // d/dz of z / max(||z||, eps): projection unless the clamp was active
+                    if (p.normalize) o = (inv_s == kInvNormClamped) ? o / kNormEps : (o - hs[u] * t) * inv_s;
+                } else {
+                    // L1 normalisation of a positive vector, then softplus'(x) = sigmoid(beta x)
+                    o = (inv_s == kInvNormClamped) ? o / kNormEps : (o - t) * inv_s;
+                    o *= softplus_beta_grad(raw[u]);
+                }
+                store_elem(g_self, static_cast<size_t>(img) * p.d + k, p.in_bf16, o);
+            }
+        }
+    }
+}
+
+// Debug: per-CTA %globaltimer stamps, ktrace[64 + cta*8 + k]  (k: 0 start, 1/3 segment 0/1 tiles done,
+// 2/4 segment 0/1 finalize done, 5 end).
+SIMCLR_DEVICE void cta_stamp(const TileParams& p, int k) {
+    if (p.ktrace != nullptr) p.ktrace[64 + blockIdx.x * 8 + k] = global_timer_ns();
+}
+
 // Walks a CTA's contiguous tile range without per-tile 64-bit divisions.
 struct TileWalker {
     int rb, j, nct, idx, n;
@@ -317,6 +566,9 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
     uint64_t* w_full = s_free + kMaxSlots;        // [kSlots] backward only: W written to TMEM
     uint64_t* w_done = w_full + kMaxSlots;        // [kSlots] backward only: gradient MMAs finished reading W
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + L::kOffTmemPtr);
+    int* smem_flags = reinterpret_cast<int*>(smem + L::kOffFlags);
+    float* smem_red = reinterpret_cast<float*>(smem + L::kOffFlags + 16);   // 12 floats
+    float* smem_merge = reinterpret_cast<float*>(smem + L::kOffMerge);
 
     // warp index through a shuffle so that the compiler knows it is warp-uniform (role branches stay uniform and
     // tcgen05 / TMA operands can live in uniform registers instead of per-instruction ELECT/R2UR waterfall loops)
@@ -329,10 +581,14 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
     const int nct = p.n_col_tiles;
     const int blocks_per_view = p.bl_pad / kBlockM;
 
+    ktrace_begin(p.ktrace, kBackward ? 3 : 1);
+    if (threadIdx.x == 0) {
+        cta_stamp(p, 0);
+        if (p.ktrace != nullptr) p.ktrace[64 + blockIdx.x * 8 + 6] = clock64();
+    }
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_rows);
         tma_prefetch_desc(&tmap_cols);
-        if (blockIdx.x == 0 && p.ticket != nullptr) *p.ticket = 0u;
     }
     if (warp == kMmaWarp && lane == 0) {
         mbar_init(a_full, 1);
@@ -579,14 +835,46 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             }
 
             // ---- end of segment ----
+            if (threadIdx.x == 0 && seg < 2) cta_stamp(p, 1 + 2 * seg);
             if constexpr (!kBackward) {
-                float* dst = p.part + ((static_cast<size_t>(blockIdx.x) * p.max_segs + seg) * kNumSoftmaxWG + wg) *
-                                          (kFwdFields * kBlockM) + row_in_block;
-                dst[0 * kBlockM] = fs.sum;
-                dst[1 * kBlockM] = fs.run_max;
-                dst[2 * kBlockM] = fs.max_prec;
-                dst[3 * kBlockM] = fs.max_foll;
-                dst[4 * kBlockM] = fs.pos_mma;
+                // merge the four warpgroups' partial (max, sum, argmax bookkeeping) through shared memory ...
+                float* mg = smem_merge + (seg & 1) * (kNumSoftmaxWG * kFwdFields * kBlockM);
+                float* mine = mg + wg * (kFwdFields * kBlockM) + row_in_block;
+                mine[0 * kBlockM] = fs.sum;
+                mine[1 * kBlockM] = fs.run_max;
+                mine[2 * kBlockM] = fs.max_prec;
+                mine[3 * kBlockM] = fs.max_foll;
+                mine[4 * kBlockM] = fs.pos_mma;
+                named_bar_sync(1, 32 * kNumSoftmaxWarps);
+                if (wg == 0) {
+                    float m = kNegBig, mp = kNegBig, mf = kNegBig, pm = kNegBig;
+#pragma unroll
+                    for (int g2 = 0; g2 < kNumSoftmaxWG; ++g2) {
+                        const float* o = mg + g2 * (kFwdFields * kBlockM) + row_in_block;
+                        m = fmaxf(m, o[1 * kBlockM]);
+                        mp = fmaxf(mp, o[2 * kBlockM]);
+                        mf = fmaxf(mf, o[3 * kBlockM]);
+                        pm = fmaxf(pm, o[4 * kBlockM]);
+                    }
+                    float total = 0.f;
+                    if (m > kNegBig) {
+                        const float top = logit2<kLoss>(p, m);
+#pragma unroll
+                        for (int g2 = 0; g2 < kNumSoftmaxWG; ++g2) {
+                            const float* o = mg + g2 * (kFwdFields * kBlockM) + row_in_block;
+                            const float mo = o[1 * kBlockM];
+                            if (mo > kNegBig) total += o[0] * ex2_approx(logit2<kLoss>(p, mo) - top);
+                        }
+                    }
+                    // ... and publish one partial per (CTA, segment) for the finalize kernel
+                    float* dst = p.part + (static_cast<size_t>(blockIdx.x) * p.max_segs + seg) * (kFwdFields * kBlockM) +
+                                 row_in_block;
+                    __stcg(dst + 0 * kBlockM, total);
+                    __stcg(dst + 1 * kBlockM, m);
+                    __stcg(dst + 2 * kBlockM, mp);
+                    __stcg(dst + 3 * kBlockM, mf);
+                    __stcg(dst + 4 * kBlockM, pm);
+                }
             } else {
                 // flush the gradient accumulator: the D columns are split in 32-column chunks over the warpgroups
                 mbar_wait(acc_full, seg & 1, 302);
@@ -608,6 +896,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 tc_fence_before_sync();
                 mbar_arrive(acc_empty);
             }
+            if (threadIdx.x == 0 && seg < 2) cta_stamp(p, 2 + 2 * seg);
             idx += seg_len;
             ++seg;
         }
@@ -616,6 +905,11 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
     // ================================ teardown ================================
     tc_fence_before_sync();
     __syncthreads();
+    ktrace_end(p.ktrace, kBackward ? 3 : 1);
+    if (threadIdx.x == 0) {
+        cta_stamp(p, 5);
+        if (p.ktrace != nullptr) p.ktrace[64 + blockIdx.x * 8 + 7] = clock64();
+    }
     if (warp == kAllocWarp) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, kTmemCols);

@@ -42,6 +42,22 @@ SIMCLR_DEVICE bool elect_one() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Optional kernel-level timeline (debug): every kernel stamps min(start) / max(end) of %globaltimer (ns) into
+// ktrace[2*id], ktrace[2*id+1] when a buffer has been installed with simclr_debug_set_kernel_trace.
+// ---------------------------------------------------------------------------------------------
+SIMCLR_DEVICE unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+SIMCLR_DEVICE void ktrace_begin(unsigned long long* ktrace, int id) {
+    if (ktrace != nullptr && threadIdx.x == 0) atomicMin(ktrace + 2 * id, global_timer_ns());
+}
+SIMCLR_DEVICE void ktrace_end(unsigned long long* ktrace, int id) {
+    if (ktrace != nullptr && threadIdx.x == 0) atomicMax(ktrace + 2 * id + 1, global_timer_ns());
+}
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 SIMCLR_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {

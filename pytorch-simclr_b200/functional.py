@@ -92,8 +92,11 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
         rowvec = torch.empty((4, 2 * bp), dtype=torch.float32, device=dev)   # inv_norm, pos_dot, lse2, row_loss
         stats = torch.empty(4, dtype=torch.float32, device=dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
+        b_global_hint = b if gather is None else b * gather.world
+        ws_bytes = lib.simclr_forward_workspace_bytes(loss_kind, b, b_global_hint, d)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         check(lib.simclr_prepare(loss_kind, x1.data_ptr(), x2.data_ptr(), b, d, code, int(bool(normalize)),
-                                 operand.data_ptr(), rowvec[0].data_ptr(), rowvec[1].data_ptr(), stream),
+                                 operand.data_ptr(), rowvec[0].data_ptr(), rowvec[1].data_ptr(), ws.data_ptr(), stream),
               "simclr_prepare")
         if gather is None:
             operand_cols, b_global, row_offset = operand, b, 0
@@ -104,8 +107,6 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
             w_local = weight.to(device=dev, dtype=torch.float32).contiguous()
             if w_local.numel() != 2 * b:
                 raise ValueError(f"weight must have {2 * b} entries, got {w_local.numel()}")
-        ws_bytes = lib.simclr_forward_workspace_bytes(loss_kind, b, b_global, d)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         check(lib.simclr_forward(loss_kind, operand.data_ptr(), operand_cols.data_ptr(), b, b_global, row_offset, d,
                                  float(temperature), rowvec[1].data_ptr(), _ptr(w_local), rowvec[2].data_ptr(),
                                  rowvec[3].data_ptr(), stats.data_ptr(), loss.data_ptr(), ws.data_ptr(), ws_bytes,

@@ -52,7 +52,7 @@ class ContrastiveStep:
         lib, st = self.lib, self._stream()
         check(lib.simclr_prepare(self.kind, self.x1.data_ptr(), self.x2.data_ptr(), self.b, self.d, self.code,
                                  int(self.normalize), self.operand.data_ptr(), self.rowvec[0].data_ptr(),
-                                 self.rowvec[1].data_ptr(), st), "simclr_prepare")
+                                 self.rowvec[1].data_ptr(), self.fwd_ws.data_ptr(), st), "simclr_prepare")
         check(lib.simclr_forward(self.kind, self.operand.data_ptr(), self.operand.data_ptr(), self.b, self.b, 0, self.d,
                                  self.temperature, self.rowvec[1].data_ptr(), None, self.rowvec[2].data_ptr(),
                                  self.rowvec[3].data_ptr(), self.stats.data_ptr(), self.loss.data_ptr(),

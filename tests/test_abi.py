@@ -28,7 +28,7 @@ def _declared_functions():
 def test_header_symbols_are_exported(lib):
     from pytorch_simclr_b200 import _lib
     declared = _declared_functions()
-    assert len(declared) >= 9
+    assert len(declared) >= 11
     raw = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(raw, name), f"{name} declared in include/simclr_b200.h but not exported"
@@ -66,13 +66,13 @@ def test_argument_validation_without_gpu(lib):
     p = ctypes.addressof(buf)
     p = (p + 255) & ~255
     # null pointers
-    assert lib.simclr_prepare(0, None, p, 4, 8, 0, 1, p, p, p, None) == -1
+    assert lib.simclr_prepare(0, None, p, 4, 8, 0, 1, p, p, p, None, None) == -1
     assert lib.simclr_forward(0, None, p, 4, 4, 0, 8, 0.5, p, None, p, p, p, None, p, 1 << 15, None) == -1
     # bad dtype / shape / dim / loss / temperature / workspace
-    assert lib.simclr_prepare(0, p, p, 4, 8, 9, 1, p, p, p, None) == -4
-    assert lib.simclr_prepare(0, p, p, 0, 8, 0, 1, p, p, p, None) == -2
-    assert lib.simclr_prepare(0, p, p, 4, 300, 0, 1, p, p, p, None) == -3
-    assert lib.simclr_prepare(5, p, p, 4, 8, 0, 1, p, p, p, None) == -11
+    assert lib.simclr_prepare(0, p, p, 4, 8, 9, 1, p, p, p, None, None) == -4
+    assert lib.simclr_prepare(0, p, p, 0, 8, 0, 1, p, p, p, None, None) == -2
+    assert lib.simclr_prepare(0, p, p, 4, 300, 0, 1, p, p, p, None, None) == -3
+    assert lib.simclr_prepare(5, p, p, 4, 8, 0, 1, p, p, p, None, None) == -11
     assert lib.simclr_forward(0, p, p, 4, 4, 0, 8, 0.0, p, None, p, p, p, None, p, 1 << 15, None) == -7
     assert lib.simclr_forward(0, p, p, 4, 2, 0, 8, 0.5, p, None, p, p, p, None, p, 1 << 15, None) == -2   # b_glob < b_loc
     assert lib.simclr_forward(0, p, p, 4, 8, 6, 8, 0.5, p, None, p, p, p, None, p, 1 << 15, None) == -2   # shard outside

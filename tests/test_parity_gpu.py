@@ -190,8 +190,9 @@ def test_row_sharded_kernels_equal_single_shot():
     from pytorch_simclr_b200 import functional as F
 
     class FakeGather:
-        def __init__(self, full_operand, full_lse2, b_glob, row_off):
+        def __init__(self, full_operand, full_lse2, b_glob, row_off, world):
             self.full_operand, self.full_lse2, self.b_glob, self.row_off = full_operand, full_lse2, b_glob, row_off
+            self.world = world
 
         def operand(self, operand_local, b):
             return self.full_operand, self.b_glob, self.row_off
@@ -214,7 +215,7 @@ def test_row_sharded_kernels_equal_single_shot():
     tot = torch.zeros(3, device="cuda")
     for r in range(ranks):
         sl = slice(r * bl, (r + 1) * bl)
-        gather = FakeGather(saved.operand_cols, rowvec[2], b, r * bl)
+        gather = FakeGather(saved.operand_cols, rowvec[2], b, r * bl, ranks)
         l_r, st_r, _, sv_r = F.run_forward(F.LOSS_NTXENT, x1[sl].contiguous(), x2[sl].contiguous(), tau, True, None, gather)
         tot += st_r[:3]
         h1, h2 = F.run_backward(sv_r, x1[sl].contiguous(), x2[sl].contiguous(), None)
