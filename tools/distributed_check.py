@@ -1,0 +1,65 @@
+"""Row-sharded global-batch check, launched with torchrun (one process per GPU, NCCL):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
+        tools/distributed_check.py [--b 2048] [--d 128]
+
+Every rank compares the global loss / accuracy and its local gradients with the single-process fp64 oracle
+evaluated on the gathered batch (test infrastructure: imports oracle/)."""
+import argparse
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "oracle"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import contrastive_oracle as oracle  # noqa: E402
+from pytorch_simclr_b200.distributed import (global_contrastive_loss, global_modified_contrastive_loss,  # noqa: E402
+                                             shard_rows)
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--b", type=int, default=2048)
+ap.add_argument("--d", type=int, default=128)
+ap.add_argument("--tau", type=float, default=0.5)
+args = ap.parse_args()
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+local = int(os.environ.get("LOCAL_RANK", rank))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ok = True
+for name, fn, ref_fn, use_weight in (
+        ("ntxent", global_contrastive_loss, oracle.ntxent_closed_form, False),
+        ("ntxent+weight", global_contrastive_loss, oracle.ntxent_closed_form, True),
+        ("modified", global_modified_contrastive_loss, oracle.modified_closed_form, False)):
+    z1, z2 = oracle.make_embeddings(args.b, args.d, seed=17, kind="correlated", noise=1.0)   # same on every rank
+    w = None
+    if use_weight:
+        w = torch.rand(2 * args.b, generator=torch.Generator().manual_seed(3)) + 0.25
+    off, bl = shard_rows(args.b, world, rank)
+    a = z1[off:off + bl].cuda().requires_grad_(True)
+    c = z2[off:off + bl].cuda().requires_grad_(True)
+    kw = dict(temperature=args.tau)
+    if use_weight:
+        kw["weight"] = torch.cat((w[off:off + bl], w[args.b + off:args.b + off + bl])).cuda()
+    loss, acc = fn(a, c, **kw)
+    loss.backward()
+    torch.cuda.synchronize()
+    ref = ref_fn(z1, z2, temperature=args.tau, **({"weight": w.numpy()} if use_weight else {}))
+    gmax = max(np.abs(ref.grad1).max(), np.abs(ref.grad2).max())
+    e1 = np.abs(a.grad.cpu().numpy() - ref.grad1[off:off + bl]).max() / gmax
+    e2 = np.abs(c.grad.cpu().numpy() - ref.grad2[off:off + bl]).max() / gmax
+    lrel = abs(float(loss.detach()) - ref.loss) / abs(ref.loss)
+    # accuracy is decided on bf16-rounded operands: a near-tie within bf16 resolution may flip one or two rows
+    good = lrel < 2e-3 and e1 < 1e-2 and e2 < 1e-2 and abs(acc - ref.acc) * 2 * args.b / 100.0 <= 2.5
+    ok = ok and good
+    print(f"[rank {rank}/{world}] {name}: loss {float(loss.detach()):.6f} (oracle {ref.loss:.6f}, rel {lrel:.1e}) "
+          f"acc {acc:.3f} (oracle {ref.acc:.3f}) grad err {e1:.1e} {e2:.1e} -> {'OK' if good else 'FAIL'}", flush=True)
+flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1.0 else 1)
