@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIMCLR_ABI_VERSION 1
+#define SIMCLR_ABI_VERSION 2
 
 /* loss kinds */
 #define SIMCLR_LOSS_NTXENT 0   /* objective.py:6-55  */
@@ -88,11 +88,13 @@ int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t
  *                           modify in place, as utils/model_utils.py:31,116 does); may be NULL
  * `row_weight` is the reference's `weight` argument restricted to this rank: f32 [2*b_local] in the
  * reference's compact order (view-1 rows then view-2 rows), or NULL.
+ * `normalize` must repeat the value given to simclr_prepare: normalised rows bound the scores (|S| <= 1), which
+ * lets the NT-Xent kernel use a constant softmax shift instead of a running maximum.
  */
 int simclr_forward(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
-                   int64_t row_offset, int64_t d, float temperature, const float* pos_dot, const float* row_weight,
-                   float* lse2, float* row_loss, float* stats, float* loss_out, void* workspace, size_t workspace_bytes,
-                   void* stream);
+                   int64_t row_offset, int64_t d, float temperature, int normalize, const float* pos_dot,
+                   const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out, void* workspace,
+                   size_t workspace_bytes, void* stream);
 
 /*
  * Stage 3 -- backward: gradients of  grad_out * loss  with respect to x_batch1 / x_batch2 of this rank.
@@ -119,6 +121,13 @@ int simclr_debug_set_kernel_trace(void* device_buffer);
 /* Diagnostics: tcgen05.mma issue / execution rate probe under contention (tools/mma_rate.py).
  * out: int64[4 configs][4]; mode 0 idle, 1 tcgen05.ld, 2 MUFU, 3 FFMA, 4 all; sink: float[640] scratch. */
 int simclr_debug_mma_rate(long long* out_device, int batches, int grid, int mode, float* sink, void* stream);
+
+/* Diagnostics: throughput of the softmax warps' per-chunk arithmetic without MMA/TMA (tools/chunk_rate.py).
+ * out: int64[10 variants][32 warps] cycles per 32-column chunk (CTA 0); sink: float[640] scratch. */
+int simclr_debug_chunk_rate(long long* out_device, int iters, int grid, int nwarps, float k2, float* sink, void* stream);
+
+/* Diagnostics: issue rate of single SASS opcodes with 1..16 warps per SM (tools/pipe_rate.py). out: int64[10]. */
+int simclr_debug_pipe_rate(long long* out_device, int iters, int grid, int nwarps, float* sink, void* stream);
 
 /* Diagnostics: UMMA/TMA primitive self-test (tests/test_primitives.py). out_f32 receives 3*128*128 floats. */
 int simclr_selftest_umma(const void* a_bf16_128x128, const void* b_bf16_128x128, float* out_f32, void* stream);

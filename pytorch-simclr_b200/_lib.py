@@ -12,7 +12,7 @@ LOSS_NTXENT = 0
 LOSS_MODIFIED = 1
 DTYPE_F32 = 0
 DTYPE_BF16 = 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lock = threading.Lock()
 _lib = None
@@ -32,13 +32,15 @@ SIGNATURES = {
     "simclr_forward_workspace_bytes": (_sz, [_int, _i64, _i64, _i64]),
     "simclr_backward_workspace_bytes": (_sz, [_int, _i64, _i64, _i64]),
     "simclr_prepare": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp]),
-    "simclr_forward": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
-                              _vp]),
+    "simclr_forward": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                              _sz, _vp]),
     "simclr_backward": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp,
                                _vp, _vp, _vp, _vp, _sz, _vp]),
     "simclr_selftest_umma": (_int, [_vp, _vp, _vp, _vp]),
     "simclr_debug_set_trace": (_int, [_vp, _int]),
     "simclr_debug_set_kernel_trace": (_int, [_vp]),
+    "simclr_debug_chunk_rate": (_int, [_vp, _int, _int, _int, _f32, _vp, _vp]),
+    "simclr_debug_pipe_rate": (_int, [_vp, _int, _int, _int, _vp, _vp]),
     "simclr_debug_mma_rate": (_int, [_vp, _int, _int, _int, _vp, _vp]),
 }
 

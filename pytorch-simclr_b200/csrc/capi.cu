@@ -7,6 +7,7 @@
 
 #include "../../include/simclr_b200.h"
 #include "aux_kernels.cuh"
+#include "probes.cuh"
 #include "selftest.cuh"
 
 using namespace simclr;
@@ -153,7 +154,7 @@ Scales make_scales(int loss, float temperature, int normalize, int64_t b_global)
     if (loss == SIMCLR_LOSS_NTXENT) {
         s.k2 = 1.4426950408889634f * s.inv_tau;
         // |S| <= 1 (+ bf16 rounding) when rows are normalised: exp2(S*k2 - m2) <= 1 and a_r <= 2^(2*k2)
-        s.m2 = s.k2 * 1.0078125f;
+        s.m2 = s.k2 * kConstShiftRaw;
         s.const_shift = (normalize && 2.0f * s.k2 <= 80.0f) ? 1 : 0;
     } else {
         s.k2 = s.inv_tau;
@@ -167,9 +168,25 @@ Scales make_scales(int loss, float temperature, int normalize, int64_t b_global)
     return s;
 }
 
-template <int D, int kLoss, bool kBackward>
-int launch_tile(const CUtensorMap& rows, const CUtensorMap& cols, const TileParams& p, int grid, cudaStream_t st) {
-    auto kern = contrastive_tile_kernel<D, kLoss, kBackward>;
+// fp32 [rows][d_pad] row-major (the gradient accumulation buffer), box = 128 rows x 32 floats (128 B), 128-byte
+// swizzle: target of the backward kernel's TMA reduce-add
+int make_dacc_map(CUtensorMap* map, const void* base, int64_t rows, int64_t d_pad) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return SIMCLR_ERR_DRIVER_ENTRY;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d_pad), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(d_pad) * 4};
+    cuuint32_t box[2] = {32u, static_cast<cuuint32_t>(kBlockM)};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? SIMCLR_OK : SIMCLR_ERR_TENSOR_MAP;
+}
+
+template <int D, int kLoss, bool kBackward, bool kConst>
+int launch_tile(const CUtensorMap& rows, const CUtensorMap& cols, const CUtensorMap& dacc, const TileParams& p, int grid,
+                cudaStream_t st) {
+    auto kern = contrastive_tile_kernel<D, kLoss, kBackward, kConst>;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -179,23 +196,35 @@ int launch_tile(const CUtensorMap& rows, const CUtensorMap& cols, const TilePara
         if (e != cudaSuccess) return static_cast<int>(e);
         configured[dev & 63] = true;
     }
-    kern<<<grid, kNumThreads, SmemLayout<D>::kDynamicBytes, st>>>(rows, cols, p);
+    kern<<<grid, kBackward ? kThreadsBackward : kThreadsForward, SmemLayout<D>::kDynamicBytes, st>>>(rows, cols, dacc, p);
     return static_cast<int>(cudaGetLastError());
 }
 
-template <bool kBackward>
-int dispatch_tile(int loss, int64_t d_pad, const CUtensorMap& rows, const CUtensorMap& cols, const TileParams& p,
+// kConst = p.const_shift (bounded scores: one exponential per element, no running maximum).  The forward kernel of
+// the modified loss has no constant-shift variant.
+template <int D, bool kBackward>
+int launch_tile_d(int loss, const CUtensorMap& rows, const CUtensorMap& cols, const CUtensorMap& dacc, const TileParams& p,
                   int grid, cudaStream_t st) {
-#define SIMCLR_CASE(DV)                                                                          \
-    case DV:                                                                                     \
-        return loss == SIMCLR_LOSS_NTXENT ? launch_tile<DV, kNtXent, kBackward>(rows, cols, p, grid, st) \
-                                          : launch_tile<DV, kModified, kBackward>(rows, cols, p, grid, st);
-    switch (d_pad) {
-        SIMCLR_CASE(64)
-        SIMCLR_CASE(128)
-        SIMCLR_CASE(256)
+    const bool c = p.const_shift != 0;
+    if (loss == SIMCLR_LOSS_NTXENT)
+        return c ? launch_tile<D, kNtXent, kBackward, true>(rows, cols, dacc, p, grid, st)
+                 : launch_tile<D, kNtXent, kBackward, false>(rows, cols, dacc, p, grid, st);
+    if constexpr (kBackward) {
+        return c ? launch_tile<D, kModified, true, true>(rows, cols, dacc, p, grid, st)
+                 : launch_tile<D, kModified, true, false>(rows, cols, dacc, p, grid, st);
+    } else {
+        return launch_tile<D, kModified, false, false>(rows, cols, dacc, p, grid, st);
     }
-#undef SIMCLR_CASE
+}
+
+template <bool kBackward>
+int dispatch_tile(int loss, int64_t d_pad, const CUtensorMap& rows, const CUtensorMap& cols, const CUtensorMap& dacc,
+                  const TileParams& p, int grid, cudaStream_t st) {
+    switch (d_pad) {
+        case 64: return launch_tile_d<64, kBackward>(loss, rows, cols, dacc, p, grid, st);
+        case 128: return launch_tile_d<128, kBackward>(loss, rows, cols, dacc, p, grid, st);
+        case 256: return launch_tile_d<256, kBackward>(loss, rows, cols, dacc, p, grid, st);
+    }
     return SIMCLR_ERR_UNSUPPORTED_DIM;
 }
 
@@ -328,9 +357,9 @@ int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t
 }
 
 int simclr_forward(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
-                   int64_t row_offset, int64_t d, float temperature, const float* pos_dot, const float* row_weight,
-                   float* lse2, float* row_loss, float* stats, float* loss_out, void* workspace, size_t workspace_bytes,
-                   void* stream) {
+                   int64_t row_offset, int64_t d, float temperature, int normalize, const float* pos_dot,
+                   const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out, void* workspace,
+                   size_t workspace_bytes, void* stream) {
     if (!operand_rows || !operand_cols || !pos_dot || !lse2 || !row_loss || !stats || !workspace)
         return SIMCLR_ERR_NULL_POINTER;
     if (!(temperature > 0.f) || !std::isfinite(temperature)) return SIMCLR_ERR_BAD_TEMPERATURE;
@@ -346,8 +375,8 @@ int simclr_forward(int loss, const void* operand_rows, const void* operand_cols,
     if ((rc = make_operand_map(&map_rows, operand_rows, 2 * g.bl_pad, g.d_pad))) return rc;
     if ((rc = make_operand_map(&map_cols, operand_cols, 2 * g.bg_pad, g.d_pad))) return rc;
 
-    // the forward never needs the bounded-score shortcut: normalize=1 only affects backward's const_shift
-    Scales s = make_scales(loss, temperature, 1, b_global);
+    // normalised NT-Xent rows bound the scores: constant softmax shift (no running maximum) in the tile kernel
+    Scales s = make_scales(loss, temperature, normalize, b_global);
     TileParams p = make_tile_params(g, s, b_local, b_global, row_offset);
     p.d = static_cast<int>(d);
     p.ticket = w.ticket;
@@ -360,7 +389,7 @@ int simclr_forward(int loss, const void* operand_rows, const void* operand_cols,
     p.stats = stats;
     p.loss_out = loss_out;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if ((rc = dispatch_tile<false>(loss, g.d_pad, map_rows, map_cols, p, g.grid, st))) return rc;
+    if ((rc = dispatch_tile<false>(loss, g.d_pad, map_rows, map_cols, map_rows, p, g.grid, st))) return rc;
     if (loss == SIMCLR_LOSS_NTXENT) forward_finalize_kernel<kNtXent><<<g.n_row_blocks, kBlockM, 0, st>>>(p);
     else forward_finalize_kernel<kModified><<<g.n_row_blocks, kBlockM, 0, st>>>(p);
     return static_cast<int>(cudaGetLastError());
@@ -387,6 +416,8 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
     CUtensorMap map_rows, map_cols;
     if ((rc = make_operand_map(&map_rows, operand_rows, 2 * g.bl_pad, g.d_pad))) return rc;
     if ((rc = make_operand_map(&map_cols, operand_cols, 2 * g.bg_pad, g.d_pad))) return rc;
+    CUtensorMap map_dacc;
+    if ((rc = make_dacc_map(&map_dacc, w.dacc, 2 * g.bl_pad, g.d_pad))) return rc;
 
     Scales s = make_scales(loss, temperature, normalize, b_global);
     AuxParams a = make_aux(g, s, b_local, b_global, row_offset, d, normalize);
@@ -410,7 +441,7 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
     p.pos_dot = pos_dot;
     p.col_scale = col_scale;
     p.grad_out = grad_out;
-    if ((rc = dispatch_tile<true>(loss, g.d_pad, map_rows, map_cols, p, g.grid, st))) return rc;
+    if ((rc = dispatch_tile<true>(loss, g.d_pad, map_rows, map_cols, map_dacc, p, g.grid, st))) return rc;
 #define SIMCLR_BFIN(DV)                                                                                  \
     case DV:                                                                                             \
         if (loss == SIMCLR_LOSS_NTXENT) backward_finalize_kernel<DV, kNtXent><<<g.n_row_blocks * kBwdFinBlocksPerRowBlock, 512, 0, st>>>(p); \
@@ -443,6 +474,30 @@ int simclr_debug_mma_rate(long long* out_device, int batches, int grid, int mode
     cudaError_t e = cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRateSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
     mma_rate_kernel<<<grid, 640, kRateSmemBytes, static_cast<cudaStream_t>(stream)>>>(out_device, batches, mode, sink);
+    return static_cast<int>(cudaGetLastError());
+}
+
+int simclr_debug_chunk_rate(long long* out_device, int iters, int grid, int nwarps, float k2, float* sink, void* stream) {
+    if (!out_device || !sink) return SIMCLR_ERR_NULL_POINTER;
+    int rc = check_device();
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define SIMCLR_RATE(V) chunk_rate_kernel<V><<<grid, kThreadsForward, 0, st>>>(out_device, iters, nwarps, k2, sink);
+    SIMCLR_RATE(0) SIMCLR_RATE(1) SIMCLR_RATE(2) SIMCLR_RATE(3) SIMCLR_RATE(4) SIMCLR_RATE(5) SIMCLR_RATE(6) SIMCLR_RATE(7)
+    SIMCLR_RATE(8) SIMCLR_RATE(9)
+#undef SIMCLR_RATE
+    return static_cast<int>(cudaGetLastError());
+}
+
+int simclr_debug_pipe_rate(long long* out_device, int iters, int grid, int nwarps, float* sink, void* stream) {
+    if (!out_device || !sink) return SIMCLR_ERR_NULL_POINTER;
+    int rc = check_device();
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define SIMCLR_PIPE(V) pipe_rate_kernel<V><<<grid, kThreadsForward, 0, st>>>(out_device, iters, nwarps, 1.0f, sink);
+    SIMCLR_PIPE(0) SIMCLR_PIPE(1) SIMCLR_PIPE(2) SIMCLR_PIPE(3) SIMCLR_PIPE(4) SIMCLR_PIPE(5) SIMCLR_PIPE(6) SIMCLR_PIPE(7)
+    SIMCLR_PIPE(8) SIMCLR_PIPE(9)
+#undef SIMCLR_PIPE
     return static_cast<int>(cudaGetLastError());
 }
 

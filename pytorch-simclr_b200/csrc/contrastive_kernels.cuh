@@ -18,16 +18,19 @@
 //              tile and used as the A operand of a second tcgen05.mma:  dacc[r,:] += W[r,:] * op[c,:]
 // The 2N x 2N matrix never exists outside one 128 x 128 TMEM tile.
 //
-// Warp roles (640 threads, 1 CTA / SM, each CTA owns a contiguous range of (row block, column tile)):
-//   warp 16     TMA producer (row-block tile once per segment, column tiles through an mbarrier ring)
-//   warp 17     UMMA issuer for the score tiles (one elected lane)
-//   warp 18     TMEM allocator / deallocator
-//   warp 19     backward only: UMMA issuer for the gradient MMAs (a tcgen05.mma blocks its issuing thread while it
-//               executes, so two issuers let the barrier waits of one overlap the MMAs of the other)
-//   warps 0-15  four softmax warpgroups = two pairs.  CTA iteration `it` lives in TMEM score buffer it % NB
+// Warp roles (forward 640 threads, backward 672; 1 CTA / SM, each CTA owns a contiguous range of (row block, column tile)):
+//   warps 0-15  four softmax warpgroups = two pairs.  CTA tile `it` lives in TMEM score buffer it % NB
 //               (NB = 4 forward, (512 - D) / 128 backward) and is consumed by pair it % 2, each warpgroup of the
 //               pair taking 64 of the 128 columns; a pair therefore always has a second buffer being filled by
 //               the tensor core while it works (the MMA runs ahead of the softmax)
+//   warp 16     TMA producer (row-block tile once per segment, column tiles through an mbarrier ring)
+//   warps 17,18 UMMA issuers for the score tiles (one elected lane each; warp 18 also owns the TMEM allocation)
+//   warps 19,20 backward only: UMMA issuers for the gradient MMAs
+// A tcgen05.mma blocks its issuing thread while it executes and the issuer's barrier waits cost several hundred
+// cycles per tile, so ONE issuer keeps the tensor pipe busy only ~35 % of the time (profiles/r01_notes.md).  Issuer k of
+// a kind owns the ring stages with (stage & 1) == k -- the ring size is even and the flush borrows two stages, so a
+// stage, a hand-off slot and a softmax pair always meet the same issuer and every mbarrier keeps a single waiter
+// that sees all of its phases in order.
 #pragma once
 
 #include <cstdint>
@@ -47,21 +50,27 @@ constexpr int kAtomBytes = kBlockM * kAtomK * 2;   // one TMA box: 128 rows x 12
 constexpr int kNumSoftmaxWG = 4;      // softmax warpgroups (4 warps each: one per TMEM lane quarter)
 // The warp arbiter favours the highest warp id of an SM sub-partition, so the latency-critical single-thread
 // roles (UMMA issue, TMA issue) sit ABOVE the 16 softmax warps; as warps 0/1 they were starved of issue slots
-// and every batch of eight tcgen05.mma took >1000 cycles to issue (profiles/r01_timeline_before_after.md).
+// and every batch of eight tcgen05.mma took >1000 cycles to issue (profiles/r01_notes.md).
 constexpr int kSoftmaxWarp0 = 0;
 constexpr int kNumSoftmaxWarps = 4 * kNumSoftmaxWG;
 constexpr int kProducerWarp = kNumSoftmaxWarps + 0;
-constexpr int kMmaWarp = kNumSoftmaxWarps + 1;
-constexpr int kAllocWarp = kNumSoftmaxWarps + 2;
-constexpr int kGradWarp = kNumSoftmaxWarps + 3;   // backward: issues the gradient MMAs (the score MMAs stay on kMmaWarp)
-constexpr int kNumThreads = 32 * (kNumSoftmaxWarps + 4);   // 640
+constexpr int kNumIssuers = 2;                          // per kind (score / gradient)
+constexpr int kScoreWarp0 = kNumSoftmaxWarps + 1;       // warps 17, 18
+constexpr int kAllocWarp = kScoreWarp0 + 1;             // warp 18 allocates TMEM before it starts issuing
+constexpr int kGradWarp0 = kScoreWarp0 + kNumIssuers;   // warps 19, 20 (backward)
+constexpr int kThreadsForward = 32 * (kNumSoftmaxWarps + 4);                    // 640 (warp 19 idles)
+constexpr int kThreadsBackward = 32 * (kNumSoftmaxWarps + 1 + 2 * kNumIssuers); // 672
 constexpr int kMaxScoreBufs = 4;
 constexpr int kNumPairs = kNumSoftmaxWG / 2;             // a tile is shared by a pair of warpgroups
 constexpr int kMaxSlots = kMaxScoreBufs * kNumPairs;      // barrier slots for the score / W hand-off
 constexpr int kTmemCols = 512;
+constexpr int kTokenBar0 = 2;         // named barriers 2, 3: ping-pong tokens of the two softmax pairs
 constexpr int kFwdFields = 5;         // per-row partial: sum, run-max, max-preceding, max-following, pos(mma)
 constexpr float kNegBig = -3.0e38f;   // finite stand-in for -inf
 constexpr float kClampMin = 1e-4f;    // reference objective.py:87-88
+// NT-Xent with normalised rows: |S| <= 1 (+ bf16 rounding), so exp2(S*k2 - m2) with m2 = k2 * kConstShiftRaw never
+// overflows and no running maximum is needed ("constant shift")
+constexpr float kConstShiftRaw = 1.0078125f;
 
 enum LossKind : int { kNtXent = 0, kModified = 1 };
 
@@ -122,7 +131,7 @@ template <int D>
 struct SmemLayout {
     static constexpr int kAtoms = D / kAtomK;
     static constexpr int kTileBytes = kAtoms * kAtomBytes;          // 128 x D bf16
-    static constexpr int kStages = (D <= 64) ? 8 : (D <= 128 ? 5 : 2);
+    static constexpr int kStages = (D <= 64) ? 8 : (D <= 128 ? 4 : 2);   // even: see the issuer ownership rule
     static constexpr int kColvecBytes = 2 * kBlockN * 4;             // two planes of 128 floats
     static constexpr int kOffA = 0;
     static constexpr int kOffB = kTileBytes;
@@ -175,6 +184,7 @@ struct RowCtx {
 
 struct FwdState {
     float run_max = kNegBig, sum = 0.f, max_prec = kNegBig, max_foll = kNegBig, pos_mma = kNegBig;
+    float s1 = 0.f, s2 = 0.f, s3 = 0.f;   // constant-shift path: three more independent partial sums (folded at segment end)
 };
 
 struct BwdRow {
@@ -187,70 +197,162 @@ SIMCLR_DEVICE float4 lds_f4(uint32_t addr) {
     return v;
 }
 
-// ---- forward: one 32-column chunk ----
-template <int kLoss, bool kSpecial>
-SIMCLR_DEVICE void fwd_chunk(const TileParams& p, const uint32_t (&r)[32], int cq, int vc, const RowCtx& rc,
-                             bool tile_prec, FwdState& st) {
-    float v[32];
-    float cm = kNegBig;
-    if constexpr (!kSpecial) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = raw_value<kLoss>(p, __uint_as_float(r[i]));
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) cm = fmaxf(cm, fmaxf(v[i], v[i + 1]));     // FMNMX3
-        st.max_prec = fmaxf(st.max_prec, tile_prec ? cm : kNegBig);
-        st.max_foll = fmaxf(st.max_foll, tile_prec ? kNegBig : cm);
+// exp2 on the FMA pipe: Cody-Waite range reduction (round(x) lands in the low mantissa bits of x + 1.5*2^23)
+// and a minimax polynomial for 2^f on [-0.5, 0.5].  Degree 3: max rel. error 7.5e-5 (mean 5e-6); degree 4: 2.7e-6
+// (mean 4e-8).  The MUFU pipe retires 16 ex2 per clock and SM against 128 FMA lanes, so a quarter of the
+// exponentials of a tile is moved here to take the tile off the MUFU bound.  Valid for finite -120 < x < 120.
+template <int kDeg>
+SIMCLR_DEVICE float ex2_poly(float x) {
+    const float t = x + 12582912.0f;
+    const float f = x - (t - 12582912.0f);
+    float q;
+    if constexpr (kDeg == 3) {
+        q = fmaf(f, 0.0551716685295105f, 0.2426111251115799f);
+        q = fmaf(f, q, 0.6932609677314758f);
+        q = fmaf(f, q, 0.9999280571937561f);
     } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const int c = cq + i;
-            const int ic = c - vc * p.bg_pad;
-            const float x = raw_value<kLoss>(p, __uint_as_float(r[i]));
-            if (c == rc.pos_col) st.pos_mma = x;
-            const bool valid = rc.row_ok && ic < p.b_glob && c != rc.diag_col && c != rc.pos_col;
-            v[i] = valid ? x : kNegBig;
-            if (valid) {
-                cm = fmaxf(cm, x);
-                bool prec;
-                if constexpr (kLoss == kNtXent) prec = (rc.vr == 0) ? (vc == 1 && ic < rc.g) : (vc == 1 || ic < rc.g);
-                else prec = ic < rc.g;
-                if (prec) st.max_prec = fmaxf(st.max_prec, x); else st.max_foll = fmaxf(st.max_foll, x);
-            }
-        }
+        q = fmaf(f, 0.009570101276040077f, 0.05591785907745361f);
+        q = fmaf(f, q, 0.240247443318367f);
+        q = fmaf(f, q, 0.6931217908859253f);
+        q = fmaf(f, q, 0.9999992847442627f);
     }
-    // online max without a data-dependent branch in the fast path: rescale the running sum by
-    // exp2(old_shift - new_shift) (== 1 when the maximum did not move)
-    const float new_max = fmaxf(st.run_max, cm);
-    if (!kSpecial || new_max != kNegBig) {                 // special tiles may have seen nothing valid yet
-        const float shift = logit2<kLoss>(p, new_max);
-        const float old_shift = (st.run_max == kNegBig) ? shift : logit2<kLoss>(p, st.run_max);
+    return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
+}
+// element i of a 32-column chunk goes to the FMA-pipe exponential
+SIMCLR_DEVICE constexpr bool poly_lane(int i) { return (i & 3) == 3; }
+
+constexpr int kChunk = 16;     // columns per softmax step: two 16-register TMEM loads are kept in flight per thread
+
+// Loop-invariant scalars of the per-element maths, hoisted out of the kernel-parameter constant bank once per CTA
+// (a dependent chain of LDC / LDCU between two tiles costs the softmax warps hundreds of cycles).
+struct Hot {
+    float k2, m2, qscale;
+    int bg_pad, b_glob;
+    bool const_shift;
+};
+
+template <int kLoss>
+SIMCLR_DEVICE float raw_value_h(const Hot& h, float s) {
+    if constexpr (kLoss == kNtXent) return s;
+    else return fmaxf(s * h.qscale, kClampMin);
+}
+template <int kLoss>
+SIMCLR_DEVICE float logit2_h(const Hot& h, float v) {
+    if constexpr (kLoss == kNtXent) return v * h.k2;
+    else return lg2_approx(v) * h.k2;
+}
+
+// ---- forward: one 16-column chunk, no masked element (warp-uniform fact) ----
+// kConst (NT-Xent with bounded scores): constant log2-domain shift m2, no running maximum; `cm` collects the chunk
+// maximum for the caller (the first-argmax bookkeeping is folded into the state once per tile).
+template <int kLoss, bool kConst>
+SIMCLR_DEVICE void fwd_chunk_fast(const Hot& h, const uint32_t (&r)[kChunk], float& cm, FwdState& st) {
+    float v[kChunk];
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) v[i] = raw_value_h<kLoss>(h, __uint_as_float(r[i]));
+    float c2 = fmaxf(v[0], v[1]);
+#pragma unroll
+    for (int i = 2; i < kChunk; i += 2) c2 = fmaxf(c2, fmaxf(v[i], v[i + 1]));     // FMNMX3
+    if constexpr (kConst) {
+        static_assert(kLoss == kNtXent, "constant shift is an NT-Xent fast path");
+        cm = fmaxf(cm, c2);
+#pragma unroll
+        for (int i = 0; i < kChunk; i += 4) {
+            st.sum += ex2_approx(fmaf(v[i + 0], h.k2, -h.m2));
+            st.s1 += ex2_approx(fmaf(v[i + 1], h.k2, -h.m2));
+            st.s2 += ex2_approx(fmaf(v[i + 2], h.k2, -h.m2));
+            st.s3 += ex2_poly<4>(fmaf(v[i + 3], h.k2, -h.m2));
+        }
+    } else {
+        cm = fmaxf(cm, c2);
+        // online max without a data-dependent branch: rescale the running sum by exp2(old_shift - new_shift)
+        const float new_max = fmaxf(st.run_max, c2);
+        const float shift = logit2_h<kLoss>(h, new_max);
+        const float old_shift = (st.run_max == kNegBig) ? shift : logit2_h<kLoss>(h, st.run_max);
         st.sum *= ex2_approx(old_shift - shift);
         st.run_max = new_max;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-            float e[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if constexpr (kLoss == kNtXent) e[u] = ex2_approx(fmaf(v[i + u], p.k2, -shift));
-                else e[u] = ex2_approx(fmaf(lg2_approx(v[i + u]), p.k2, -shift));
-                if constexpr (kSpecial) e[u] = (v[i + u] == kNegBig) ? 0.f : e[u];
-            }
-            a0 += e[0];
-            a1 += e[1];
-            a2 += e[2];
-            a3 += e[3];
+        for (int i = 0; i < kChunk; i += 4) {
+            a0 += ex2_approx(logit2_h<kLoss>(h, v[i + 0]) - shift);
+            a1 += ex2_approx(logit2_h<kLoss>(h, v[i + 1]) - shift);
+            a2 += ex2_approx(logit2_h<kLoss>(h, v[i + 2]) - shift);
+            a3 += ex2_approx(logit2_h<kLoss>(h, v[i + 3]) - shift);
         }
         st.sum += (a0 + a1) + (a2 + a3);
     }
 }
 
-// ---- backward: one 32-column chunk -> 16 packed bf16x2 words of W ----
-template <int kLoss, bool kConst, bool kSpecial>
-SIMCLR_DEVICE void bwd_chunk(const TileParams& p, const uint32_t (&r)[32], uint32_t cv_addr, int cq, const RowCtx& rc,
-                             const BwdRow& br, uint32_t (&w)[16]) {
+// ---- forward: a chunk that may hold the diagonal, the positive or padded columns for some of the warp's rows.
+// Branch-free: the (at most two) masked elements of a row are found by comparing the unrolled column index with the
+// row's two special positions; `split` separates the columns that precede the positive in the reference's order.
+template <int kLoss, bool kConst>
+SIMCLR_DEVICE void fwd_chunk_special(const Hot& h, const uint32_t (&r)[kChunk], int cq, int vc, const RowCtx& rc,
+                                     FwdState& st) {
+    const int icq = cq - vc * h.bg_pad;                          // image index of the chunk's first column
+    const int n_valid = rc.row_ok ? h.b_glob - icq : 0;          // elements i >= n_valid are padding (or the row is)
+    const int i_diag = rc.diag_col - cq;                         // outside [0, kChunk) when not in this chunk
+    const int i_pos = rc.pos_col - cq;
+    int split;                                                   // elements i < split precede the positive
+    if constexpr (kLoss == kNtXent) split = (rc.vr == 0) ? (vc == 1 ? rc.g - icq : 0) : (vc == 1 ? kChunk : rc.g - icq);
+    else split = rc.g - icq;
+    float v[kChunk];
+    float cp = kNegBig, cf = kNegBig;
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
+    for (int i = 0; i < kChunk; ++i) {
+        const float x = raw_value_h<kLoss>(h, __uint_as_float(r[i]));
+        st.pos_mma = (i == i_pos) ? x : st.pos_mma;
+        const bool dead = (i == i_diag) | (i == i_pos) | (i >= n_valid);
+        const float vi = dead ? kNegBig : x;
+        v[i] = vi;
+        cp = fmaxf(cp, (i < split) ? vi : kNegBig);
+        cf = fmaxf(cf, (i < split) ? kNegBig : vi);
+    }
+    st.max_prec = fmaxf(st.max_prec, cp);
+    st.max_foll = fmaxf(st.max_foll, cf);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if constexpr (kConst) {
+        // exp2(fma(-3e38, k2, -m2)) = exp2(-inf) = 0: masked elements drop out by themselves
+#pragma unroll
+        for (int i = 0; i < kChunk; i += 4) {
+            a0 += ex2_approx(fmaf(v[i + 0], h.k2, -h.m2));
+            a1 += ex2_approx(fmaf(v[i + 1], h.k2, -h.m2));
+            a2 += ex2_approx(fmaf(v[i + 2], h.k2, -h.m2));
+            a3 += ex2_approx(fmaf(v[i + 3], h.k2, -h.m2));
+        }
+        st.sum += (a0 + a1) + (a2 + a3);
+    } else {
+        const float new_max = fmaxf(st.run_max, fmaxf(cp, cf));
+        if (new_max != kNegBig) {                                // nothing valid seen so far: keep the empty state
+            const float shift = logit2_h<kLoss>(h, new_max);
+            const float old_shift = (st.run_max == kNegBig) ? shift : logit2_h<kLoss>(h, st.run_max);
+            st.sum *= ex2_approx(old_shift - shift);
+            st.run_max = new_max;
+#pragma unroll
+            for (int i = 0; i < kChunk; i += 4) {
+                float e[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    e[u] = ex2_approx(logit2_h<kLoss>(h, v[i + u]) - shift);
+                    e[u] = (v[i + u] == kNegBig) ? 0.f : e[u];
+                }
+                a0 += e[0];
+                a1 += e[1];
+                a2 += e[2];
+                a3 += e[3];
+            }
+            st.sum += (a0 + a1) + (a2 + a3);
+        }
+    }
+}
+
+// ---- backward: one 16-column chunk -> 8 packed bf16x2 words of W ----
+template <int kLoss, bool kConst, bool kSpecial>
+SIMCLR_DEVICE void bwd_chunk(const Hot& h, const uint32_t (&r)[kChunk], uint32_t cv_addr, int cq, const RowCtx& rc,
+                             const BwdRow& br, uint32_t (&w)[kChunk / 2]) {
+    const int i_diag = rc.diag_col - cq, i_pos = rc.pos_col - cq;
+#pragma unroll
+    for (int i = 0; i < kChunk; i += 4) {
         const float4 ac = lds_f4(cv_addr + i * 4);
         float4 lc = make_float4(0.f, 0.f, 0.f, 0.f);
         if constexpr (!kConst) lc = lds_f4(cv_addr + kBlockN * 4 + i * 4);
@@ -263,25 +365,24 @@ SIMCLR_DEVICE void bwd_chunk(const TileParams& p, const uint32_t (&r)[32], uint3
             float wval;
             if constexpr (kLoss == kNtXent) {
                 if constexpr (kConst) {
-                    // one exp per element: W = exp2(S*k2 - m2) * (a_r + a_c)
-                    wval = ex2_approx(fmaf(sraw, p.k2, -p.m2)) * (br.row_a + acs[u]);
+                    // one exp per element: W = exp2(S*k2 - m2) * (a_r + a_c); every fourth one on the FMA pipe
+                    const float x = fmaf(sraw, h.k2, -h.m2);
+                    const float e = poly_lane(i + u) ? ex2_poly<3>(x) : ex2_approx(x);
+                    wval = e * (br.row_a + acs[u]);
                 } else {
                     // general form: W = g_r exp2(S*k2 - lse2_r) + g_c exp2(S*k2 - lse2_c)
-                    wval = br.row_a * ex2_approx(fmaf(sraw, p.k2, -br.row_l2)) +
-                           acs[u] * ex2_approx(fmaf(sraw, p.k2, -lcs[u]));
+                    wval = br.row_a * ex2_approx(fmaf(sraw, h.k2, -br.row_l2)) +
+                           acs[u] * ex2_approx(fmaf(sraw, h.k2, -lcs[u]));
                 }
             } else {
                 // d/dP of log(max(B P,1e-4))/tau = 1/(tau P) where live; folded: e^{A}/P = B q^{1/tau - 1}
-                const float qv = sraw * p.qscale;
-                const float y = lg2_approx(fmaxf(qv, kClampMin)) * (p.k2 - 1.0f);
-                if constexpr (kConst) wval = ex2_approx(y - p.m2) * (br.row_a + acs[u]);
+                const float qv = sraw * h.qscale;
+                const float y = lg2_approx(fmaxf(qv, kClampMin)) * (h.k2 - 1.0f);
+                if constexpr (kConst) wval = ex2_approx(y - h.m2) * (br.row_a + acs[u]);
                 else wval = br.row_a * ex2_approx(y - br.row_l2) + acs[u] * ex2_approx(y - lcs[u]);
                 wval = (qv >= kClampMin) ? wval : 0.f;
             }
-            if constexpr (kSpecial) {
-                const int c = cq + i + u;
-                if (c == rc.diag_col || c == rc.pos_col) wval = 0.f;
-            }
+            if constexpr (kSpecial) wval = ((i + u == i_diag) | (i + u == i_pos)) ? 0.f : wval;
             wv[u] = wval;
         }
         w[(i >> 1) + 0] = pack_bf16x2(wv[0], wv[1]);
@@ -532,15 +633,32 @@ struct TileWalker {
     }
 };
 
+// Position in a ring of kSize entries: entry index + parity of its current use (flips on every wrap).
+template <int kSize>
+struct RingPos {
+    int idx = 0, par = 0;
+    SIMCLR_DEVICE void advance() {
+        if (++idx == kSize) {
+            idx = 0;
+            par ^= 1;
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // The tile kernel
 // ---------------------------------------------------------------------------------------------
-template <int D, int kLoss, bool kBackward>
-__global__ void __launch_bounds__(kNumThreads, 1)
+// Ring positions.  Every tile occupies one position of the B-stage ring; in the backward kernel every segment end
+// additionally occupies TWO positions whose stages the producer hands (empty) to the softmax warps as staging space
+// for the accumulator flush.  All roles walk the same position sequence, so stage index and parity never need a
+// division and stage / slot / pair / issuer ownership stays aligned (position parity == tile parity).
+template <int D, int kLoss, bool kBackward, bool kConst>
+__global__ void __launch_bounds__(kBackward ? kThreadsBackward : kThreadsForward, 1)
 contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
-                        const TileParams p) {
+                        const __grid_constant__ CUtensorMap tmap_dacc, const TileParams p) {
     using L = SmemLayout<D>;
     constexpr int S = L::kStages;
+    static_assert(S % 2 == 0, "issuer ownership needs an even ring");
     constexpr uint32_t kIdescScore = make_idesc_bf16(kBlockM, kBlockN, 0, 0);
     constexpr uint32_t kIdescGrad = make_idesc_bf16(kBlockM, D, 0, 1);
     // TMEM: NB score buffers of 128 columns, then (backward) the D-column gradient accumulator
@@ -548,6 +666,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                                  : kMaxScoreBufs;
     constexpr uint32_t kTmemAcc = NB * kBlockN;
     constexpr int kSlots = NB * kNumPairs;            // slot -> fixed (pair, buffer)
+    constexpr int kBoxesPerStage = D / 64;            // 16 KB fp32 boxes (128 rows x 32 columns) per ring stage
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -566,8 +685,6 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
     uint64_t* w_full = s_free + kMaxSlots;        // [kSlots] backward only: W written to TMEM
     uint64_t* w_done = w_full + kMaxSlots;        // [kSlots] backward only: gradient MMAs finished reading W
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + L::kOffTmemPtr);
-    int* smem_flags = reinterpret_cast<int*>(smem + L::kOffFlags);
-    float* smem_red = reinterpret_cast<float*>(smem + L::kOffFlags + 16);   // 12 floats
     float* smem_merge = reinterpret_cast<float*>(smem + L::kOffMerge);
 
     // warp index through a shuffle so that the compiler knows it is warp-uniform (role branches stay uniform and
@@ -589,11 +706,12 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_rows);
         tma_prefetch_desc(&tmap_cols);
+        if constexpr (kBackward) tma_prefetch_desc(&tmap_dacc);
     }
-    if (warp == kMmaWarp && lane == 0) {
+    if (warp == kScoreWarp0 && lane == 0) {
         mbar_init(a_full, 1);
-        mbar_init(a_empty, 1);
-        mbar_init(acc_full, 1);
+        mbar_init(a_empty, kNumIssuers);
+        mbar_init(acc_full, kNumIssuers);
         mbar_init(acc_empty, 128 * kNumSoftmaxWG);
         for (int i = 0; i < S; ++i) {
             mbar_init(b_full + i, 1);
@@ -619,6 +737,8 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
     if (warp == kProducerWarp) {
         // ================================ TMA producer ================================
         if (elect_one()) {
+            RingPos<S> ring;
+            bool wrapped = false;
             int seg = 0;
             for (TileWalker w(t_begin, t_end, nct); w.valid(); w.next()) {
                 const int it = w.idx;
@@ -630,97 +750,141 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         tma_load_2d(smem_a + ka * kAtomBytes, &tmap_rows, a_full, ka * kAtomK, w.rb * kBlockM);
                     ++seg;
                 }
-                const int stage = it % S;
-                const int use = it / S;
                 trace_event(p, 0, it, 0);
-                if (use > 0) mbar_wait(b_empty + stage, (use - 1) & 1, 101);
+                if (wrapped) mbar_wait(b_empty + ring.idx, ring.par ^ 1, 101);   // previous use of the stage released
                 trace_event(p, 0, it, 1);
                 const int c0 = tile_col0<kLoss>(p, w.rb / blocks_per_view, w.j);
-                mbar_arrive_expect_tx(b_full + stage, L::kTileBytes + (kBackward ? L::kColvecBytes : 0));
+                mbar_arrive_expect_tx(b_full + ring.idx, L::kTileBytes + (kBackward ? L::kColvecBytes : 0));
 #pragma unroll
                 for (int ka = 0; ka < L::kAtoms; ++ka)
-                    tma_load_2d(smem_b + stage * L::kTileBytes + ka * kAtomBytes, &tmap_cols, b_full + stage,
+                    tma_load_2d(smem_b + ring.idx * L::kTileBytes + ka * kAtomBytes, &tmap_cols, b_full + ring.idx,
                                 ka * kAtomK, c0);
                 if constexpr (kBackward) {
-                    float* cv = smem_cv + stage * 2 * kBlockN;
-                    bulk_load_1d(cv, p.colvec + c0, kBlockN * 4, b_full + stage);
-                    bulk_load_1d(cv + kBlockN, p.colvec + 2 * p.bg_pad + c0, kBlockN * 4, b_full + stage);
+                    float* cv = smem_cv + ring.idx * 2 * kBlockN;
+                    bulk_load_1d(cv, p.colvec + c0, kBlockN * 4, b_full + ring.idx);
+                    bulk_load_1d(cv + kBlockN, p.colvec + 2 * p.bg_pad + c0, kBlockN * 4, b_full + ring.idx);
+                }
+                if (ring.idx == S - 1) wrapped = true;
+                ring.advance();
+                if (kBackward && w.seg_last()) {
+                    // hand two empty stages to the softmax warps: staging space of the accumulator flush
+#pragma unroll 1
+                    for (int k = 0; k < 2; ++k) {
+                        if (wrapped) mbar_wait(b_empty + ring.idx, ring.par ^ 1, 102);
+                        mbar_arrive(b_full + ring.idx);
+                        if (ring.idx == S - 1) wrapped = true;
+                        ring.advance();
+                    }
                 }
             }
         }
-    } else if (warp == kMmaWarp) {
-        // ================================ UMMA issuer: score tiles ================================
+    } else if (warp >= kScoreWarp0 && warp < kScoreWarp0 + kNumIssuers) {
+        // ================================ UMMA issuers: score tiles ================================
         // S[buf] = A * B_stage^T (both operands K-major).  The whole warp walks the loop and waits on the
         // barriers; one elected lane issues the tcgen05 ops (operands stay in uniform registers).
+        const int me = warp - kScoreWarp0;
         const uint32_t a_addr = smem_u32(smem_a);
         const uint32_t b_addr0 = smem_u32(smem_b);
+        RingPos<S> ring;
+        RingPos<kSlots> slot, freed;          // freed: slot of tile idx - NB (the buffer's previous tenant)
+        int buf = 0;
         int seg_seen = 0;
         for (TileWalker w(t_begin, t_end, nct); w.valid(); w.next()) {
             const int idx = w.idx;
-            const int stage = idx % S;
-            const int buf = idx % NB;
-            if (lane == 0) trace_event(p, 1, idx, 0);
             if (w.seg_first()) {
-                mbar_wait(a_full, seg_seen & 1, 200);
+                mbar_wait(a_full, seg_seen & 1, 200);      // every issuer observes every phase
                 ++seg_seen;
             }
-            mbar_wait(b_full + stage, (idx / S) & 1, 201);
-            if (idx >= NB) {
+            if ((ring.idx & 1) == me) {
+                if (lane == 0) trace_event(p, 1, idx, 0);
+                mbar_wait(b_full + ring.idx, ring.par, 201);
                 // the buffer's previous tenant (tile idx-NB) must be finished: read by the softmax (forward) or
                 // consumed as W by the gradient MMAs (backward)
-                uint64_t* freed = (kBackward ? w_done : s_free) + (idx - NB) % kSlots;
-                mbar_wait(freed, ((idx - NB) / kSlots) & 1, 202);
-            }
-            tc_fence_after_sync();
-            if (lane == 0) trace_event(p, 1, idx, 1);
-            if (elect_one()) {
-                const uint32_t b_addr = b_addr0 + stage * L::kTileBytes;
+                if (idx >= NB) mbar_wait((kBackward ? w_done : s_free) + freed.idx, freed.par, 202);
+                tc_fence_after_sync();
+                if (lane == 0) trace_event(p, 1, idx, 1);
+                if (elect_one()) {
+                    const uint32_t b_addr = b_addr0 + ring.idx * L::kTileBytes;
 #pragma unroll
-                for (int ka = 0; ka < L::kAtoms; ++ka) {
+                    for (int ka = 0; ka < L::kAtoms; ++ka) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint32_t off = ka * kAtomBytes + kk * 32;
-                        umma_ss(tmem_base + buf * kBlockN, make_smem_desc(a_addr + off, 0, 1024),
-                                make_smem_desc(b_addr + off, 0, 1024), kIdescScore, (ka | kk) != 0);
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint32_t off = ka * kAtomBytes + kk * 32;
+                            umma_ss(tmem_base + buf * kBlockN, make_smem_desc(a_addr + off, 0, 1024),
+                                    make_smem_desc(b_addr + off, 0, 1024), kIdescScore, (ka | kk) != 0);
+                        }
                     }
+                    if constexpr (!kBackward) umma_commit(b_empty + ring.idx);
+                    umma_commit(s_full + slot.idx);
+                    if constexpr (!kBackward) trace_event(p, 1, idx, 2);
                 }
-                // s_full is committed last so that, when the softmax sees it, the other arrivals have landed
-                if constexpr (!kBackward) umma_commit(b_empty + stage);
-                if (w.seg_last()) umma_commit(a_empty);
-                umma_commit(s_full + idx % kSlots);
+                __syncwarp();
             }
-            __syncwarp();
+            if (w.seg_last()) {
+                // the row-block tile may be overwritten once the score MMAs of BOTH issuers are complete
+                if (elect_one()) umma_commit(a_empty);
+                __syncwarp();
+            }
+            if (idx >= NB) freed.advance();
+            ring.advance();
+            slot.advance();
+            if (++buf == NB) buf = 0;
+            if (kBackward && w.seg_last()) {
+                // The two flush positions.  With S >= 4 this issuer's next own stage is filled by a TMA the producer
+                // issues after both hand-overs, so the skipped phases are complete when it next waits on these
+                // stages; with S == 2 the very next wait is on such a stage and the phase has to be observed.
+#pragma unroll 1
+                for (int k = 0; k < 2; ++k) {
+                    if (S == 2 && (ring.idx & 1) == me) mbar_wait(b_full + ring.idx, ring.par, 205);
+                    ring.advance();
+                }
+            }
         }
-    } else if (kBackward && warp == kGradWarp) {
-        // ================================ UMMA issuer: gradient MMAs ================================
-        // acc += W[buf] (TMEM, 128 x 128 bf16) * B_stage (MN-major: K = column index)
+    } else if (kBackward && warp >= kGradWarp0 && warp < kGradWarp0 + kNumIssuers) {
+        // ================================ UMMA issuers: gradient MMAs ================================
+        // acc += W[buf] (TMEM, 128 x 128 bf16) * B_stage (MN-major: K = column index).  The accumulator is zeroed by
+        // the softmax warps (at start and after every flush), so every MMA accumulates and the two issuers need no
+        // mutual ordering.
+        const int me = warp - kGradWarp0;
         const uint32_t b_addr0 = smem_u32(smem_b);
-        int seg_done = 0;     // segments whose accumulator has been handed to the flush
+        RingPos<S> ring;
+        RingPos<kSlots> slot;
+        int buf = 0;
+        int seg = 0;
         for (TileWalker w(t_begin, t_end, nct); w.valid(); w.next()) {
             const int idx = w.idx;
-            const int stage = idx % S;
-            const int buf = idx % NB;
-            const bool seg_first = w.seg_first();
-            if (seg_first && seg_done > 0) mbar_wait(acc_empty, (seg_done - 1) & 1, 203);
-            if (lane == 0) trace_event(p, 1, idx, 2);
-            mbar_wait(w_full + idx % kSlots, (idx / kSlots) & 1, 204);
-            tc_fence_after_sync();
-            if (lane == 0) trace_event(p, 1, idx, 3);
-            if (elect_one()) {
-                const uint32_t b_addr = b_addr0 + stage * L::kTileBytes;
+            // phase 0 of acc_empty = initial zeroing, phase s = flush (and re-zeroing) of segment s-1
+            if (w.seg_first()) mbar_wait(acc_empty, seg & 1, 203);
+            if ((ring.idx & 1) == me) {
+                if (lane == 0) trace_event(p, 1, idx, 2);
+                mbar_wait(w_full + slot.idx, slot.par, 204);
+                tc_fence_after_sync();
+                if (lane == 0) trace_event(p, 1, idx, 3);
+                if (elect_one()) {
+                    const uint32_t b_addr = b_addr0 + ring.idx * L::kTileBytes;
 #pragma unroll
-                for (int kc = 0; kc < kBlockN / 16; ++kc) {
-                    // W of column half h (K chunks 4h..4h+3) sits at columns [64h, 64h+32) of the buffer
-                    umma_ts(tmem_base + kTmemAcc, tmem_base + buf * kBlockN + (kc >> 2) * 64 + (kc & 3) * 8,
-                            make_smem_desc(b_addr + kc * 2048, kAtomBytes, 1024), kIdescGrad,
-                            !(seg_first && kc == 0));
+                    for (int kc = 0; kc < kBlockN / 16; ++kc) {
+                        // W of column half h (K chunks 4h..4h+3) sits at columns [64h, 64h+32) of the buffer
+                        umma_ts(tmem_base + kTmemAcc, tmem_base + buf * kBlockN + (kc >> 2) * 64 + (kc & 3) * 8,
+                                make_smem_desc(b_addr + kc * 2048, kAtomBytes, 1024), kIdescGrad, 1);
+                    }
+                    umma_commit(b_empty + ring.idx);         // B tile (and its column vectors) may be overwritten
+                    umma_commit(w_done + slot.idx);          // score buffer may be overwritten
                 }
-                umma_commit(b_empty + stage);            // B tile (and its column vectors) may be overwritten
-                umma_commit(w_done + idx % kSlots);      // score buffer may be overwritten
-                if (w.seg_last()) umma_commit(acc_full);
+                __syncwarp();
             }
-            __syncwarp();
-            if (w.seg_last()) ++seg_done;
+            if (w.seg_last()) {
+                if (elect_one()) umma_commit(acc_full);      // both issuers: count 2
+                __syncwarp();
+                ++seg;
+            }
+            ring.advance();
+            slot.advance();
+            if (++buf == NB) buf = 0;
+            if (w.seg_last()) {                              // flush positions
+                ring.advance();
+                ring.advance();
+            }
         }
     } else if (warp < kNumSoftmaxWarps) {
         // ================================ softmax warpgroups ================================
@@ -730,51 +894,73 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         const int quarter = warp & 3;                         // TMEM lane quarter this warp may touch
         const int row_in_block = quarter * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-        const int n = static_cast<int>(t_end - t_begin);
         const uint32_t cv_base = smem_u32(smem_cv);
+        const int n = static_cast<int>(t_end - t_begin);
+        // loop invariants out of the constant bank, once
+        Hot h;
+        h.k2 = p.k2;
+        h.m2 = p.m2;
+        h.qscale = p.qscale;
+        h.bg_pad = p.bg_pad;
+        h.b_glob = p.b_glob;
+        h.const_shift = kConst;
+        const int b_loc = p.b_loc, row_off = p.row_off;
+        const bool tracing = p.trace != nullptr && static_cast<int>(blockIdx.x) == p.trace_cta && quarter == 0 && lane == 0;
+        constexpr int kLogS = S == 2 ? 1 : (S == 4 ? 2 : 3);
+        static_assert((1 << kLogS) == S, "ring size must be 2, 4 or 8");
 
-        int idx = 0;
-        int seg = 0;
-        while (idx < n) {
-            // ---- segment = run of tiles sharing one row block ----
-            const long long t0 = t_begin + idx;
-            const int rb = static_cast<int>(t0 / nct);
-            const int j0 = static_cast<int>(t0 % nct);
-            const int seg_len = min(n - idx, nct - j0);
+        if constexpr (kBackward) {
+            // zero the gradient accumulator (TMEM is not cleared by the allocation)
+#pragma unroll 1
+            for (int q = wg; q < D / 32; q += kNumSoftmaxWG) tmem_st32_fill(tmem_base + lane_addr + kTmemAcc + q * 32, 0u);
+            tmem_st_wait();
+            tc_fence_before_sync();
+            mbar_arrive(acc_empty);
+        }
 
+        // Segments (runs of tiles sharing a row block) -> the tiles of this warpgroup's pair inside each segment.
+        // CTA tile `it` sits at ring position it (+ 2 per finished segment in the backward kernel: the flush
+        // positions), in hand-off slot it % kSlots and TMEM buffer it % NB; the counters below step by two tiles.
+        int slot = pair, slot_par = 0;
+        int buf = pair % NB;
+        int idx0 = 0, seg = 0;
+        int rb = static_cast<int>(t_begin / nct);
+        int j0 = static_cast<int>(t_begin - static_cast<long long>(rb) * nct);
+        while (idx0 < n) {
+            const int seg_len = min(n - idx0, nct - j0);
+            // ---- segment setup ----
             RowCtx rc;
             rc.vr = rb / blocks_per_view;                                            // view of this row block
             const int img = (rb - rc.vr * blocks_per_view) * kBlockM + row_in_block; // local image index
-            rc.row_ok = img < p.b_loc;
-            rc.g = p.row_off + img;                                                  // global image index
-            rc.diag_col = (kLoss == kNtXent && rc.row_ok) ? rc.vr * p.bg_pad + rc.g : -1;
-            rc.pos_col = rc.row_ok ? (1 - rc.vr) * p.bg_pad + rc.g : -1;
+            rc.row_ok = img < b_loc;
+            rc.g = row_off + img;                                                    // global image index
+            rc.diag_col = (kLoss == kNtXent && rc.row_ok) ? rc.vr * h.bg_pad + rc.g : -1;
+            rc.pos_col = rc.row_ok ? (1 - rc.vr) * h.bg_pad + rc.g : -1;
             // warp-uniform description of this warp's 32 rows
             const int img_lo = (rb - rc.vr * blocks_per_view) * kBlockM + quarter * 32;
-            const bool warp_rows_ok = img_lo + 31 < p.b_loc;
-            const int g_lo = p.row_off + img_lo, g_hi = g_lo + 31;
-
+            const bool warp_rows_ok = img_lo + 31 < b_loc;
+            const int g_lo = row_off + img_lo, g_hi = g_lo + 31;
             FwdState fs;
+            if (!kBackward && kConst) fs.run_max = kConstShiftRaw;
             BwdRow br;
             br.row_a = 0.f;
             br.row_l2 = 0.f;
             if constexpr (kBackward) {
                 if (rc.row_ok) {
-                    br.row_a = __ldg(p.colvec + rc.vr * p.bg_pad + rc.g);
-                    br.row_l2 = __ldg(p.colvec + 2 * p.bg_pad + rc.vr * p.bg_pad + rc.g);
+                    br.row_a = __ldg(p.colvec + rc.vr * h.bg_pad + rc.g);
+                    br.row_l2 = __ldg(p.colvec + 2 * h.bg_pad + rc.vr * h.bg_pad + rc.g);
                 }
             }
+            const int pos_off = kBackward ? 2 * seg : 0;
 
-            for (int s = 0; s < seg_len; ++s) {
-                const int it = idx + s;
-                if ((it % kNumPairs) != pair) continue;
+#pragma unroll 1
+            for (int s = (idx0 ^ pair) & 1; s < seg_len; s += 2) {
+                const int it = idx0 + s;
+                const int pos = it + pos_off;
+                const int stage = pos & (S - 1), stage_par = (pos >> kLogS) & 1;
                 const int c0 = tile_col0<kLoss>(p, rc.vr, j0 + s);
-                const int vc = c0 >= p.bg_pad ? 1 : 0;            // a tile never mixes views
-                const int ic0 = c0 - vc * p.bg_pad;               // image index of the tile's first column
-                const int buf = it % NB;
-                const int stage = it % S;
-                const uint32_t tmem_tile = tmem_base + lane_addr + buf * kBlockN;
-
+                const int vc = c0 >= h.bg_pad ? 1 : 0;            // a tile never mixes views
+                const int ic0 = c0 - vc * h.bg_pad;               // image index of the tile's first column
                 // ---- warp-uniform classification (first-argmax rule: does the tile precede the positive in the
                 // reference's column order?  NT-Xent rows see [view-2 block | view-1 block] (objective.py:48-49);
                 // modified rows see the other view in natural order (objective.py:93)) ----
@@ -784,45 +970,91 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                     if constexpr (kLoss == kNtXent) tile_prec = (rc.vr == 0) ? (vc == 1 && before) : (vc == 1 || before);
                     else tile_prec = before;
                 }
-                // One barrier per slot = it % (NB * #warpgroups): a slot always maps to the same warpgroup pair and the
+                // can any chunk of this tile hold a masked element for one of this warp's rows?
+                bool tile_special = !(ic0 > g_hi || ic0 + kBlockN - 1 < g_lo);
+                if constexpr (!kBackward) tile_special = tile_special || !warp_rows_ok || (ic0 + kBlockN - 1 >= h.b_glob);
+
+                // One barrier per slot = it % (NB * #pairs): a slot always maps to the same warpgroup pair and the
                 // same TMEM buffer, so every barrier has a single waiter that observes all of its phases in order
                 // (a parity wait is only meaningful when the waiter is at most one phase away from the barrier).
-                const int slot = it % kSlots;
-                if (quarter == 0 && lane == 0) trace_event(p, 2 + wg, it, 0);
-                mbar_wait(s_full + slot, (it / kSlots) & 1, 300);
-                if (quarter == 0 && lane == 0) trace_event(p, 2 + wg, it, 1);
-                if constexpr (kBackward) mbar_wait(b_full + stage, (it / S) & 1, 301);   // colvec visibility
+                if (tracing) trace_event(p, 2 + wg, it, 0);
+                mbar_wait(s_full + slot, slot_par, 300);
+                if (tracing) trace_event(p, 2 + wg, it, 1);
+                if constexpr (kBackward) mbar_wait(b_full + stage, stage_par, 301);   // colvec visibility
                 tc_fence_after_sync();
 
-                // this warpgroup's two 32-column chunks; "special" = the chunk may contain the diagonal, the positive
-                // or padded columns for one of this warp's 32 rows (warp-uniform)
-#pragma unroll 1
-                for (int qq = 0; qq < 2; ++qq) {
-                    const int q = half * 2 + qq;
-                    const int icq = ic0 + q * 32;
-                    bool special = !warp_rows_ok || !(icq > g_hi || icq + 31 < g_lo);
-                    if constexpr (!kBackward) special = special || (icq + 31 >= p.b_glob);
-                    uint32_t r[32];
-                    tmem_ld32(tmem_tile + q * 32, r);
-                    tmem_ld_wait();
-                    if constexpr (!kBackward) {
-                        if (special) fwd_chunk<kLoss, true>(p, r, c0 + q * 32, vc, rc, tile_prec, fs);
-                        else fwd_chunk<kLoss, false>(p, r, c0 + q * 32, vc, rc, tile_prec, fs);
-                    } else {
-                        const uint32_t cv_addr = cv_base + stage * (2 * kBlockN * 4) + q * 128;
-                        uint32_t w[16];
-                        if (p.const_shift) {
-                            if (special) bwd_chunk<kLoss, true, true>(p, r, cv_addr, c0 + q * 32, rc, br, w);
-                            else bwd_chunk<kLoss, true, false>(p, r, cv_addr, c0 + q * 32, rc, br, w);
+                // This warpgroup's 64 columns in four 16-column chunks; the TMEM load of chunk k+1 is in flight while
+                // chunk k is processed.  "special" = the chunk may contain the diagonal, the positive or padded
+                // columns for one of this warp's 32 rows (warp-uniform).
+                const uint32_t t0 = tmem_base + lane_addr + buf * kBlockN + half * 64;
+                const int cbase = c0 + half * 64;
+                const uint32_t cv_tile = cv_base + stage * (2 * kBlockN * 4) + half * 64 * 4;
+                uint32_t ra[kChunk], rb2[kChunk];
+                tmem_ld16(t0, ra);
+                // Ping-pong: the arithmetic of tile `it` starts when the other pair has finished that of tile it-1.
+                // Two warps per sub-partition already saturate the MUFU / FMA pipes on this code, so running the two
+                // pairs' maths back to back costs nothing, while the per-tile bookkeeping of one pair (barrier waits,
+                // address arithmetic, fences: ~800 cycles) now hides behind the other pair's maths instead of both
+                // pairs idling together (they otherwise drift into lock step).
+                if (it > 0) named_bar_sync(kTokenBar0 + pair, 32 * kNumSoftmaxWarps);
+                if (!tile_special) {
+                    // Common case: no masked element anywhere in the tile for this warp.  One straight-line block over
+                    // the four chunks, so that the tail of chunk k overlaps the head of chunk k+1.
+                    float cm = kNegBig;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t (&cur)[kChunk] = (k & 1) ? rb2 : ra;
+                        uint32_t (&nxt)[kChunk] = (k & 1) ? ra : rb2;
+                        tmem_ld_wait16(cur);
+                        if (k < 3) tmem_ld16(t0 + (k + 1) * kChunk, nxt);
+                        if constexpr (!kBackward) {
+                            fwd_chunk_fast<kLoss, kConst>(h, cur, cm, fs);
                         } else {
-                            if (special) bwd_chunk<kLoss, false, true>(p, r, cv_addr, c0 + q * 32, rc, br, w);
-                            else bwd_chunk<kLoss, false, false>(p, r, cv_addr, c0 + q * 32, rc, br, w);
+                            uint32_t wq[kChunk / 2];
+                            bwd_chunk<kLoss, kConst, false>(h, cur, cv_tile + k * kChunk * 4, 0, rc, br, wq);
+                            tmem_st8(t0 + k * (kChunk / 2), wq);
                         }
-                        // bf16 W of chunk q goes to columns [64*half + 16*qq, +16): inside this warpgroup's own
-                        // 64-column region and already consumed by this thread
-                        tmem_st16(tmem_tile + half * 64 + qq * 16, w);
+                    }
+                    if constexpr (!kBackward) {
+                        fs.max_prec = fmaxf(fs.max_prec, tile_prec ? cm : kNegBig);
+                        fs.max_foll = fmaxf(fs.max_foll, tile_prec ? kNegBig : cm);
+                    }
+                } else {
+                    auto process = [&](const uint32_t (&r)[kChunk], int k) {
+                        const int cq = cbase + k * kChunk;
+                        const int icq = cq - vc * h.bg_pad;
+                        bool special = !(icq > g_hi || icq + kChunk - 1 < g_lo);
+                        if constexpr (!kBackward) special = special || !warp_rows_ok || (icq + kChunk - 1 >= h.b_glob);
+                        if constexpr (!kBackward) {
+                            if (special) {
+                                fwd_chunk_special<kLoss, kConst>(h, r, cq, vc, rc, fs);
+                            } else {
+                                float cm = kNegBig;
+                                fwd_chunk_fast<kLoss, kConst>(h, r, cm, fs);
+                                fs.max_prec = fmaxf(fs.max_prec, tile_prec ? cm : kNegBig);
+                                fs.max_foll = fmaxf(fs.max_foll, tile_prec ? kNegBig : cm);
+                            }
+                        } else {
+                            uint32_t wq[kChunk / 2];
+                            const uint32_t cv_addr = cv_tile + k * kChunk * 4;
+                            if (special) bwd_chunk<kLoss, kConst, true>(h, r, cv_addr, cq, rc, br, wq);
+                            else bwd_chunk<kLoss, kConst, false>(h, r, cv_addr, cq, rc, br, wq);
+                            // bf16 W of chunk k goes to columns [64*half + 8*k, +8): inside this warpgroup's own
+                            // 64-column region and over scores this thread has already consumed
+                            tmem_st8(t0 + k * (kChunk / 2), wq);
+                        }
+                    };
+#pragma unroll 1
+                    for (int kk = 0; kk < 2; ++kk) {
+                        tmem_ld_wait16(ra);
+                        tmem_ld16(t0 + (2 * kk + 1) * kChunk, rb2);
+                        process(ra, 2 * kk);
+                        tmem_ld_wait16(rb2);
+                        if (kk == 0) tmem_ld16(t0 + 2 * kChunk, ra);
+                        process(rb2, 2 * kk + 1);
                     }
                 }
+                if (it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
                 if constexpr (!kBackward) {
                     tc_fence_before_sync();
                     mbar_arrive(s_free + slot);
@@ -831,7 +1063,14 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                     tc_fence_before_sync();
                     mbar_arrive(w_full + slot);
                 }
-                if (quarter == 0 && lane == 0) trace_event(p, 2 + wg, it, 2);
+                if (tracing) trace_event(p, 2 + wg, it, 2);
+                slot += 2;
+                if (slot >= kSlots) {
+                    slot -= kSlots;
+                    slot_par ^= 1;
+                }
+                buf += 2;
+                if (buf >= NB) buf -= NB;
             }
 
             // ---- end of segment ----
@@ -840,7 +1079,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 // merge the four warpgroups' partial (max, sum, argmax bookkeeping) through shared memory ...
                 float* mg = smem_merge + (seg & 1) * (kNumSoftmaxWG * kFwdFields * kBlockM);
                 float* mine = mg + wg * (kFwdFields * kBlockM) + row_in_block;
-                mine[0 * kBlockM] = fs.sum;
+                mine[0 * kBlockM] = (fs.sum + fs.s1) + (fs.s2 + fs.s3);
                 mine[1 * kBlockM] = fs.run_max;
                 mine[2 * kBlockM] = fs.max_prec;
                 mine[3 * kBlockM] = fs.max_foll;
@@ -876,29 +1115,53 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                     __stcg(dst + 4 * kBlockM, pm);
                 }
             } else {
-                // flush the gradient accumulator: the D columns are split in 32-column chunks over the warpgroups
-                mbar_wait(acc_full, seg & 1, 302);
+                // ---- flush the gradient accumulator: TMEM -> registers -> 128B-swizzled fp32 boxes in the two ring
+                // stages the producer handed over -> ONE TMA reduce-add per 128 x 32 box into dacc ----
+                const int fpos = idx0 + seg_len + pos_off;    // ring positions fpos, fpos + 1
+                const int st0 = fpos & (S - 1), par0 = (fpos >> kLogS) & 1;
+                const int st1 = (fpos + 1) & (S - 1), par1 = ((fpos + 1) >> kLogS) & 1;
+                mbar_wait(acc_full, seg & 1, 302);            // every gradient MMA of the segment has completed
+                mbar_wait(b_full + st0, par0, 303);           // the two staging stages are ours
+                mbar_wait(b_full + st1, par1, 304);
                 tc_fence_after_sync();
 #pragma unroll 1
                 for (int q = wg; q < D / 32; q += kNumSoftmaxWG) {
                     uint32_t r[32];
-                    const int col = q * 32;
-                    tmem_ld32(tmem_base + lane_addr + kTmemAcc + col, r);
+                    tmem_ld32(tmem_base + lane_addr + kTmemAcc + q * 32, r);
                     tmem_ld_wait();
-                    if (rc.row_ok) {
-                        float* dst = p.dacc + static_cast<size_t>(rb * kBlockM + row_in_block) * D + col;
+                    tmem_st32_fill(tmem_base + lane_addr + kTmemAcc + q * 32, 0u);     // zero for the next segment
+                    const int stage = (q / kBoxesPerStage) == 0 ? st0 : st1;
+                    const uint32_t row_addr = smem_u32(smem_b + stage * L::kTileBytes + (q % kBoxesPerStage) * kAtomBytes) +
+                                              row_in_block * 128;
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            red_add_v4(dst + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]),
-                                       __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-                    }
+                    for (int j = 0; j < 8; ++j)
+                        sts_v4(row_addr + ((j ^ (row_in_block & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                 }
+                tmem_st_wait();
                 tc_fence_before_sync();
-                mbar_arrive(acc_empty);
+                mbar_arrive(acc_empty);                       // the next segment's gradient MMAs may start
+                fence_proxy_async_smem();                     // generic-proxy stores -> visible to the TMA engine
+                named_bar_sync(1, 32 * kNumSoftmaxWarps);
+                if (threadIdx.x == 0) {
+#pragma unroll 1
+                    for (int q = 0; q < D / 32; ++q) {
+                        const int stage = (q / kBoxesPerStage) == 0 ? st0 : st1;
+                        tma_reduce_add_2d(&tmap_dacc, smem_b + stage * L::kTileBytes + (q % kBoxesPerStage) * kAtomBytes,
+                                          q * 32, rb * kBlockM);
+                    }
+                    bulk_commit_group();
+                    if (idx0 + seg_len == n) bulk_wait_group0();   // last segment: the adds are performed before exit
+                    else bulk_wait_group_read0();                  // staging space may be reused
+                    mbar_arrive(b_empty + st0);
+                    mbar_arrive(b_empty + st1);
+                }
+                __syncwarp();
             }
             if (threadIdx.x == 0 && seg < 2) cta_stamp(p, 2 + 2 * seg);
-            idx += seg_len;
+            idx0 += seg_len;
             ++seg;
+            ++rb;
+            j0 = 0;
         }
     }
 

@@ -43,6 +43,9 @@ SIMCLR_DEVICE float softplus_beta_grad(float x) {
     return bx > kSoftplusThreshold ? 1.f : 1.f / (1.f + expf(-bx));
 }
 
+SIMCLR_DEVICE void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 SIMCLR_DEVICE void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -108,7 +108,8 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
             if w_local.numel() != 2 * b:
                 raise ValueError(f"weight must have {2 * b} entries, got {w_local.numel()}")
         check(lib.simclr_forward(loss_kind, operand.data_ptr(), operand_cols.data_ptr(), b, b_global, row_offset, d,
-                                 float(temperature), rowvec[1].data_ptr(), _ptr(w_local), rowvec[2].data_ptr(),
+                                 float(temperature), int(bool(normalize)), rowvec[1].data_ptr(), _ptr(w_local),
+                                 rowvec[2].data_ptr(),
                                  rowvec[3].data_ptr(), stats.data_ptr(), loss.data_ptr(), ws.data_ptr(), ws_bytes,
                                  stream), "simclr_forward")
     saved = _Saved()

@@ -54,7 +54,8 @@ class ContrastiveStep:
                                  int(self.normalize), self.operand.data_ptr(), self.rowvec[0].data_ptr(),
                                  self.rowvec[1].data_ptr(), self.fwd_ws.data_ptr(), st), "simclr_prepare")
         check(lib.simclr_forward(self.kind, self.operand.data_ptr(), self.operand.data_ptr(), self.b, self.b, 0, self.d,
-                                 self.temperature, self.rowvec[1].data_ptr(), None, self.rowvec[2].data_ptr(),
+                                 self.temperature, int(self.normalize), self.rowvec[1].data_ptr(), None,
+                                 self.rowvec[2].data_ptr(),
                                  self.rowvec[3].data_ptr(), self.stats.data_ptr(), self.loss.data_ptr(),
                                  self.fwd_ws.data_ptr(), self.fwd_ws_bytes, st), "simclr_forward")
 
