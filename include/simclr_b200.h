@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIMCLR_ABI_VERSION 2
+#define SIMCLR_ABI_VERSION 3
 
 /* loss kinds */
 #define SIMCLR_LOSS_NTXENT 0   /* objective.py:6-55  */
@@ -65,7 +65,10 @@ size_t simclr_backward_workspace_bytes(int loss, int64_t b_local, int64_t b_glob
 /*
  * Stage 1 -- prologue (objective.py:25-30 L2 normalise, or :70-78 softplus + L1 normalise).
  * Reads x_batch1 / x_batch2 ([b_local][d], row-major contiguous, `in_dtype`), writes
- *   operand  bf16 [2*Blpad][Dpad]  round-to-nearest operands for the tensor cores (padding zeroed)
+ *   operand  bf16 [2*Blpad][Dpad]  round-to-nearest operands for the tensor cores (padding zeroed).  NT-Xent rows
+ *                                  carry a factor sqrt(log2(e)/temperature), so that the tensor-core product of
+ *                                  two rows is the logit in the log2 domain (the same temperature must be passed
+ *                                  to simclr_forward / simclr_backward); the modified loss ignores `temperature`
  *   inv_norm f32  [2*Blpad]        1 / max(||z||, 1e-12)   (1 when normalize == 0)
  *   pos_dot  f32  [2*Blpad]        exact fp32 <op_r, op_pos(r)> of the positive pair
  * `forward_workspace` (may be NULL) is the workspace the following simclr_forward call will use; its counter
@@ -73,8 +76,8 @@ size_t simclr_backward_workspace_bytes(int loss, int64_t b_local, int64_t b_glob
  * 4 * (2*Blpad/128 + 4) bytes) to be zero on entry and leaves it zero on exit.
  */
 int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
-                   int normalize, void* operand, float* inv_norm, float* pos_dot, void* forward_workspace,
-                   void* stream);
+                   int normalize, float temperature, void* operand, float* inv_norm, float* pos_dot,
+                   void* forward_workspace, void* stream);
 
 /*
  * Stage 2 -- forward over this rank's rows against the global batch's columns

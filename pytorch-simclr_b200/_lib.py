@@ -12,7 +12,7 @@ LOSS_NTXENT = 0
 LOSS_MODIFIED = 1
 DTYPE_F32 = 0
 DTYPE_BF16 = 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _lock = threading.Lock()
 _lib = None
@@ -31,7 +31,7 @@ SIGNATURES = {
     "simclr_pad_dim": (_i64, [_i64]),
     "simclr_forward_workspace_bytes": (_sz, [_int, _i64, _i64, _i64]),
     "simclr_backward_workspace_bytes": (_sz, [_int, _i64, _i64, _i64]),
-    "simclr_prepare": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp]),
+    "simclr_prepare": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _vp, _vp, _vp, _vp, _vp]),
     "simclr_forward": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                               _sz, _vp]),
     "simclr_backward": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -16,6 +16,7 @@ struct AuxParams {
     float m2;
     int const_shift;
     float qscale;    // (float) b_glob
+    float op_scale;  // factor applied to the normalised rows before bf16 rounding (NT-Xent: sqrt(log2(e)/tau), else 1)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -95,8 +96,8 @@ __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x
 #pragma unroll
     for (int u = 0; u < kMaxDimPerLane; ++u) {
         if (u < per_lane) {
-            o1[lane + 32 * u] = __float2bfloat16_rn(v1[u] * s1);
-            o2[lane + 32 * u] = __float2bfloat16_rn(v2[u] * s2);
+            o1[lane + 32 * u] = __float2bfloat16_rn(v1[u] * (s1 * a.op_scale));
+            o2[lane + 32 * u] = __float2bfloat16_rn(v2[u] * (s2 * a.op_scale));
         }
     }
     if (lane == 0) {

@@ -144,7 +144,7 @@ BwdWorkspace carve_backward(const Geometry& g, void* base) {
 
 // log2-domain constants shared by forward and backward
 struct Scales {
-    float k2, inv_tau, m2, qscale;
+    float k2, inv_tau, m2, qscale, op_scale;
     int const_shift;
 };
 Scales make_scales(int loss, float temperature, int normalize, int64_t b_global) {
@@ -153,11 +153,15 @@ Scales make_scales(int loss, float temperature, int normalize, int64_t b_global)
     s.qscale = static_cast<float>(b_global);
     if (loss == SIMCLR_LOSS_NTXENT) {
         s.k2 = 1.4426950408889634f * s.inv_tau;
-        // |S| <= 1 (+ bf16 rounding) when rows are normalised: exp2(S*k2 - m2) <= 1 and a_r <= 2^(2*k2)
-        s.m2 = s.k2 * kConstShiftRaw;
+        // the operands carry sqrt(k2) each: the MMA yields log2-domain logits S' = k2 * S
+        s.op_scale = std::sqrt(s.k2);
+        // |S'| <= k2 (+ bf16 rounding) when rows are normalised: with k2 <= 40, exp2(S') <= 2^41 and
+        // a_r = g 2^(-lse2_r) >= 2^-13 2^-(41+17) stay far inside the fp32 range without any shift
+        s.m2 = kConstShiftRaw;
         s.const_shift = (normalize && 2.0f * s.k2 <= 80.0f) ? 1 : 0;
     } else {
         s.k2 = s.inv_tau;
+        s.op_scale = 1.0f;
         // y = log2(q) * (1/tau - 1) with q in [1e-4, B]
         const float lo = std::log2(kClampMin) * (s.k2 - 1.0f), hi = std::log2(s.qscale) * (s.k2 - 1.0f);
         s.m2 = std::fmax(lo, hi);
@@ -244,6 +248,7 @@ AuxParams make_aux(const Geometry& g, const Scales& s, int64_t b_local, int64_t 
     a.m2 = s.m2;
     a.const_shift = s.const_shift;
     a.qscale = s.qscale;
+    a.op_scale = s.op_scale;
     return a;
 }
 
@@ -264,6 +269,7 @@ TileParams make_tile_params(const Geometry& g, const Scales& s, int64_t b_local,
     p.const_shift = s.const_shift;
     p.qscale = s.qscale;
     p.inv_tau = s.inv_tau;
+    p.acc_scale = 1.0f / s.op_scale;
     p.trace = g_trace_ptr;
     p.trace_cta = g_trace_cta;
     p.ktrace = g_ktrace_ptr;
@@ -326,16 +332,17 @@ size_t simclr_backward_workspace_bytes(int loss, int64_t b_local, int64_t b_glob
 }
 
 int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
-                   int normalize, void* operand, float* inv_norm, float* pos_dot, void* forward_workspace,
-                   void* stream) {
+                   int normalize, float temperature, void* operand, float* inv_norm, float* pos_dot,
+                   void* forward_workspace, void* stream) {
     if (!x_batch1 || !x_batch2 || !operand || !inv_norm || !pos_dot) return SIMCLR_ERR_NULL_POINTER;
     if (in_dtype != SIMCLR_DTYPE_F32 && in_dtype != SIMCLR_DTYPE_BF16) return SIMCLR_ERR_BAD_DTYPE;
+    if (!(temperature > 0.f) || !std::isfinite(temperature)) return SIMCLR_ERR_BAD_TEMPERATURE;
     Geometry g;
     int rc = make_geometry(loss, b_local, b_local, 0, d, &g);
     if (rc) return rc;
     if (misaligned(operand) || misaligned(forward_workspace)) return SIMCLR_ERR_MISALIGNED;
     if ((rc = check_device())) return rc;
-    Scales s = make_scales(loss, 1.0f, normalize, b_local);
+    Scales s = make_scales(loss, temperature, normalize, b_local);
     unsigned int* zero_ptr = static_cast<unsigned int*>(forward_workspace);
     const int zero_words = static_cast<int>(header_bytes(g) / 4);
     AuxParams a = make_aux(g, s, b_local, b_local, 0, d, normalize);

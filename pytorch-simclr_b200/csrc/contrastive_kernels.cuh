@@ -68,9 +68,9 @@ constexpr int kTokenBar0 = 2;         // named barriers 2, 3: ping-pong tokens o
 constexpr int kFwdFields = 5;         // per-row partial: sum, run-max, max-preceding, max-following, pos(mma)
 constexpr float kNegBig = -3.0e38f;   // finite stand-in for -inf
 constexpr float kClampMin = 1e-4f;    // reference objective.py:87-88
-// NT-Xent with normalised rows: |S| <= 1 (+ bf16 rounding), so exp2(S*k2 - m2) with m2 = k2 * kConstShiftRaw never
-// overflows and no running maximum is needed ("constant shift")
-constexpr float kConstShiftRaw = 1.0078125f;
+// NT-Xent with normalised rows: |S'| <= k2 (+ bf16 rounding) and k2 <= 40 is required for this path, so exp2(S') stays
+// far inside the fp32 range: no running maximum and no shift at all ("constant shift" of zero)
+constexpr float kConstShiftRaw = 0.f;
 
 enum LossKind : int { kNtXent = 0, kModified = 1 };
 
@@ -84,7 +84,8 @@ struct TileParams {
     int n_col_tiles;   // column tiles per row block (NT-Xent: 2*bg_pad/128, modified: bg_pad/128)
     int max_segs;      // max number of row blocks one CTA touches
     long long total_tiles;
-    float k2;          // NT-Xent: log2(e)/tau.  modified: 1/tau (scores are already log2)
+    float k2;          // NT-Xent: log2(e)/tau (carried by the operands as sqrt(k2) each).  modified: 1/tau
+    float acc_scale;   // backward finalize: 1/sqrt(k2) undoes the operand factor in dacc = W * operand (modified: 1)
     float m2;          // constant log2-domain shift of the one-exp backward form
     int const_shift;   // backward: 1 -> one exp per element (bounded scores), 0 -> general two-exp form
     float qscale;      // modified loss: (float) b_glob, the factor inside the clamp
@@ -156,7 +157,8 @@ SIMCLR_DEVICE int tile_col0(const TileParams& p, int vr, int j) {
 
 // ---------------------------------------------------------------------------------------------
 // Per-element maths.  "v" is the tracked raw value (monotone in the logit):
-//   NT-Xent : v = S              logit2 = v * k2                     (k2 = log2(e)/tau)
+//   NT-Xent : v = S' = k2 * S    logit2 = v      the operands carry a factor sqrt(k2), k2 = log2(e)/tau, so the MMA
+//                                                delivers log2-domain logits and exp2 needs no multiply
 //   modified: v = max(B*S, 1e-4) logit2 = log2(v) * k2               (k2 = 1/tau)
 // ---------------------------------------------------------------------------------------------
 template <int kLoss>
@@ -166,7 +168,7 @@ SIMCLR_DEVICE float raw_value(const TileParams& p, float s) {
 }
 template <int kLoss>
 SIMCLR_DEVICE float logit2(const TileParams& p, float v) {
-    if constexpr (kLoss == kNtXent) return v * p.k2;
+    if constexpr (kLoss == kNtXent) return v;
     else return lg2_approx(v) * p.k2;
 }
 
@@ -238,7 +240,7 @@ SIMCLR_DEVICE float raw_value_h(const Hot& h, float s) {
 }
 template <int kLoss>
 SIMCLR_DEVICE float logit2_h(const Hot& h, float v) {
-    if constexpr (kLoss == kNtXent) return v * h.k2;
+    if constexpr (kLoss == kNtXent) return v;
     else return lg2_approx(v) * h.k2;
 }
 
@@ -258,10 +260,10 @@ SIMCLR_DEVICE void fwd_chunk_fast(const Hot& h, const uint32_t (&r)[kChunk], flo
         cm = fmaxf(cm, c2);
 #pragma unroll
         for (int i = 0; i < kChunk; i += 4) {
-            st.sum += ex2_approx(fmaf(v[i + 0], h.k2, -h.m2));
-            st.s1 += ex2_approx(fmaf(v[i + 1], h.k2, -h.m2));
-            st.s2 += ex2_approx(fmaf(v[i + 2], h.k2, -h.m2));
-            st.s3 += ex2_poly<4>(fmaf(v[i + 3], h.k2, -h.m2));
+            st.sum += ex2_approx(v[i + 0]);
+            st.s1 += ex2_approx(v[i + 1]);
+            st.s2 += ex2_approx(v[i + 2]);
+            st.s3 += ex2_poly<3>(v[i + 3]);
         }
     } else {
         cm = fmaxf(cm, c2);
@@ -312,13 +314,13 @@ SIMCLR_DEVICE void fwd_chunk_special(const Hot& h, const uint32_t (&r)[kChunk], 
     st.max_foll = fmaxf(st.max_foll, cf);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     if constexpr (kConst) {
-        // exp2(fma(-3e38, k2, -m2)) = exp2(-inf) = 0: masked elements drop out by themselves
+        // exp2(-3e38) = 0: masked elements drop out by themselves
 #pragma unroll
         for (int i = 0; i < kChunk; i += 4) {
-            a0 += ex2_approx(fmaf(v[i + 0], h.k2, -h.m2));
-            a1 += ex2_approx(fmaf(v[i + 1], h.k2, -h.m2));
-            a2 += ex2_approx(fmaf(v[i + 2], h.k2, -h.m2));
-            a3 += ex2_approx(fmaf(v[i + 3], h.k2, -h.m2));
+            a0 += ex2_approx(v[i + 0]);
+            a1 += ex2_approx(v[i + 1]);
+            a2 += ex2_approx(v[i + 2]);
+            a3 += ex2_approx(v[i + 3]);
         }
         st.sum += (a0 + a1) + (a2 + a3);
     } else {
@@ -365,14 +367,12 @@ SIMCLR_DEVICE void bwd_chunk(const Hot& h, const uint32_t (&r)[kChunk], uint32_t
             float wval;
             if constexpr (kLoss == kNtXent) {
                 if constexpr (kConst) {
-                    // one exp per element: W = exp2(S*k2 - m2) * (a_r + a_c); every fourth one on the FMA pipe
-                    const float x = fmaf(sraw, h.k2, -h.m2);
-                    const float e = poly_lane(i + u) ? ex2_poly<3>(x) : ex2_approx(x);
+                    // one exp per element: W = exp2(S') * (a_r + a_c); every fourth one on the FMA pipe
+                    const float e = poly_lane(i + u) ? ex2_poly<3>(sraw) : ex2_approx(sraw);
                     wval = e * (br.row_a + acs[u]);
                 } else {
-                    // general form: W = g_r exp2(S*k2 - lse2_r) + g_c exp2(S*k2 - lse2_c)
-                    wval = br.row_a * ex2_approx(fmaf(sraw, h.k2, -br.row_l2)) +
-                           acs[u] * ex2_approx(fmaf(sraw, h.k2, -lcs[u]));
+                    // general form: W = g_r exp2(S' - lse2_r) + g_c exp2(S' - lse2_c)
+                    wval = br.row_a * ex2_approx(sraw - br.row_l2) + acs[u] * ex2_approx(sraw - lcs[u]);
                 }
             } else {
                 // d/dP of log(max(B P,1e-4))/tau = 1/(tau P) where live; folded: e^{A}/P = B q^{1/tau - 1}
@@ -405,7 +405,7 @@ SIMCLR_DEVICE void contributing_ctas(const TileParams& p, int rb, int& k_first, 
 
 template <int kLoss>
 SIMCLR_DEVICE float exact_logit2(const TileParams& p, float v) {
-    if constexpr (kLoss == kNtXent) return v * p.k2;
+    if constexpr (kLoss == kNtXent) return v;
     else return log2f(v) * p.k2;
 }
 
@@ -424,6 +424,7 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
 
     float v_pos = __ldg(p.pos_dot + slot);
     if constexpr (kLoss == kModified) v_pos = fmaxf(v_pos * p.qscale, kClampMin);
+    else v_pos *= p.k2;               // exact fp32 positive logit in the log2 domain of the MMA scores
     // Partials of CTA k live at part[(k * max_segs + seg_k)]: the first contributing CTA may have started in an
     // earlier row block (seg_k = rb - its first row block); every later one starts inside this row block (seg 0).
     const long long c_first = (p.total_tiles * k_first) / p.tile_grid;
@@ -584,7 +585,7 @@ SIMCLR_DEVICE void backward_finalize_rowblock(const TileParams& p, int rb, int w
             hs[u] = es * mul_s;
             const float ho = eo * mul_o;
             const float acc = __ldcg(p.dacc + static_cast<size_t>(slot_self) * D + k);
-            dv[u] = (acc + coef * ho) * outer;
+            dv[u] = (acc * p.acc_scale + coef * ho) * outer;
             t = fmaf(dv[u], hs[u], t);
         }
         t = warp_sum(t);
@@ -670,20 +671,21 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* smem_a = smem + L::kOffA;
-    uint8_t* smem_b = smem + L::kOffB;
-    float* smem_cv = reinterpret_cast<float*>(smem + L::kOffCv);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
-    uint64_t* a_full = bars + 0;
-    uint64_t* a_empty = bars + 1;
-    uint64_t* acc_full = bars + 2;
-    uint64_t* acc_empty = bars + 3;
-    uint64_t* b_full = bars + 4;
-    uint64_t* b_empty = b_full + S;
-    uint64_t* s_full = b_empty + S;               // [kSlots] score tile ready in TMEM
-    uint64_t* s_free = s_full + kMaxSlots;        // [kSlots] forward only: softmax finished reading the score tile
-    uint64_t* w_full = s_free + kMaxSlots;        // [kSlots] backward only: W written to TMEM
-    uint64_t* w_done = w_full + kMaxSlots;        // [kSlots] backward only: gradient MMAs finished reading W
+    // barriers and tiles by 32-bit shared-space address (computed once)
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t sa_addr = smem_base + L::kOffA;
+    const uint32_t sb_addr = smem_base + L::kOffB;
+    const uint32_t bars = smem_base + L::kOffBar;
+    const uint32_t a_full = bars + 0 * 8;
+    const uint32_t a_empty = bars + 1 * 8;
+    const uint32_t acc_full = bars + 2 * 8;
+    const uint32_t acc_empty = bars + 3 * 8;
+    const uint32_t b_full = bars + 4 * 8;
+    const uint32_t b_empty = b_full + S * 8;
+    const uint32_t s_full = b_empty + S * 8;               // [kSlots] score tile ready in TMEM
+    const uint32_t s_free = s_full + kMaxSlots * 8;        // [kSlots] forward only: softmax finished reading the score tile
+    const uint32_t w_full = s_free + kMaxSlots * 8;        // [kSlots] backward only: W written to TMEM
+    const uint32_t w_done = w_full + kMaxSlots * 8;        // [kSlots] backward only: gradient MMAs finished reading W
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + L::kOffTmemPtr);
     float* smem_merge = reinterpret_cast<float*>(smem + L::kOffMerge);
 
@@ -714,14 +716,14 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         mbar_init(acc_full, kNumIssuers);
         mbar_init(acc_empty, 128 * kNumSoftmaxWG);
         for (int i = 0; i < S; ++i) {
-            mbar_init(b_full + i, 1);
-            mbar_init(b_empty + i, 1);
+            mbar_init(b_full + 8 * i, 1);
+            mbar_init(b_empty + 8 * i, 1);
         }
         for (int i = 0; i < kMaxSlots; ++i) {
-            mbar_init(s_full + i, 1);
-            mbar_init(s_free + i, 256);
-            mbar_init(w_full + i, 256);
-            mbar_init(w_done + i, 1);
+            mbar_init(s_full + 8 * i, 1);
+            mbar_init(s_free + 8 * i, 256);
+            mbar_init(w_full + 8 * i, 256);
+            mbar_init(w_done + 8 * i, 1);
         }
         mbar_fence_init();
     }
@@ -747,22 +749,22 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                     mbar_arrive_expect_tx(a_full, L::kTileBytes);
 #pragma unroll
                     for (int ka = 0; ka < L::kAtoms; ++ka)
-                        tma_load_2d(smem_a + ka * kAtomBytes, &tmap_rows, a_full, ka * kAtomK, w.rb * kBlockM);
+                        tma_load_2d(sa_addr + ka * kAtomBytes, &tmap_rows, a_full, ka * kAtomK, w.rb * kBlockM);
                     ++seg;
                 }
                 trace_event(p, 0, it, 0);
-                if (wrapped) mbar_wait(b_empty + ring.idx, ring.par ^ 1, 101);   // previous use of the stage released
+                if (wrapped) mbar_wait(b_empty + 8 * ring.idx, ring.par ^ 1, 101);   // previous use of the stage released
                 trace_event(p, 0, it, 1);
                 const int c0 = tile_col0<kLoss>(p, w.rb / blocks_per_view, w.j);
-                mbar_arrive_expect_tx(b_full + ring.idx, L::kTileBytes + (kBackward ? L::kColvecBytes : 0));
+                mbar_arrive_expect_tx(b_full + 8 * ring.idx, L::kTileBytes + (kBackward ? L::kColvecBytes : 0));
 #pragma unroll
                 for (int ka = 0; ka < L::kAtoms; ++ka)
-                    tma_load_2d(smem_b + ring.idx * L::kTileBytes + ka * kAtomBytes, &tmap_cols, b_full + ring.idx,
+                    tma_load_2d(sb_addr + ring.idx * L::kTileBytes + ka * kAtomBytes, &tmap_cols, b_full + 8 * ring.idx,
                                 ka * kAtomK, c0);
                 if constexpr (kBackward) {
-                    float* cv = smem_cv + ring.idx * 2 * kBlockN;
-                    bulk_load_1d(cv, p.colvec + c0, kBlockN * 4, b_full + ring.idx);
-                    bulk_load_1d(cv + kBlockN, p.colvec + 2 * p.bg_pad + c0, kBlockN * 4, b_full + ring.idx);
+                    const uint32_t cv = smem_base + L::kOffCv + ring.idx * (2 * kBlockN * 4);
+                    bulk_load_1d(cv, p.colvec + c0, kBlockN * 4, b_full + 8 * ring.idx);
+                    bulk_load_1d(cv + kBlockN * 4, p.colvec + 2 * p.bg_pad + c0, kBlockN * 4, b_full + 8 * ring.idx);
                 }
                 if (ring.idx == S - 1) wrapped = true;
                 ring.advance();
@@ -770,8 +772,8 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                     // hand two empty stages to the softmax warps: staging space of the accumulator flush
 #pragma unroll 1
                     for (int k = 0; k < 2; ++k) {
-                        if (wrapped) mbar_wait(b_empty + ring.idx, ring.par ^ 1, 102);
-                        mbar_arrive(b_full + ring.idx);
+                        if (wrapped) mbar_wait(b_empty + 8 * ring.idx, ring.par ^ 1, 102);
+                        mbar_arrive(b_full + 8 * ring.idx);
                         if (ring.idx == S - 1) wrapped = true;
                         ring.advance();
                     }
@@ -783,8 +785,8 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         // S[buf] = A * B_stage^T (both operands K-major).  The whole warp walks the loop and waits on the
         // barriers; one elected lane issues the tcgen05 ops (operands stay in uniform registers).
         const int me = warp - kScoreWarp0;
-        const uint32_t a_addr = smem_u32(smem_a);
-        const uint32_t b_addr0 = smem_u32(smem_b);
+        const uint32_t a_addr = sa_addr;
+        const uint32_t b_addr0 = sb_addr;
         RingPos<S> ring;
         RingPos<kSlots> slot, freed;          // freed: slot of tile idx - NB (the buffer's previous tenant)
         int buf = 0;
@@ -797,10 +799,10 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             }
             if ((ring.idx & 1) == me) {
                 if (lane == 0) trace_event(p, 1, idx, 0);
-                mbar_wait(b_full + ring.idx, ring.par, 201);
+                mbar_wait(b_full + 8 * ring.idx, ring.par, 201);
                 // the buffer's previous tenant (tile idx-NB) must be finished: read by the softmax (forward) or
                 // consumed as W by the gradient MMAs (backward)
-                if (idx >= NB) mbar_wait((kBackward ? w_done : s_free) + freed.idx, freed.par, 202);
+                if (idx >= NB) mbar_wait((kBackward ? w_done : s_free) + 8 * freed.idx, freed.par, 202);
                 tc_fence_after_sync();
                 if (lane == 0) trace_event(p, 1, idx, 1);
                 if (elect_one()) {
@@ -814,8 +816,8 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                                     make_smem_desc(b_addr + off, 0, 1024), kIdescScore, (ka | kk) != 0);
                         }
                     }
-                    if constexpr (!kBackward) umma_commit(b_empty + ring.idx);
-                    umma_commit(s_full + slot.idx);
+                    if constexpr (!kBackward) umma_commit(b_empty + 8 * ring.idx);
+                    umma_commit(s_full + 8 * slot.idx);
                     if constexpr (!kBackward) trace_event(p, 1, idx, 2);
                 }
                 __syncwarp();
@@ -835,7 +837,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 // stages; with S == 2 the very next wait is on such a stage and the phase has to be observed.
 #pragma unroll 1
                 for (int k = 0; k < 2; ++k) {
-                    if (S == 2 && (ring.idx & 1) == me) mbar_wait(b_full + ring.idx, ring.par, 205);
+                    if (S == 2 && (ring.idx & 1) == me) mbar_wait(b_full + 8 * ring.idx, ring.par, 205);
                     ring.advance();
                 }
             }
@@ -846,7 +848,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         // the softmax warps (at start and after every flush), so every MMA accumulates and the two issuers need no
         // mutual ordering.
         const int me = warp - kGradWarp0;
-        const uint32_t b_addr0 = smem_u32(smem_b);
+        const uint32_t b_addr0 = sb_addr;
         RingPos<S> ring;
         RingPos<kSlots> slot;
         int buf = 0;
@@ -857,7 +859,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             if (w.seg_first()) mbar_wait(acc_empty, seg & 1, 203);
             if ((ring.idx & 1) == me) {
                 if (lane == 0) trace_event(p, 1, idx, 2);
-                mbar_wait(w_full + slot.idx, slot.par, 204);
+                mbar_wait(w_full + 8 * slot.idx, slot.par, 204);
                 tc_fence_after_sync();
                 if (lane == 0) trace_event(p, 1, idx, 3);
                 if (elect_one()) {
@@ -868,8 +870,8 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         umma_ts(tmem_base + kTmemAcc, tmem_base + buf * kBlockN + (kc >> 2) * 64 + (kc & 3) * 8,
                                 make_smem_desc(b_addr + kc * 2048, kAtomBytes, 1024), kIdescGrad, 1);
                     }
-                    umma_commit(b_empty + ring.idx);         // B tile (and its column vectors) may be overwritten
-                    umma_commit(w_done + slot.idx);          // score buffer may be overwritten
+                    umma_commit(b_empty + 8 * ring.idx);         // B tile (and its column vectors) may be overwritten
+                    umma_commit(w_done + 8 * slot.idx);          // score buffer may be overwritten
                 }
                 __syncwarp();
             }
@@ -894,7 +896,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         const int quarter = warp & 3;                         // TMEM lane quarter this warp may touch
         const int row_in_block = quarter * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-        const uint32_t cv_base = smem_u32(smem_cv);
+        const uint32_t cv_base = smem_base + L::kOffCv;
         const int n = static_cast<int>(t_end - t_begin);
         // loop invariants out of the constant bank, once
         Hot h;
@@ -978,9 +980,9 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 // same TMEM buffer, so every barrier has a single waiter that observes all of its phases in order
                 // (a parity wait is only meaningful when the waiter is at most one phase away from the barrier).
                 if (tracing) trace_event(p, 2 + wg, it, 0);
-                mbar_wait(s_full + slot, slot_par, 300);
+                mbar_wait(s_full + 8 * slot, slot_par, 300);
                 if (tracing) trace_event(p, 2 + wg, it, 1);
-                if constexpr (kBackward) mbar_wait(b_full + stage, stage_par, 301);   // colvec visibility
+                if constexpr (kBackward) mbar_wait(b_full + 8 * stage, stage_par, 301);   // colvec visibility
                 tc_fence_after_sync();
 
                 // This warpgroup's 64 columns in four 16-column chunks; the TMEM load of chunk k+1 is in flight while
@@ -1057,11 +1059,11 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 if (it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
                 if constexpr (!kBackward) {
                     tc_fence_before_sync();
-                    mbar_arrive(s_free + slot);
+                    mbar_arrive(s_free + 8 * slot);
                 } else {
                     tmem_st_wait();
                     tc_fence_before_sync();
-                    mbar_arrive(w_full + slot);
+                    mbar_arrive(w_full + 8 * slot);
                 }
                 if (tracing) trace_event(p, 2 + wg, it, 2);
                 slot += 2;
@@ -1121,8 +1123,8 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 const int st0 = fpos & (S - 1), par0 = (fpos >> kLogS) & 1;
                 const int st1 = (fpos + 1) & (S - 1), par1 = ((fpos + 1) >> kLogS) & 1;
                 mbar_wait(acc_full, seg & 1, 302);            // every gradient MMA of the segment has completed
-                mbar_wait(b_full + st0, par0, 303);           // the two staging stages are ours
-                mbar_wait(b_full + st1, par1, 304);
+                mbar_wait(b_full + 8 * st0, par0, 303);           // the two staging stages are ours
+                mbar_wait(b_full + 8 * st1, par1, 304);
                 tc_fence_after_sync();
 #pragma unroll 1
                 for (int q = wg; q < D / 32; q += kNumSoftmaxWG) {
@@ -1131,7 +1133,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                     tmem_ld_wait();
                     tmem_st32_fill(tmem_base + lane_addr + kTmemAcc + q * 32, 0u);     // zero for the next segment
                     const int stage = (q / kBoxesPerStage) == 0 ? st0 : st1;
-                    const uint32_t row_addr = smem_u32(smem_b + stage * L::kTileBytes + (q % kBoxesPerStage) * kAtomBytes) +
+                    const uint32_t row_addr = sb_addr + stage * L::kTileBytes + (q % kBoxesPerStage) * kAtomBytes +
                                               row_in_block * 128;
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
@@ -1146,14 +1148,14 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
 #pragma unroll 1
                     for (int q = 0; q < D / 32; ++q) {
                         const int stage = (q / kBoxesPerStage) == 0 ? st0 : st1;
-                        tma_reduce_add_2d(&tmap_dacc, smem_b + stage * L::kTileBytes + (q % kBoxesPerStage) * kAtomBytes,
+                        tma_reduce_add_2d(&tmap_dacc, sb_addr + stage * L::kTileBytes + (q % kBoxesPerStage) * kAtomBytes,
                                           q * 32, rb * kBlockM);
                     }
                     bulk_commit_group();
                     if (idx0 + seg_len == n) bulk_wait_group0();   // last segment: the adds are performed before exit
                     else bulk_wait_group_read0();                  // staging space may be reused
-                    mbar_arrive(b_empty + st0);
-                    mbar_arrive(b_empty + st1);
+                    mbar_arrive(b_empty + 8 * st0);
+                    mbar_arrive(b_empty + 8 * st1);
                 }
                 __syncwarp();
             }

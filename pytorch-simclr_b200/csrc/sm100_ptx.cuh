@@ -60,24 +60,25 @@ SIMCLR_DEVICE void ktrace_end(unsigned long long* ktrace, int id) {
 // ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
-SIMCLR_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+// Barriers are addressed by their 32-bit shared-space address (`smem_u32(ptr)` once per kernel, not per call: the
+// generic -> shared conversion is a chain of S2UR / ULEA / ULOP3 that otherwise sits in front of every wait).
+SIMCLR_DEVICE void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 
 SIMCLR_DEVICE void mbar_fence_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
-SIMCLR_DEVICE void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+SIMCLR_DEVICE void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-SIMCLR_DEVICE void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
+SIMCLR_DEVICE void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 
-SIMCLR_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+SIMCLR_DEVICE bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
         "{\n\t"
@@ -86,23 +87,51 @@ SIMCLR_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n\t"
         "}\n"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+// try_wait that lets the hardware park the thread for up to `ns` nanoseconds before it reports "not yet"
+SIMCLR_DEVICE bool mbar_try_wait_parked(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(ns)
         : "memory");
     return done != 0;
 }
 
-// Blocking wait with a watchdog.  `tag` identifies the barrier in the trap message.
-SIMCLR_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+// Blocking wait with a watchdog.  `tag` identifies the barrier in the trap message.  The spin loop is three
+// instructions (a waiting warp shares its sub-partition's issue slots with the softmax warps: ten-instruction spins of
+// five control warps were a quarter of all instructions the backward kernel executed); the clock is only read every
+// 4096 polls.
+SIMCLR_DEVICE void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > SIMCLR_WATCHDOG_CYCLES) {
-            printf("[simclr_b200] mbarrier watchdog: block %d thread %d tag %d parity %u\n", (int)blockIdx.x,
-                   (int)threadIdx.x, tag, parity);
-            __trap();
+    long long t0 = 0;
+    uint32_t polls = 0;
+    while (!mbar_try_wait_parked(bar, parity, 2000u)) {
+        if ((++polls & 4095u) == 0u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > SIMCLR_WATCHDOG_CYCLES) {
+                printf("[simclr_b200] mbarrier watchdog: block %d thread %d tag %d parity %u\n", (int)blockIdx.x,
+                       (int)threadIdx.x, tag, parity);
+                __trap();
+            }
         }
     }
 }
+
+// pointer forms (self-test and probe kernels)
+SIMCLR_DEVICE void mbar_init(uint64_t* bar, uint32_t count) { mbar_init(smem_u32(bar), count); }
+SIMCLR_DEVICE void mbar_arrive(uint64_t* bar) { mbar_arrive(smem_u32(bar)); }
+SIMCLR_DEVICE void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) { mbar_arrive_expect_tx(smem_u32(bar), bytes); }
+SIMCLR_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity, int tag) { mbar_wait(smem_u32(bar), parity, tag); }
 
 // ---------------------------------------------------------------------------------------------
 // Proxy fences
@@ -119,26 +148,29 @@ SIMCLR_DEVICE void tma_prefetch_desc(const void* tmap) {
 }
 
 // 2-D tiled load: box lands at `smem_dst`, completes `bytes` on `bar`.  x = inner (contiguous) coord.
-SIMCLR_DEVICE void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int32_t x, int32_t y) {
+SIMCLR_DEVICE void tma_load_2d(uint32_t smem_dst, const void* tmap, uint32_t bar, int32_t x, int32_t y) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(x), "r"(y)
         : "memory");
+}
+SIMCLR_DEVICE void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int32_t x, int32_t y) {
+    tma_load_2d(smem_u32(smem_dst), tmap, smem_u32(bar), x, y);
 }
 
 // 1-D bulk copy global -> shared (16-byte aligned, size multiple of 16).
-SIMCLR_DEVICE void bulk_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+SIMCLR_DEVICE void bulk_load_1d(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes), "r"(smem_u32(bar))
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes), "r"(bar)
         : "memory");
 }
 
 // 2-D tiled reduction shared -> global: every element of the box is ADDED to the tensor (element type and swizzle
 // come from the tensor map).  Completion is tracked by the thread's bulk async-group.
-SIMCLR_DEVICE void tma_reduce_add_2d(const void* tmap, const void* smem_src, int32_t x, int32_t y) {
+SIMCLR_DEVICE void tma_reduce_add_2d(const void* tmap, uint32_t smem_src, int32_t x, int32_t y) {
     asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(x), "r"(y)
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(x), "r"(y)
                  : "memory");
 }
 SIMCLR_DEVICE void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -218,10 +250,10 @@ SIMCLR_DEVICE void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, ui
 }
 // Arrive on `bar` once every previously issued MMA of this thread has completed (implies
 // tcgen05.fence::before_thread_sync).
-SIMCLR_DEVICE void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
+SIMCLR_DEVICE void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+SIMCLR_DEVICE void umma_commit(uint64_t* bar) { umma_commit(smem_u32(bar)); }
 
 // ---------------------------------------------------------------------------------------------
 // tcgen05: TMEM <-> registers.  Shape 32x32b: lane i of the warp owns TMEM lane (warp%4)*32 + i and

@@ -96,7 +96,7 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
         ws_bytes = lib.simclr_forward_workspace_bytes(loss_kind, b, b_global_hint, d)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         check(lib.simclr_prepare(loss_kind, x1.data_ptr(), x2.data_ptr(), b, d, code, int(bool(normalize)),
-                                 operand.data_ptr(), rowvec[0].data_ptr(), rowvec[1].data_ptr(), ws.data_ptr(), stream),
+                                 float(temperature), operand.data_ptr(), rowvec[0].data_ptr(), rowvec[1].data_ptr(), ws.data_ptr(), stream),
               "simclr_prepare")
         if gather is None:
             operand_cols, b_global, row_offset = operand, b, 0

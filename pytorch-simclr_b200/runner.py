@@ -51,7 +51,8 @@ class ContrastiveStep:
     def forward(self) -> None:
         lib, st = self.lib, self._stream()
         check(lib.simclr_prepare(self.kind, self.x1.data_ptr(), self.x2.data_ptr(), self.b, self.d, self.code,
-                                 int(self.normalize), self.operand.data_ptr(), self.rowvec[0].data_ptr(),
+                                 int(self.normalize), self.temperature, self.operand.data_ptr(),
+                                 self.rowvec[0].data_ptr(),
                                  self.rowvec[1].data_ptr(), self.fwd_ws.data_ptr(), st), "simclr_prepare")
         check(lib.simclr_forward(self.kind, self.operand.data_ptr(), self.operand.data_ptr(), self.b, self.b, 0, self.d,
                                  self.temperature, int(self.normalize), self.rowvec[1].data_ptr(), None,
