@@ -6,7 +6,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsimclr_b200.so")
+# SIMCLR_B200_LIB selects another build of the same library (kernel experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("SIMCLR_B200_LIB") or os.path.join(_HERE, "lib", "libsimclr_b200.so")
 
 LOSS_NTXENT = 0
 LOSS_MODIFIED = 1

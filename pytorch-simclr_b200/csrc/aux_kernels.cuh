@@ -29,6 +29,8 @@ __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x
                                __nv_bfloat16* __restrict__ operand, float* __restrict__ inv_norm,
                                float* __restrict__ pos_dot, unsigned int* __restrict__ zero_ptr, int zero_words,
                                unsigned long long* ktrace) {
+    pdl_launch_dependents();
+    pdl_wait();
     ktrace_begin(ktrace, 0);
     struct End { unsigned long long* k; __device__ ~End() { ktrace_end(k, 0); } } end_guard{ktrace};
     if (zero_ptr != nullptr && blockIdx.x == 0)
@@ -115,6 +117,8 @@ __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x
 __global__ void backward_prepare_kernel(AuxParams a, const float* __restrict__ lse2_cols,
                                         const float* __restrict__ col_scale, float* __restrict__ colvec,
                                         float4* __restrict__ dacc4, size_t dacc_vec4, unsigned long long* ktrace) {
+    pdl_launch_dependents();
+    pdl_wait();
     ktrace_begin(ktrace, 2);
     const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -140,6 +144,8 @@ template <int kLoss>
 __global__ void __launch_bounds__(kBlockM) forward_finalize_kernel(const TileParams p) {
     __shared__ float red[16];
     __shared__ int flags[4];
+    pdl_launch_dependents();
+    pdl_wait();
     ktrace_begin(p.ktrace, 4);
     forward_finalize_rowblock<kLoss>(p, blockIdx.x, threadIdx.x, red, flags);
     ktrace_end(p.ktrace, 4);
@@ -152,6 +158,8 @@ __global__ void __launch_bounds__(kBlockM) forward_finalize_kernel(const TilePar
 constexpr int kBwdFinBlocksPerRowBlock = 8;
 template <int D, int kLoss>
 __global__ void __launch_bounds__(512) backward_finalize_kernel(const TileParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     ktrace_begin(p.ktrace, 5);
     const int rb = blockIdx.x / kBwdFinBlocksPerRowBlock;
     const int sub = blockIdx.x % kBwdFinBlocksPerRowBlock;

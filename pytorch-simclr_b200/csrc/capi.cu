@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <utility>
 
 #include "../../include/simclr_b200.h"
 #include "aux_kernels.cuh"
@@ -51,6 +52,24 @@ int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, int64_t d
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? SIMCLR_OK : SIMCLR_ERR_TENSOR_MAP;
+}
+
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait() in sm100_ptx.cuh): the kernel may be
+// staged while its predecessor in the stream is still running.  Works in eager streams and under stream capture
+// (the graph records a programmatic dependency edge).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
 }
 
 struct DeviceInfo {
@@ -200,8 +219,8 @@ int launch_tile(const CUtensorMap& rows, const CUtensorMap& cols, const CUtensor
         if (e != cudaSuccess) return static_cast<int>(e);
         configured[dev & 63] = true;
     }
-    kern<<<grid, kBackward ? kThreadsBackward : kThreadsForward, SmemLayout<D>::kDynamicBytes, st>>>(rows, cols, dacc, p);
-    return static_cast<int>(cudaGetLastError());
+    return static_cast<int>(launch_pdl(kern, dim3(grid), dim3(kBackward ? kThreadsBackward : kThreadsForward),
+                                       SmemLayout<D>::kDynamicBytes, st, rows, cols, dacc, p));
 }
 
 // kConst = p.const_shift (bounded scores: one exponential per element, no running maximum).  The forward kernel of
@@ -350,8 +369,9 @@ int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t
     const int warps = 8;
     const int blocks = static_cast<int>((g.bl_pad + warps - 1) / warps);
     auto* op = static_cast<__nv_bfloat16*>(operand);
+    cudaError_t launch_rc = cudaSuccess;
 #define SIMCLR_PREP(T, LOSS) \
-    prepare_kernel<T, LOSS><<<blocks, warps * 32, 0, st>>>(static_cast<const T*>(x_batch1), static_cast<const T*>(x_batch2), a, op, inv_norm, pos_dot, zero_ptr, zero_words, g_ktrace_ptr)
+    launch_rc = launch_pdl(prepare_kernel<T, LOSS>, dim3(blocks), dim3(warps * 32), 0, st, static_cast<const T*>(x_batch1), static_cast<const T*>(x_batch2), a, op, inv_norm, pos_dot, zero_ptr, zero_words, g_ktrace_ptr)
     if (loss == SIMCLR_LOSS_NTXENT) {
         if (in_dtype == SIMCLR_DTYPE_F32) SIMCLR_PREP(float, kNtXent);
         else SIMCLR_PREP(__nv_bfloat16, kNtXent);
@@ -360,7 +380,7 @@ int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t
         else SIMCLR_PREP(__nv_bfloat16, kModified);
     }
 #undef SIMCLR_PREP
-    return static_cast<int>(cudaGetLastError());
+    return static_cast<int>(launch_rc);
 }
 
 int simclr_forward(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
@@ -397,9 +417,10 @@ int simclr_forward(int loss, const void* operand_rows, const void* operand_cols,
     p.loss_out = loss_out;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if ((rc = dispatch_tile<false>(loss, g.d_pad, map_rows, map_cols, map_rows, p, g.grid, st))) return rc;
-    if (loss == SIMCLR_LOSS_NTXENT) forward_finalize_kernel<kNtXent><<<g.n_row_blocks, kBlockM, 0, st>>>(p);
-    else forward_finalize_kernel<kModified><<<g.n_row_blocks, kBlockM, 0, st>>>(p);
-    return static_cast<int>(cudaGetLastError());
+    cudaError_t e;
+    if (loss == SIMCLR_LOSS_NTXENT) e = launch_pdl(forward_finalize_kernel<kNtXent>, dim3(g.n_row_blocks), dim3(kBlockM), 0, st, p);
+    else e = launch_pdl(forward_finalize_kernel<kModified>, dim3(g.n_row_blocks), dim3(kBlockM), 0, st, p);
+    return static_cast<int>(e);
 }
 
 int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t b_global,
@@ -430,9 +451,10 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
     AuxParams a = make_aux(g, s, b_local, b_global, row_offset, d, normalize);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-    backward_prepare_kernel<<<device_info().sm_count * 2, 256, 0, st>>>(
-        a, lse2_cols, col_scale, w.colvec, reinterpret_cast<float4*>(w.dacc), w.dacc_floats / 4, g_ktrace_ptr);
-    if ((rc = static_cast<int>(cudaGetLastError()))) return rc;
+    if ((rc = static_cast<int>(launch_pdl(backward_prepare_kernel, dim3(device_info().sm_count * 2), dim3(256), 0, st, a,
+                                          lse2_cols, col_scale, w.colvec, reinterpret_cast<float4*>(w.dacc),
+                                          w.dacc_floats / 4, g_ktrace_ptr))))
+        return rc;
 
     TileParams p = make_tile_params(g, s, b_local, b_global, row_offset);
     p.d = static_cast<int>(d);
@@ -449,10 +471,11 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
     p.col_scale = col_scale;
     p.grad_out = grad_out;
     if ((rc = dispatch_tile<true>(loss, g.d_pad, map_rows, map_cols, map_dacc, p, g.grid, st))) return rc;
+    cudaError_t fin_rc = cudaSuccess;
 #define SIMCLR_BFIN(DV)                                                                                  \
     case DV:                                                                                             \
-        if (loss == SIMCLR_LOSS_NTXENT) backward_finalize_kernel<DV, kNtXent><<<g.n_row_blocks * kBwdFinBlocksPerRowBlock, 512, 0, st>>>(p); \
-        else backward_finalize_kernel<DV, kModified><<<g.n_row_blocks * kBwdFinBlocksPerRowBlock, 512, 0, st>>>(p); \
+        if (loss == SIMCLR_LOSS_NTXENT) fin_rc = launch_pdl(backward_finalize_kernel<DV, kNtXent>, dim3(g.n_row_blocks * kBwdFinBlocksPerRowBlock), dim3(512), 0, st, p); \
+        else fin_rc = launch_pdl(backward_finalize_kernel<DV, kModified>, dim3(g.n_row_blocks * kBwdFinBlocksPerRowBlock), dim3(512), 0, st, p); \
         break;
     switch (g.d_pad) {
         SIMCLR_BFIN(64)
@@ -460,7 +483,7 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
         SIMCLR_BFIN(256)
     }
 #undef SIMCLR_BFIN
-    return static_cast<int>(cudaGetLastError());
+    return static_cast<int>(fin_rc);
 }
 
 int simclr_debug_set_trace(void* device_buffer, int cta) {

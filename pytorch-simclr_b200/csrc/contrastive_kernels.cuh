@@ -26,6 +26,10 @@
 //   warp 16     TMA producer (row-block tile once per segment, column tiles through an mbarrier ring)
 //   warps 17,18 UMMA issuers for the score tiles (one elected lane each; warp 18 also owns the TMEM allocation)
 //   warps 19,20 backward only: UMMA issuers for the gradient MMAs
+//   warps 20-23 backward only: flush warpgroup (one warp per TMEM lane quarter; warp 20 doubles as an issuer): at the
+//               end of a segment it drains the gradient accumulator TMEM -> 128B-swizzled fp32 boxes in two ring stages
+//               the producer hands over -> TMA reduce-add into dacc, and re-zeroes the accumulator.  The softmax
+//               warps never stop at a segment boundary.
 // A tcgen05.mma blocks its issuing thread while it executes and the issuer's barrier waits cost several hundred
 // cycles per tile, so ONE issuer keeps the tensor pipe busy only ~35 % of the time (profiles/r01_notes.md).  Issuer k of
 // a kind owns the ring stages with (stage & 1) == k -- the ring size is even and the flush borrows two stages, so a
@@ -59,11 +63,17 @@ constexpr int kScoreWarp0 = kNumSoftmaxWarps + 1;       // warps 17, 18
 constexpr int kAllocWarp = kScoreWarp0 + 1;             // warp 18 allocates TMEM before it starts issuing
 constexpr int kGradWarp0 = kScoreWarp0 + kNumIssuers;   // warps 19, 20 (backward)
 constexpr int kThreadsForward = 32 * (kNumSoftmaxWarps + 4);                    // 640 (warp 19 idles)
-constexpr int kThreadsBackward = 32 * (kNumSoftmaxWarps + 1 + 2 * kNumIssuers); // 672
+constexpr int kFlushWarp0 = kGradWarp0 + kNumIssuers - 1;   // warps 20..23: TMEM lane quarters 0..3
+constexpr int kFlushIssueWarp = kFlushWarp0 + 1;            // warp 21 issues the TMA reductions
+constexpr int kThreadsBackward = 32 * (kFlushWarp0 + 4);    // 768 (registers are allocated in units of four warps anyway)
+constexpr int kFlushBar = 4;                                // named barrier of the flush warpgroup
 constexpr int kMaxScoreBufs = 4;
 constexpr int kNumPairs = kNumSoftmaxWG / 2;             // a tile is shared by a pair of warpgroups
 constexpr int kMaxSlots = kMaxScoreBufs * kNumPairs;      // barrier slots for the score / W hand-off
 constexpr int kTmemCols = 512;
+#ifndef SIMCLR_TOKEN_CHUNK
+#define SIMCLR_TOKEN_CHUNK 3          // chunk (0..3) before which a pair passes the ping-pong token on; 4 = after the tile
+#endif
 constexpr int kTokenBar0 = 2;         // named barriers 2, 3: ping-pong tokens of the two softmax pairs
 constexpr int kFwdFields = 5;         // per-row partial: sum, run-max, max-preceding, max-following, pos(mma)
 constexpr float kNegBig = -3.0e38f;   // finite stand-in for -inf
@@ -538,6 +548,9 @@ SIMCLR_DEVICE void backward_finalize_rowblock(const TileParams& p, int rb, int w
     const void* x_other = vr == 0 ? p.x2 : p.x1;
     void* g_self = vr == 0 ? p.g1 : p.g2;
     constexpr int kPerLane = D / 32;
+    const bool vec4 = kPerLane == 4 && p.d == D && !p.in_bf16 &&
+                      ((reinterpret_cast<uintptr_t>(p.x1) | reinterpret_cast<uintptr_t>(p.x2) |
+                        reinterpret_cast<uintptr_t>(p.g1) | reinterpret_cast<uintptr_t>(p.g2)) & 15u) == 0;
     for (int r = warp; r < kBlockM; r += nwarps) {
         const int img = img0 + r;
         if (img >= p.b_loc) break;
@@ -568,15 +581,33 @@ SIMCLR_DEVICE void backward_finalize_rowblock(const TileParams& p, int rb, int w
         const float mul_o = scaled ? (inv_o == kInvNormClamped ? 1.f / kNormEps : inv_o) : 1.f;
         float raw[kPerLane], hs[kPerLane], dv[kPerLane];
         float t = 0.f;
+        // Lane l owns the kPerLane consecutive columns [l * kPerLane, (l + 1) * kPerLane).  `vec4`: fp32 rows of exactly
+        // D = 128 columns at 16-byte aligned addresses move as one float4 per array and lane.
+        float xs[kPerLane], xo[kPerLane], ac[kPerLane];
+        if (vec4) {
+            if constexpr (kPerLane == 4) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(x_self) + static_cast<size_t>(img) * D) + lane);
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(x_other) + static_cast<size_t>(img) * D) + lane);
+                const float4 c4 = __ldcg(reinterpret_cast<const float4*>(p.dacc + static_cast<size_t>(slot_self) * D) + lane);
+                xs[0] = a4.x; xs[1] = a4.y; xs[2] = a4.z; xs[3] = a4.w;
+                xo[0] = b4.x; xo[1] = b4.y; xo[2] = b4.z; xo[3] = b4.w;
+                ac[0] = c4.x; ac[1] = c4.y; ac[2] = c4.z; ac[3] = c4.w;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < kPerLane; ++u) {
+                const int k = lane * kPerLane + u;
+                const bool in = k < p.d;
+                xs[u] = in ? load_elem(x_self, static_cast<size_t>(img) * p.d + k, p.in_bf16) : 0.f;
+                xo[u] = in ? load_elem(x_other, static_cast<size_t>(img) * p.d + k, p.in_bf16) : 0.f;
+                ac[u] = __ldcg(p.dacc + static_cast<size_t>(slot_self) * D + k);
+            }
+        }
 #pragma unroll
         for (int u = 0; u < kPerLane; ++u) {
-            const int k = lane + 32 * u;
+            const int k = lane * kPerLane + u;
             const bool in = k < p.d;
-            float es = 0.f, eo = 0.f;
-            if (in) {
-                es = load_elem(x_self, static_cast<size_t>(img) * p.d + k, p.in_bf16);
-                eo = load_elem(x_other, static_cast<size_t>(img) * p.d + k, p.in_bf16);
-            }
+            float es = xs[u], eo = xo[u];
             raw[u] = es;
             if constexpr (kLoss == kModified) {
                 es = in ? softplus_beta(es) : 0.f;
@@ -584,25 +615,33 @@ SIMCLR_DEVICE void backward_finalize_rowblock(const TileParams& p, int rb, int w
             }
             hs[u] = es * mul_s;
             const float ho = eo * mul_o;
-            const float acc = __ldcg(p.dacc + static_cast<size_t>(slot_self) * D + k);
-            dv[u] = (acc * p.acc_scale + coef * ho) * outer;
+            dv[u] = (ac[u] * p.acc_scale + coef * ho) * outer;
             t = fmaf(dv[u], hs[u], t);
         }
         t = warp_sum(t);
+        float out[kPerLane];
 #pragma unroll
         for (int u = 0; u < kPerLane; ++u) {
-            const int k = lane + 32 * u;
-            if (k < p.d) {
-                float o = dv[u];
-                if constexpr (kLoss == kNtXent) {
-                    // d/dz of z / max(||z||, eps): projection unless the clamp was active
-                    if (p.normalize) o = (inv_s == kInvNormClamped) ? o / kNormEps : (o - hs[u] * t) * inv_s;
-                } else {
-                    // L1 normalisation of a positive vector, then softplus'(x) = sigmoid(beta x)
-                    o = (inv_s == kInvNormClamped) ? o / kNormEps : (o - t) * inv_s;
-                    o *= softplus_beta_grad(raw[u]);
-                }
-                store_elem(g_self, static_cast<size_t>(img) * p.d + k, p.in_bf16, o);
+            float o = dv[u];
+            if constexpr (kLoss == kNtXent) {
+                // d/dz of z / max(||z||, eps): projection unless the clamp was active
+                if (p.normalize) o = (inv_s == kInvNormClamped) ? o / kNormEps : (o - hs[u] * t) * inv_s;
+            } else {
+                // L1 normalisation of a positive vector, then softplus'(x) = sigmoid(beta x)
+                o = (inv_s == kInvNormClamped) ? o / kNormEps : (o - t) * inv_s;
+                o *= softplus_beta_grad(raw[u]);
+            }
+            out[u] = o;
+        }
+        if (vec4) {
+            if constexpr (kPerLane == 4)
+                reinterpret_cast<float4*>(static_cast<float*>(g_self) + static_cast<size_t>(img) * D)[lane] =
+                    make_float4(out[0], out[1], out[2], out[3]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < kPerLane; ++u) {
+                const int k = lane * kPerLane + u;
+                if (k < p.d) store_elem(g_self, static_cast<size_t>(img) * p.d + k, p.in_bf16, out[u]);
             }
         }
     }
@@ -700,11 +739,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
     const int nct = p.n_col_tiles;
     const int blocks_per_view = p.bl_pad / kBlockM;
 
-    ktrace_begin(p.ktrace, kBackward ? 3 : 1);
-    if (threadIdx.x == 0) {
-        cta_stamp(p, 0);
-        if (p.ktrace != nullptr) p.ktrace[64 + blockIdx.x * 8 + 6] = clock64();
-    }
+    pdl_launch_dependents();
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_rows);
         tma_prefetch_desc(&tmap_cols);
@@ -714,7 +749,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         mbar_init(a_full, 1);
         mbar_init(a_empty, kNumIssuers);
         mbar_init(acc_full, kNumIssuers);
-        mbar_init(acc_empty, 128 * kNumSoftmaxWG);
+        mbar_init(acc_empty, 128);
         for (int i = 0; i < S; ++i) {
             mbar_init(b_full + 8 * i, 1);
             mbar_init(b_empty + 8 * i, 1);
@@ -735,6 +770,13 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the predecessor's tail
+    pdl_wait();
+    ktrace_begin(p.ktrace, kBackward ? 3 : 1);
+    if (threadIdx.x == 0) {
+        cta_stamp(p, 0);
+        if (p.ktrace != nullptr) p.ktrace[64 + blockIdx.x * 8 + 6] = clock64();
+    }
 
     if (warp == kProducerWarp) {
         // ================================ TMA producer ================================
@@ -842,51 +884,110 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 }
             }
         }
-    } else if (kBackward && warp >= kGradWarp0 && warp < kGradWarp0 + kNumIssuers) {
-        // ================================ UMMA issuers: gradient MMAs ================================
+    } else if (kBackward && warp >= kGradWarp0 && warp < kFlushWarp0 + 4) {
+        // ================================ UMMA issuers: gradient MMAs / flush warpgroup ================================
         // acc += W[buf] (TMEM, 128 x 128 bf16) * B_stage (MN-major: K = column index).  The accumulator is zeroed by
-        // the softmax warps (at start and after every flush), so every MMA accumulates and the two issuers need no
+        // the flush warpgroup (at start and after every flush), so every MMA accumulates and the two issuers need no
         // mutual ordering.
+        const bool issuer = warp < kGradWarp0 + kNumIssuers;
+        const bool flusher = warp >= kFlushWarp0;
         const int me = warp - kGradWarp0;
+        const int quarter = warp & 3;
+        const int row_in_block = quarter * 32 + lane;
+        const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
         const uint32_t b_addr0 = sb_addr;
+        constexpr int kLogS = S == 2 ? 1 : (S == 4 ? 2 : 3);
+
+        if (flusher) {
+            // zero the gradient accumulator (TMEM is not cleared by the allocation); phase 0 of acc_empty
+#pragma unroll 1
+            for (int q = 0; q < D / 32; ++q) tmem_st32_fill(tmem_base + lane_addr + kTmemAcc + q * 32, 0u);
+            tmem_st_wait();
+            tc_fence_before_sync();
+            mbar_arrive(acc_empty);
+        }
+
         RingPos<S> ring;
         RingPos<kSlots> slot;
         int buf = 0;
         int seg = 0;
         for (TileWalker w(t_begin, t_end, nct); w.valid(); w.next()) {
             const int idx = w.idx;
-            // phase 0 of acc_empty = initial zeroing, phase s = flush (and re-zeroing) of segment s-1
-            if (w.seg_first()) mbar_wait(acc_empty, seg & 1, 203);
-            if ((ring.idx & 1) == me) {
-                if (lane == 0) trace_event(p, 1, idx, 2);
-                mbar_wait(w_full + 8 * slot.idx, slot.par, 204);
-                tc_fence_after_sync();
-                if (lane == 0) trace_event(p, 1, idx, 3);
-                if (elect_one()) {
-                    const uint32_t b_addr = b_addr0 + ring.idx * L::kTileBytes;
+            if (issuer) {
+                // phase 0 of acc_empty = initial zeroing, phase s = flush (and re-zeroing) of segment s-1
+                if (w.seg_first()) mbar_wait(acc_empty, seg & 1, 203);
+                if ((ring.idx & 1) == me) {
+                    if (lane == 0) trace_event(p, 1, idx, 2);
+                    mbar_wait(w_full + 8 * slot.idx, slot.par, 204);
+                    tc_fence_after_sync();
+                    if (lane == 0) trace_event(p, 1, idx, 3);
+                    if (elect_one()) {
+                        const uint32_t b_addr = b_addr0 + ring.idx * L::kTileBytes;
 #pragma unroll
-                    for (int kc = 0; kc < kBlockN / 16; ++kc) {
-                        // W of column half h (K chunks 4h..4h+3) sits at columns [64h, 64h+32) of the buffer
-                        umma_ts(tmem_base + kTmemAcc, tmem_base + buf * kBlockN + (kc >> 2) * 64 + (kc & 3) * 8,
-                                make_smem_desc(b_addr + kc * 2048, kAtomBytes, 1024), kIdescGrad, 1);
+                        for (int kc = 0; kc < kBlockN / 16; ++kc) {
+                            // W of column half h (K chunks 4h..4h+3) sits at columns [64h, 64h+32) of the buffer
+                            umma_ts(tmem_base + kTmemAcc, tmem_base + buf * kBlockN + (kc >> 2) * 64 + (kc & 3) * 8,
+                                    make_smem_desc(b_addr + kc * 2048, kAtomBytes, 1024), kIdescGrad, 1);
+                        }
+                        umma_commit(b_empty + 8 * ring.idx);     // B tile (and its column vectors) may be overwritten
+                        umma_commit(w_done + 8 * slot.idx);      // score buffer may be overwritten
                     }
-                    umma_commit(b_empty + 8 * ring.idx);         // B tile (and its column vectors) may be overwritten
-                    umma_commit(w_done + 8 * slot.idx);          // score buffer may be overwritten
+                    __syncwarp();
                 }
-                __syncwarp();
-            }
-            if (w.seg_last()) {
-                if (elect_one()) umma_commit(acc_full);      // both issuers: count 2
-                __syncwarp();
-                ++seg;
+                if (w.seg_last()) {
+                    if (elect_one()) umma_commit(acc_full);      // both issuers: count 2
+                    __syncwarp();
+                }
             }
             ring.advance();
             slot.advance();
             if (++buf == NB) buf = 0;
-            if (w.seg_last()) {                              // flush positions
-                ring.advance();
-                ring.advance();
+            if (!w.seg_last()) continue;
+
+            // ---- end of segment: ring positions ring.idx, ring.idx + 1 are the flush's staging stages ----
+            if (flusher) {
+                RingPos<S> st1 = ring;
+                st1.advance();
+                mbar_wait(acc_full, seg & 1, 302);            // every gradient MMA of the segment has completed
+                mbar_wait(b_full + 8 * ring.idx, ring.par, 303);   // the two staging stages are ours
+                mbar_wait(b_full + 8 * st1.idx, st1.par, 304);
+                tc_fence_after_sync();
+#pragma unroll 1
+                for (int q = 0; q < D / 32; ++q) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + lane_addr + kTmemAcc + q * 32, r);
+                    tmem_ld_wait();
+                    tmem_st32_fill(tmem_base + lane_addr + kTmemAcc + q * 32, 0u);     // zero for the next segment
+                    const int stage = (q / kBoxesPerStage) == 0 ? ring.idx : st1.idx;
+                    const uint32_t row_addr = sb_addr + stage * L::kTileBytes + (q % kBoxesPerStage) * kAtomBytes +
+                                              row_in_block * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        sts_v4(row_addr + ((j ^ (row_in_block & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                }
+                tmem_st_wait();
+                tc_fence_before_sync();
+                mbar_arrive(acc_empty);                       // the next segment's gradient MMAs may start
+                fence_proxy_async_smem();                     // generic-proxy stores -> visible to the TMA engine
+                named_bar_sync(kFlushBar, 128);
+                if (warp == kFlushIssueWarp && elect_one()) {
+#pragma unroll 1
+                    for (int q = 0; q < D / 32; ++q) {
+                        const int stage = (q / kBoxesPerStage) == 0 ? ring.idx : st1.idx;
+                        tma_reduce_add_2d(&tmap_dacc, sb_addr + stage * L::kTileBytes + (q % kBoxesPerStage) * kAtomBytes,
+                                          q * 32, w.rb * kBlockM);
+                    }
+                    bulk_commit_group();
+                    if (idx == w.n - 1) bulk_wait_group0();    // last segment: the adds are performed before exit
+                    else bulk_wait_group_read0();              // staging space may be reused
+                    mbar_arrive(b_empty + 8 * ring.idx);
+                    mbar_arrive(b_empty + 8 * st1.idx);
+                }
+                __syncwarp();
             }
+            ++seg;
+            ring.advance();
+            ring.advance();
         }
     } else if (warp < kNumSoftmaxWarps) {
         // ================================ softmax warpgroups ================================
@@ -910,15 +1011,6 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         const bool tracing = p.trace != nullptr && static_cast<int>(blockIdx.x) == p.trace_cta && quarter == 0 && lane == 0;
         constexpr int kLogS = S == 2 ? 1 : (S == 4 ? 2 : 3);
         static_assert((1 << kLogS) == S, "ring size must be 2, 4 or 8");
-
-        if constexpr (kBackward) {
-            // zero the gradient accumulator (TMEM is not cleared by the allocation)
-#pragma unroll 1
-            for (int q = wg; q < D / 32; q += kNumSoftmaxWG) tmem_st32_fill(tmem_base + lane_addr + kTmemAcc + q * 32, 0u);
-            tmem_st_wait();
-            tc_fence_before_sync();
-            mbar_arrive(acc_empty);
-        }
 
         // Segments (runs of tiles sharing a row block) -> the tiles of this warpgroup's pair inside each segment.
         // CTA tile `it` sits at ring position it (+ 2 per finished segment in the backward kernel: the flush
@@ -1009,6 +1101,9 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         uint32_t (&nxt)[kChunk] = (k & 1) ? ra : rb2;
                         tmem_ld_wait16(cur);
                         if (k < 3) tmem_ld16(t0 + (k + 1) * kChunk, nxt);
+                        // hand the token over one chunk early: the other pair's first chunk fills the pipes while this
+                        // pair drains its last one (covers the bar.arrive -> bar.sync wake-up latency)
+                        if (k == SIMCLR_TOKEN_CHUNK && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
                         if constexpr (!kBackward) {
                             fwd_chunk_fast<kLoss, kConst>(h, cur, cm, fs);
                         } else {
@@ -1056,7 +1151,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         process(rb2, 2 * kk + 1);
                     }
                 }
-                if (it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
+                if ((tile_special || SIMCLR_TOKEN_CHUNK > 3) && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
                 if constexpr (!kBackward) {
                     tc_fence_before_sync();
                     mbar_arrive(s_free + 8 * slot);
@@ -1116,48 +1211,6 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                     __stcg(dst + 3 * kBlockM, mf);
                     __stcg(dst + 4 * kBlockM, pm);
                 }
-            } else {
-                // ---- flush the gradient accumulator: TMEM -> registers -> 128B-swizzled fp32 boxes in the two ring
-                // stages the producer handed over -> ONE TMA reduce-add per 128 x 32 box into dacc ----
-                const int fpos = idx0 + seg_len + pos_off;    // ring positions fpos, fpos + 1
-                const int st0 = fpos & (S - 1), par0 = (fpos >> kLogS) & 1;
-                const int st1 = (fpos + 1) & (S - 1), par1 = ((fpos + 1) >> kLogS) & 1;
-                mbar_wait(acc_full, seg & 1, 302);            // every gradient MMA of the segment has completed
-                mbar_wait(b_full + 8 * st0, par0, 303);           // the two staging stages are ours
-                mbar_wait(b_full + 8 * st1, par1, 304);
-                tc_fence_after_sync();
-#pragma unroll 1
-                for (int q = wg; q < D / 32; q += kNumSoftmaxWG) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + lane_addr + kTmemAcc + q * 32, r);
-                    tmem_ld_wait();
-                    tmem_st32_fill(tmem_base + lane_addr + kTmemAcc + q * 32, 0u);     // zero for the next segment
-                    const int stage = (q / kBoxesPerStage) == 0 ? st0 : st1;
-                    const uint32_t row_addr = sb_addr + stage * L::kTileBytes + (q % kBoxesPerStage) * kAtomBytes +
-                                              row_in_block * 128;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        sts_v4(row_addr + ((j ^ (row_in_block & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-                }
-                tmem_st_wait();
-                tc_fence_before_sync();
-                mbar_arrive(acc_empty);                       // the next segment's gradient MMAs may start
-                fence_proxy_async_smem();                     // generic-proxy stores -> visible to the TMA engine
-                named_bar_sync(1, 32 * kNumSoftmaxWarps);
-                if (threadIdx.x == 0) {
-#pragma unroll 1
-                    for (int q = 0; q < D / 32; ++q) {
-                        const int stage = (q / kBoxesPerStage) == 0 ? st0 : st1;
-                        tma_reduce_add_2d(&tmap_dacc, sb_addr + stage * L::kTileBytes + (q % kBoxesPerStage) * kAtomBytes,
-                                          q * 32, rb * kBlockM);
-                    }
-                    bulk_commit_group();
-                    if (idx0 + seg_len == n) bulk_wait_group0();   // last segment: the adds are performed before exit
-                    else bulk_wait_group_read0();                  // staging space may be reused
-                    mbar_arrive(b_empty + 8 * st0);
-                    mbar_arrive(b_empty + 8 * st1);
-                }
-                __syncwarp();
             }
             if (threadIdx.x == 0 && seg < 2) cta_stamp(p, 2 + 2 * seg);
             idx0 += seg_len;

@@ -58,6 +58,16 @@ SIMCLR_DEVICE void ktrace_end(unsigned long long* ktrace, int id) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Every kernel of this library is launched with the programmatic-stream-serialization
+// attribute: it may start while its predecessor in the stream is still running, executes pdl_launch_dependents() at
+// once (so that its own successor can be staged the same way) and pdl_wait() before it touches global memory -- the
+// wait returns when the predecessor grid has completed and its writes are visible.  Because every kernel waits, grid
+// completion stays transitive along the chain.  Hides the ~1.3 us launch gap between the six kernels of a step.
+// ---------------------------------------------------------------------------------------------
+SIMCLR_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+SIMCLR_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 // Barriers are addressed by their 32-bit shared-space address (`smem_u32(ptr)` once per kernel, not per call: the
