@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIMCLR_ABI_VERSION 3
+#define SIMCLR_ABI_VERSION 4
 
 /* loss kinds */
 #define SIMCLR_LOSS_NTXENT 0   /* objective.py:6-55  */
@@ -50,6 +50,7 @@ extern "C" {
 #define SIMCLR_ERR_DRIVER_ENTRY (-9)    /* cuTensorMapEncodeTiled unavailable */
 #define SIMCLR_ERR_TENSOR_MAP (-10)
 #define SIMCLR_ERR_BAD_LOSS (-11)
+#define SIMCLR_ERR_BAD_PEERS (-12)
 
 int simclr_abi_version(void);
 const char* simclr_error_string(int code);
@@ -111,6 +112,35 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
                     const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,
                     const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
                     void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Row-sharded global batch over peer memory (one process per GPU of one NVLink / NVSwitch node; not in the reference,
+ * whose only batch-scaling device is gradient accumulation, utils/model_utils.py:113-123).  Buffers named *_peers are
+ * arrays of `world` device pointers: entry r is THIS process's mapping of rank r's copy of a symmetric allocation
+ * (torch.distributed._symmetric_memory, CUDA IPC / fabric handles).  Rank r owns images [r*b_local, (r+1)*b_local).
+ *
+ * simclr_prepare_peer : simclr_prepare that additionally stores every operand row into all ranks' global operand
+ *                       matrix bf16 [2*Bgpad][Dpad] (Bgpad = simclr_pad_rows(world*b_local); the padding rows must have
+ *                       been zeroed once) -- the operand "all-gather" is these NVLink stores, fused into the kernel.
+ * simclr_forward_peer : simclr_forward whose finalize kernel pushes the local rows' lse2 into all ranks' global lse2
+ *                       vector f32 [2*Bgpad] and {sum w L, sum w, #correct} into slot `rank` of all ranks'
+ *                       stats_all f32 [world][4].
+ * simclr_peer_barrier : device-side barrier over flags u32 [world] in symmetric memory (zero-initialised once);
+ *                       `epoch_local` is a private device counter, also zero-initialised once.  With `stats_all` it
+ *                       then sums the per-rank statistics into stats_out[4] / loss_out (the GLOBAL loss, identical on
+ *                       all ranks).  Must follow simclr_prepare_peer / simclr_forward_peer in the same stream, on every
+ *                       rank, before the pushed data is consumed.  world == 0 / NULL peers degrade to the local calls.
+ */
+int simclr_prepare_peer(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
+                        int normalize, float temperature, void* operand, float* inv_norm, float* pos_dot,
+                        void* forward_workspace, int world, int rank, void* const* operand_global_peers, void* stream);
+int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
+                        int64_t row_offset, int64_t d, float temperature, int normalize, const float* pos_dot,
+                        const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out,
+                        void* workspace, size_t workspace_bytes, int world, int rank, void* const* lse2_global_peers,
+                        void* const* stats_peers, void* stream);
+int simclr_peer_barrier(int world, int rank, void* const* flag_peers, unsigned int* epoch_local, const float* stats_all,
+                        float* stats_out, float* loss_out, void* stream);
 
 /* Diagnostics: per-role clock64() timeline of one CTA of the tile kernels (tools/trace_timeline.py).
  * device_buffer: int64[6 roles][64 iterations][4] or NULL to switch tracing off. */

@@ -21,14 +21,24 @@ struct AuxParams {
 
 // ---------------------------------------------------------------------------------------------
 // Stage 1: x_batch{1,2} -> bf16 operand rows, inv_norm, exact positive-pair dot product.
-// One warp per image (both views); a single round of warp reductions (norms and the raw dot together).
+// One warp per image (both views); lane l owns the d_pad/32 consecutive columns [l*per, (l+1)*per) so that a row leaves
+// the warp as ONE packed store of 2*d_pad bytes; a single round of warp reductions (norms and the raw dot together).
 // Also zeroes `zero_words` 32-bit words at `zero_ptr` (the forward workspace header) when given.
+// Row-sharded global batch: with peers.world > 0 every row is additionally stored into ALL ranks' copies of the global
+// operand matrix (view-padded, rank-major inside a view) -- the "all-gather" is these NVLink stores, fused here.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int kLoss>
+template <int kWords>
+SIMCLR_DEVICE void store_words(__nv_bfloat16* row, int lane, const uint32_t (&w)[4]) {
+    if constexpr (kWords == 1) reinterpret_cast<uint32_t*>(row)[lane] = w[0];
+    else if constexpr (kWords == 2) reinterpret_cast<uint2*>(row)[lane] = make_uint2(w[0], w[1]);
+    else reinterpret_cast<uint4*>(row)[lane] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <typename T, int kLoss, int kPer /* d_pad / 32: 2, 4 or 8 */>
 __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x2, AuxParams a,
                                __nv_bfloat16* __restrict__ operand, float* __restrict__ inv_norm,
                                float* __restrict__ pos_dot, unsigned int* __restrict__ zero_ptr, int zero_words,
-                               unsigned long long* ktrace) {
+                               unsigned long long* ktrace, PeerTable peers) {
     pdl_launch_dependents();
     pdl_wait();
     ktrace_begin(ktrace, 0);
@@ -39,14 +49,13 @@ __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x
     const int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5);   // local image slot
     const int lane = threadIdx.x & 31;
     if (i >= a.bl_pad) return;
-    const int per_lane = a.d_pad >> 5;
+    constexpr int kWords = kPer / 2;
     __nv_bfloat16* o1 = operand + static_cast<size_t>(i) * a.d_pad;
     __nv_bfloat16* o2 = operand + static_cast<size_t>(a.bl_pad + i) * a.d_pad;
+    uint32_t w1[4] = {0u, 0u, 0u, 0u}, w2[4] = {0u, 0u, 0u, 0u};
     if (i >= a.b_loc) {     // padding slot: zero operands and neutral per-row values
-        for (int u = 0; u < per_lane; ++u) {
-            o1[lane + 32 * u] = __float2bfloat16_rn(0.f);
-            o2[lane + 32 * u] = __float2bfloat16_rn(0.f);
-        }
+        store_words<kWords>(o1, lane, w1);
+        store_words<kWords>(o2, lane, w2);
         if (lane == 0) {
             inv_norm[i] = 0.f;
             inv_norm[a.bl_pad + i] = 0.f;
@@ -55,26 +64,43 @@ __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x
         }
         return;
     }
-    float v1[kMaxDimPerLane], v2[kMaxDimPerLane];
+    float v1[kPer], v2[kPer];
+    const T* r1 = x1 + static_cast<size_t>(i) * a.d;
+    const T* r2 = x2 + static_cast<size_t>(i) * a.d;
+    bool vec = false;
+    if constexpr (sizeof(T) == 4 && kPer == 4) {
+        // fp32 rows of exactly 128 columns at 16-byte aligned addresses: one float4 per lane
+        vec = a.d == a.d_pad && ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(x2)) & 15u) == 0;
+        if (vec) {
+            const float4 p4 = __ldg(reinterpret_cast<const float4*>(r1) + lane);
+            const float4 q4 = __ldg(reinterpret_cast<const float4*>(r2) + lane);
+            v1[0] = p4.x; v1[1] = p4.y; v1[2] = p4.z; v1[3] = p4.w;
+            v2[0] = q4.x; v2[1] = q4.y; v2[2] = q4.z; v2[3] = q4.w;
+        }
+    }
+    if (!vec) {
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int k = lane * kPer + u;
+            v1[u] = k < a.d ? load_as_float(r1 + k) : 0.f;
+            v2[u] = k < a.d ? load_as_float(r2 + k) : 0.f;
+        }
+    }
     float n1 = 0.f, n2 = 0.f, dot = 0.f;
 #pragma unroll
-    for (int u = 0; u < kMaxDimPerLane; ++u) {
-        const int k = lane + 32 * u;
-        float e1 = 0.f, e2 = 0.f;
-        if (u < per_lane && k < a.d) {
-            e1 = load_as_float(x1 + static_cast<size_t>(i) * a.d + k);
-            e2 = load_as_float(x2 + static_cast<size_t>(i) * a.d + k);
-            if constexpr (kLoss == kModified) {
-                e1 = softplus_beta(e1);
-                e2 = softplus_beta(e2);
-                n1 += fabsf(e1);
-                n2 += fabsf(e2);
-            } else {
-                n1 = fmaf(e1, e1, n1);
-                n2 = fmaf(e2, e2, n2);
-            }
-            dot = fmaf(e1, e2, dot);
+    for (int u = 0; u < kPer; ++u) {
+        float e1 = v1[u], e2 = v2[u];
+        if constexpr (kLoss == kModified) {
+            const bool in = lane * kPer + u < a.d;
+            e1 = in ? softplus_beta(e1) : 0.f;
+            e2 = in ? softplus_beta(e2) : 0.f;
+            n1 += fabsf(e1);
+            n2 += fabsf(e2);
+        } else {
+            n1 = fmaf(e1, e1, n1);
+            n2 = fmaf(e2, e2, n2);
         }
+        dot = fmaf(e1, e2, dot);
         v1[u] = e1;
         v2[u] = e2;
     }
@@ -95,12 +121,18 @@ __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x
         inv1 = n1 < kNormEps ? kInvNormClamped : s1;
         inv2 = n2 < kNormEps ? kInvNormClamped : s2;
     }
+    const float f1 = s1 * a.op_scale, f2 = s2 * a.op_scale;
 #pragma unroll
-    for (int u = 0; u < kMaxDimPerLane; ++u) {
-        if (u < per_lane) {
-            o1[lane + 32 * u] = __float2bfloat16_rn(v1[u] * (s1 * a.op_scale));
-            o2[lane + 32 * u] = __float2bfloat16_rn(v2[u] * (s2 * a.op_scale));
-        }
+    for (int u = 0; u < kPer; u += 2) {
+        w1[u >> 1] = pack_bf16x2(v1[u] * f1, v1[u + 1] * f1);
+        w2[u >> 1] = pack_bf16x2(v2[u] * f2, v2[u + 1] * f2);
+    }
+    store_words<kWords>(o1, lane, w1);
+    store_words<kWords>(o2, lane, w2);
+    for (int r = 0; r < peers.world; ++r) {
+        __nv_bfloat16* g = static_cast<__nv_bfloat16*>(peers.ptr[r]);
+        store_words<kWords>(g + static_cast<size_t>(a.row_off + i) * a.d_pad, lane, w1);
+        store_words<kWords>(g + static_cast<size_t>(a.bg_pad + a.row_off + i) * a.d_pad, lane, w2);
     }
     if (lane == 0) {
         inv_norm[i] = inv1;
@@ -108,6 +140,60 @@ __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x
         const float pd = dot * s1 * s2;
         pos_dot[i] = pd;
         pos_dot[a.bl_pad + i] = pd;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cross-GPU barrier of the row-sharded global batch (one process per GPU; flags live in symmetric memory).
+// Rank r bumps its local epoch, stores it into flags[r] of EVERY rank and waits until all `world` flags of its own
+// copy have reached the epoch.  The kernels before it in the stream are complete (and their peer stores performed)
+// when it runs, so everything they pushed is visible to the peers' kernels that follow their barrier.
+// With `stats_all` it also adds up the per-rank loss statistics that the forward finalize kernels pushed.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) peer_barrier_kernel(PeerTable flags, unsigned int* __restrict__ epoch_local,
+                                                          const float* __restrict__ stats_all,
+                                                          float* __restrict__ stats_out, float* __restrict__ loss_out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int t = threadIdx.x;
+    unsigned int target = 0;
+    if (t == 0) {
+        target = *epoch_local + 1u;
+        *epoch_local = target;
+    }
+    target = __shfl_sync(0xffffffffu, target, 0);
+    __threadfence_system();
+    if (t < flags.world) {
+        unsigned int* remote = static_cast<unsigned int*>(flags.ptr[t]) + flags.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(target) : "memory");
+        const unsigned int* mine = static_cast<const unsigned int*>(flags.ptr[flags.rank]) + t;
+        unsigned int seen;
+        long long spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+            if (static_cast<int>(seen - target) >= 0) break;
+            __nanosleep(64);
+            if (++spins > (1ll << 26)) {            // ~ seconds: a peer never arrived
+                printf("[simclr_b200] peer barrier watchdog: rank %d waits for rank %d (epoch %u, seen %u)\n", flags.rank, t,
+                       target, seen);
+                __trap();
+            }
+        } while (true);
+    }
+    __syncwarp();
+    __threadfence_system();
+    if (stats_all != nullptr && t == 0) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int r = 0; r < flags.world; ++r) {      // fixed order: identical result on every rank
+            s0 += __ldcv(stats_all + 4 * r + 0);
+            s1 += __ldcv(stats_all + 4 * r + 1);
+            s2 += __ldcv(stats_all + 4 * r + 2);
+        }
+        stats_out[0] = s0;
+        stats_out[1] = s1;
+        stats_out[2] = s2;
+        stats_out[3] = s0 / s1;
+        if (loss_out) *loss_out = s0 / s1;
     }
 }
 

@@ -305,6 +305,21 @@ int check_device() {
     return SIMCLR_OK;
 }
 
+// PeerTable from the C-ABI arguments (world == 0 / NULL: no peers)
+int make_peer_table(int world, int rank, void* const* ptrs, PeerTable* t) {
+    std::memset(t, 0, sizeof(*t));
+    if (world == 0 || ptrs == nullptr) return SIMCLR_OK;
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return SIMCLR_ERR_BAD_PEERS;
+    for (int r = 0; r < world; ++r) {
+        if (ptrs[r] == nullptr) return SIMCLR_ERR_NULL_POINTER;
+        if (misaligned(ptrs[r])) return SIMCLR_ERR_MISALIGNED;
+        t->ptr[r] = ptrs[r];
+    }
+    t->world = world;
+    t->rank = rank;
+    return SIMCLR_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -325,6 +340,7 @@ const char* simclr_error_string(int code) {
         case SIMCLR_ERR_DRIVER_ENTRY: return "cuTensorMapEncodeTiled not available from the driver";
         case SIMCLR_ERR_TENSOR_MAP: return "cuTensorMapEncodeTiled failed";
         case SIMCLR_ERR_BAD_LOSS: return "unknown loss kind";
+        case SIMCLR_ERR_BAD_PEERS: return "bad peer table (1 <= world <= 16, 0 <= rank < world, shard = rank * b_local)";
         default: break;
     }
     if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
@@ -350,43 +366,84 @@ size_t simclr_backward_workspace_bytes(int loss, int64_t b_local, int64_t b_glob
     return carve_backward(g, nullptr).bytes;
 }
 
-int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
-                   int normalize, float temperature, void* operand, float* inv_norm, float* pos_dot,
-                   void* forward_workspace, void* stream) {
+int simclr_prepare_peer(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
+                        int normalize, float temperature, void* operand, float* inv_norm, float* pos_dot,
+                        void* forward_workspace, int world, int rank, void* const* operand_global_peers, void* stream) {
     if (!x_batch1 || !x_batch2 || !operand || !inv_norm || !pos_dot) return SIMCLR_ERR_NULL_POINTER;
     if (in_dtype != SIMCLR_DTYPE_F32 && in_dtype != SIMCLR_DTYPE_BF16) return SIMCLR_ERR_BAD_DTYPE;
     if (!(temperature > 0.f) || !std::isfinite(temperature)) return SIMCLR_ERR_BAD_TEMPERATURE;
-    Geometry g;
-    int rc = make_geometry(loss, b_local, b_local, 0, d, &g);
+    PeerTable peers;
+    int rc = make_peer_table(world, rank, operand_global_peers, &peers);
     if (rc) return rc;
+    const int64_t b_global = peers.world > 0 ? b_local * peers.world : b_local;
+    const int64_t row_offset = peers.world > 0 ? b_local * peers.rank : 0;
+    Geometry g;
+    if ((rc = make_geometry(loss, b_local, b_global, row_offset, d, &g))) return rc;
     if (misaligned(operand) || misaligned(forward_workspace)) return SIMCLR_ERR_MISALIGNED;
     if ((rc = check_device())) return rc;
-    Scales s = make_scales(loss, temperature, normalize, b_local);
+    Scales s = make_scales(loss, temperature, normalize, b_global);
     unsigned int* zero_ptr = static_cast<unsigned int*>(forward_workspace);
     const int zero_words = static_cast<int>(header_bytes(g) / 4);
-    AuxParams a = make_aux(g, s, b_local, b_local, 0, d, normalize);
+    AuxParams a = make_aux(g, s, b_local, b_global, row_offset, d, normalize);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int warps = 8;
     const int blocks = static_cast<int>((g.bl_pad + warps - 1) / warps);
     auto* op = static_cast<__nv_bfloat16*>(operand);
     cudaError_t launch_rc = cudaSuccess;
-#define SIMCLR_PREP(T, LOSS) \
-    launch_rc = launch_pdl(prepare_kernel<T, LOSS>, dim3(blocks), dim3(warps * 32), 0, st, static_cast<const T*>(x_batch1), static_cast<const T*>(x_batch2), a, op, inv_norm, pos_dot, zero_ptr, zero_words, g_ktrace_ptr)
+#define SIMCLR_PREP2(T, LOSS, PER) \
+    launch_rc = launch_pdl(prepare_kernel<T, LOSS, PER>, dim3(blocks), dim3(warps * 32), 0, st, static_cast<const T*>(x_batch1), static_cast<const T*>(x_batch2), a, op, inv_norm, pos_dot, zero_ptr, zero_words, g_ktrace_ptr, peers)
+#define SIMCLR_PREP(T, LOSS)                          \
+    switch (g.d_pad) {                                \
+        case 64: SIMCLR_PREP2(T, LOSS, 2); break;     \
+        case 128: SIMCLR_PREP2(T, LOSS, 4); break;    \
+        default: SIMCLR_PREP2(T, LOSS, 8); break;     \
+    }
     if (loss == SIMCLR_LOSS_NTXENT) {
-        if (in_dtype == SIMCLR_DTYPE_F32) SIMCLR_PREP(float, kNtXent);
-        else SIMCLR_PREP(__nv_bfloat16, kNtXent);
+        if (in_dtype == SIMCLR_DTYPE_F32) SIMCLR_PREP(float, kNtXent)
+        else SIMCLR_PREP(__nv_bfloat16, kNtXent)
     } else {
-        if (in_dtype == SIMCLR_DTYPE_F32) SIMCLR_PREP(float, kModified);
-        else SIMCLR_PREP(__nv_bfloat16, kModified);
+        if (in_dtype == SIMCLR_DTYPE_F32) SIMCLR_PREP(float, kModified)
+        else SIMCLR_PREP(__nv_bfloat16, kModified)
     }
 #undef SIMCLR_PREP
+#undef SIMCLR_PREP2
     return static_cast<int>(launch_rc);
+}
+
+int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
+                   int normalize, float temperature, void* operand, float* inv_norm, float* pos_dot,
+                   void* forward_workspace, void* stream) {
+    return simclr_prepare_peer(loss, x_batch1, x_batch2, b_local, d, in_dtype, normalize, temperature, operand, inv_norm,
+                               pos_dot, forward_workspace, 0, 0, nullptr, stream);
+}
+
+int simclr_peer_barrier(int world, int rank, void* const* flag_peers, unsigned int* epoch_local, const float* stats_all,
+                        float* stats_out, float* loss_out, void* stream) {
+    if (!flag_peers || !epoch_local) return SIMCLR_ERR_NULL_POINTER;
+    if (stats_all != nullptr && stats_out == nullptr) return SIMCLR_ERR_NULL_POINTER;
+    if (world < 1) return SIMCLR_ERR_BAD_PEERS;
+    PeerTable flags;
+    int rc = make_peer_table(world, rank, flag_peers, &flags);
+    if (rc) return rc;
+    if ((rc = check_device())) return rc;
+    return static_cast<int>(launch_pdl(peer_barrier_kernel, dim3(1), dim3(32), 0, static_cast<cudaStream_t>(stream), flags,
+                                       epoch_local, stats_all, stats_out, loss_out));
 }
 
 int simclr_forward(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
                    int64_t row_offset, int64_t d, float temperature, int normalize, const float* pos_dot,
                    const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out, void* workspace,
                    size_t workspace_bytes, void* stream) {
+    return simclr_forward_peer(loss, operand_rows, operand_cols, b_local, b_global, row_offset, d, temperature, normalize,
+                               pos_dot, row_weight, lse2, row_loss, stats, loss_out, workspace, workspace_bytes, 0, 0, nullptr,
+                               nullptr, stream);
+}
+
+int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
+                        int64_t row_offset, int64_t d, float temperature, int normalize, const float* pos_dot,
+                        const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out,
+                        void* workspace, size_t workspace_bytes, int world, int rank, void* const* lse2_global_peers,
+                        void* const* stats_peers, void* stream) {
     if (!operand_rows || !operand_cols || !pos_dot || !lse2 || !row_loss || !stats || !workspace)
         return SIMCLR_ERR_NULL_POINTER;
     if (!(temperature > 0.f) || !std::isfinite(temperature)) return SIMCLR_ERR_BAD_TEMPERATURE;
@@ -415,6 +472,9 @@ int simclr_forward(int loss, const void* operand_rows, const void* operand_cols,
     p.block_part = w.block_part;
     p.stats = stats;
     p.loss_out = loss_out;
+    if ((rc = make_peer_table(world, rank, lse2_global_peers, &p.lse2_peers))) return rc;
+    if ((rc = make_peer_table(world, rank, stats_peers, &p.stats_peers))) return rc;
+    if (p.lse2_peers.world > 0 && (b_global != b_local * world || row_offset != b_local * rank)) return SIMCLR_ERR_BAD_PEERS;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if ((rc = dispatch_tile<false>(loss, g.d_pad, map_rows, map_cols, map_rows, p, g.grid, st))) return rc;
     cudaError_t e;

@@ -84,6 +84,15 @@ constexpr float kConstShiftRaw = 0.f;
 
 enum LossKind : int { kNtXent = 0, kModified = 1 };
 
+// Peer (NVLink / NVSwitch) addressing of a symmetric buffer: ptr[r] is THIS process's mapping of rank r's copy.
+// world == 0 switches the peer stores off.  Passed by value inside the kernel parameters.
+constexpr int kMaxPeers = 16;
+struct PeerTable {
+    void* ptr[kMaxPeers];
+    int world;
+    int rank;
+};
+
 struct TileParams {
     int b_loc;         // images held by this rank
     int b_glob;        // images in the global batch
@@ -123,6 +132,10 @@ struct TileParams {
     const float* inv_norm;     // [2*bl_pad]
     const float* col_scale;    // [2*bg_pad] w_c / sum(w) or nullptr
     const float* grad_out;     // [1] or nullptr
+    // row-sharded global batch over peer memory: every rank's forward finalize pushes its rows' lse2 and its three
+    // loss statistics into all ranks' global buffers (no collective call)
+    PeerTable lse2_peers;      // float [2*bg_pad] per rank
+    PeerTable stats_peers;     // float [world][4] per rank
     long long* trace;      // optional (debug): per-role clock64() timestamps of CTA `trace_cta`
     int trace_cta;
     int tile_grid;         // grid size of the tile kernel (the finalize kernels need it to locate partials)
@@ -495,6 +508,11 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
     }
     p.lse2[slot] = l2;
     p.row_loss[slot] = loss_r;
+    if (p.lse2_peers.world > 0 && row_ok) {
+        // the column vector of the global batch, written straight into every rank's copy over NVLink
+        const int gslot = vr * p.bg_pad + p.row_off + img;
+        for (int r = 0; r < p.lse2_peers.world; ++r) static_cast<float*>(p.lse2_peers.ptr[r])[gslot] = l2;
+    }
 
     // block sums in a fixed order (deterministic)
     const float r0 = warp_sum(w * loss_r), r1 = warp_sum(w), r2 = warp_sum(hit);
@@ -530,6 +548,12 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
             p.stats[2] = s2;
             p.stats[3] = s0 / s1;
             if (p.loss_out) *p.loss_out = s0 / s1;
+            for (int r = 0; r < p.stats_peers.world; ++r) {
+                float* dst = static_cast<float*>(p.stats_peers.ptr[r]) + 4 * p.stats_peers.rank;
+                dst[0] = s0;
+                dst[1] = s1;
+                dst[2] = s2;
+            }
             *p.ticket = 0u;                        // leave the workspace header clean for the next call
         }
     }

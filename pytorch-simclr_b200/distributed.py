@@ -13,6 +13,15 @@ enlarge the set of negatives (utils/model_utils.py:113-123).  Here the 2B x 2B p
 
 Every rank must hold the same number of images.  The returned loss is the global loss (identical on all
 ranks); its gradient w.r.t. the local inputs is exact, so DDP-style parameter all-reduce composes as usual.
+
+Two transports:
+  * ``PeerBatch`` (default on GPUs): the exchange is fused into our own kernels over peer memory.  The operand rows
+    are stored by the prepare kernel straight into every rank's copy of the global operand matrix (symmetric
+    memory, NVLink / NVSwitch), the forward finalize kernel stores lse2 and the loss statistics the same way, and
+    two device-side flag barriers order producers and consumers.  No NCCL call on the data path, CUDA-graph capturable.
+  * ``RowShardGather``: the same exchange with ``torch.distributed`` collectives (NCCL on GPUs, gloo on CPU tensors --
+    which is how tests/test_distributed_cpu.py covers the layout logic without a GPU).  Used when per-row weights
+    are given, and as the baseline the fused path is measured against.
 """
 from __future__ import annotations
 
@@ -21,9 +30,14 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
-from .functional import LOSS_MODIFIED, LOSS_NTXENT, ContrastiveLossFunction, pad_rows
+import ctypes
 
-__all__ = ["RowShardGather", "global_contrastive_loss", "global_modified_contrastive_loss", "shard_rows"]
+from . import _lib
+from ._lib import check
+from .functional import (LOSS_MODIFIED, LOSS_NTXENT, ContrastiveLossFunction, _Saved, _dtype_code, _validate, pad_dim,
+                         pad_rows)
+
+__all__ = ["RowShardGather", "PeerBatch", "global_contrastive_loss", "global_modified_contrastive_loss", "shard_rows"]
 
 
 def shard_rows(b_global: int, world: int, rank: int):
@@ -82,7 +96,140 @@ class RowShardGather:
         return self._gather_views(padded, b) / g_stats[1]
 
 
-def _global_loss(kind, x1, x2, temperature, normalize, weight, group):
+def _align(n: int, a: int = 256) -> int:
+    return (n + a - 1) // a * a
+
+
+class PeerBatch:
+    """Symmetric-memory state of the row-sharded global batch for one (b_local, d) on this rank.
+
+    One symmetric allocation per rank holds two generations (double buffering: a fast rank may already push step
+    k+1 while a slow one still reads step k) of  operand_all bf16 [2*Bgpad][Dpad] | lse2_all f32 [2*Bgpad] |
+    stats_all f32 [world][4]  plus the barrier flags u32 [world].  Everything else is ordinary device memory.
+    """
+    peer = True
+    GENERATIONS = 2
+
+    def __init__(self, b_local: int, d: int, group=None, device=None):
+        import torch.distributed._symmetric_memory as symm
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 16:
+            raise ValueError("PeerBatch supports up to 16 ranks of one node")
+        self.b_local, self.d = int(b_local), int(d)
+        self.b_global = self.b_local * self.world
+        self.row_offset = self.b_local * self.rank
+        self.bg_pad, self.dp = pad_rows(self.b_global), pad_dim(d)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        op_bytes = _align(2 * self.bg_pad * self.dp * 2)
+        lse_bytes = _align(2 * self.bg_pad * 4)
+        st_bytes = _align(self.world * 4 * 4)
+        self._gen_bytes = op_bytes + lse_bytes + st_bytes
+        flag_off = self.GENERATIONS * self._gen_bytes
+        total = flag_off + _align(16 * 4)
+        self.buf = symm.empty(total, dtype=torch.uint8, device=self.device)
+        self.buf.zero_()                       # padding rows of operand_all and the flags start (and stay) zero
+        torch.cuda.synchronize(self.device)
+        self.handle = symm.rendezvous(self.buf, self.group)
+        dist.barrier(group=self.group)         # every rank has zeroed its copy before anybody pushes
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        arr = ctypes.c_void_p * self.world
+        self._tables = []
+        for g in range(self.GENERATIONS):
+            base = g * self._gen_bytes
+            self._tables.append({
+                "operand": arr(*[p + base for p in ptrs]),
+                "lse2": arr(*[p + base + op_bytes for p in ptrs]),
+                "stats": arr(*[p + base + op_bytes + lse_bytes for p in ptrs]),
+            })
+        self._flags = arr(*[p + flag_off for p in ptrs])
+        local = self.buf
+        self._views = []
+        for g in range(self.GENERATIONS):
+            base = g * self._gen_bytes
+            self._views.append({
+                "operand": local[base: base + 2 * self.bg_pad * self.dp * 2].view(torch.bfloat16).view(2 * self.bg_pad, self.dp),
+                "lse2": local[base + op_bytes: base + op_bytes + 2 * self.bg_pad * 4].view(torch.float32),
+                "stats": local[base + op_bytes + lse_bytes: base + op_bytes + lse_bytes + self.world * 16].view(torch.float32),
+            })
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.generation = 0                    # number of forwards issued so far
+        self.lib = _lib.load()
+
+    # ------------------------------------------------------------------------------------------------------
+    def forward(self, loss_kind, x1, x2, temperature, normalize, operand, rowvec, stats_local, stats_global, loss,
+                ws, ws_bytes, stream):
+        """prepare(+push) -> barrier -> forward(+push) -> barrier(+global statistics); enqueue only."""
+        lib, gen = self.lib, self.generation % self.GENERATIONS
+        tab, view = self._tables[gen], self._views[gen]
+        code = _dtype_code(x1)
+        check(lib.simclr_prepare_peer(loss_kind, x1.data_ptr(), x2.data_ptr(), self.b_local, self.d, code,
+                                      int(bool(normalize)), float(temperature), operand.data_ptr(), rowvec[0].data_ptr(),
+                                      rowvec[1].data_ptr(), ws.data_ptr(), self.world, self.rank, tab["operand"], stream),
+              "simclr_prepare_peer")
+        check(lib.simclr_peer_barrier(self.world, self.rank, self._flags, self.epoch.data_ptr(), None, None, None, stream),
+              "simclr_peer_barrier")
+        check(lib.simclr_forward_peer(loss_kind, operand.data_ptr(), view["operand"].data_ptr(), self.b_local,
+                                      self.b_global, self.row_offset, self.d, float(temperature), int(bool(normalize)),
+                                      rowvec[1].data_ptr(), None, rowvec[2].data_ptr(), rowvec[3].data_ptr(),
+                                      stats_local.data_ptr(), None, ws.data_ptr(), ws_bytes, self.world, self.rank,
+                                      tab["lse2"], tab["stats"], stream), "simclr_forward_peer")
+        check(lib.simclr_peer_barrier(self.world, self.rank, self._flags, self.epoch.data_ptr(), view["stats"].data_ptr(),
+                                      stats_global.data_ptr(), loss.data_ptr(), stream), "simclr_peer_barrier")
+        self.generation += 1
+        return view["operand"], view["lse2"], self.generation
+
+
+def run_forward_peer(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature: float, normalize: bool,
+                     peer: PeerBatch):
+    """Peer-memory counterpart of functional.run_forward (same return tuple)."""
+    lib = _lib.load()
+    b, d = _validate(x1, x2)
+    if (b, d) != (peer.b_local, peer.d):
+        raise ValueError(f"PeerBatch was built for batches of {peer.b_local} x {peer.d}, got {b} x {d}")
+    x1, x2 = x1.contiguous(), x2.contiguous()
+    dev = x1.device
+    bp, dp = pad_rows(b), pad_dim(d)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        operand = torch.empty((2 * bp, dp), dtype=torch.bfloat16, device=dev)
+        rowvec = torch.empty((4, 2 * bp), dtype=torch.float32, device=dev)
+        stats_local = torch.empty(4, dtype=torch.float32, device=dev)
+        stats = torch.empty(4, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        ws_bytes = lib.simclr_forward_workspace_bytes(loss_kind, b, peer.b_global, d)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        operand_cols, lse2_cols, generation = peer.forward(loss_kind, x1, x2, temperature, normalize, operand, rowvec,
+                                                           stats_local, stats, loss, ws, ws_bytes, stream)
+    saved = _Saved()
+    saved.operand_rows, saved.operand_cols = operand, operand_cols
+    saved.inv_norm, saved.pos_dot = rowvec[0], rowvec[1]
+    saved.lse2_cols, saved.col_scale = lse2_cols, None
+    saved.b_local, saved.b_global, saved.row_offset, saved.d = b, peer.b_global, peer.row_offset, d
+    saved.loss, saved.temperature, saved.normalize, saved.dtype_code = loss_kind, float(temperature), bool(normalize), _dtype_code(x1)
+    saved.peer, saved.generation = peer, generation
+    return loss, stats, rowvec, saved
+
+
+_PEER_CACHE = {}
+
+
+def _peer_for(x1: torch.Tensor, group) -> PeerBatch:
+    key = (id(group), x1.device, x1.shape[0], x1.shape[1])
+    if key not in _PEER_CACHE:
+        _PEER_CACHE[key] = PeerBatch(x1.shape[0], x1.shape[1], group, x1.device)
+    return _PEER_CACHE[key]
+
+
+def _global_loss(kind, x1, x2, temperature, normalize, weight, group, transport="auto"):
+    use_peer = transport == "peer" or (transport == "auto" and weight is None and x1.is_cuda)
+    if use_peer:
+        gather = _peer_for(x1, group)
+        loss, stats = ContrastiveLossFunction.apply(x1, x2, kind, float(temperature), bool(normalize), None, gather)
+        correct = stats[2].item()
+        return loss, 100.0 * correct / (2 * x1.shape[0] * gather.world)
     gather = RowShardGather(group)
     loss, stats = ContrastiveLossFunction.apply(x1, x2, kind, float(temperature), bool(normalize), weight, gather)
     correct = stats[2].item()
@@ -90,12 +237,13 @@ def _global_loss(kind, x1, x2, temperature, normalize, weight, group):
 
 
 def global_contrastive_loss(x_batch1, x_batch2, temperature=1.0, normalize=True, weight: Optional[torch.Tensor] = None,
-                            group=None):
+                            group=None, transport: str = "auto"):
     """NT-Xent over the union of all ranks' batches.  Same signature and return convention as
-    ``contrastive_loss`` (reference objective.py:6-10,55); ``weight`` is this rank's [2*B_local] slice."""
-    return _global_loss(LOSS_NTXENT, x_batch1, x_batch2, temperature, normalize, weight, group)
+    ``contrastive_loss`` (reference objective.py:6-10,55); ``weight`` is this rank's [2*B_local] slice.
+    ``transport``: "peer" (fused NVLink stores + device barriers), "nccl" (collectives) or "auto"."""
+    return _global_loss(LOSS_NTXENT, x_batch1, x_batch2, temperature, normalize, weight, group, transport)
 
 
-def global_modified_contrastive_loss(x_batch1, x_batch2, group=None, **kwargs):
+def global_modified_contrastive_loss(x_batch1, x_batch2, group=None, transport: str = "auto", **kwargs):
     """Probabilistic loss over the union of all ranks' batches (reference objective.py:58-98)."""
-    return _global_loss(LOSS_MODIFIED, x_batch1, x_batch2, kwargs.get("temperature", 1.0), True, None, group)
+    return _global_loss(LOSS_MODIFIED, x_batch1, x_batch2, kwargs.get("temperature", 1.0), True, None, group, transport)

@@ -72,7 +72,7 @@ def _validate(x1: torch.Tensor, x2: torch.Tensor) -> Tuple[int, int]:
 class _Saved:
     """State a forward leaves for its backward (device buffers only)."""
     __slots__ = ("operand_rows", "operand_cols", "inv_norm", "pos_dot", "lse2_cols", "col_scale", "b_local",
-                 "b_global", "row_offset", "d", "loss", "temperature", "normalize", "dtype_code")
+                 "b_global", "row_offset", "d", "loss", "temperature", "normalize", "dtype_code", "peer", "generation")
 
 
 def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature: float, normalize: bool,
@@ -132,6 +132,10 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
 def run_backward(saved: "_Saved", x1: torch.Tensor, x2: torch.Tensor, grad_out: Optional[torch.Tensor]):
     lib = _lib.load()
     dev = x1.device
+    peer = getattr(saved, "peer", None)
+    if peer is not None and peer.generation - saved.generation >= peer.GENERATIONS:
+        raise RuntimeError("the peer-memory buffers of this forward have been reused: call backward before the "
+                           f"{peer.GENERATIONS}nd following global forward (or use transport='nccl')")
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream().cuda_stream
         g1 = torch.empty_like(x1)
@@ -159,7 +163,11 @@ class ContrastiveLossFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x1, x2, loss_kind, temperature, normalize, weight, gather):
-        loss, stats, _rowvec, saved = run_forward(loss_kind, x1, x2, temperature, normalize, weight, gather)
+        if getattr(gather, "peer", False):
+            from .distributed import run_forward_peer
+            loss, stats, _rowvec, saved = run_forward_peer(loss_kind, x1, x2, temperature, normalize, gather)
+        else:
+            loss, stats, _rowvec, saved = run_forward(loss_kind, x1, x2, temperature, normalize, weight, gather)
         ctx.saved_state = saved
         ctx.save_for_backward(x1, x2)
         ctx.mark_non_differentiable(stats)

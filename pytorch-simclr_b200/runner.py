@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import check
 from .functional import _dtype_code, pad_dim, pad_rows
 
-__all__ = ["ContrastiveStep"]
+__all__ = ["ContrastiveStep", "PeerStep"]
 
 
 class ContrastiveStep:
@@ -68,6 +68,62 @@ class ContrastiveStep:
                                   self.rowvec[2].data_ptr(), None, None if grad_out is None else grad_out.data_ptr(),
                                   self.grad1.data_ptr(), self.grad2.data_ptr(), self.bwd_ws.data_ptr(),
                                   self.bwd_ws_bytes, st), "simclr_backward")
+
+    def step(self) -> None:
+        self.forward()
+        self.backward()
+
+
+class PeerStep:
+    """Allocation-free step of the row-sharded global batch over peer memory (distributed.PeerBatch): what bench.py
+    captures into one CUDA graph per rank at N > 1.  No collective call inside: the exchange is NVLink stores from the
+    prepare / forward-finalize kernels plus two device-side barriers."""
+    KERNELS_FORWARD = 5     # prepare(+push), barrier, tile kernel, finalize(+push), barrier(+statistics)
+    KERNELS_BACKWARD = 3
+
+    def __init__(self, loss_kind: int, b_local: int, dim: int, temperature: float, group=None, normalize: bool = True,
+                 dtype: torch.dtype = torch.float32, device="cuda"):
+        from .distributed import PeerBatch
+        self.lib = _lib.load()
+        self.kind, self.b, self.d = int(loss_kind), int(b_local), int(dim)
+        self.temperature, self.normalize = float(temperature), bool(normalize)
+        self.device = torch.device(device)
+        self.peer = PeerBatch(b_local, dim, group, self.device)
+        bp, dp = pad_rows(b_local), pad_dim(dim)
+        dev = self.device
+        self.x1 = torch.zeros((b_local, dim), dtype=dtype, device=dev)
+        self.x2 = torch.zeros((b_local, dim), dtype=dtype, device=dev)
+        self.code = _dtype_code(self.x1)
+        self.operand = torch.empty((2 * bp, dp), dtype=torch.bfloat16, device=dev)
+        self.rowvec = torch.empty((4, 2 * bp), dtype=torch.float32, device=dev)
+        self.stats_local = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.stats = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.grad1 = torch.empty_like(self.x1)
+        self.grad2 = torch.empty_like(self.x2)
+        self.fwd_ws_bytes = self.lib.simclr_forward_workspace_bytes(self.kind, b_local, self.peer.b_global, dim)
+        self.bwd_ws_bytes = self.lib.simclr_backward_workspace_bytes(self.kind, b_local, self.peer.b_global, dim)
+        self.fwd_ws = torch.empty(self.fwd_ws_bytes, dtype=torch.uint8, device=dev)
+        self.bwd_ws = torch.empty(self.bwd_ws_bytes, dtype=torch.uint8, device=dev)
+        self._cols = None
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def forward(self) -> None:
+        self._cols = self.peer.forward(self.kind, self.x1, self.x2, self.temperature, self.normalize, self.operand,
+                                       self.rowvec, self.stats_local, self.stats, self.loss, self.fwd_ws,
+                                       self.fwd_ws_bytes, self._stream())
+
+    def backward(self, grad_out: Optional[torch.Tensor] = None) -> None:
+        operand_cols, lse2_cols, _gen = self._cols
+        p = self.peer
+        check(self.lib.simclr_backward(self.kind, self.x1.data_ptr(), self.x2.data_ptr(), self.b, p.b_global, p.row_offset,
+                                       self.d, self.code, int(self.normalize), self.temperature, self.operand.data_ptr(),
+                                       operand_cols.data_ptr(), self.rowvec[0].data_ptr(), self.rowvec[1].data_ptr(),
+                                       lse2_cols.data_ptr(), None, None if grad_out is None else grad_out.data_ptr(),
+                                       self.grad1.data_ptr(), self.grad2.data_ptr(), self.bwd_ws.data_ptr(),
+                                       self.bwd_ws_bytes, self._stream()), "simclr_backward")
 
     def step(self) -> None:
         self.forward()

@@ -1,7 +1,7 @@
 """Row-sharded global-batch check, launched with torchrun (one process per GPU, NCCL):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
-        tools/distributed_check.py [--b 2048] [--d 128]
+        tools/distributed_check.py [--batch 2048] [--dim 128]
 
 Every rank compares the global loss / accuracy and its local gradients with the single-process fp64 oracle
 evaluated on the gathered batch (test infrastructure: imports oracle/)."""
@@ -22,8 +22,8 @@ from pytorch_simclr_b200.distributed import (global_contrastive_loss, global_mod
                                              shard_rows)
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--b", type=int, default=2048)
-ap.add_argument("--d", type=int, default=128)
+ap.add_argument("--batch", dest="b", type=int, default=2048)
+ap.add_argument("--dim", dest="d", type=int, default=128)
 ap.add_argument("--tau", type=float, default=0.5)
 args = ap.parse_args()
 
@@ -32,10 +32,13 @@ local = int(os.environ.get("LOCAL_RANK", rank))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
-for name, fn, ref_fn, use_weight in (
-        ("ntxent", global_contrastive_loss, oracle.ntxent_closed_form, False),
-        ("ntxent+weight", global_contrastive_loss, oracle.ntxent_closed_form, True),
-        ("modified", global_modified_contrastive_loss, oracle.modified_closed_form, False)):
+for name, fn, ref_fn, use_weight, transport in (
+        ("ntxent/peer", global_contrastive_loss, oracle.ntxent_closed_form, False, "peer"),
+        ("ntxent/peer again", global_contrastive_loss, oracle.ntxent_closed_form, False, "peer"),
+        ("ntxent/nccl", global_contrastive_loss, oracle.ntxent_closed_form, False, "nccl"),
+        ("ntxent+weight/nccl", global_contrastive_loss, oracle.ntxent_closed_form, True, "nccl"),
+        ("modified/peer", global_modified_contrastive_loss, oracle.modified_closed_form, False, "peer"),
+        ("modified/nccl", global_modified_contrastive_loss, oracle.modified_closed_form, False, "nccl")):
     z1, z2 = oracle.make_embeddings(args.b, args.d, seed=17, kind="correlated", noise=1.0)   # same on every rank
     w = None
     if use_weight:
@@ -43,7 +46,7 @@ for name, fn, ref_fn, use_weight in (
     off, bl = shard_rows(args.b, world, rank)
     a = z1[off:off + bl].cuda().requires_grad_(True)
     c = z2[off:off + bl].cuda().requires_grad_(True)
-    kw = dict(temperature=args.tau)
+    kw = dict(temperature=args.tau, transport=transport)
     if use_weight:
         kw["weight"] = torch.cat((w[off:off + bl], w[args.b + off:args.b + off + bl])).cuda()
     loss, acc = fn(a, c, **kw)
