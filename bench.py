@@ -7,9 +7,12 @@ N = 1  : one NT-Xent forward+backward over 2N = 8192 views, d = 128, tau = 0.5, 
          CUDA graph of the six kernels, L2 flushed between steps, timed with CUDA events); `e2e` = the same
          step through the public `contrastive_loss` API from pinned HOST buffers, H2D copy and loss/accuracy
          read-back inside the timed region.
-N > 1  : global batch 2N = 65536 sharded by rows over N ranks (torchrun, NCCL): all-gather of operands and
-         lse2 inside the timed region, strong scaling ("scaling": "strong").
---impl reference : the reference algorithm on the host CPU (oracle dense port of objective.py, all cores).
+N > 1  : global batch 2N = 65536 sharded by rows over N ranks (torchrun, one process per GPU): the operand / lse2
+         exchange is fused into our kernels over peer memory (NVLink stores + device barriers, no collective call on
+         the data path) and is inside the timed region; strong scaling ("scaling": "strong").  The N = 1 line carries
+         `scaling_base`: the same 2N = 65536 problem on one GPU, the denominator of the strong-scaling efficiency.
+--impl reference : the reference algorithm on the host CPU (oracle dense port of objective.py, all cores); at N > 1 a
+         bounded row sample of the 2N = 65536 problem.
 
 One JSON line on stdout (rank 0).
 """
@@ -118,6 +121,54 @@ def cpu_reference_arm(steps, warmup, b=B_SINGLE, d=DIM):
     return 2 * b / dt, dt * 1e3, cores
 
 
+def cpu_reference_rows(steps, warmup, b_global=B_GLOBAL, d=DIM, rows=1024):
+    """Bounded sample of the 2N = 65536 workload on the host cores: NT-Xent forward+backward (reference arithmetic,
+    fp32 torch CPU: normalise, similarity block, self-mask, cross-entropy, autograd) for `rows` view-1 rows against all
+    2*b_global columns.  views/s = rows processed per second at that batch size (dense 65536 x 65536 does not fit)."""
+    import torch
+    import torch.nn.functional as F
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gen = torch.Generator().manual_seed(0)
+    z = torch.randn(2 * b_global, d, generator=gen)
+
+    def one():
+        x = z.clone().requires_grad_(True)
+        zn = F.normalize(x, p=2, dim=1)                          # objective.py:25-30
+        logits = zn[:rows] @ zn.t() / TAU                        # objective.py:35-36,42-43 (row sample)
+        logits[torch.arange(rows), torch.arange(rows)] -= 1e9    # objective.py:39-40
+        labels = torch.arange(rows) + b_global                   # positive of view-1 row i is view-2 row i
+        loss = F.cross_entropy(logits, labels)                   # objective.py:47,50
+        loss.backward()
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / steps
+    return rows / dt, dt * 1e3, cores
+
+
+def timed_replays(torch, graph, flush, n, warm):
+    """CUDA-event time of n graph replays, L2 flushed (256 MiB memset, outside the event pair) before each."""
+    for _ in range(warm):
+        flush.zero_()
+        graph.replay()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+    torch.cuda.synchronize()
+    for i in range(n):
+        flush.zero_()
+        starts[i].record()
+        graph.replay()
+        stops[i].record()
+    torch.cuda.synchronize()
+    ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
+    return sum(ms) / n, min(ms)
+
+
 def bench_single(args):
     import torch
     import pytorch_simclr_b200 as sb
@@ -150,20 +201,7 @@ def bench_single(args):
         step.backward()
 
     def timed(g, n, warm):
-        for _ in range(warm):
-            flush.zero_()
-            g.replay()
-        starts = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
-        stops = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
-        torch.cuda.synchronize()
-        for i in range(n):
-            flush.zero_()                   # evict the operands from L2 between steps
-            starts[i].record()
-            g.replay()
-            stops[i].record()
-        torch.cuda.synchronize()
-        ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
-        return sum(ms) / n, min(ms)
+        return timed_replays(torch, g, flush, n, warm)
 
     sampler = ClockSampler(0)
     sampler.start()
@@ -197,6 +235,21 @@ def bench_single(args):
     e2e_ms = max(e2e_ms - flush_ms, 1e-6)
     clocks = sampler.stop()
 
+    # strong-scaling base: the N > 1 workload (2N = 65536) on this one GPU
+    big = ContrastiveStep(LOSS_NTXENT, B_GLOBAL, d, TAU, True, torch.float32, dev)
+    genb = torch.Generator().manual_seed(1000)
+    big.x1.copy_(torch.randn(B_GLOBAL, d, generator=genb))
+    big.x2.copy_(torch.randn(B_GLOBAL, d, generator=genb))
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            big.step()
+    torch.cuda.synchronize()
+    g_big = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_big, stream=side):
+        big.step()
+    ms_big, _ = timed_replays(torch, g_big, flush, max(3, min(args.steps, 10)), 2)
+    del g_big, big
+
     peak, peak_src = load_peaks()
     flops = algorithmic_flops(m, d)
     bwd_flops = 4.0 * m * m * d           # dominant kernel: backward tile kernel (row + column terms)
@@ -221,6 +274,10 @@ def bench_single(args):
         "cpu_baseline": {"value": cpu_value, "unit": "views/s", "cores": cores, "kind": "port",
                          "sample": "8 fwd+bwd calls of the same workload (2N=8192, d=128, fp32) after 2 warm-ups",
                          "ms_per_step": cpu_ms},
+        "scaling_base": {"workload": "ntxent_fwd_bwd 2N=65536 d=128 tau=0.5 (the N>1 workload) on 1 GPU",
+                         "ms_per_step": ms_big, "value": 2 * B_GLOBAL / (ms_big * 1e-3), "unit": "views/s",
+                         "tflops": algorithmic_flops(2 * B_GLOBAL, d) / (ms_big * 1e-3) / 1e12,
+                         "frac_of_peak": algorithmic_flops(2 * B_GLOBAL, d) / (ms_big * 1e-3) / 1e12 / peak},
     }
     print(json.dumps(line))
 
@@ -228,8 +285,9 @@ def bench_single(args):
 def bench_multi(args):
     import torch
     import torch.distributed as dist
-    from pytorch_simclr_b200 import functional as F
-    from pytorch_simclr_b200.distributed import RowShardGather, global_contrastive_loss, shard_rows
+    from pytorch_simclr_b200.distributed import global_contrastive_loss, shard_rows
+    from pytorch_simclr_b200.functional import LOSS_NTXENT
+    from pytorch_simclr_b200.runner import PeerStep
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -241,29 +299,46 @@ def bench_multi(args):
     gen = torch.Generator().manual_seed(1000 + rank)
     h1 = torch.randn(bl, d, generator=gen).pin_memory()
     h2 = torch.randn(bl, d, generator=gen).pin_memory()
-    x1, x2 = h1.to(dev), h2.to(dev)
-    gather = RowShardGather()
+    step = PeerStep(LOSS_NTXENT, bl, d, TAU, None, True, torch.float32, dev)
+    step.x1.copy_(h1)
+    step.x2.copy_(h2)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
-    def step():
-        loss, stats, _rv, saved = F.run_forward(F.LOSS_NTXENT, x1, x2, TAU, True, None, gather)
-        return loss, F.run_backward(saved, x1, x2, None)
+    side = torch.cuda.Stream(dev)
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step.step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    # one CUDA graph per rank: 8 kernels + 2 device-side cross-GPU barriers, no collective call inside.  Every rank
+    # replays it the same number of times (the barriers pair up across ranks).
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        step.step()
+    torch.cuda.synchronize()
+    dist.barrier()
 
-    for _ in range(max(3, args.warmup)):
-        step()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(3, args.warmup)):
+        flush.zero_()
+        graph.replay()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    start.record()
-    for _ in range(args.steps):
-        step()
-    stop.record()
+    for i in range(args.steps):
+        flush.zero_()                       # evict the operands from L2 between steps (outside the event pair)
+        starts[i].record()
+        graph.replay()
+        stops[i].record()
     torch.cuda.synchronize()
     dist.barrier()
-    t = torch.tensor([start.elapsed_time(stop) / args.steps], device=dev)
+    # a step ends on each rank when its own backward is done; its cross-GPU barriers make it wait for the slowest
+    # rank's forward, so the per-rank sums differ only by the last backward: take the MAX over ranks
+    t = torch.tensor([sum(a.elapsed_time(z) for a, z in zip(starts, stops)) / args.steps], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t)
 
@@ -295,12 +370,14 @@ def bench_multi(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "ntxent_fwd_bwd global 2N=65536 d=128 tau=0.5 row-sharded", "global_batch": b,
-                       "parallelism": f"rows/{world} + all-gather(operands, lse2)",
-                       "l2": "operand matrix (16.8 MB) re-read per row block; inputs not flushed",
-                       "collectives": "2x all_gather operands, 1x all_reduce stats, 2x all_gather lse2 (NCCL)"},
+                       "parallelism": f"rows/{world}; operands, lse2 and loss statistics pushed over NVLink by the prepare / "
+                                      "finalize kernels (symmetric memory), 2 device-side barriers per step",
+                       "l2": "flushed between steps (256 MiB memset outside the event pair)",
+                       "launch": "one CUDA graph of 10 kernels per rank and step, no collective call inside",
+                       "scaling_base": "the N=1 line's scaling_base (same 2N=65536 problem on one GPU)"},
             "e2e": {"value": m / (e2e_ms * 1e-3), "unit": "views/s", "h2d_bytes_per_step": 2 * bl * d * 4 * world,
                     "d2h_bytes_per_step": 8 * world, "ms_per_step": e2e_ms},
-            "gpu_launches": 6 * args.steps * world,
+            "gpu_launches": 10 * args.steps * world,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": None, "kernel": "whole step per GPU (fwd+bwd tile kernels)",
@@ -323,15 +400,23 @@ def main():
         if rank != 0:
             return
         steps = min(args.steps, 20)
-        value, ms, cores = cpu_reference_arm(steps=steps, warmup=min(args.warmup, 3))
+        multi = args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1
+        if multi:
+            value, ms, cores = cpu_reference_rows(steps=min(steps, 10), warmup=1)
+            workload = "ntxent_fwd_bwd global 2N=65536 d=128 tau=0.5 fp32 (reference arithmetic, host CPU, row sample)"
+            sample = f"{min(steps, 10)} fwd+bwd passes over a 1024-row sample of the 65536 x 65536 problem on the host cores"
+            gb = B_GLOBAL
+        else:
+            value, ms, cores = cpu_reference_arm(steps=steps, warmup=min(args.warmup, 3))
+            workload = "ntxent_fwd_bwd 2N=8192 d=128 tau=0.5 fp32 (reference algorithm, host CPU)"
+            sample = f"{steps} fwd+bwd calls of the workload on the host cores"
+            gb = B_SINGLE
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ntxent_fwd_bwd 2N=8192 d=128 tau=0.5 fp32 (reference algorithm, host CPU)",
-                       "global_batch": B_SINGLE},
-            "cpu_baseline": {"value": value, "unit": "views/s", "cores": cores, "kind": "port",
-                             "sample": f"{steps} fwd+bwd calls of the workload on the host cores"},
+            "scaling": "strong" if multi else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "global_batch": gb},
+            "cpu_baseline": {"value": value, "unit": "views/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return
