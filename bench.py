@@ -374,6 +374,7 @@ def bench_multi(args):
                                       "finalize kernels (symmetric memory), 2 device-side barriers per step",
                        "l2": "flushed between steps (256 MiB memset outside the event pair)",
                        "launch": "one CUDA graph of 10 kernels per rank and step, no collective call inside",
+                       "operand_push": "multimem.st (NVLS multicast)" if step.peer.multicast else "per-peer st.global",
                        "scaling_base": "the N=1 line's scaling_base (same 2N=65536 problem on one GPU)"},
             "e2e": {"value": m / (e2e_ms * 1e-3), "unit": "views/s", "h2d_bytes_per_step": 2 * bl * d * 4 * world,
                     "d2h_bytes_per_step": 8 * world, "ms_per_step": e2e_ms},

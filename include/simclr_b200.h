@@ -122,6 +122,8 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
  * simclr_prepare_peer : simclr_prepare that additionally stores every operand row into all ranks' global operand
  *                       matrix bf16 [2*Bgpad][Dpad] (Bgpad = simclr_pad_rows(world*b_local); the padding rows must have
  *                       been zeroed once) -- the operand "all-gather" is these NVLink stores, fused into the kernel.
+ *                       `operand_global_multicast` (may be NULL) is the NVLS multicast mapping of the same buffer:
+ *                       when given, each row leaves the GPU once (multimem.st) and the NVSwitch replicates it.
  * simclr_forward_peer : simclr_forward whose finalize kernel pushes the local rows' lse2 into all ranks' global lse2
  *                       vector f32 [2*Bgpad] and {sum w L, sum w, #correct} into slot `rank` of all ranks'
  *                       stats_all f32 [world][4].
@@ -133,7 +135,8 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
  */
 int simclr_prepare_peer(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
                         int normalize, float temperature, void* operand, float* inv_norm, float* pos_dot,
-                        void* forward_workspace, int world, int rank, void* const* operand_global_peers, void* stream);
+                        void* forward_workspace, int world, int rank, void* const* operand_global_peers,
+                        void* operand_global_multicast, void* stream);
 int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
                         int64_t row_offset, int64_t d, float temperature, int normalize, const float* pos_dot,
                         const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out,

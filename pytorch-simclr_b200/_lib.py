@@ -37,7 +37,8 @@ SIGNATURES = {
                               _sz, _vp]),
     "simclr_backward": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp,
                                _vp, _vp, _vp, _vp, _sz, _vp]),
-    "simclr_prepare_peer": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _vp, _vp, _vp, _vp, _int, _int, _vp, _vp]),
+    "simclr_prepare_peer": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _vp, _vp, _vp, _vp, _int, _int, _vp, _vp,
+                                   _vp]),
     "simclr_forward_peer": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                    _sz, _int, _int, _vp, _vp, _vp]),
     "simclr_peer_barrier": (_int, [_int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),

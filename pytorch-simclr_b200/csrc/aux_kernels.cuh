@@ -34,6 +34,25 @@ SIMCLR_DEVICE void store_words(__nv_bfloat16* row, int lane, const uint32_t (&w)
     else reinterpret_cast<uint4*>(row)[lane] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// the same packed store through a multicast address: the NVSwitch replicates it into every rank's copy
+template <int kWords>
+SIMCLR_DEVICE void store_words_multicast(__nv_bfloat16* row, int lane, const uint32_t (&w)[4]) {
+    if constexpr (kWords == 1) {
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(reinterpret_cast<uint32_t*>(row) + lane),
+                     "f"(__uint_as_float(w[0]))
+                     : "memory");
+    } else if constexpr (kWords == 2) {
+        asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint2*>(row) + lane),
+                     "f"(__uint_as_float(w[0])), "f"(__uint_as_float(w[1]))
+                     : "memory");
+    } else {
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<uint4*>(row) + lane),
+                     "f"(__uint_as_float(w[0])), "f"(__uint_as_float(w[1])), "f"(__uint_as_float(w[2])),
+                     "f"(__uint_as_float(w[3]))
+                     : "memory");
+    }
+}
+
 template <typename T, int kLoss, int kPer /* d_pad / 32: 2, 4 or 8 */>
 __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x2, AuxParams a,
                                __nv_bfloat16* __restrict__ operand, float* __restrict__ inv_norm,
@@ -129,10 +148,16 @@ __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x
     }
     store_words<kWords>(o1, lane, w1);
     store_words<kWords>(o2, lane, w2);
-    for (int r = 0; r < peers.world; ++r) {
-        __nv_bfloat16* g = static_cast<__nv_bfloat16*>(peers.ptr[r]);
-        store_words<kWords>(g + static_cast<size_t>(a.row_off + i) * a.d_pad, lane, w1);
-        store_words<kWords>(g + static_cast<size_t>(a.bg_pad + a.row_off + i) * a.d_pad, lane, w2);
+    if (peers.mc != nullptr) {
+        __nv_bfloat16* g = static_cast<__nv_bfloat16*>(peers.mc);
+        store_words_multicast<kWords>(g + static_cast<size_t>(a.row_off + i) * a.d_pad, lane, w1);
+        store_words_multicast<kWords>(g + static_cast<size_t>(a.bg_pad + a.row_off + i) * a.d_pad, lane, w2);
+    } else {
+        for (int r = 0; r < peers.world; ++r) {
+            __nv_bfloat16* g = static_cast<__nv_bfloat16*>(peers.ptr[r]);
+            store_words<kWords>(g + static_cast<size_t>(a.row_off + i) * a.d_pad, lane, w1);
+            store_words<kWords>(g + static_cast<size_t>(a.bg_pad + a.row_off + i) * a.d_pad, lane, w2);
+        }
     }
     if (lane == 0) {
         inv_norm[i] = inv1;

@@ -368,13 +368,18 @@ size_t simclr_backward_workspace_bytes(int loss, int64_t b_local, int64_t b_glob
 
 int simclr_prepare_peer(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
                         int normalize, float temperature, void* operand, float* inv_norm, float* pos_dot,
-                        void* forward_workspace, int world, int rank, void* const* operand_global_peers, void* stream) {
+                        void* forward_workspace, int world, int rank, void* const* operand_global_peers,
+                        void* operand_global_multicast, void* stream) {
     if (!x_batch1 || !x_batch2 || !operand || !inv_norm || !pos_dot) return SIMCLR_ERR_NULL_POINTER;
     if (in_dtype != SIMCLR_DTYPE_F32 && in_dtype != SIMCLR_DTYPE_BF16) return SIMCLR_ERR_BAD_DTYPE;
     if (!(temperature > 0.f) || !std::isfinite(temperature)) return SIMCLR_ERR_BAD_TEMPERATURE;
     PeerTable peers;
     int rc = make_peer_table(world, rank, operand_global_peers, &peers);
     if (rc) return rc;
+    if (peers.world > 0 && operand_global_multicast != nullptr) {
+        if (misaligned(operand_global_multicast)) return SIMCLR_ERR_MISALIGNED;
+        peers.mc = operand_global_multicast;
+    }
     const int64_t b_global = peers.world > 0 ? b_local * peers.world : b_local;
     const int64_t row_offset = peers.world > 0 ? b_local * peers.rank : 0;
     Geometry g;
@@ -414,7 +419,7 @@ int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t
                    int normalize, float temperature, void* operand, float* inv_norm, float* pos_dot,
                    void* forward_workspace, void* stream) {
     return simclr_prepare_peer(loss, x_batch1, x_batch2, b_local, d, in_dtype, normalize, temperature, operand, inv_norm,
-                               pos_dot, forward_workspace, 0, 0, nullptr, stream);
+                               pos_dot, forward_workspace, 0, 0, nullptr, nullptr, stream);
 }
 
 int simclr_peer_barrier(int world, int rank, void* const* flag_peers, unsigned int* epoch_local, const float* stats_all,

@@ -89,6 +89,7 @@ enum LossKind : int { kNtXent = 0, kModified = 1 };
 constexpr int kMaxPeers = 16;
 struct PeerTable {
     void* ptr[kMaxPeers];
+    void* mc;      // multicast (NVLS) mapping of the same symmetric buffer, or nullptr: one multimem.st reaches every rank
     int world;
     int rank;
 };

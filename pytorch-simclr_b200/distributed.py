@@ -110,7 +110,7 @@ class PeerBatch:
     peer = True
     GENERATIONS = 2
 
-    def __init__(self, b_local: int, d: int, group=None, device=None):
+    def __init__(self, b_local: int, d: int, group=None, device=None, use_multicast: bool = True):
         import torch.distributed._symmetric_memory as symm
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
@@ -145,6 +145,15 @@ class PeerBatch:
                 "stats": arr(*[p + base + op_bytes + lse_bytes for p in ptrs]),
             })
         self._flags = arr(*[p + flag_off for p in ptrs])
+        # NVLS multicast mapping of the same allocation (0 when the fabric has no multicast support)
+        mc = 0
+        if use_multicast:
+            try:
+                mc = int(self.handle.multicast_ptr or 0)
+            except Exception:       # handle without multicast support
+                mc = 0
+        self.multicast = bool(mc)
+        self._mc = [None if not mc else mc + g * self._gen_bytes for g in range(self.GENERATIONS)]
         local = self.buf
         self._views = []
         for g in range(self.GENERATIONS):
@@ -167,7 +176,8 @@ class PeerBatch:
         code = _dtype_code(x1)
         check(lib.simclr_prepare_peer(loss_kind, x1.data_ptr(), x2.data_ptr(), self.b_local, self.d, code,
                                       int(bool(normalize)), float(temperature), operand.data_ptr(), rowvec[0].data_ptr(),
-                                      rowvec[1].data_ptr(), ws.data_ptr(), self.world, self.rank, tab["operand"], stream),
+                                      rowvec[1].data_ptr(), ws.data_ptr(), self.world, self.rank, tab["operand"],
+                                      self._mc[gen], stream),
               "simclr_prepare_peer")
         check(lib.simclr_peer_barrier(self.world, self.rank, self._flags, self.epoch.data_ptr(), None, None, None, stream),
               "simclr_peer_barrier")
