@@ -4,7 +4,7 @@
 
 N = 1  : one NT-Xent forward+backward over 2N = 8192 views, d = 128, tau = 0.5, fp32 inputs, bf16 tensor-core
          operands with fp32 accumulation.  `value` = views/s with inputs resident in HBM (the step is one
-         CUDA graph of the six kernels, L2 flushed between steps, timed with CUDA events); `e2e` = the same
+         CUDA graph of the five kernels, L2 flushed between steps, timed with CUDA events); `e2e` = the same
          step through the public `contrastive_loss` API from pinned HOST buffers, H2D copy and loss/accuracy
          read-back inside the timed region.
 N > 1  : global batch 2N = 65536 sharded by rows over N ranks (torchrun, one process per GPU): the operand / lse2
@@ -261,10 +261,10 @@ def bench_single(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "ntxent_fwd_bwd 2N=8192 d=128 tau=0.5 fp32-in bf16-mma fp32-acc", "global_batch": b,
                    "l2": "flushed between steps (256 MiB memset outside the event pair)",
-                   "launch": "one CUDA graph of 6 kernels per step"},
+                   "launch": "one CUDA graph of 5 kernels per step (programmatic dependent launch between them)"},
         "e2e": {"value": m / (e2e_ms * 1e-3), "unit": "views/s", "h2d_bytes_per_step": 2 * b * d * 4,
                 "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms},
-        "gpu_launches": 6 * args.steps,
+        "gpu_launches": 5 * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": None, "kernel": "contrastive_tile_kernel<128,0,true> (backward)",
@@ -310,7 +310,7 @@ def bench_multi(args):
             step.step()
     torch.cuda.synchronize()
     dist.barrier()
-    # one CUDA graph per rank: 8 kernels + 2 device-side cross-GPU barriers, no collective call inside.  Every rank
+    # one CUDA graph per rank: 5 kernels + 2 device-side cross-GPU barriers, no collective call inside.  Every rank
     # replays it the same number of times (the barriers pair up across ranks).
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph, stream=side):
@@ -373,12 +373,12 @@ def bench_multi(args):
                        "parallelism": f"rows/{world}; operands, lse2 and loss statistics pushed over NVLink by the prepare / "
                                       "finalize kernels (symmetric memory), 2 device-side barriers per step",
                        "l2": "flushed between steps (256 MiB memset outside the event pair)",
-                       "launch": "one CUDA graph of 10 kernels per rank and step, no collective call inside",
+                       "launch": "one CUDA graph of 7 kernels per rank and step (5 compute + 2 device-side barriers), no collective call inside",
                        "operand_push": "multimem.st (NVLS multicast)" if step.peer.multicast else "per-peer st.global",
                        "scaling_base": "the N=1 line's scaling_base (same 2N=65536 problem on one GPU)"},
             "e2e": {"value": m / (e2e_ms * 1e-3), "unit": "views/s", "h2d_bytes_per_step": 2 * bl * d * 4 * world,
                     "d2h_bytes_per_step": 8 * world, "ms_per_step": e2e_ms},
-            "gpu_launches": 10 * args.steps * world,
+            "gpu_launches": 7 * args.steps * world,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": None, "kernel": "whole step per GPU (fwd+bwd tile kernels)",

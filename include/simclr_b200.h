@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIMCLR_ABI_VERSION 4
+#define SIMCLR_ABI_VERSION 5
 
 /* loss kinds */
 #define SIMCLR_LOSS_NTXENT 0   /* objective.py:6-55  */
@@ -106,12 +106,16 @@ int simclr_forward(int loss, const void* operand_rows, const void* operand_cols,
  *   col_scale  f32 [2*Bgpad]  w_c / sum(w) in view-padded order, or NULL for the unweighted 1/(2B)
  *   grad_out   f32 [1] on the device, or NULL for 1.0
  *   grad1/2    [b_local][d] in `in_dtype`
+ *   primed_colvec  NULL, or the column vectors f32 [2][2*Bgpad] a forward call already produced together with a
+ *              zeroed accumulation buffer in `workspace` (simclr_forward_peer with `backward_workspace`): the
+ *              backward-prepare kernel is then skipped and lse2_cols may be NULL.  On one GPU the vectors sit at the
+ *              start of the backward workspace; in the row-sharded batch they are the rank's symmetric colvec buffer.
  */
 int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t b_global,
                     int64_t row_offset, int64_t d, int in_dtype, int normalize, float temperature,
                     const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,
                     const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
-                    void* workspace, size_t workspace_bytes, void* stream);
+                    void* workspace, size_t workspace_bytes, const float* primed_colvec, void* stream);
 
 /*
  * Row-sharded global batch over peer memory (one process per GPU of one NVLink / NVSwitch node; not in the reference,
@@ -124,9 +128,12 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
  *                       been zeroed once) -- the operand "all-gather" is these NVLink stores, fused into the kernel.
  *                       `operand_global_multicast` (may be NULL) is the NVLS multicast mapping of the same buffer:
  *                       when given, each row leaves the GPU once (multimem.st) and the NVSwitch replicates it.
- * simclr_forward_peer : simclr_forward whose finalize kernel pushes the local rows' lse2 into all ranks' global lse2
- *                       vector f32 [2*Bgpad] and {sum w L, sum w, #correct} into slot `rank` of all ranks'
- *                       stats_all f32 [world][4].
+ * simclr_forward_peer : simclr_forward whose finalize kernel pushes the backward's column vectors of the local rows
+ *                       (a_c | lse2_c) into all ranks' colvec f32 [2][2*Bgpad] (padding zeroed once) and
+ *                       {sum w L, sum w, #correct} into slot `rank` of all ranks' stats_all f32 [world][4].
+ *                       `backward_workspace` (may be NULL; unweighted losses only) primes the following
+ *                       simclr_backward: its accumulation buffer is zeroed by a spare warp of the forward tile kernel
+ *                       and, on one GPU (world == 0), the column vectors are written to its start.
  * simclr_peer_barrier : device-side barrier over flags u32 [world] in symmetric memory (zero-initialised once);
  *                       `epoch_local` is a private device counter, also zero-initialised once.  With `stats_all` it
  *                       then sums the per-rank statistics into stats_out[4] / loss_out (the GLOBAL loss, identical on
@@ -140,7 +147,8 @@ int simclr_prepare_peer(int loss, const void* x_batch1, const void* x_batch2, in
 int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
                         int64_t row_offset, int64_t d, float temperature, int normalize, const float* pos_dot,
                         const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out,
-                        void* workspace, size_t workspace_bytes, int world, int rank, void* const* lse2_global_peers,
+                        void* workspace, size_t workspace_bytes, void* backward_workspace,
+                        size_t backward_workspace_bytes, int world, int rank, void* const* colvec_peers,
                         void* const* stats_peers, void* stream);
 int simclr_peer_barrier(int world, int rank, void* const* flag_peers, unsigned int* epoch_local, const float* stats_all,
                         float* stats_out, float* loss_out, void* stream);

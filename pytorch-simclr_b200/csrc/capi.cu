@@ -440,14 +440,15 @@ int simclr_forward(int loss, const void* operand_rows, const void* operand_cols,
                    const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out, void* workspace,
                    size_t workspace_bytes, void* stream) {
     return simclr_forward_peer(loss, operand_rows, operand_cols, b_local, b_global, row_offset, d, temperature, normalize,
-                               pos_dot, row_weight, lse2, row_loss, stats, loss_out, workspace, workspace_bytes, 0, 0, nullptr,
-                               nullptr, stream);
+                               pos_dot, row_weight, lse2, row_loss, stats, loss_out, workspace, workspace_bytes, nullptr, 0,
+                               0, 0, nullptr, nullptr, stream);
 }
 
 int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
                         int64_t row_offset, int64_t d, float temperature, int normalize, const float* pos_dot,
                         const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out,
-                        void* workspace, size_t workspace_bytes, int world, int rank, void* const* lse2_global_peers,
+                        void* workspace, size_t workspace_bytes, void* backward_workspace,
+                        size_t backward_workspace_bytes, int world, int rank, void* const* colvec_peers,
                         void* const* stats_peers, void* stream) {
     if (!operand_rows || !operand_cols || !pos_dot || !lse2 || !row_loss || !stats || !workspace)
         return SIMCLR_ERR_NULL_POINTER;
@@ -477,9 +478,22 @@ int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_
     p.block_part = w.block_part;
     p.stats = stats;
     p.loss_out = loss_out;
-    if ((rc = make_peer_table(world, rank, lse2_global_peers, &p.lse2_peers))) return rc;
+    if ((rc = make_peer_table(world, rank, colvec_peers, &p.colvec_peers))) return rc;
     if ((rc = make_peer_table(world, rank, stats_peers, &p.stats_peers))) return rc;
-    if (p.lse2_peers.world > 0 && (b_global != b_local * world || row_offset != b_local * rank)) return SIMCLR_ERR_BAD_PEERS;
+    if (p.colvec_peers.world > 0 && (b_global != b_local * world || row_offset != b_local * rank)) return SIMCLR_ERR_BAD_PEERS;
+    if (backward_workspace != nullptr) {
+        // prime the backward: zeroed accumulation buffer, column vectors (weighted losses need sum(w): not primed)
+        if (row_weight != nullptr) return SIMCLR_ERR_BAD_PEERS;
+        if (misaligned(backward_workspace)) return SIMCLR_ERR_MISALIGNED;
+        BwdWorkspace bw = carve_backward(g, backward_workspace);
+        if (backward_workspace_bytes < bw.bytes) return SIMCLR_ERR_WORKSPACE_TOO_SMALL;
+        p.prime_dacc = reinterpret_cast<float4*>(bw.dacc);
+        p.prime_dacc_vec4 = bw.dacc_floats / 4;
+        if (p.colvec_peers.world == 0) {
+            if (b_local != b_global) return SIMCLR_ERR_BAD_PEERS;     // a shard cannot know the other ranks' lse2
+            p.prime_colvec = bw.colvec;
+        }
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if ((rc = dispatch_tile<false>(loss, g.d_pad, map_rows, map_cols, map_rows, p, g.grid, st))) return rc;
     cudaError_t e;
@@ -492,10 +506,11 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
                     int64_t row_offset, int64_t d, int in_dtype, int normalize, float temperature,
                     const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,
                     const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
-                    void* workspace, size_t workspace_bytes, void* stream) {
-    if (!x_batch1 || !x_batch2 || !operand_rows || !operand_cols || !inv_norm || !pos_dot || !lse2_cols || !grad1 ||
-        !grad2 || !workspace)
+                    void* workspace, size_t workspace_bytes, const float* primed_colvec, void* stream) {
+    if (!x_batch1 || !x_batch2 || !operand_rows || !operand_cols || !inv_norm || !pos_dot || !grad1 || !grad2 || !workspace)
         return SIMCLR_ERR_NULL_POINTER;
+    if (!lse2_cols && !primed_colvec) return SIMCLR_ERR_NULL_POINTER;
+    if (primed_colvec && col_scale) return SIMCLR_ERR_BAD_PEERS;      // weighted losses are never primed
     if (in_dtype != SIMCLR_DTYPE_F32 && in_dtype != SIMCLR_DTYPE_BF16) return SIMCLR_ERR_BAD_DTYPE;
     if (!(temperature > 0.f) || !std::isfinite(temperature)) return SIMCLR_ERR_BAD_TEMPERATURE;
     Geometry g;
@@ -516,16 +531,18 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
     AuxParams a = make_aux(g, s, b_local, b_global, row_offset, d, normalize);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-    if ((rc = static_cast<int>(launch_pdl(backward_prepare_kernel, dim3(device_info().sm_count * 2), dim3(256), 0, st, a,
-                                          lse2_cols, col_scale, w.colvec, reinterpret_cast<float4*>(w.dacc),
-                                          w.dacc_floats / 4, g_ktrace_ptr))))
-        return rc;
+    if (primed_colvec == nullptr) {
+        if ((rc = static_cast<int>(launch_pdl(backward_prepare_kernel, dim3(device_info().sm_count * 2), dim3(256), 0, st, a,
+                                              lse2_cols, col_scale, w.colvec, reinterpret_cast<float4*>(w.dacc),
+                                              w.dacc_floats / 4, g_ktrace_ptr))))
+            return rc;
+    }
 
     TileParams p = make_tile_params(g, s, b_local, b_global, row_offset);
     p.d = static_cast<int>(d);
     p.in_bf16 = in_dtype == SIMCLR_DTYPE_BF16 ? 1 : 0;
     p.normalize = normalize;
-    p.colvec = w.colvec;
+    p.colvec = primed_colvec ? primed_colvec : w.colvec;
     p.dacc = w.dacc;
     p.x1 = x_batch1;
     p.x2 = x_batch2;

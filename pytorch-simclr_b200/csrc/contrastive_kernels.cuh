@@ -135,8 +135,13 @@ struct TileParams {
     const float* grad_out;     // [1] or nullptr
     // row-sharded global batch over peer memory: every rank's forward finalize pushes its rows' lse2 and its three
     // loss statistics into all ranks' global buffers (no collective call)
-    PeerTable lse2_peers;      // float [2*bg_pad] per rank
+    PeerTable colvec_peers;    // float [2 planes][2*bg_pad] per rank: the backward's column vectors (a_c | lse2_c)
     PeerTable stats_peers;     // float [world][4] per rank
+    // "priming" the backward from the forward (saves the backward-prepare kernel): the finalize kernel writes the column
+    // vectors, an idle warp of the forward tile kernel zeroes the gradient accumulation buffer
+    float* prime_colvec;       // local [2][2*bg_pad] or nullptr
+    float4* prime_dacc;        // or nullptr
+    unsigned long long prime_dacc_vec4;
     long long* trace;      // optional (debug): per-role clock64() timestamps of CTA `trace_cta`
     int trace_cta;
     int tile_grid;         // grid size of the tile kernel (the finalize kernels need it to locate partials)
@@ -509,10 +514,25 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
     }
     p.lse2[slot] = l2;
     p.row_loss[slot] = loss_r;
-    if (p.lse2_peers.world > 0 && row_ok) {
-        // the column vector of the global batch, written straight into every rank's copy over NVLink
+    if (p.prime_colvec != nullptr || p.colvec_peers.world > 0) {
+        // the backward's column vectors: a_c = g_c 2^(m2 - lse2_c) (or g_c in the general form) and lse2_c, with the
+        // unweighted g_c = 1/(2B).  Row-sharded batch: written straight into every rank's copy over NVLink.
         const int gslot = vr * p.bg_pad + p.row_off + img;
-        for (int r = 0; r < p.lse2_peers.world; ++r) static_cast<float*>(p.lse2_peers.ptr[r])[gslot] = l2;
+        const int plane = 2 * p.bg_pad;
+        const float g = 0.5f / static_cast<float>(p.b_glob);
+        const float a_c = row_ok ? (p.const_shift ? g * exp2f(p.m2 - l2) : g) : 0.f;
+        if (p.colvec_peers.world > 0) {
+            if (row_ok) {
+                for (int r = 0; r < p.colvec_peers.world; ++r) {
+                    float* cv = static_cast<float*>(p.colvec_peers.ptr[r]);
+                    cv[gslot] = a_c;
+                    cv[plane + gslot] = l2;
+                }
+            }
+        } else {                          // single GPU: bl_pad == bg_pad, padding slots are zeroed here as well
+            p.prime_colvec[gslot] = a_c;
+            p.prime_colvec[plane + gslot] = l2;
+        }
     }
 
     // block sums in a fixed order (deterministic)
@@ -1013,6 +1033,14 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             ++seg;
             ring.advance();
             ring.advance();
+        }
+    } else if (!kBackward && warp == kScoreWarp0 + kNumIssuers) {
+        // ================================ forward: the spare warp primes the backward ================================
+        if (p.prime_dacc != nullptr) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * 32 + lane; i < p.prime_dacc_vec4;
+                 i += static_cast<unsigned long long>(gridDim.x) * 32)
+                p.prime_dacc[i] = z;
         }
     } else if (warp < kNumSoftmaxWarps) {
         // ================================ softmax warpgroups ================================

@@ -104,8 +104,8 @@ class PeerBatch:
     """Symmetric-memory state of the row-sharded global batch for one (b_local, d) on this rank.
 
     One symmetric allocation per rank holds two generations (double buffering: a fast rank may already push step
-    k+1 while a slow one still reads step k) of  operand_all bf16 [2*Bgpad][Dpad] | lse2_all f32 [2*Bgpad] |
-    stats_all f32 [world][4]  plus the barrier flags u32 [world].  Everything else is ordinary device memory.
+    k+1 while a slow one still reads step k) of  operand_all bf16 [2*Bgpad][Dpad] | colvec f32 [2][2*Bgpad] (the backward's column
+    vectors a_c | lse2_c) | stats_all f32 [world][4]  plus the barrier flags u32 [world].  Everything else is ordinary device memory.
     """
     peer = True
     GENERATIONS = 2
@@ -124,7 +124,7 @@ class PeerBatch:
         self.bg_pad, self.dp = pad_rows(self.b_global), pad_dim(d)
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         op_bytes = _align(2 * self.bg_pad * self.dp * 2)
-        lse_bytes = _align(2 * self.bg_pad * 4)
+        lse_bytes = _align(2 * 2 * self.bg_pad * 4)
         st_bytes = _align(self.world * 4 * 4)
         self._gen_bytes = op_bytes + lse_bytes + st_bytes
         flag_off = self.GENERATIONS * self._gen_bytes
@@ -141,7 +141,7 @@ class PeerBatch:
             base = g * self._gen_bytes
             self._tables.append({
                 "operand": arr(*[p + base for p in ptrs]),
-                "lse2": arr(*[p + base + op_bytes for p in ptrs]),
+                "colvec": arr(*[p + base + op_bytes for p in ptrs]),
                 "stats": arr(*[p + base + op_bytes + lse_bytes for p in ptrs]),
             })
         self._flags = arr(*[p + flag_off for p in ptrs])
@@ -160,7 +160,7 @@ class PeerBatch:
             base = g * self._gen_bytes
             self._views.append({
                 "operand": local[base: base + 2 * self.bg_pad * self.dp * 2].view(torch.bfloat16).view(2 * self.bg_pad, self.dp),
-                "lse2": local[base + op_bytes: base + op_bytes + 2 * self.bg_pad * 4].view(torch.float32),
+                "colvec": local[base + op_bytes: base + op_bytes + 2 * 2 * self.bg_pad * 4].view(torch.float32),
                 "stats": local[base + op_bytes + lse_bytes: base + op_bytes + lse_bytes + self.world * 16].view(torch.float32),
             })
         self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -169,7 +169,7 @@ class PeerBatch:
 
     # ------------------------------------------------------------------------------------------------------
     def forward(self, loss_kind, x1, x2, temperature, normalize, operand, rowvec, stats_local, stats_global, loss,
-                ws, ws_bytes, stream):
+                ws, ws_bytes, stream, bwd_ws=None):
         """prepare(+push) -> barrier -> forward(+push) -> barrier(+global statistics); enqueue only."""
         lib, gen = self.lib, self.generation % self.GENERATIONS
         tab, view = self._tables[gen], self._views[gen]
@@ -184,16 +184,17 @@ class PeerBatch:
         check(lib.simclr_forward_peer(loss_kind, operand.data_ptr(), view["operand"].data_ptr(), self.b_local,
                                       self.b_global, self.row_offset, self.d, float(temperature), int(bool(normalize)),
                                       rowvec[1].data_ptr(), None, rowvec[2].data_ptr(), rowvec[3].data_ptr(),
-                                      stats_local.data_ptr(), None, ws.data_ptr(), ws_bytes, self.world, self.rank,
-                                      tab["lse2"], tab["stats"], stream), "simclr_forward_peer")
+                                      stats_local.data_ptr(), None, ws.data_ptr(), ws_bytes,
+                                      None if bwd_ws is None else bwd_ws.data_ptr(), 0 if bwd_ws is None else bwd_ws.numel(),
+                                      self.world, self.rank, tab["colvec"], tab["stats"], stream), "simclr_forward_peer")
         check(lib.simclr_peer_barrier(self.world, self.rank, self._flags, self.epoch.data_ptr(), view["stats"].data_ptr(),
                                       stats_global.data_ptr(), loss.data_ptr(), stream), "simclr_peer_barrier")
         self.generation += 1
-        return view["operand"], view["lse2"], self.generation
+        return view["operand"], view["colvec"], self.generation
 
 
 def run_forward_peer(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature: float, normalize: bool,
-                     peer: PeerBatch):
+                     peer: PeerBatch, prime_backward: bool = True):
     """Peer-memory counterpart of functional.run_forward (same return tuple)."""
     lib = _lib.load()
     b, d = _validate(x1, x2)
@@ -211,12 +212,18 @@ def run_forward_peer(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, tempera
         loss = torch.empty((), dtype=torch.float32, device=dev)
         ws_bytes = lib.simclr_forward_workspace_bytes(loss_kind, b, peer.b_global, d)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        operand_cols, lse2_cols, generation = peer.forward(loss_kind, x1, x2, temperature, normalize, operand, rowvec,
-                                                           stats_local, stats, loss, ws, ws_bytes, stream)
+        bwd_ws = None
+        if prime_backward:
+            bwd_ws = torch.empty(lib.simclr_backward_workspace_bytes(loss_kind, b, peer.b_global, d), dtype=torch.uint8,
+                                 device=dev)
+        operand_cols, colvec, generation = peer.forward(loss_kind, x1, x2, temperature, normalize, operand, rowvec,
+                                                        stats_local, stats, loss, ws, ws_bytes, stream, bwd_ws)
     saved = _Saved()
     saved.operand_rows, saved.operand_cols = operand, operand_cols
     saved.inv_norm, saved.pos_dot = rowvec[0], rowvec[1]
-    saved.lse2_cols, saved.col_scale = lse2_cols, None
+    saved.lse2_cols, saved.col_scale = colvec[2 * peer.bg_pad:], None      # plane 1 of the column vectors is lse2
+    saved.bwd_ws = bwd_ws
+    saved.primed_colvec = colvec.data_ptr() if bwd_ws is not None else None
     saved.b_local, saved.b_global, saved.row_offset, saved.d = b, peer.b_global, peer.row_offset, d
     saved.loss, saved.temperature, saved.normalize, saved.dtype_code = loss_kind, float(temperature), bool(normalize), _dtype_code(x1)
     saved.peer, saved.generation = peer, generation

@@ -72,11 +72,12 @@ def _validate(x1: torch.Tensor, x2: torch.Tensor) -> Tuple[int, int]:
 class _Saved:
     """State a forward leaves for its backward (device buffers only)."""
     __slots__ = ("operand_rows", "operand_cols", "inv_norm", "pos_dot", "lse2_cols", "col_scale", "b_local",
-                 "b_global", "row_offset", "d", "loss", "temperature", "normalize", "dtype_code", "peer", "generation")
+                 "b_global", "row_offset", "d", "loss", "temperature", "normalize", "dtype_code", "peer", "generation",
+                 "bwd_ws", "primed_colvec")
 
 
 def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature: float, normalize: bool,
-                weight: Optional[torch.Tensor], gather=None):
+                weight: Optional[torch.Tensor], gather=None, prime_backward: bool = False):
     """prepare + forward through the C ABI.  ``gather`` (distributed.py) turns the local operand / lse2 into
     their global-batch counterparts and returns (operand_cols, b_global, row_offset, reducer)."""
     lib = _lib.load()
@@ -107,11 +108,17 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
             w_local = weight.to(device=dev, dtype=torch.float32).contiguous()
             if w_local.numel() != 2 * b:
                 raise ValueError(f"weight must have {2 * b} entries, got {w_local.numel()}")
-        check(lib.simclr_forward(loss_kind, operand.data_ptr(), operand_cols.data_ptr(), b, b_global, row_offset, d,
-                                 float(temperature), int(bool(normalize)), rowvec[1].data_ptr(), _ptr(w_local),
-                                 rowvec[2].data_ptr(),
-                                 rowvec[3].data_ptr(), stats.data_ptr(), loss.data_ptr(), ws.data_ptr(), ws_bytes,
-                                 stream), "simclr_forward")
+        # single GPU, unweighted, gradients wanted: the forward also prepares the backward workspace (zeroed
+        # accumulation buffer + column vectors), which saves the backward-prepare kernel
+        bwd_ws = None
+        if prime_backward and gather is None and weight is None:
+            bwd_bytes = lib.simclr_backward_workspace_bytes(loss_kind, b, b, d)
+            bwd_ws = torch.empty(bwd_bytes, dtype=torch.uint8, device=dev)
+        check(lib.simclr_forward_peer(loss_kind, operand.data_ptr(), operand_cols.data_ptr(), b, b_global, row_offset, d,
+                                      float(temperature), int(bool(normalize)), rowvec[1].data_ptr(), _ptr(w_local),
+                                      rowvec[2].data_ptr(), rowvec[3].data_ptr(), stats.data_ptr(), loss.data_ptr(),
+                                      ws.data_ptr(), ws_bytes, _ptr(bwd_ws), 0 if bwd_ws is None else bwd_ws.numel(), 0, 0,
+                                      None, None, stream), "simclr_forward")
     saved = _Saved()
     saved.operand_rows, saved.operand_cols = operand, operand_cols
     saved.inv_norm, saved.pos_dot = rowvec[0], rowvec[1]
@@ -119,6 +126,7 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
     saved.col_scale = None
     saved.b_local, saved.b_global, saved.row_offset, saved.d = b, b_global, row_offset, d
     saved.loss, saved.temperature, saved.normalize, saved.dtype_code = loss_kind, float(temperature), bool(normalize), code
+    saved.bwd_ws, saved.primed_colvec = bwd_ws, (None if bwd_ws is None else bwd_ws.data_ptr())
     if gather is not None:
         loss, stats = gather.reduce(stats, loss)
         saved.lse2_cols = gather.rowvec(rowvec[2], b)
@@ -143,14 +151,18 @@ def run_backward(saved: "_Saved", x1: torch.Tensor, x2: torch.Tensor, grad_out: 
         go = None
         if grad_out is not None:
             go = grad_out.to(device=dev, dtype=torch.float32).contiguous()
-        ws_bytes = lib.simclr_backward_workspace_bytes(saved.loss, saved.b_local, saved.b_global, saved.d)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ws = getattr(saved, "bwd_ws", None)
+        primed = getattr(saved, "primed_colvec", None) if ws is not None else None
+        if ws is None:
+            ws = torch.empty(lib.simclr_backward_workspace_bytes(saved.loss, saved.b_local, saved.b_global, saved.d),
+                             dtype=torch.uint8, device=dev)
+        ws_bytes = ws.numel()
         check(lib.simclr_backward(saved.loss, x1.data_ptr(), x2.data_ptr(), saved.b_local, saved.b_global,
                                   saved.row_offset, saved.d, saved.dtype_code, int(saved.normalize), saved.temperature,
                                   saved.operand_rows.data_ptr(), saved.operand_cols.data_ptr(),
                                   saved.inv_norm.data_ptr(), saved.pos_dot.data_ptr(), saved.lse2_cols.data_ptr(),
                                   _ptr(saved.col_scale), _ptr(go), g1.data_ptr(), g2.data_ptr(), ws.data_ptr(),
-                                  ws_bytes, stream), "simclr_backward")
+                                  ws_bytes, primed, stream), "simclr_backward")
     return g1, g2
 
 
@@ -165,9 +177,11 @@ class ContrastiveLossFunction(torch.autograd.Function):
     def forward(ctx, x1, x2, loss_kind, temperature, normalize, weight, gather):
         if getattr(gather, "peer", False):
             from .distributed import run_forward_peer
-            loss, stats, _rowvec, saved = run_forward_peer(loss_kind, x1, x2, temperature, normalize, gather)
+            loss, stats, _rowvec, saved = run_forward_peer(loss_kind, x1, x2, temperature, normalize, gather,
+                                                           any(ctx.needs_input_grad[:2]))
         else:
-            loss, stats, _rowvec, saved = run_forward(loss_kind, x1, x2, temperature, normalize, weight, gather)
+            want_grad = any(ctx.needs_input_grad[:2])
+            loss, stats, _rowvec, saved = run_forward(loss_kind, x1, x2, temperature, normalize, weight, gather, want_grad)
         ctx.saved_state = saved
         ctx.save_for_backward(x1, x2)
         ctx.mark_non_differentiable(stats)
@@ -184,6 +198,6 @@ def contrastive_forward_backward(loss_kind: int, x1: torch.Tensor, x2: torch.Ten
                                  normalize: bool = True, weight: Optional[torch.Tensor] = None,
                                  grad_out: Optional[torch.Tensor] = None):
     """Autograd-free fused call used by bench.py: returns (loss, stats, grad1, grad2), all on the device."""
-    loss, stats, _rowvec, saved = run_forward(loss_kind, x1, x2, temperature, normalize, weight)
+    loss, stats, _rowvec, saved = run_forward(loss_kind, x1, x2, temperature, normalize, weight, None, True)
     g1, g2 = run_backward(saved, x1.contiguous(), x2.contiguous(), grad_out)
     return loss, stats, g1, g2

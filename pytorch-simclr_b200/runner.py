@@ -18,8 +18,8 @@ __all__ = ["ContrastiveStep", "PeerStep"]
 
 
 class ContrastiveStep:
-    KERNELS_FORWARD = 3     # prepare, tile kernel, finalize
-    KERNELS_BACKWARD = 3    # prepare (+zero accumulator), tile kernel, finalize
+    KERNELS_FORWARD = 3     # prepare, tile kernel (+ zeroes the backward accumulator), finalize (+ column vectors)
+    KERNELS_BACKWARD = 2    # tile kernel, finalize
 
     def __init__(self, loss_kind: int, batch: int, dim: int, temperature: float, normalize: bool = True,
                  dtype: torch.dtype = torch.float32, device="cuda"):
@@ -54,11 +54,12 @@ class ContrastiveStep:
                                  int(self.normalize), self.temperature, self.operand.data_ptr(),
                                  self.rowvec[0].data_ptr(),
                                  self.rowvec[1].data_ptr(), self.fwd_ws.data_ptr(), st), "simclr_prepare")
-        check(lib.simclr_forward(self.kind, self.operand.data_ptr(), self.operand.data_ptr(), self.b, self.b, 0, self.d,
-                                 self.temperature, int(self.normalize), self.rowvec[1].data_ptr(), None,
-                                 self.rowvec[2].data_ptr(),
-                                 self.rowvec[3].data_ptr(), self.stats.data_ptr(), self.loss.data_ptr(),
-                                 self.fwd_ws.data_ptr(), self.fwd_ws_bytes, st), "simclr_forward")
+        # the forward primes the backward workspace (zeroed accumulation buffer, column vectors)
+        check(lib.simclr_forward_peer(self.kind, self.operand.data_ptr(), self.operand.data_ptr(), self.b, self.b, 0, self.d,
+                                      self.temperature, int(self.normalize), self.rowvec[1].data_ptr(), None,
+                                      self.rowvec[2].data_ptr(), self.rowvec[3].data_ptr(), self.stats.data_ptr(),
+                                      self.loss.data_ptr(), self.fwd_ws.data_ptr(), self.fwd_ws_bytes,
+                                      self.bwd_ws.data_ptr(), self.bwd_ws_bytes, 0, 0, None, None, st), "simclr_forward")
 
     def backward(self, grad_out: Optional[torch.Tensor] = None) -> None:
         lib, st = self.lib, self._stream()
@@ -67,7 +68,7 @@ class ContrastiveStep:
                                   self.operand.data_ptr(), self.rowvec[0].data_ptr(), self.rowvec[1].data_ptr(),
                                   self.rowvec[2].data_ptr(), None, None if grad_out is None else grad_out.data_ptr(),
                                   self.grad1.data_ptr(), self.grad2.data_ptr(), self.bwd_ws.data_ptr(),
-                                  self.bwd_ws_bytes, st), "simclr_backward")
+                                  self.bwd_ws_bytes, self.bwd_ws.data_ptr(), st), "simclr_backward")
 
     def step(self) -> None:
         self.forward()
@@ -79,7 +80,7 @@ class PeerStep:
     captures into one CUDA graph per rank at N > 1.  No collective call inside: the exchange is NVLink stores from the
     prepare / forward-finalize kernels plus two device-side barriers."""
     KERNELS_FORWARD = 5     # prepare(+push), barrier, tile kernel, finalize(+push), barrier(+statistics)
-    KERNELS_BACKWARD = 3
+    KERNELS_BACKWARD = 2    # tile kernel, finalize (the forward primed the workspace)
 
     def __init__(self, loss_kind: int, b_local: int, dim: int, temperature: float, group=None, normalize: bool = True,
                  dtype: torch.dtype = torch.float32, device="cuda"):
@@ -113,17 +114,17 @@ class PeerStep:
     def forward(self) -> None:
         self._cols = self.peer.forward(self.kind, self.x1, self.x2, self.temperature, self.normalize, self.operand,
                                        self.rowvec, self.stats_local, self.stats, self.loss, self.fwd_ws,
-                                       self.fwd_ws_bytes, self._stream())
+                                       self.fwd_ws_bytes, self._stream(), self.bwd_ws)
 
     def backward(self, grad_out: Optional[torch.Tensor] = None) -> None:
-        operand_cols, lse2_cols, _gen = self._cols
+        operand_cols, colvec, _gen = self._cols
         p = self.peer
         check(self.lib.simclr_backward(self.kind, self.x1.data_ptr(), self.x2.data_ptr(), self.b, p.b_global, p.row_offset,
                                        self.d, self.code, int(self.normalize), self.temperature, self.operand.data_ptr(),
                                        operand_cols.data_ptr(), self.rowvec[0].data_ptr(), self.rowvec[1].data_ptr(),
-                                       lse2_cols.data_ptr(), None, None if grad_out is None else grad_out.data_ptr(),
+                                       None, None, None if grad_out is None else grad_out.data_ptr(),
                                        self.grad1.data_ptr(), self.grad2.data_ptr(), self.bwd_ws.data_ptr(),
-                                       self.bwd_ws_bytes, self._stream()), "simclr_backward")
+                                       self.bwd_ws_bytes, colvec.data_ptr(), self._stream()), "simclr_backward")
 
     def step(self) -> None:
         self.forward()
