@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIMCLR_ABI_VERSION 5
+#define SIMCLR_ABI_VERSION 6
 
 /* loss kinds */
 #define SIMCLR_LOSS_NTXENT 0   /* objective.py:6-55  */
@@ -36,6 +36,11 @@ extern "C" {
 /* input element types of x_batch1 / x_batch2 (and of the returned gradients) */
 #define SIMCLR_DTYPE_F32 0
 #define SIMCLR_DTYPE_BF16 1
+
+/* arithmetic of the tensor-core products */
+#define SIMCLR_PRECISION_BF16 0  /* bf16 operands, fp32 accumulate: loss 2e-3, gradients 1e-2 (the fast path) */
+#define SIMCLR_PRECISION_SPLIT 1 /* hi + lo bf16 planes, three products each: fp32-grade, loss 1e-5, gradients 1e-4;
+                                    d <= 128, single GPU or NCCL transport; operand buffers hold two planes */
 
 /* error codes */
 #define SIMCLR_OK 0
@@ -58,6 +63,10 @@ const char* simclr_error_string(int code);
 /* Bpad / Dpad helpers (pure host arithmetic). simclr_pad_dim returns 0 when d is unsupported. */
 int64_t simclr_pad_rows(int64_t b);
 int64_t simclr_pad_dim(int64_t d);
+
+/* Bytes of the operand matrix of b images (0 when unsupported): 2*Bpad*Dpad bf16, twice that in split precision
+ * (plane 0 = hi, plane 1 = lo, each [2*Bpad][Dpad]). */
+size_t simclr_operand_bytes(int64_t b, int64_t d, int precision);
 
 /* Bytes of scratch each stage needs.  b_local == b_global on a single GPU. */
 size_t simclr_forward_workspace_bytes(int loss, int64_t b_local, int64_t b_global, int64_t d);
@@ -112,7 +121,7 @@ int simclr_forward(int loss, const void* operand_rows, const void* operand_cols,
  *              start of the backward workspace; in the row-sharded batch they are the rank's symmetric colvec buffer.
  */
 int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t b_global,
-                    int64_t row_offset, int64_t d, int in_dtype, int normalize, float temperature,
+                    int64_t row_offset, int64_t d, int in_dtype, int normalize, float temperature, int precision,
                     const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,
                     const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
                     void* workspace, size_t workspace_bytes, const float* primed_colvec, void* stream);
@@ -138,14 +147,17 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
  *                       `epoch_local` is a private device counter, also zero-initialised once.  With `stats_all` it
  *                       then sums the per-rank statistics into stats_out[4] / loss_out (the GLOBAL loss, identical on
  *                       all ranks).  Must follow simclr_prepare_peer / simclr_forward_peer in the same stream, on every
- *                       rank, before the pushed data is consumed.  world == 0 / NULL peers degrade to the local calls.
+ *                       rank, before the pushed data is consumed.  world == 0 / NULL peers degrade to the local calls
+ *                       (these are also the entry points that take `precision`; simclr_prepare / simclr_forward are
+ *                       their SIMCLR_PRECISION_BF16 single-rank forms).
  */
 int simclr_prepare_peer(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
-                        int normalize, float temperature, void* operand, float* inv_norm, float* pos_dot,
+                        int normalize, float temperature, int precision, void* operand, float* inv_norm, float* pos_dot,
                         void* forward_workspace, int world, int rank, void* const* operand_global_peers,
                         void* operand_global_multicast, void* stream);
 int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
-                        int64_t row_offset, int64_t d, float temperature, int normalize, const float* pos_dot,
+                        int64_t row_offset, int64_t d, float temperature, int normalize, int precision,
+                        const float* pos_dot,
                         const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out,
                         void* workspace, size_t workspace_bytes, void* backward_workspace,
                         size_t backward_workspace_bytes, int world, int rank, void* const* colvec_peers,

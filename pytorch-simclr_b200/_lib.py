@@ -13,7 +13,9 @@ LOSS_NTXENT = 0
 LOSS_MODIFIED = 1
 DTYPE_F32 = 0
 DTYPE_BF16 = 1
-ABI_VERSION = 5
+PRECISION_BF16 = 0
+PRECISION_SPLIT = 1
+ABI_VERSION = 6
 
 _lock = threading.Lock()
 _lib = None
@@ -35,12 +37,13 @@ SIGNATURES = {
     "simclr_prepare": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _vp, _vp, _vp, _vp, _vp]),
     "simclr_forward": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                               _sz, _vp]),
-    "simclr_backward": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp,
+    "simclr_operand_bytes": (_sz, [_i64, _i64, _int]),
+    "simclr_backward": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp,
                                _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
-    "simclr_prepare_peer": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _vp, _vp, _vp, _vp, _int, _int, _vp, _vp,
-                                   _vp]),
-    "simclr_forward_peer": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                   _sz, _vp, _sz, _int, _int, _vp, _vp, _vp]),
+    "simclr_prepare_peer": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _int, _int, _vp,
+                                   _vp, _vp]),
+    "simclr_forward_peer": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp,
+                                   _vp, _sz, _vp, _sz, _int, _int, _vp, _vp, _vp]),
     "simclr_peer_barrier": (_int, [_int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "simclr_selftest_umma": (_int, [_vp, _vp, _vp, _vp]),
     "simclr_debug_set_trace": (_int, [_vp, _int]),

@@ -17,6 +17,7 @@ struct AuxParams {
     int const_shift;
     float qscale;    // (float) b_glob
     float op_scale;  // factor applied to the normalised rows before bf16 rounding (NT-Xent: sqrt(log2(e)/tau), else 1)
+    int split;       // 1: also write the residual plane lo = bf16(x - float(bf16(x))) behind the hi plane (fp32-grade mode)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -72,9 +73,14 @@ __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x
     __nv_bfloat16* o1 = operand + static_cast<size_t>(i) * a.d_pad;
     __nv_bfloat16* o2 = operand + static_cast<size_t>(a.bl_pad + i) * a.d_pad;
     uint32_t w1[4] = {0u, 0u, 0u, 0u}, w2[4] = {0u, 0u, 0u, 0u};
+    const size_t lo_plane = static_cast<size_t>(2) * a.bl_pad * a.d_pad;      // elements between the hi and lo planes
     if (i >= a.b_loc) {     // padding slot: zero operands and neutral per-row values
         store_words<kWords>(o1, lane, w1);
         store_words<kWords>(o2, lane, w2);
+        if (a.split) {
+            store_words<kWords>(o1 + lo_plane, lane, w1);
+            store_words<kWords>(o2 + lo_plane, lane, w2);
+        }
         if (lane == 0) {
             inv_norm[i] = 0.f;
             inv_norm[a.bl_pad + i] = 0.f;
@@ -148,6 +154,17 @@ __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x
     }
     store_words<kWords>(o1, lane, w1);
     store_words<kWords>(o2, lane, w2);
+    if (a.split) {
+        uint32_t l1[4] = {0u, 0u, 0u, 0u}, l2[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int u = 0; u < kPer; u += 2) {
+            const uint32_t p1 = w1[u >> 1], p2 = w2[u >> 1];
+            l1[u >> 1] = pack_bf16x2(v1[u] * f1 - __uint_as_float(p1 << 16), v1[u + 1] * f1 - __uint_as_float(p1 & 0xffff0000u));
+            l2[u >> 1] = pack_bf16x2(v2[u] * f2 - __uint_as_float(p2 << 16), v2[u + 1] * f2 - __uint_as_float(p2 & 0xffff0000u));
+        }
+        store_words<kWords>(o1 + lo_plane, lane, l1);
+        store_words<kWords>(o2 + lo_plane, lane, l2);
+    }
     if (peers.mc != nullptr) {
         __nv_bfloat16* g = static_cast<__nv_bfloat16*>(peers.mc);
         store_words_multicast<kWords>(g + static_cast<size_t>(a.row_off + i) * a.d_pad, lane, w1);

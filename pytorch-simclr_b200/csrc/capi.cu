@@ -206,50 +206,59 @@ int make_dacc_map(CUtensorMap* map, const void* base, int64_t rows, int64_t d_pa
     return r == CUDA_SUCCESS ? SIMCLR_OK : SIMCLR_ERR_TENSOR_MAP;
 }
 
-template <int D, int kLoss, bool kBackward, bool kConst>
+template <int D, int kLoss, bool kBackward, bool kConst, int kPrec>
 int launch_tile(const CUtensorMap& rows, const CUtensorMap& cols, const CUtensorMap& dacc, const TileParams& p, int grid,
                 cudaStream_t st) {
-    auto kern = contrastive_tile_kernel<D, kLoss, kBackward, kConst>;
+    auto kern = contrastive_tile_kernel<D, kLoss, kBackward, kConst, kPrec>;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             SmemLayout<D>::kDynamicBytes);
+                                             SmemLayout<D, kPrec>::kDynamicBytes);
         if (e != cudaSuccess) return static_cast<int>(e);
         configured[dev & 63] = true;
     }
     return static_cast<int>(launch_pdl(kern, dim3(grid), dim3(kBackward ? kThreadsBackward : kThreadsForward),
-                                       SmemLayout<D>::kDynamicBytes, st, rows, cols, dacc, p));
+                                       SmemLayout<D, kPrec>::kDynamicBytes, st, rows, cols, dacc, p));
 }
 
 // kConst = p.const_shift (bounded scores: one exponential per element, no running maximum).  The forward kernel of
 // the modified loss has no constant-shift variant.
-template <int D, bool kBackward>
+template <int D, bool kBackward, int kPrec>
 int launch_tile_d(int loss, const CUtensorMap& rows, const CUtensorMap& cols, const CUtensorMap& dacc, const TileParams& p,
                   int grid, cudaStream_t st) {
     const bool c = p.const_shift != 0;
     if (loss == SIMCLR_LOSS_NTXENT)
-        return c ? launch_tile<D, kNtXent, kBackward, true>(rows, cols, dacc, p, grid, st)
-                 : launch_tile<D, kNtXent, kBackward, false>(rows, cols, dacc, p, grid, st);
+        return c ? launch_tile<D, kNtXent, kBackward, true, kPrec>(rows, cols, dacc, p, grid, st)
+                 : launch_tile<D, kNtXent, kBackward, false, kPrec>(rows, cols, dacc, p, grid, st);
     if constexpr (kBackward) {
-        return c ? launch_tile<D, kModified, true, true>(rows, cols, dacc, p, grid, st)
-                 : launch_tile<D, kModified, true, false>(rows, cols, dacc, p, grid, st);
+        return c ? launch_tile<D, kModified, true, true, kPrec>(rows, cols, dacc, p, grid, st)
+                 : launch_tile<D, kModified, true, false, kPrec>(rows, cols, dacc, p, grid, st);
     } else {
-        return launch_tile<D, kModified, false, false>(rows, cols, dacc, p, grid, st);
+        return launch_tile<D, kModified, false, false, kPrec>(rows, cols, dacc, p, grid, st);
     }
 }
 
 template <bool kBackward>
-int dispatch_tile(int loss, int64_t d_pad, const CUtensorMap& rows, const CUtensorMap& cols, const CUtensorMap& dacc,
-                  const TileParams& p, int grid, cudaStream_t st) {
+int dispatch_tile(int loss, int64_t d_pad, int precision, const CUtensorMap& rows, const CUtensorMap& cols,
+                  const CUtensorMap& dacc, const TileParams& p, int grid, cudaStream_t st) {
+    if (precision == SIMCLR_PRECISION_SPLIT) {
+        switch (d_pad) {
+            case 64: return launch_tile_d<64, kBackward, 1>(loss, rows, cols, dacc, p, grid, st);
+            case 128: return launch_tile_d<128, kBackward, 1>(loss, rows, cols, dacc, p, grid, st);
+        }
+        return SIMCLR_ERR_UNSUPPORTED_DIM;      // split operands of d > 128 do not fit shared memory
+    }
     switch (d_pad) {
-        case 64: return launch_tile_d<64, kBackward>(loss, rows, cols, dacc, p, grid, st);
-        case 128: return launch_tile_d<128, kBackward>(loss, rows, cols, dacc, p, grid, st);
-        case 256: return launch_tile_d<256, kBackward>(loss, rows, cols, dacc, p, grid, st);
+        case 64: return launch_tile_d<64, kBackward, 0>(loss, rows, cols, dacc, p, grid, st);
+        case 128: return launch_tile_d<128, kBackward, 0>(loss, rows, cols, dacc, p, grid, st);
+        case 256: return launch_tile_d<256, kBackward, 0>(loss, rows, cols, dacc, p, grid, st);
     }
     return SIMCLR_ERR_UNSUPPORTED_DIM;
 }
+
+inline bool bad_precision(int precision) { return precision != SIMCLR_PRECISION_BF16 && precision != SIMCLR_PRECISION_SPLIT; }
 
 AuxParams make_aux(const Geometry& g, const Scales& s, int64_t b_local, int64_t b_global, int64_t row_offset,
                    int64_t d, int normalize) {
@@ -268,6 +277,7 @@ AuxParams make_aux(const Geometry& g, const Scales& s, int64_t b_local, int64_t 
     a.const_shift = s.const_shift;
     a.qscale = s.qscale;
     a.op_scale = s.op_scale;
+    a.split = 0;
     return a;
 }
 
@@ -366,16 +376,25 @@ size_t simclr_backward_workspace_bytes(int loss, int64_t b_local, int64_t b_glob
     return carve_backward(g, nullptr).bytes;
 }
 
+size_t simclr_operand_bytes(int64_t b, int64_t d, int precision) {
+    const int64_t bp = simclr_pad_rows(b), dp = simclr_pad_dim(d);
+    if (bp == 0 || dp == 0 || bad_precision(precision)) return 0;
+    if (precision == SIMCLR_PRECISION_SPLIT && dp > 128) return 0;
+    return static_cast<size_t>(precision == SIMCLR_PRECISION_SPLIT ? 2 : 1) * 2 * bp * dp * sizeof(__nv_bfloat16);
+}
+
 int simclr_prepare_peer(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
-                        int normalize, float temperature, void* operand, float* inv_norm, float* pos_dot,
+                        int normalize, float temperature, int precision, void* operand, float* inv_norm, float* pos_dot,
                         void* forward_workspace, int world, int rank, void* const* operand_global_peers,
                         void* operand_global_multicast, void* stream) {
+    if (bad_precision(precision)) return SIMCLR_ERR_BAD_DTYPE;
     if (!x_batch1 || !x_batch2 || !operand || !inv_norm || !pos_dot) return SIMCLR_ERR_NULL_POINTER;
     if (in_dtype != SIMCLR_DTYPE_F32 && in_dtype != SIMCLR_DTYPE_BF16) return SIMCLR_ERR_BAD_DTYPE;
     if (!(temperature > 0.f) || !std::isfinite(temperature)) return SIMCLR_ERR_BAD_TEMPERATURE;
     PeerTable peers;
     int rc = make_peer_table(world, rank, operand_global_peers, &peers);
     if (rc) return rc;
+    if (peers.world > 0 && precision != SIMCLR_PRECISION_BF16) return SIMCLR_ERR_BAD_PEERS;   // bf16 operands only
     if (peers.world > 0 && operand_global_multicast != nullptr) {
         if (misaligned(operand_global_multicast)) return SIMCLR_ERR_MISALIGNED;
         peers.mc = operand_global_multicast;
@@ -389,7 +408,9 @@ int simclr_prepare_peer(int loss, const void* x_batch1, const void* x_batch2, in
     Scales s = make_scales(loss, temperature, normalize, b_global);
     unsigned int* zero_ptr = static_cast<unsigned int*>(forward_workspace);
     const int zero_words = static_cast<int>(header_bytes(g) / 4);
+    if (precision == SIMCLR_PRECISION_SPLIT && g.d_pad > 128) return SIMCLR_ERR_UNSUPPORTED_DIM;
     AuxParams a = make_aux(g, s, b_local, b_global, row_offset, d, normalize);
+    a.split = precision == SIMCLR_PRECISION_SPLIT ? 1 : 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int warps = 8;
     const int blocks = static_cast<int>((g.bl_pad + warps - 1) / warps);
@@ -418,8 +439,9 @@ int simclr_prepare_peer(int loss, const void* x_batch1, const void* x_batch2, in
 int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
                    int normalize, float temperature, void* operand, float* inv_norm, float* pos_dot,
                    void* forward_workspace, void* stream) {
-    return simclr_prepare_peer(loss, x_batch1, x_batch2, b_local, d, in_dtype, normalize, temperature, operand, inv_norm,
-                               pos_dot, forward_workspace, 0, 0, nullptr, nullptr, stream);
+    return simclr_prepare_peer(loss, x_batch1, x_batch2, b_local, d, in_dtype, normalize, temperature,
+                               SIMCLR_PRECISION_BF16, operand, inv_norm, pos_dot, forward_workspace, 0, 0, nullptr, nullptr,
+                               stream);
 }
 
 int simclr_peer_barrier(int world, int rank, void* const* flag_peers, unsigned int* epoch_local, const float* stats_all,
@@ -440,12 +462,13 @@ int simclr_forward(int loss, const void* operand_rows, const void* operand_cols,
                    const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out, void* workspace,
                    size_t workspace_bytes, void* stream) {
     return simclr_forward_peer(loss, operand_rows, operand_cols, b_local, b_global, row_offset, d, temperature, normalize,
-                               pos_dot, row_weight, lse2, row_loss, stats, loss_out, workspace, workspace_bytes, nullptr, 0,
+                               SIMCLR_PRECISION_BF16, pos_dot, row_weight, lse2, row_loss, stats, loss_out, workspace, workspace_bytes, nullptr, 0,
                                0, 0, nullptr, nullptr, stream);
 }
 
 int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
-                        int64_t row_offset, int64_t d, float temperature, int normalize, const float* pos_dot,
+                        int64_t row_offset, int64_t d, float temperature, int normalize, int precision,
+                        const float* pos_dot,
                         const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out,
                         void* workspace, size_t workspace_bytes, void* backward_workspace,
                         size_t backward_workspace_bytes, int world, int rank, void* const* colvec_peers,
@@ -461,9 +484,11 @@ int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_
     if (workspace_bytes < w.bytes) return SIMCLR_ERR_WORKSPACE_TOO_SMALL;
     if ((rc = check_device())) return rc;
 
+    if (bad_precision(precision)) return SIMCLR_ERR_BAD_DTYPE;
+    const int planes = precision == SIMCLR_PRECISION_SPLIT ? 2 : 1;       // hi (+ lo) operand planes
     CUtensorMap map_rows, map_cols;
-    if ((rc = make_operand_map(&map_rows, operand_rows, 2 * g.bl_pad, g.d_pad))) return rc;
-    if ((rc = make_operand_map(&map_cols, operand_cols, 2 * g.bg_pad, g.d_pad))) return rc;
+    if ((rc = make_operand_map(&map_rows, operand_rows, planes * 2 * g.bl_pad, g.d_pad))) return rc;
+    if ((rc = make_operand_map(&map_cols, operand_cols, planes * 2 * g.bg_pad, g.d_pad))) return rc;
 
     // normalised NT-Xent rows bound the scores: constant softmax shift (no running maximum) in the tile kernel
     Scales s = make_scales(loss, temperature, normalize, b_global);
@@ -495,7 +520,7 @@ int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_
         }
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if ((rc = dispatch_tile<false>(loss, g.d_pad, map_rows, map_cols, map_rows, p, g.grid, st))) return rc;
+    if ((rc = dispatch_tile<false>(loss, g.d_pad, precision, map_rows, map_cols, map_rows, p, g.grid, st))) return rc;
     cudaError_t e;
     if (loss == SIMCLR_LOSS_NTXENT) e = launch_pdl(forward_finalize_kernel<kNtXent>, dim3(g.n_row_blocks), dim3(kBlockM), 0, st, p);
     else e = launch_pdl(forward_finalize_kernel<kModified>, dim3(g.n_row_blocks), dim3(kBlockM), 0, st, p);
@@ -503,7 +528,7 @@ int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_
 }
 
 int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t b_global,
-                    int64_t row_offset, int64_t d, int in_dtype, int normalize, float temperature,
+                    int64_t row_offset, int64_t d, int in_dtype, int normalize, float temperature, int precision,
                     const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,
                     const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
                     void* workspace, size_t workspace_bytes, const float* primed_colvec, void* stream) {
@@ -521,9 +546,11 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
     if (workspace_bytes < w.bytes) return SIMCLR_ERR_WORKSPACE_TOO_SMALL;
     if ((rc = check_device())) return rc;
 
+    if (bad_precision(precision)) return SIMCLR_ERR_BAD_DTYPE;
+    const int planes = precision == SIMCLR_PRECISION_SPLIT ? 2 : 1;       // hi (+ lo) operand planes
     CUtensorMap map_rows, map_cols;
-    if ((rc = make_operand_map(&map_rows, operand_rows, 2 * g.bl_pad, g.d_pad))) return rc;
-    if ((rc = make_operand_map(&map_cols, operand_cols, 2 * g.bg_pad, g.d_pad))) return rc;
+    if ((rc = make_operand_map(&map_rows, operand_rows, planes * 2 * g.bl_pad, g.d_pad))) return rc;
+    if ((rc = make_operand_map(&map_cols, operand_cols, planes * 2 * g.bg_pad, g.d_pad))) return rc;
     CUtensorMap map_dacc;
     if ((rc = make_dacc_map(&map_dacc, w.dacc, 2 * g.bl_pad, g.d_pad))) return rc;
 
@@ -552,7 +579,7 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
     p.pos_dot = pos_dot;
     p.col_scale = col_scale;
     p.grad_out = grad_out;
-    if ((rc = dispatch_tile<true>(loss, g.d_pad, map_rows, map_cols, map_dacc, p, g.grid, st))) return rc;
+    if ((rc = dispatch_tile<true>(loss, g.d_pad, precision, map_rows, map_cols, map_dacc, p, g.grid, st))) return rc;
     cudaError_t fin_rc = cudaSuccess;
 #define SIMCLR_BFIN(DV)                                                                                  \
     case DV:                                                                                             \

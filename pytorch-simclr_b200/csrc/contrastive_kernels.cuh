@@ -157,11 +157,18 @@ SIMCLR_DEVICE void trace_event(const TileParams& p, int role, int it, int k) {
         p.trace[(role * kTraceIters + it) * 4 + k] = clock64();
 }
 
-template <int D>
+// kPrec = 0: bf16 operands.  kPrec = 1 ("split", fp32-grade): every operand row is stored as hi = bf16(x) and
+// lo = bf16(x - hi) in two planes; S = hi*hi + hi*lo + lo*hi on the tensor cores reproduces the fp32 product to ~2^-17,
+// and W is split the same way for the gradient MMA.  Three times the tensor work: the correctness path of the
+// fp32 contract (loss 1e-5, gradients 1e-4), not the fast path.  d <= 128 only (shared memory).
+template <int D, int kPrec = 0>
 struct SmemLayout {
+    static constexpr int kPlanes = kPrec ? 2 : 1;
     static constexpr int kAtoms = D / kAtomK;
-    static constexpr int kTileBytes = kAtoms * kAtomBytes;          // 128 x D bf16
-    static constexpr int kStages = (D <= 64) ? 8 : (D <= 128 ? 4 : 2);   // even: see the issuer ownership rule
+    static constexpr int kPlaneBytes = kAtoms * kAtomBytes;          // 128 x D bf16
+    static constexpr int kTileBytes = kPlanes * kPlaneBytes;
+    // even: see the issuer ownership rule
+    static constexpr int kStages = kPrec ? ((D <= 64) ? 4 : 2) : ((D <= 64) ? 8 : (D <= 128 ? 4 : 2));
     static constexpr int kColvecBytes = 2 * kBlockN * 4;             // two planes of 128 floats
     static constexpr int kOffA = 0;
     static constexpr int kOffB = kTileBytes;
@@ -176,6 +183,7 @@ struct SmemLayout {
     static constexpr int kBytes = kOffMerge + kMergeBytes;
     static constexpr int kDynamicBytes = kBytes + 1024;              // slack for manual 1024 B alignment
 };
+
 
 // First global column of tile j for a row block of view vr.
 template <int kLoss>
@@ -276,7 +284,7 @@ SIMCLR_DEVICE float logit2_h(const Hot& h, float v) {
 // ---- forward: one 16-column chunk, no masked element (warp-uniform fact) ----
 // kConst (NT-Xent with bounded scores): constant log2-domain shift m2, no running maximum; `cm` collects the chunk
 // maximum for the caller (the first-argmax bookkeeping is folded into the state once per tile).
-template <int kLoss, bool kConst>
+template <int kLoss, bool kConst, bool kPoly = true>
 SIMCLR_DEVICE void fwd_chunk_fast(const Hot& h, const uint32_t (&r)[kChunk], float& cm, FwdState& st) {
     float v[kChunk];
 #pragma unroll
@@ -292,7 +300,7 @@ SIMCLR_DEVICE void fwd_chunk_fast(const Hot& h, const uint32_t (&r)[kChunk], flo
             st.sum += ex2_approx(v[i + 0]);
             st.s1 += ex2_approx(v[i + 1]);
             st.s2 += ex2_approx(v[i + 2]);
-            st.s3 += ex2_poly<3>(v[i + 3]);
+            st.s3 += kPoly ? ex2_poly<3>(v[i + 3]) : ex2_approx(v[i + 3]);
         }
     } else {
         cm = fmaxf(cm, c2);
@@ -378,9 +386,10 @@ SIMCLR_DEVICE void fwd_chunk_special(const Hot& h, const uint32_t (&r)[kChunk], 
 }
 
 // ---- backward: one 16-column chunk -> 8 packed bf16x2 words of W ----
-template <int kLoss, bool kConst, bool kSpecial>
+// kSplit: additionally emits wlo = bf16(W - float(bf16(W))) (fp32-grade mode)
+template <int kLoss, bool kConst, bool kSpecial, bool kSplit = false>
 SIMCLR_DEVICE void bwd_chunk(const Hot& h, const uint32_t (&r)[kChunk], uint32_t cv_addr, int cq, const RowCtx& rc,
-                             const BwdRow& br, uint32_t (&w)[kChunk / 2]) {
+                             const BwdRow& br, uint32_t (&w)[kChunk / 2], uint32_t (&wlo)[kChunk / 2]) {
     const int i_diag = rc.diag_col - cq, i_pos = rc.pos_col - cq;
 #pragma unroll
     for (int i = 0; i < kChunk; i += 4) {
@@ -397,7 +406,7 @@ SIMCLR_DEVICE void bwd_chunk(const Hot& h, const uint32_t (&r)[kChunk], uint32_t
             if constexpr (kLoss == kNtXent) {
                 if constexpr (kConst) {
                     // one exp per element: W = exp2(S') * (a_r + a_c); every fourth one on the FMA pipe
-                    const float e = poly_lane(i + u) ? ex2_poly<3>(sraw) : ex2_approx(sraw);
+                    const float e = (!kSplit && poly_lane(i + u)) ? ex2_poly<3>(sraw) : ex2_approx(sraw);
                     wval = e * (br.row_a + acs[u]);
                 } else {
                     // general form: W = g_r exp2(S' - lse2_r) + g_c exp2(S' - lse2_c)
@@ -416,6 +425,11 @@ SIMCLR_DEVICE void bwd_chunk(const Hot& h, const uint32_t (&r)[kChunk], uint32_t
         }
         w[(i >> 1) + 0] = pack_bf16x2(wv[0], wv[1]);
         w[(i >> 1) + 1] = pack_bf16x2(wv[2], wv[3]);
+        if constexpr (kSplit) {
+            const uint32_t p0 = w[(i >> 1) + 0], p1 = w[(i >> 1) + 1];
+            wlo[(i >> 1) + 0] = pack_bf16x2(wv[0] - __uint_as_float(p0 << 16), wv[1] - __uint_as_float(p0 & 0xffff0000u));
+            wlo[(i >> 1) + 1] = pack_bf16x2(wv[2] - __uint_as_float(p1 << 16), wv[3] - __uint_as_float(p1 & 0xffff0000u));
+        }
     }
 }
 
@@ -737,11 +751,14 @@ struct RingPos {
 // additionally occupies TWO positions whose stages the producer hands (empty) to the softmax warps as staging space
 // for the accumulator flush.  All roles walk the same position sequence, so stage index and parity never need a
 // division and stage / slot / pair / issuer ownership stays aligned (position parity == tile parity).
-template <int D, int kLoss, bool kBackward, bool kConst>
+template <int D, int kLoss, bool kBackward, bool kConst, int kPrec>
 __global__ void __launch_bounds__(kBackward ? kThreadsBackward : kThreadsForward, 1)
 contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
                         const __grid_constant__ CUtensorMap tmap_dacc, const TileParams p) {
-    using L = SmemLayout<D>;
+    using L = SmemLayout<D, kPrec>;
+    constexpr int kPlanes = L::kPlanes;
+    // split mode: the three operand-plane products that make up one fp32-grade product (lo*lo is below 2^-17)
+    constexpr int kProducts = kPrec ? 3 : 1;
     constexpr int S = L::kStages;
     static_assert(S % 2 == 0, "issuer ownership needs an even ring");
     constexpr uint32_t kIdescScore = make_idesc_bf16(kBlockM, kBlockN, 0, 0);
@@ -751,7 +768,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                                  : kMaxScoreBufs;
     constexpr uint32_t kTmemAcc = NB * kBlockN;
     constexpr int kSlots = NB * kNumPairs;            // slot -> fixed (pair, buffer)
-    constexpr int kBoxesPerStage = D / 64;            // 16 KB fp32 boxes (128 rows x 32 columns) per ring stage
+    constexpr int kBoxesPerStage = L::kTileBytes / kAtomBytes;   // 16 KB fp32 boxes (128 rows x 32 columns) per ring stage
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -835,8 +852,11 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                     if (seg > 0) mbar_wait(a_empty, (seg - 1) & 1, 100);
                     mbar_arrive_expect_tx(a_full, L::kTileBytes);
 #pragma unroll
-                    for (int ka = 0; ka < L::kAtoms; ++ka)
-                        tma_load_2d(sa_addr + ka * kAtomBytes, &tmap_rows, a_full, ka * kAtomK, w.rb * kBlockM);
+                    for (int pl = 0; pl < kPlanes; ++pl)
+#pragma unroll
+                        for (int ka = 0; ka < L::kAtoms; ++ka)
+                            tma_load_2d(sa_addr + pl * L::kPlaneBytes + ka * kAtomBytes, &tmap_rows, a_full, ka * kAtomK,
+                                        pl * 2 * p.bl_pad + w.rb * kBlockM);
                     ++seg;
                 }
                 trace_event(p, 0, it, 0);
@@ -845,9 +865,11 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 const int c0 = tile_col0<kLoss>(p, w.rb / blocks_per_view, w.j);
                 mbar_arrive_expect_tx(b_full + 8 * ring.idx, L::kTileBytes + (kBackward ? L::kColvecBytes : 0));
 #pragma unroll
-                for (int ka = 0; ka < L::kAtoms; ++ka)
-                    tma_load_2d(sb_addr + ring.idx * L::kTileBytes + ka * kAtomBytes, &tmap_cols, b_full + 8 * ring.idx,
-                                ka * kAtomK, c0);
+                for (int pl = 0; pl < kPlanes; ++pl)
+#pragma unroll
+                    for (int ka = 0; ka < L::kAtoms; ++ka)
+                        tma_load_2d(sb_addr + ring.idx * L::kTileBytes + pl * L::kPlaneBytes + ka * kAtomBytes, &tmap_cols,
+                                    b_full + 8 * ring.idx, ka * kAtomK, pl * 2 * p.bg_pad + c0);
                 if constexpr (kBackward) {
                     const uint32_t cv = smem_base + L::kOffCv + ring.idx * (2 * kBlockN * 4);
                     bulk_load_1d(cv, p.colvec + c0, kBlockN * 4, b_full + 8 * ring.idx);
@@ -895,12 +917,18 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 if (elect_one()) {
                     const uint32_t b_addr = b_addr0 + ring.idx * L::kTileBytes;
 #pragma unroll
-                    for (int ka = 0; ka < L::kAtoms; ++ka) {
+                    for (int pr = 0; pr < kProducts; ++pr) {
+                        // (A plane, B plane): hi*hi, hi*lo, lo*hi
+                        const uint32_t a_pl = a_addr + (pr == 2 ? L::kPlaneBytes : 0);
+                        const uint32_t b_pl = b_addr + (pr == 1 ? L::kPlaneBytes : 0);
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const uint32_t off = ka * kAtomBytes + kk * 32;
-                            umma_ss(tmem_base + buf * kBlockN, make_smem_desc(a_addr + off, 0, 1024),
-                                    make_smem_desc(b_addr + off, 0, 1024), kIdescScore, (ka | kk) != 0);
+                        for (int ka = 0; ka < L::kAtoms; ++ka) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const uint32_t off = ka * kAtomBytes + kk * 32;
+                                umma_ss(tmem_base + buf * kBlockN, make_smem_desc(a_pl + off, 0, 1024),
+                                        make_smem_desc(b_pl + off, 0, 1024), kIdescScore, (pr | ka | kk) != 0);
+                            }
                         }
                     }
                     if constexpr (!kBackward) umma_commit(b_empty + 8 * ring.idx);
@@ -969,10 +997,15 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                     if (elect_one()) {
                         const uint32_t b_addr = b_addr0 + ring.idx * L::kTileBytes;
 #pragma unroll
-                        for (int kc = 0; kc < kBlockN / 16; ++kc) {
-                            // W of column half h (K chunks 4h..4h+3) sits at columns [64h, 64h+32) of the buffer
-                            umma_ts(tmem_base + kTmemAcc, tmem_base + buf * kBlockN + (kc >> 2) * 64 + (kc & 3) * 8,
-                                    make_smem_desc(b_addr + kc * 2048, kAtomBytes, 1024), kIdescGrad, 1);
+                        for (int pr = 0; pr < kProducts; ++pr) {
+                            // (W plane, operand plane): hi*hi, lo*hi, hi*lo.  W_hi of column half h (K chunks 4h..4h+3)
+                            // sits at columns [64h, 64h+32) of the buffer, W_lo (split mode) at [64h+32, 64h+64)
+                            const uint32_t w_pl = tmem_base + buf * kBlockN + (pr == 1 ? 32 : 0);
+                            const uint32_t b_pl = b_addr + (pr == 2 ? L::kPlaneBytes : 0);
+#pragma unroll
+                            for (int kc = 0; kc < kBlockN / 16; ++kc)
+                                umma_ts(tmem_base + kTmemAcc, w_pl + (kc >> 2) * 64 + (kc & 3) * 8,
+                                        make_smem_desc(b_pl + kc * 2048, kAtomBytes, 1024), kIdescGrad, 1);
                         }
                         umma_commit(b_empty + 8 * ring.idx);     // B tile (and its column vectors) may be overwritten
                         umma_commit(w_done + 8 * slot.idx);      // score buffer may be overwritten
@@ -1144,7 +1177,36 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 // address arithmetic, fences: ~800 cycles) now hides behind the other pair's maths instead of both
                 // pairs idling together (they otherwise drift into lock step).
                 if (it > 0) named_bar_sync(kTokenBar0 + pair, 32 * kNumSoftmaxWarps);
-                if (!tile_special) {
+                if constexpr (kBackward && kPrec != 0) {
+                    // Split mode: W_hi goes where it always goes, W_lo into the upper half [64h+32, 64h+64) of this
+                    // warpgroup's region -- over scores of chunks 2 and 3, so the W_lo words are held in registers until
+                    // the last chunk has been loaded.
+                    uint32_t lo[3][kChunk / 2];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t (&cur)[kChunk] = (k & 1) ? rb2 : ra;
+                        uint32_t (&nxt)[kChunk] = (k & 1) ? ra : rb2;
+                        tmem_ld_wait16(cur);
+                        if (k < 3) tmem_ld16(t0 + (k + 1) * kChunk, nxt);
+                        const int cq = cbase + k * kChunk;
+                        const int icq = cq - vc * h.bg_pad;
+                        const bool special = tile_special && !(icq > g_hi || icq + kChunk - 1 < g_lo);
+                        uint32_t wq[kChunk / 2], wl[kChunk / 2];
+                        if (special) bwd_chunk<kLoss, kConst, true, true>(h, cur, cv_tile + k * kChunk * 4, cq, rc, br, wq, wl);
+                        else bwd_chunk<kLoss, kConst, false, true>(h, cur, cv_tile + k * kChunk * 4, cq, rc, br, wq, wl);
+                        tmem_st8(t0 + k * (kChunk / 2), wq);
+                        if (k < 3) {
+#pragma unroll
+                            for (int i = 0; i < kChunk / 2; ++i) lo[k][i] = wl[i];
+                        } else {
+                            tmem_st8(t0 + 32 + 0 * (kChunk / 2), lo[0]);
+                            tmem_st8(t0 + 32 + 1 * (kChunk / 2), lo[1]);
+                            tmem_st8(t0 + 32 + 2 * (kChunk / 2), lo[2]);
+                            tmem_st8(t0 + 32 + 3 * (kChunk / 2), wl);
+                        }
+                    }
+                    if (it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
+                } else if (!tile_special) {
                     // Common case: no masked element anywhere in the tile for this warp.  One straight-line block over
                     // the four chunks, so that the tail of chunk k overlaps the head of chunk k+1.
                     float cm = kNegBig;
@@ -1158,10 +1220,10 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         // pair drains its last one (covers the bar.arrive -> bar.sync wake-up latency)
                         if (k == SIMCLR_TOKEN_CHUNK && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
                         if constexpr (!kBackward) {
-                            fwd_chunk_fast<kLoss, kConst>(h, cur, cm, fs);
-                        } else {
-                            uint32_t wq[kChunk / 2];
-                            bwd_chunk<kLoss, kConst, false>(h, cur, cv_tile + k * kChunk * 4, 0, rc, br, wq);
+                            fwd_chunk_fast<kLoss, kConst, kPrec == 0>(h, cur, cm, fs);
+                        } else if constexpr (kPrec == 0) {
+                            uint32_t wq[kChunk / 2], unused[kChunk / 2];
+                            bwd_chunk<kLoss, kConst, false>(h, cur, cv_tile + k * kChunk * 4, 0, rc, br, wq, unused);
                             tmem_st8(t0 + k * (kChunk / 2), wq);
                         }
                     }
@@ -1180,15 +1242,15 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                                 fwd_chunk_special<kLoss, kConst>(h, r, cq, vc, rc, fs);
                             } else {
                                 float cm = kNegBig;
-                                fwd_chunk_fast<kLoss, kConst>(h, r, cm, fs);
+                                fwd_chunk_fast<kLoss, kConst, kPrec == 0>(h, r, cm, fs);
                                 fs.max_prec = fmaxf(fs.max_prec, tile_prec ? cm : kNegBig);
                                 fs.max_foll = fmaxf(fs.max_foll, tile_prec ? kNegBig : cm);
                             }
                         } else {
-                            uint32_t wq[kChunk / 2];
+                            uint32_t wq[kChunk / 2], unused[kChunk / 2];
                             const uint32_t cv_addr = cv_tile + k * kChunk * 4;
-                            if (special) bwd_chunk<kLoss, kConst, true>(h, r, cv_addr, cq, rc, br, wq);
-                            else bwd_chunk<kLoss, kConst, false>(h, r, cv_addr, cq, rc, br, wq);
+                            if (special) bwd_chunk<kLoss, kConst, true>(h, r, cv_addr, cq, rc, br, wq, unused);
+                            else bwd_chunk<kLoss, kConst, false>(h, r, cv_addr, cq, rc, br, wq, unused);
                             // bf16 W of chunk k goes to columns [64*half + 8*k, +8): inside this warpgroup's own
                             // 64-column region and over scores this thread has already consumed
                             tmem_st8(t0 + k * (kChunk / 2), wq);
@@ -1204,7 +1266,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         process(rb2, 2 * kk + 1);
                     }
                 }
-                if ((tile_special || SIMCLR_TOKEN_CHUNK > 3) && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
+                if (!(kBackward && kPrec != 0) && (tile_special || SIMCLR_TOKEN_CHUNK > 3) && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
                 if constexpr (!kBackward) {
                     tc_fence_before_sync();
                     mbar_arrive(s_free + 8 * slot);

@@ -30,7 +30,8 @@ SIMCLR_DEVICE void probe_chunk(const Hot& h, const uint32_t (&r)[kChunk], FwdSta
     } else if constexpr (kVariant == kVarBwdProd || kVariant == kVarBwdAllMufu) {
         uint32_t w[kChunk / 2];
         if constexpr (kVariant == kVarBwdProd) {
-            bwd_chunk<kNtXent, true, false>(h, r, cv_addr, 0, rc, br, w);
+            uint32_t unused[kChunk / 2];
+            bwd_chunk<kNtXent, true, false>(h, r, cv_addr, 0, rc, br, w, unused);
         } else {
 #pragma unroll
             for (int i = 0; i < kChunk; i += 4) {

@@ -62,12 +62,14 @@ class RowShardGather:
         self.rank = dist.get_rank(group)
 
     def _gather_views(self, local: torch.Tensor, b: int) -> torch.Tensor:
-        """local: [2*pad(b), ...] view-padded  ->  [2*pad(b*world), ...] view-padded, rank-major inside a view."""
-        bl_pad = local.shape[0] // 2
+        """local: [P*2*pad(b), ...] view-padded (P operand planes: 1, or 2 in split precision)  ->
+        [P*2*pad(b*world), ...] view-padded, rank-major inside a view."""
+        bl_pad = pad_rows(b)
+        planes = local.shape[0] // (2 * bl_pad)
         bg = b * self.world
         bg_pad = pad_rows(bg)
-        out = local.new_zeros((2 * bg_pad,) + tuple(local.shape[1:]))
-        for v in (0, 1):
+        out = local.new_zeros((planes * 2 * bg_pad,) + tuple(local.shape[1:]))
+        for v in range(2 * planes):
             dist.all_gather_into_tensor(out[v * bg_pad: v * bg_pad + bg], local[v * bl_pad: v * bl_pad + b].contiguous(),
                                         group=self.group)
         return out
@@ -175,15 +177,16 @@ class PeerBatch:
         tab, view = self._tables[gen], self._views[gen]
         code = _dtype_code(x1)
         check(lib.simclr_prepare_peer(loss_kind, x1.data_ptr(), x2.data_ptr(), self.b_local, self.d, code,
-                                      int(bool(normalize)), float(temperature), operand.data_ptr(), rowvec[0].data_ptr(),
-                                      rowvec[1].data_ptr(), ws.data_ptr(), self.world, self.rank, tab["operand"],
-                                      self._mc[gen], stream),
+                                      int(bool(normalize)), float(temperature), _lib.PRECISION_BF16, operand.data_ptr(),
+                                      rowvec[0].data_ptr(), rowvec[1].data_ptr(), ws.data_ptr(), self.world, self.rank,
+                                      tab["operand"], self._mc[gen], stream),
               "simclr_prepare_peer")
         check(lib.simclr_peer_barrier(self.world, self.rank, self._flags, self.epoch.data_ptr(), None, None, None, stream),
               "simclr_peer_barrier")
         check(lib.simclr_forward_peer(loss_kind, operand.data_ptr(), view["operand"].data_ptr(), self.b_local,
                                       self.b_global, self.row_offset, self.d, float(temperature), int(bool(normalize)),
-                                      rowvec[1].data_ptr(), None, rowvec[2].data_ptr(), rowvec[3].data_ptr(),
+                                      _lib.PRECISION_BF16, rowvec[1].data_ptr(), None, rowvec[2].data_ptr(),
+                                      rowvec[3].data_ptr(),
                                       stats_local.data_ptr(), None, ws.data_ptr(), ws_bytes,
                                       None if bwd_ws is None else bwd_ws.data_ptr(), 0 if bwd_ws is None else bwd_ws.numel(),
                                       self.world, self.rank, tab["colvec"], tab["stats"], stream), "simclr_forward_peer")
@@ -227,6 +230,7 @@ def run_forward_peer(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, tempera
     saved.b_local, saved.b_global, saved.row_offset, saved.d = b, peer.b_global, peer.row_offset, d
     saved.loss, saved.temperature, saved.normalize, saved.dtype_code = loss_kind, float(temperature), bool(normalize), _dtype_code(x1)
     saved.peer, saved.generation = peer, generation
+    saved.precision = _lib.PRECISION_BF16
     return loss, stats, rowvec, saved
 
 

@@ -11,12 +11,42 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import DTYPE_BF16, DTYPE_F32, LOSS_MODIFIED, LOSS_NTXENT, check
+from ._lib import DTYPE_BF16, DTYPE_F32, LOSS_MODIFIED, LOSS_NTXENT, PRECISION_BF16, PRECISION_SPLIT, check
 
 __all__ = ["contrastive_forward_backward", "ContrastiveLossFunction", "LOSS_NTXENT", "LOSS_MODIFIED", "pad_rows",
-           "pad_dim", "compact_to_padded", "padded_to_compact"]
+           "pad_dim", "compact_to_padded", "padded_to_compact", "set_precision", "get_precision", "resolve_precision"]
 
 BLOCK = 128
+
+# Arithmetic of the tensor-core products (include/simclr_b200.h SIMCLR_PRECISION_*):
+#   "bf16"  bf16 operands, fp32 accumulate -- the fast path (loss 2e-3, gradients 1e-2 against the fp32 reference)
+#   "fp32"  hi + lo bf16 operand planes, three products each -- fp32-grade (loss 1e-5, gradients 1e-4), d <= 128
+#   "auto"  fp32-grade for float32 inputs of d <= 128 on one GPU (what the fp32 reference delivers), bf16 otherwise
+_PRECISION = "auto"
+
+
+def set_precision(mode: str) -> None:
+    """Select the arithmetic of the loss for subsequent calls: "auto" (default), "bf16" or "fp32"."""
+    global _PRECISION
+    if mode not in ("auto", "bf16", "fp32"):
+        raise ValueError("precision must be 'auto', 'bf16' or 'fp32'")
+    _PRECISION = mode
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+def resolve_precision(x: torch.Tensor, distributed: bool = False, mode: Optional[str] = None) -> int:
+    mode = mode or _PRECISION
+    if mode == "bf16":
+        return PRECISION_BF16
+    fits = x.shape[1] <= 128
+    if mode == "fp32":
+        if not fits:
+            raise ValueError("precision 'fp32' (split bf16 operands) supports embedding dimensions up to 128")
+        return PRECISION_SPLIT
+    return PRECISION_SPLIT if (x.dtype == torch.float32 and fits and not distributed) else PRECISION_BF16
 
 
 def pad_rows(b: int) -> int:
@@ -73,11 +103,12 @@ class _Saved:
     """State a forward leaves for its backward (device buffers only)."""
     __slots__ = ("operand_rows", "operand_cols", "inv_norm", "pos_dot", "lse2_cols", "col_scale", "b_local",
                  "b_global", "row_offset", "d", "loss", "temperature", "normalize", "dtype_code", "peer", "generation",
-                 "bwd_ws", "primed_colvec")
+                 "bwd_ws", "primed_colvec", "precision")
 
 
 def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature: float, normalize: bool,
-                weight: Optional[torch.Tensor], gather=None, prime_backward: bool = False):
+                weight: Optional[torch.Tensor], gather=None, prime_backward: bool = False,
+                precision: Optional[int] = None):
     """prepare + forward through the C ABI.  ``gather`` (distributed.py) turns the local operand / lse2 into
     their global-batch counterparts and returns (operand_cols, b_global, row_offset, reducer)."""
     lib = _lib.load()
@@ -87,18 +118,21 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
     dev = x1.device
     bp, dp = pad_rows(b), pad_dim(d)
     code = _dtype_code(x1)
+    if precision is None:
+        precision = resolve_precision(x1, gather is not None)
+    planes = 2 if precision == PRECISION_SPLIT else 1
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream().cuda_stream
-        operand = torch.empty((2 * bp, dp), dtype=torch.bfloat16, device=dev)
+        operand = torch.empty((planes * 2 * bp, dp), dtype=torch.bfloat16, device=dev)
         rowvec = torch.empty((4, 2 * bp), dtype=torch.float32, device=dev)   # inv_norm, pos_dot, lse2, row_loss
         stats = torch.empty(4, dtype=torch.float32, device=dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
         b_global_hint = b if gather is None else b * gather.world
         ws_bytes = lib.simclr_forward_workspace_bytes(loss_kind, b, b_global_hint, d)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        check(lib.simclr_prepare(loss_kind, x1.data_ptr(), x2.data_ptr(), b, d, code, int(bool(normalize)),
-                                 float(temperature), operand.data_ptr(), rowvec[0].data_ptr(), rowvec[1].data_ptr(), ws.data_ptr(), stream),
-              "simclr_prepare")
+        check(lib.simclr_prepare_peer(loss_kind, x1.data_ptr(), x2.data_ptr(), b, d, code, int(bool(normalize)),
+                                      float(temperature), precision, operand.data_ptr(), rowvec[0].data_ptr(),
+                                      rowvec[1].data_ptr(), ws.data_ptr(), 0, 0, None, None, stream), "simclr_prepare")
         if gather is None:
             operand_cols, b_global, row_offset = operand, b, 0
         else:
@@ -115,7 +149,8 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
             bwd_bytes = lib.simclr_backward_workspace_bytes(loss_kind, b, b, d)
             bwd_ws = torch.empty(bwd_bytes, dtype=torch.uint8, device=dev)
         check(lib.simclr_forward_peer(loss_kind, operand.data_ptr(), operand_cols.data_ptr(), b, b_global, row_offset, d,
-                                      float(temperature), int(bool(normalize)), rowvec[1].data_ptr(), _ptr(w_local),
+                                      float(temperature), int(bool(normalize)), precision, rowvec[1].data_ptr(),
+                                      _ptr(w_local),
                                       rowvec[2].data_ptr(), rowvec[3].data_ptr(), stats.data_ptr(), loss.data_ptr(),
                                       ws.data_ptr(), ws_bytes, _ptr(bwd_ws), 0 if bwd_ws is None else bwd_ws.numel(), 0, 0,
                                       None, None, stream), "simclr_forward")
@@ -127,6 +162,7 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
     saved.b_local, saved.b_global, saved.row_offset, saved.d = b, b_global, row_offset, d
     saved.loss, saved.temperature, saved.normalize, saved.dtype_code = loss_kind, float(temperature), bool(normalize), code
     saved.bwd_ws, saved.primed_colvec = bwd_ws, (None if bwd_ws is None else bwd_ws.data_ptr())
+    saved.precision = precision
     if gather is not None:
         loss, stats = gather.reduce(stats, loss)
         saved.lse2_cols = gather.rowvec(rowvec[2], b)
@@ -159,7 +195,7 @@ def run_backward(saved: "_Saved", x1: torch.Tensor, x2: torch.Tensor, grad_out: 
         ws_bytes = ws.numel()
         check(lib.simclr_backward(saved.loss, x1.data_ptr(), x2.data_ptr(), saved.b_local, saved.b_global,
                                   saved.row_offset, saved.d, saved.dtype_code, int(saved.normalize), saved.temperature,
-                                  saved.operand_rows.data_ptr(), saved.operand_cols.data_ptr(),
+                                  getattr(saved, "precision", PRECISION_BF16), saved.operand_rows.data_ptr(), saved.operand_cols.data_ptr(),
                                   saved.inv_norm.data_ptr(), saved.pos_dot.data_ptr(), saved.lse2_cols.data_ptr(),
                                   _ptr(saved.col_scale), _ptr(go), g1.data_ptr(), g2.data_ptr(), ws.data_ptr(),
                                   ws_bytes, primed, stream), "simclr_backward")
@@ -196,8 +232,9 @@ class ContrastiveLossFunction(torch.autograd.Function):
 
 def contrastive_forward_backward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature: float,
                                  normalize: bool = True, weight: Optional[torch.Tensor] = None,
-                                 grad_out: Optional[torch.Tensor] = None):
-    """Autograd-free fused call used by bench.py: returns (loss, stats, grad1, grad2), all on the device."""
-    loss, stats, _rowvec, saved = run_forward(loss_kind, x1, x2, temperature, normalize, weight, None, True)
+                                 grad_out: Optional[torch.Tensor] = None, precision: Optional[str] = None):
+    """Autograd-free fused call: returns (loss, stats, grad1, grad2), all on the device."""
+    prec = None if precision is None else resolve_precision(x1, False, precision)
+    loss, stats, _rowvec, saved = run_forward(loss_kind, x1, x2, temperature, normalize, weight, None, True, prec)
     g1, g2 = run_backward(saved, x1.contiguous(), x2.contiguous(), grad_out)
     return loss, stats, g1, g2

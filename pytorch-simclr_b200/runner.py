@@ -22,8 +22,11 @@ class ContrastiveStep:
     KERNELS_BACKWARD = 2    # tile kernel, finalize
 
     def __init__(self, loss_kind: int, batch: int, dim: int, temperature: float, normalize: bool = True,
-                 dtype: torch.dtype = torch.float32, device="cuda"):
+                 dtype: torch.dtype = torch.float32, device="cuda", precision: str = "bf16"):
         self.lib = _lib.load()
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.precision = _lib.PRECISION_SPLIT if precision == "fp32" else _lib.PRECISION_BF16
         self.kind, self.b, self.d = int(loss_kind), int(batch), int(dim)
         self.temperature, self.normalize = float(temperature), bool(normalize)
         self.device = torch.device(device)
@@ -32,7 +35,10 @@ class ContrastiveStep:
         self.x1 = torch.zeros((batch, dim), dtype=dtype, device=dev)
         self.x2 = torch.zeros((batch, dim), dtype=dtype, device=dev)
         self.code = _dtype_code(self.x1)
-        self.operand = torch.empty((2 * bp, dp), dtype=torch.bfloat16, device=dev)
+        op_bytes = self.lib.simclr_operand_bytes(batch, dim, self.precision)
+        if not op_bytes:
+            raise ValueError("unsupported shape / precision (fp32-grade operands need d <= 128)")
+        self.operand = torch.empty((op_bytes // (2 * dp), dp), dtype=torch.bfloat16, device=dev)
         self.rowvec = torch.empty((4, 2 * bp), dtype=torch.float32, device=dev)   # inv_norm, pos_dot, lse2, row_loss
         self.stats = torch.zeros(4, dtype=torch.float32, device=dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
@@ -50,13 +56,13 @@ class ContrastiveStep:
 
     def forward(self) -> None:
         lib, st = self.lib, self._stream()
-        check(lib.simclr_prepare(self.kind, self.x1.data_ptr(), self.x2.data_ptr(), self.b, self.d, self.code,
-                                 int(self.normalize), self.temperature, self.operand.data_ptr(),
-                                 self.rowvec[0].data_ptr(),
-                                 self.rowvec[1].data_ptr(), self.fwd_ws.data_ptr(), st), "simclr_prepare")
+        check(lib.simclr_prepare_peer(self.kind, self.x1.data_ptr(), self.x2.data_ptr(), self.b, self.d, self.code,
+                                      int(self.normalize), self.temperature, self.precision, self.operand.data_ptr(),
+                                      self.rowvec[0].data_ptr(), self.rowvec[1].data_ptr(), self.fwd_ws.data_ptr(), 0, 0,
+                                      None, None, st), "simclr_prepare")
         # the forward primes the backward workspace (zeroed accumulation buffer, column vectors)
         check(lib.simclr_forward_peer(self.kind, self.operand.data_ptr(), self.operand.data_ptr(), self.b, self.b, 0, self.d,
-                                      self.temperature, int(self.normalize), self.rowvec[1].data_ptr(), None,
+                                      self.temperature, int(self.normalize), self.precision, self.rowvec[1].data_ptr(), None,
                                       self.rowvec[2].data_ptr(), self.rowvec[3].data_ptr(), self.stats.data_ptr(),
                                       self.loss.data_ptr(), self.fwd_ws.data_ptr(), self.fwd_ws_bytes,
                                       self.bwd_ws.data_ptr(), self.bwd_ws_bytes, 0, 0, None, None, st), "simclr_forward")
@@ -64,7 +70,7 @@ class ContrastiveStep:
     def backward(self, grad_out: Optional[torch.Tensor] = None) -> None:
         lib, st = self.lib, self._stream()
         check(lib.simclr_backward(self.kind, self.x1.data_ptr(), self.x2.data_ptr(), self.b, self.b, 0, self.d,
-                                  self.code, int(self.normalize), self.temperature, self.operand.data_ptr(),
+                                  self.code, int(self.normalize), self.temperature, self.precision, self.operand.data_ptr(),
                                   self.operand.data_ptr(), self.rowvec[0].data_ptr(), self.rowvec[1].data_ptr(),
                                   self.rowvec[2].data_ptr(), None, None if grad_out is None else grad_out.data_ptr(),
                                   self.grad1.data_ptr(), self.grad2.data_ptr(), self.bwd_ws.data_ptr(),
@@ -120,7 +126,8 @@ class PeerStep:
         operand_cols, colvec, _gen = self._cols
         p = self.peer
         check(self.lib.simclr_backward(self.kind, self.x1.data_ptr(), self.x2.data_ptr(), self.b, p.b_global, p.row_offset,
-                                       self.d, self.code, int(self.normalize), self.temperature, self.operand.data_ptr(),
+                                       self.d, self.code, int(self.normalize), self.temperature, _lib.PRECISION_BF16,
+                                       self.operand.data_ptr(),
                                        operand_cols.data_ptr(), self.rowvec[0].data_ptr(), self.rowvec[1].data_ptr(),
                                        None, None, None if grad_out is None else grad_out.data_ptr(),
                                        self.grad1.data_ptr(), self.grad2.data_ptr(), self.bwd_ws.data_ptr(),

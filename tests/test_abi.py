@@ -36,7 +36,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_abi_version_and_error_strings(lib):
-    assert lib.simclr_abi_version() == 5
+    assert lib.simclr_abi_version() == 6
     assert lib.simclr_error_string(0) == b"ok"
     for code in range(-11, 0):
         assert lib.simclr_error_string(code) not in (b"", b"unknown error")
@@ -78,5 +78,5 @@ def test_argument_validation_without_gpu(lib):
     assert lib.simclr_forward(0, p, p, 4, 8, 6, 8, 0.5, 1, p, None, p, p, p, None, p, 1 << 15, None) == -2   # shard outside
     assert lib.simclr_forward(0, p, p, 4, 4, 0, 8, 0.5, 1, p, None, p, p, p, None, p, 16, None) == -5
     assert lib.simclr_forward(0, p + 4, p, 4, 4, 0, 8, 0.5, 1, p, None, p, p, p, None, p, 1 << 15, None) == -6
-    assert lib.simclr_backward(0, p, p, 4, 4, 0, 8, 0, 1, float("nan"), p, p, p, p, p, None, None, p, p, p, 1 << 15,
+    assert lib.simclr_backward(0, p, p, 4, 4, 0, 8, 0, 1, float("nan"), 0, p, p, p, p, p, None, None, p, p, p, 1 << 15,
                                None, None) == -7

