@@ -293,6 +293,7 @@ def bench_multi(args):
     local = int(os.environ.get("LOCAL_RANK", rank))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: one JSON line only
     dist.init_process_group("nccl", device_id=dev)
     b, d, m = B_GLOBAL, DIM, 2 * B_GLOBAL
     row_off, bl = shard_rows(b, world, rank)
