@@ -35,6 +35,7 @@ B_SINGLE = 4096          # 2N = 8192  (BASELINE.json metric)
 B_GLOBAL = 32768         # 2N = 65536 (BASELINE.json configs[3])
 METRIC = "NT-Xent fwd+bwd views/s (2N=8192,d=128)"
 L2_FLUSH_BYTES = 256 << 20
+NCU_DRAM_BYTES_BWD_TILE = 6410240     # ncu --set full, backward tile kernel, per launch (profiles/r01_ncu_full_tile_kernels.csv)
 
 
 def algorithmic_flops(m, d):
@@ -209,7 +210,10 @@ def bench_single(args):
     ms_fwd, _ = timed(g_fwd, args.steps, 1)
     ms_bwd, _ = timed(g_bwd, args.steps, 1)
 
-    # end to end through the public API: pinned host -> device, loss + accuracy read back
+    # end to end through the public API: pinned host -> device, loss + accuracy read back (same arithmetic mode as
+    # `value`: bf16 tensor-core operands; the API's default for float32 inputs would be the fp32-grade mode)
+    sb.set_precision("bf16")
+
     def e2e_step():
         a = h1.to(dev, non_blocking=True).requires_grad_(True)
         c = h2.to(dev, non_blocking=True).requires_grad_(True)
@@ -234,6 +238,20 @@ def bench_single(args):
     flush_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     e2e_ms = max(e2e_ms - flush_ms, 1e-6)
     clocks = sampler.stop()
+
+    # the fp32-grade arithmetic mode (split bf16 operands) on the same workload, for reference
+    step32 = ContrastiveStep(LOSS_NTXENT, b, d, TAU, True, torch.float32, dev, precision="fp32")
+    step32.x1.copy_(h1)
+    step32.x2.copy_(h2)
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step32.step()
+    torch.cuda.synchronize()
+    g32 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g32, stream=side):
+        step32.step()
+    ms_fp32, _ = timed(g32, max(3, min(args.steps, 20)), 2)
+    del g32, step32
 
     # strong-scaling base: the N > 1 workload (2N = 65536) on this one GPU
     big = ContrastiveStep(LOSS_NTXENT, B_GLOBAL, d, TAU, True, torch.float32, dev)
@@ -267,13 +285,21 @@ def bench_single(args):
         "gpu_launches": 5 * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak, "traffic": None, "kernel": "contrastive_tile_kernel<128,0,true> (backward)",
+                     "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_BWD_TILE,
+                     "traffic_source": "profiles/r01_ncu_full_tile_kernels.csv (dram__bytes_read.sum + dram__bytes_write.sum"
+                                       " of one launch; algorithmic minimum 2 MB operand read: the rest is dacc/colvec"
+                                       " first touch, everything else is L2 resident)",
+                     "kernel": "contrastive_tile_kernel<128,0,true> (backward)",
                      "peak_source": peak_src, "ms_forward_stage": ms_fwd, "ms_backward_stage": ms_bwd,
                      "whole_step_tflops": flops / (ms_step * 1e-3) / 1e12,
                      "whole_step_frac": flops / (ms_step * 1e-3) / 1e12 / peak, "best_step_ms": ms_best},
         "cpu_baseline": {"value": cpu_value, "unit": "views/s", "cores": cores, "kind": "port",
                          "sample": "8 fwd+bwd calls of the same workload (2N=8192, d=128, fp32) after 2 warm-ups",
                          "ms_per_step": cpu_ms},
+        "precision_modes": {"bf16 (this line)": {"ms_per_step": ms_step, "contract": "loss 2e-3, gradients 1e-2"},
+                            "fp32-grade (split bf16 operands)": {"ms_per_step": ms_fp32, "value": m / (ms_fp32 * 1e-3),
+                                                                 "contract": "loss 1e-5, gradients 1e-4"},
+                            "measured_errors": "profiles/r01_precision.log"},
         "scaling_base": {"workload": "ntxent_fwd_bwd 2N=65536 d=128 tau=0.5 (the N>1 workload) on 1 GPU",
                          "ms_per_step": ms_big, "value": 2 * B_GLOBAL / (ms_big * 1e-3), "unit": "views/s",
                          "tflops": algorithmic_flops(2 * B_GLOBAL, d) / (ms_big * 1e-3) / 1e12,
