@@ -182,7 +182,7 @@ int simclr_debug_mma_rate(long long* out_device, int batches, int grid, int mode
  * out: int64[10 variants][32 warps] cycles per 32-column chunk (CTA 0); sink: float[640] scratch. */
 int simclr_debug_chunk_rate(long long* out_device, int iters, int grid, int nwarps, float k2, float* sink, void* stream);
 
-/* Diagnostics: issue rate of single SASS opcodes with 1..16 warps per SM (tools/pipe_rate.py). out: int64[10]. */
+/* Diagnostics: issue rate of single SASS opcodes with 1..16 warps per SM (tools/pipe_rate.py). out: int64[16]. */
 int simclr_debug_pipe_rate(long long* out_device, int iters, int grid, int nwarps, float* sink, void* stream);
 
 /* Diagnostics: UMMA/TMA primitive self-test (tests/test_primitives.py). out_f32 receives 3*128*128 floats. */

@@ -635,7 +635,7 @@ int simclr_debug_pipe_rate(long long* out_device, int iters, int grid, int nwarp
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define SIMCLR_PIPE(V) pipe_rate_kernel<V><<<grid, kThreadsForward, 0, st>>>(out_device, iters, nwarps, 1.0f, sink);
     SIMCLR_PIPE(0) SIMCLR_PIPE(1) SIMCLR_PIPE(2) SIMCLR_PIPE(3) SIMCLR_PIPE(4) SIMCLR_PIPE(5) SIMCLR_PIPE(6) SIMCLR_PIPE(7)
-    SIMCLR_PIPE(8) SIMCLR_PIPE(9)
+    SIMCLR_PIPE(8) SIMCLR_PIPE(9) SIMCLR_PIPE(10) SIMCLR_PIPE(11) SIMCLR_PIPE(12) SIMCLR_PIPE(13) SIMCLR_PIPE(14) SIMCLR_PIPE(15)
 #undef SIMCLR_PIPE
     return static_cast<int>(cudaGetLastError());
 }

@@ -258,7 +258,13 @@ SIMCLR_DEVICE float ex2_poly(float x) {
     return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
 }
 // element i of a 32-column chunk goes to the FMA-pipe exponential
-SIMCLR_DEVICE constexpr bool poly_lane(int i) { return (i & 3) == 3; }
+#ifndef SIMCLR_POLY_MASK
+#define SIMCLR_POLY_MASK 3            // element i of a chunk is a polynomial lane when (i & mask) == mask (3: every fourth)
+#endif
+#ifndef SIMCLR_PINGPONG
+#define SIMCLR_PINGPONG 1             // softmax pairs take turns (named-barrier token) instead of running freely
+#endif
+SIMCLR_DEVICE constexpr bool poly_lane(int i) { return (i & SIMCLR_POLY_MASK) == SIMCLR_POLY_MASK; }
 
 constexpr int kChunk = 16;     // columns per softmax step: two 16-register TMEM loads are kept in flight per thread
 
@@ -297,10 +303,10 @@ SIMCLR_DEVICE void fwd_chunk_fast(const Hot& h, const uint32_t (&r)[kChunk], flo
         cm = fmaxf(cm, c2);
 #pragma unroll
         for (int i = 0; i < kChunk; i += 4) {
-            st.sum += ex2_approx(v[i + 0]);
-            st.s1 += ex2_approx(v[i + 1]);
-            st.s2 += ex2_approx(v[i + 2]);
-            st.s3 += kPoly ? ex2_poly<3>(v[i + 3]) : ex2_approx(v[i + 3]);
+            st.sum += (kPoly && poly_lane(i + 0)) ? ex2_poly<3>(v[i + 0]) : ex2_approx(v[i + 0]);
+            st.s1 += (kPoly && poly_lane(i + 1)) ? ex2_poly<3>(v[i + 1]) : ex2_approx(v[i + 1]);
+            st.s2 += (kPoly && poly_lane(i + 2)) ? ex2_poly<3>(v[i + 2]) : ex2_approx(v[i + 2]);
+            st.s3 += (kPoly && poly_lane(i + 3)) ? ex2_poly<3>(v[i + 3]) : ex2_approx(v[i + 3]);
         }
     } else {
         cm = fmaxf(cm, c2);
@@ -1176,7 +1182,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 // pairs' maths back to back costs nothing, while the per-tile bookkeeping of one pair (barrier waits,
                 // address arithmetic, fences: ~800 cycles) now hides behind the other pair's maths instead of both
                 // pairs idling together (they otherwise drift into lock step).
-                if (it > 0) named_bar_sync(kTokenBar0 + pair, 32 * kNumSoftmaxWarps);
+                if (SIMCLR_PINGPONG && it > 0) named_bar_sync(kTokenBar0 + pair, 32 * kNumSoftmaxWarps);
                 if constexpr (kBackward && kPrec != 0) {
                     // Split mode: W_hi goes where it always goes, W_lo into the upper half [64h+32, 64h+64) of this
                     // warpgroup's region -- over scores of chunks 2 and 3, so the W_lo words are held in registers until
@@ -1205,7 +1211,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                             tmem_st8(t0 + 32 + 3 * (kChunk / 2), wl);
                         }
                     }
-                    if (it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
+                    if (SIMCLR_PINGPONG && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
                 } else if (!tile_special) {
                     // Common case: no masked element anywhere in the tile for this warp.  One straight-line block over
                     // the four chunks, so that the tail of chunk k overlaps the head of chunk k+1.
@@ -1218,7 +1224,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         if (k < 3) tmem_ld16(t0 + (k + 1) * kChunk, nxt);
                         // hand the token over one chunk early: the other pair's first chunk fills the pipes while this
                         // pair drains its last one (covers the bar.arrive -> bar.sync wake-up latency)
-                        if (k == SIMCLR_TOKEN_CHUNK && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
+                        if (SIMCLR_PINGPONG && k == SIMCLR_TOKEN_CHUNK && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
                         if constexpr (!kBackward) {
                             fwd_chunk_fast<kLoss, kConst, kPrec == 0>(h, cur, cm, fs);
                         } else if constexpr (kPrec == 0) {
@@ -1266,7 +1272,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         process(rb2, 2 * kk + 1);
                     }
                 }
-                if (!(kBackward && kPrec != 0) && (tile_special || SIMCLR_TOKEN_CHUNK > 3) && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
+                if (SIMCLR_PINGPONG && !(kBackward && kPrec != 0) && (tile_special || SIMCLR_TOKEN_CHUNK > 3) && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
                 if constexpr (!kBackward) {
                     tc_fence_before_sync();
                     mbar_arrive(s_free + 8 * slot);

@@ -172,14 +172,20 @@ chunk_rate_kernel(long long* __restrict__ out, int iters, int nwarps, float k2, 
 // chains of one opcode (pinned with inline PTX); out[op] = cycles for the whole loop seen by warp 0 of CTA 0.
 //   0 FFMA 3-reg   1 FFMA reg,imm,reg   2 FADD reg,reg   3 FADD reg,imm   4 FMUL reg,reg   5 MUFU.EX2
 //   6 FMNMX reg,reg   7 IMAD (shl-add form)   8 LEA-style shl+add (integer)   9 FFMA 3-reg + MUFU interleaved 3:1
+//   10 F2FP (cvt.rn.bf16x2.f32)   11 FMNMX3 (max of three)   12 LDS.128   13 FSETP+FSEL   14 HFMA2.BF16 (fma.rn.bf16x2)
+//   15 PRMT
 // ---------------------------------------------------------------------------------------------
-constexpr int kPipeOps = 10;
+constexpr int kPipeOps = 16;
 constexpr int kPipeChains = 16;
 constexpr int kPipeUnroll = 4;      // instructions per chain per loop iteration
 
 template <int kOp>
 __global__ void __launch_bounds__(kThreadsForward, 1)
 pipe_rate_kernel(long long* __restrict__ out, int iters, int nwarps, float seed, float* __restrict__ sink) {
+    __shared__ __align__(16) float lds_src[kPipeChains * 4 + 128];
+    if (threadIdx.x < kPipeChains * 4 + 128) lds_src[threadIdx.x] = 1e-3f * threadIdx.x;
+    __syncthreads();
+    const uint32_t lds_addr = smem_u32(lds_src);
     const int warp = threadIdx.x >> 5;
     if (warp >= nwarps) return;
     float a[kPipeChains];
@@ -207,10 +213,18 @@ pipe_rate_kernel(long long* __restrict__ out, int iters, int nwarps, float seed,
                 else if constexpr (kOp == 6) asm volatile("max.f32 %0, %0, %1;" : "+f"(a[c]) : "f"(d));
                 else if constexpr (kOp == 7) asm volatile("mad.lo.s32 %0, %0, 8388608, %1;" : "+r"(ia[c]) : "r"(ib));
                 else if constexpr (kOp == 8) asm volatile("{ .reg .b32 t; shl.b32 t, %0, 23; add.s32 %0, t, %1; }" : "+r"(ia[c]) : "r"(ib));
-                else {
+                else if constexpr (kOp == 9) {
                     if ((c & 3) == 3) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[c]));
                     else asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[c]) : "f"(b), "f"(d));
-                }
+                } else if constexpr (kOp == 10) asm volatile("{ .reg .f32 t; mov.b32 t, %0; cvt.rn.bf16x2.f32 %0, t, %1; }" : "+r"(ia[c]) : "f"(b));
+                else if constexpr (kOp == 11) asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(a[c]) : "f"(d), "f"(b));
+                else if constexpr (kOp == 12) {
+                    float x0, x1, x2, x3;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(lds_addr + c * 16 + ((__float_as_uint(a[c]) & 1u) << 4)));
+                    a[c] = x0 + x3;
+                } else if constexpr (kOp == 13) asm volatile("{ .reg .pred q; setp.gt.f32 q, %1, 0f00000000; selp.f32 %0, %0, %2, q; }" : "+f"(a[c]) : "f"(b), "f"(d));
+                else if constexpr (kOp == 14) asm volatile("fma.rn.bf16x2 %0, %0, %1, %2;" : "+r"(ia[c]) : "r"(ib), "r"(ib));
+                else asm volatile("prmt.b32 %0, %0, %1, 0x5410;" : "+r"(ia[c]) : "r"(ib));
             }
         }
     }

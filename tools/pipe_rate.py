@@ -10,11 +10,11 @@ from pytorch_simclr_b200 import _lib  # noqa: E402
 
 lib = _lib.load()
 names = ["FFMA reg,reg,reg", "FFMA reg,imm,reg", "FADD reg,reg", "FADD reg,imm", "FMUL reg,reg", "MUFU.EX2", "FMNMX reg,reg",
-         "IMAD x*2^23+y", "SHL+IADD", "3 FFMA : 1 MUFU"]
+         "IMAD x*2^23+y", "SHL+IADD", "3 FFMA : 1 MUFU", "F2FP bf16x2", "FMNMX3", "LDS.128", "FSETP+FSEL", "HFMA2.BF16", "PRMT"]
 sink = torch.zeros(640, device="cuda")
 iters = 2000
 for nwarps in (4, 8, 16):
-    out = torch.zeros(16, dtype=torch.int64, device="cuda")
+    out = torch.zeros(32, dtype=torch.int64, device="cuda")
     for _ in range(2):
         _lib.check(lib.simclr_debug_pipe_rate(out.data_ptr(), iters, 148, nwarps, sink.data_ptr(),
                                               torch.cuda.current_stream().cuda_stream), "pipe_rate")
@@ -22,6 +22,6 @@ for nwarps in (4, 8, 16):
     o = out.cpu().double()
     for i, n in enumerate(names):
         ninstr = iters * 4 * 16 * (nwarps / 4)          # warp instructions issued on one sub-partition
-        if i == 8:
+        if i in (8, 13):
             ninstr *= 2
         print(f"{nwarps // 4} warps/SMSP | {n:18s}: {o[i].item() / ninstr:6.2f} cycles per warp instruction per sub-partition")
