@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIMCLR_ABI_VERSION 6
+#define SIMCLR_ABI_VERSION 7
 
 /* loss kinds */
 #define SIMCLR_LOSS_NTXENT 0   /* objective.py:6-55  */
@@ -143,6 +143,10 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
  *                       `backward_workspace` (may be NULL; unweighted losses only) primes the following
  *                       simclr_backward: its accumulation buffer is zeroed by a spare warp of the forward tile kernel
  *                       and, on one GPU (world == 0), the column vectors are written to its start.
+ *                       `flag_peers` / `epoch_local` (may be NULL) hand the barrier between simclr_prepare_peer and
+ *                       this call to the library: the tiles of the columns this rank produced itself run first,
+ *                       while the other ranks' operand rows are still crossing NVLink, then the barrier, then the
+ *                       remote columns (the caller must then NOT issue that barrier itself).
  * simclr_peer_barrier : device-side barrier over flags u32 [world] in symmetric memory (zero-initialised once);
  *                       `epoch_local` is a private device counter, also zero-initialised once.  With `stats_all` it
  *                       then sums the per-rank statistics into stats_out[4] / loss_out (the GLOBAL loss, identical on
@@ -161,7 +165,7 @@ int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_
                         const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out,
                         void* workspace, size_t workspace_bytes, void* backward_workspace,
                         size_t backward_workspace_bytes, int world, int rank, void* const* colvec_peers,
-                        void* const* stats_peers, void* stream);
+                        void* const* stats_peers, void* const* flag_peers, unsigned int* epoch_local, void* stream);
 int simclr_peer_barrier(int world, int rank, void* const* flag_peers, unsigned int* epoch_local, const float* stats_all,
                         float* stats_out, float* loss_out, void* stream);
 

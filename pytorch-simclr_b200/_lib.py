@@ -15,7 +15,7 @@ DTYPE_F32 = 0
 DTYPE_BF16 = 1
 PRECISION_BF16 = 0
 PRECISION_SPLIT = 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _lock = threading.Lock()
 _lib = None
@@ -43,7 +43,7 @@ SIGNATURES = {
     "simclr_prepare_peer": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _int, _int, _vp,
                                    _vp, _vp]),
     "simclr_forward_peer": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp,
-                                   _vp, _sz, _vp, _sz, _int, _int, _vp, _vp, _vp]),
+                                   _vp, _sz, _vp, _sz, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "simclr_peer_barrier": (_int, [_int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "simclr_selftest_umma": (_int, [_vp, _vp, _vp, _vp]),
     "simclr_debug_set_trace": (_int, [_vp, _int]),

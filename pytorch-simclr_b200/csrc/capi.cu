@@ -100,7 +100,21 @@ struct Geometry {
     int64_t bl_pad, bg_pad, d_pad;
     int n_row_blocks, n_col_tiles, grid, max_segs;
     long long total_tiles;
+    int loss, tiles_per_view, col_start, col_cnt;
 };
+void set_window(Geometry* g, int start, int cnt);
+
+// Column window of one tile-kernel launch: per view `cnt` tiles starting at view-tile `start` (cyclic).
+void set_window(Geometry* g, int start, int cnt) {
+    g->col_start = start;
+    g->col_cnt = cnt;
+    g->n_col_tiles = (g->loss == SIMCLR_LOSS_NTXENT ? 2 : 1) * cnt;
+    g->total_tiles = static_cast<long long>(g->n_row_blocks) * g->n_col_tiles;
+    const int sms = device_info().sm_count;
+    g->grid = static_cast<int>(g->total_tiles < sms ? g->total_tiles : sms);
+    const long long per_cta = (g->total_tiles + g->grid - 1) / g->grid;
+    g->max_segs = static_cast<int>((per_cta + g->n_col_tiles - 2) / g->n_col_tiles + 1);
+}
 
 int make_geometry(int loss, int64_t b_local, int64_t b_global, int64_t row_offset, int64_t d, Geometry* g) {
     if (loss != SIMCLR_LOSS_NTXENT && loss != SIMCLR_LOSS_MODIFIED) return SIMCLR_ERR_BAD_LOSS;
@@ -112,12 +126,9 @@ int make_geometry(int loss, int64_t b_local, int64_t b_global, int64_t row_offse
     g->bl_pad = round_up(b_local, kBlockM);
     g->bg_pad = round_up(b_global, kBlockM);
     g->n_row_blocks = static_cast<int>(2 * g->bl_pad / kBlockM);
-    g->n_col_tiles = static_cast<int>((loss == SIMCLR_LOSS_NTXENT ? 2 : 1) * g->bg_pad / kBlockN);
-    g->total_tiles = static_cast<long long>(g->n_row_blocks) * g->n_col_tiles;
-    const int sms = device_info().sm_count;
-    g->grid = static_cast<int>(g->total_tiles < sms ? g->total_tiles : sms);
-    const long long per_cta = (g->total_tiles + g->grid - 1) / g->grid;
-    g->max_segs = static_cast<int>((per_cta + g->n_col_tiles - 2) / g->n_col_tiles + 1);
+    g->loss = loss;
+    g->tiles_per_view = static_cast<int>(g->bg_pad / kBlockN);
+    set_window(g, 0, g->tiles_per_view);
     return SIMCLR_OK;
 }
 
@@ -128,8 +139,9 @@ inline size_t header_bytes(const Geometry&) { return 256; }
 struct FwdWorkspace {
     unsigned int* ticket;
     float* part;
+    float* part2;      // partials of the second launch of the overlapped row-sharded forward
     float* block_part;
-    size_t bytes;
+    size_t bytes, part_bytes;
 };
 FwdWorkspace carve_forward(const Geometry& g, void* base) {
     FwdWorkspace w;
@@ -138,8 +150,15 @@ FwdWorkspace carve_forward(const Geometry& g, void* base) {
     off += header_bytes(g);
     w.block_part = reinterpret_cast<float*>(static_cast<char*>(base) + off);
     off += align256(static_cast<size_t>(g.n_row_blocks) * 4 * sizeof(float));
+    // sized for the full column window; a narrower window never needs more (fewer tiles per CTA, at most as many CTAs),
+    // except that max_segs can grow by the row blocks a CTA additionally spans: bound it by n_row_blocks
+    const int segs = g.n_row_blocks < 8 ? g.n_row_blocks : (g.max_segs + 6 < g.n_row_blocks ? g.max_segs + 6 : g.n_row_blocks);
+    const size_t part_bytes = align256(static_cast<size_t>(device_info().sm_count) * segs * kFwdFields * kBlockM * sizeof(float));
     w.part = reinterpret_cast<float*>(static_cast<char*>(base) + off);
-    off += align256(static_cast<size_t>(g.grid) * g.max_segs * kFwdFields * kBlockM * sizeof(float));
+    off += part_bytes;
+    w.part2 = reinterpret_cast<float*>(static_cast<char*>(base) + off);
+    off += part_bytes;
+    w.part_bytes = part_bytes;
     w.bytes = off;
     return w;
 }
@@ -291,6 +310,9 @@ TileParams make_tile_params(const Geometry& g, const Scales& s, int64_t b_local,
     p.bg_pad = static_cast<int>(g.bg_pad);
     p.n_row_blocks = g.n_row_blocks;
     p.n_col_tiles = g.n_col_tiles;
+    p.col_start = g.col_start;
+    p.col_cnt = g.col_cnt;
+    p.tiles_per_view = g.tiles_per_view;
     p.max_segs = g.max_segs;
     p.total_tiles = g.total_tiles;
     p.k2 = s.k2;
@@ -462,8 +484,8 @@ int simclr_forward(int loss, const void* operand_rows, const void* operand_cols,
                    const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out, void* workspace,
                    size_t workspace_bytes, void* stream) {
     return simclr_forward_peer(loss, operand_rows, operand_cols, b_local, b_global, row_offset, d, temperature, normalize,
-                               SIMCLR_PRECISION_BF16, pos_dot, row_weight, lse2, row_loss, stats, loss_out, workspace, workspace_bytes, nullptr, 0,
-                               0, 0, nullptr, nullptr, stream);
+                               SIMCLR_PRECISION_BF16, pos_dot, row_weight, lse2, row_loss, stats, loss_out, workspace,
+                               workspace_bytes, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
@@ -472,7 +494,7 @@ int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_
                         const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out,
                         void* workspace, size_t workspace_bytes, void* backward_workspace,
                         size_t backward_workspace_bytes, int world, int rank, void* const* colvec_peers,
-                        void* const* stats_peers, void* stream) {
+                        void* const* stats_peers, void* const* flag_peers, unsigned int* epoch_local, void* stream) {
     if (!operand_rows || !operand_cols || !pos_dot || !lse2 || !row_loss || !stats || !workspace)
         return SIMCLR_ERR_NULL_POINTER;
     if (!(temperature > 0.f) || !std::isfinite(temperature)) return SIMCLR_ERR_BAD_TEMPERATURE;
@@ -520,7 +542,46 @@ int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_
         }
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if ((rc = dispatch_tile<false>(loss, g.d_pad, precision, map_rows, map_cols, map_rows, p, g.grid, st))) return rc;
+    const int tpr = static_cast<int>(b_local / kBlockM);                   // column tiles per rank and view
+    const bool overlap = flag_peers != nullptr && epoch_local != nullptr && p.colvec_peers.world > 1 &&
+                         b_local % kBlockM == 0 && g.tiles_per_view == tpr * world;
+    if (flag_peers != nullptr && !overlap) {
+        // the caller relies on this call to order the operand exchange: do it up front
+        if ((rc = simclr_peer_barrier(world, rank, flag_peers, epoch_local, nullptr, nullptr, nullptr, stream))) return rc;
+    }
+    if (!overlap) {
+        p.fin_set[0] = PartSet{w.part, g.total_tiles, g.n_col_tiles, g.max_segs, g.grid};
+        p.n_fin_sets = 1;
+        if ((rc = dispatch_tile<false>(loss, g.d_pad, precision, map_rows, map_cols, map_rows, p, g.grid, st))) return rc;
+    } else {
+        // Overlapped exchange: the columns this rank produced itself need no peer, so their tiles run while the other
+        // ranks' operand rows are still crossing NVLink; the barrier follows, then the remote columns.
+        Geometry ga = g, gb = g;
+        set_window(&ga, rank * tpr, tpr);
+        set_window(&gb, ((rank + 1) % world) * tpr, g.tiles_per_view - tpr);
+        if (static_cast<size_t>(ga.grid) * ga.max_segs * kFwdFields * kBlockM * sizeof(float) > w.part_bytes ||
+            static_cast<size_t>(gb.grid) * gb.max_segs * kFwdFields * kBlockM * sizeof(float) > w.part_bytes)
+            return SIMCLR_ERR_WORKSPACE_TOO_SMALL;
+        TileParams pa = p, pb = p;
+        auto window = [](TileParams& q, const Geometry& gw, float* part) {
+            q.n_col_tiles = gw.n_col_tiles;
+            q.col_start = gw.col_start;
+            q.col_cnt = gw.col_cnt;
+            q.total_tiles = gw.total_tiles;
+            q.max_segs = gw.max_segs;
+            q.tile_grid = gw.grid;
+            q.part = part;
+        };
+        window(pa, ga, w.part);
+        window(pb, gb, w.part2);
+        pb.prime_dacc = nullptr;                                  // zeroed once, by the first launch
+        if ((rc = dispatch_tile<false>(loss, g.d_pad, precision, map_rows, map_cols, map_rows, pa, ga.grid, st))) return rc;
+        if ((rc = simclr_peer_barrier(world, rank, flag_peers, epoch_local, nullptr, nullptr, nullptr, stream))) return rc;
+        if ((rc = dispatch_tile<false>(loss, g.d_pad, precision, map_rows, map_cols, map_rows, pb, gb.grid, st))) return rc;
+        p.fin_set[0] = PartSet{w.part, ga.total_tiles, ga.n_col_tiles, ga.max_segs, ga.grid};
+        p.fin_set[1] = PartSet{w.part2, gb.total_tiles, gb.n_col_tiles, gb.max_segs, gb.grid};
+        p.n_fin_sets = 2;
+    }
     cudaError_t e;
     if (loss == SIMCLR_LOSS_NTXENT) e = launch_pdl(forward_finalize_kernel<kNtXent>, dim3(g.n_row_blocks), dim3(kBlockM), 0, st, p);
     else e = launch_pdl(forward_finalize_kernel<kModified>, dim3(g.n_row_blocks), dim3(kBlockM), 0, st, p);

@@ -94,6 +94,14 @@ struct PeerTable {
     int rank;
 };
 
+// One forward tile-kernel launch as the finalize kernel sees it: where its per-CTA partials are and how its tiles were
+// dealt out.  The overlapped row-sharded forward runs two launches (local columns, then remote columns).
+struct PartSet {
+    const float* part;
+    long long total_tiles;
+    int n_col_tiles, max_segs, grid;
+};
+
 struct TileParams {
     int b_loc;         // images held by this rank
     int b_glob;        // images in the global batch
@@ -101,7 +109,10 @@ struct TileParams {
     int bl_pad;        // b_loc rounded up to 128
     int bg_pad;        // b_glob rounded up to 128
     int n_row_blocks;  // 2 * bl_pad / 128
-    int n_col_tiles;   // column tiles per row block (NT-Xent: 2*bg_pad/128, modified: bg_pad/128)
+    int n_col_tiles;   // column tiles per row block of THIS launch (NT-Xent: 2*col_cnt, modified: col_cnt)
+    // column window of this launch: per view the col_cnt tiles starting at view-tile col_start (cyclic in the view's
+    // tiles_per_view = bg_pad/128 tiles).  Full problem: col_start = 0, col_cnt = tiles_per_view.
+    int col_start, col_cnt, tiles_per_view;
     int max_segs;      // max number of row blocks one CTA touches
     long long total_tiles;
     float k2;          // NT-Xent: log2(e)/tau (carried by the operands as sqrt(k2) each).  modified: 1/tau
@@ -145,6 +156,8 @@ struct TileParams {
     long long* trace;      // optional (debug): per-role clock64() timestamps of CTA `trace_cta`
     int trace_cta;
     int tile_grid;         // grid size of the tile kernel (the finalize kernels need it to locate partials)
+    PartSet fin_set[2];    // forward finalize: the launches whose partials it merges
+    int n_fin_sets;
     unsigned long long* ktrace;   // optional (debug): kernel-level %globaltimer stamps
 };
 
@@ -188,8 +201,16 @@ struct SmemLayout {
 // First global column of tile j for a row block of view vr.
 template <int kLoss>
 SIMCLR_DEVICE int tile_col0(const TileParams& p, int vr, int j) {
-    if constexpr (kLoss == kNtXent) return j * kBlockN;
-    else return (1 - vr) * p.bg_pad + j * kBlockN;
+    int v = 0;
+    if constexpr (kLoss == kNtXent) {
+        v = j >= p.col_cnt ? 1 : 0;          // NT-Xent rows see both views' windows, view 0 first
+        j -= v * p.col_cnt;
+    } else {
+        v = 1 - vr;                           // modified rows see the other view only
+    }
+    int idx = p.col_start + j;
+    if (idx >= p.tiles_per_view) idx -= p.tiles_per_view;
+    return v * p.bg_pad + idx * kBlockN;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -443,15 +464,6 @@ SIMCLR_DEVICE void bwd_chunk(const Hot& h, const uint32_t (&r)[kChunk], uint32_t
 // Fused finalize steps.  A row block's tiles are spread over a few CTAs (contiguous tile ranges); the CTA that
 // completes its share last (atomic ticket per row block) finishes the block's 128 rows from L2-resident data.
 // ---------------------------------------------------------------------------------------------
-// CTAs whose range [T*k/G, T*(k+1)/G) overlaps row block rb: owner(t) = ((t+1)*G - 1) / T
-SIMCLR_DEVICE void contributing_ctas(const TileParams& p, int rb, int& k_first, int& k_last) {
-    const long long g = p.tile_grid;
-    const long long t_lo = static_cast<long long>(rb) * p.n_col_tiles;
-    const long long t_hi = t_lo + p.n_col_tiles;
-    k_first = static_cast<int>(((t_lo + 1) * g - 1) / p.total_tiles);
-    k_last = static_cast<int>((t_hi * g - 1) / p.total_tiles);
-}
-
 template <int kLoss>
 SIMCLR_DEVICE float exact_logit2(const TileParams& p, float v) {
     if constexpr (kLoss == kNtXent) return v;
@@ -468,21 +480,44 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
     const int img = (rb - vr * blocks_per_view) * kBlockM + tid;
     const bool row_ok = img < p.b_loc;
     const int slot = rb * kBlockM + tid;
-    int k_first, k_last;
-    contributing_ctas(p, rb, k_first, k_last);
-
     float v_pos = __ldg(p.pos_dot + slot);
     if constexpr (kLoss == kModified) v_pos = fmaxf(v_pos * p.qscale, kClampMin);
     else v_pos *= p.k2;               // exact fp32 positive logit in the log2 domain of the MMA scores
-    // Partials of CTA k live at part[(k * max_segs + seg_k)]: the first contributing CTA may have started in an
-    // earlier row block (seg_k = rb - its first row block); every later one starts inside this row block (seg 0).
-    const long long c_first = (p.total_tiles * k_first) / p.tile_grid;
-    const int seg_first = rb - static_cast<int>(c_first / p.n_col_tiles);
-    const size_t stride_k = static_cast<size_t>(p.max_segs) * (kFwdFields * kBlockM);
-    const float* base = p.part + static_cast<size_t>(k_first) * stride_k + tid;
-    const int nk = k_last - k_first + 1;
+    // Partials of CTA k of a launch live at part[(k * max_segs + seg_k)]: the first contributing CTA may have started
+    // in an earlier row block (seg_k = rb - its first row block); every later one starts inside this row block (seg 0).
+    // CTAs whose range [T*k/G, T*(k+1)/G) overlaps row block rb: owner(t) = ((t+1)*G - 1) / T.
+    auto visit = [&](auto&& f) {
+        for (int s = 0; s < p.n_fin_sets; ++s) {
+            const PartSet& ps = p.fin_set[s];
+            const long long g = ps.grid;
+            const long long t_lo = static_cast<long long>(rb) * ps.n_col_tiles, t_hi = t_lo + ps.n_col_tiles;
+            const int kf = static_cast<int>(((t_lo + 1) * g - 1) / ps.total_tiles);
+            const int kl = static_cast<int>((t_hi * g - 1) / ps.total_tiles);
+            const long long c_first = (ps.total_tiles * kf) / g;
+            const int seg_first = rb - static_cast<int>(c_first / ps.n_col_tiles);
+            const size_t stride_k = static_cast<size_t>(ps.max_segs) * (kFwdFields * kBlockM);
+            for (int k = kf; k <= kl; ++k)
+                f(ps.part + static_cast<size_t>(k) * stride_k + (k == kf ? seg_first * (kFwdFields * kBlockM) : 0) + tid);
+        }
+    };
     float vmax = v_pos, max_prec = kNegBig, max_foll = kNegBig, pos_mma = kNegBig, total;
     constexpr int kFast = 6;
+    int nk = kFast + 1;
+    const float* base = nullptr;
+    size_t stride_k = 0;
+    int seg_first = 0;
+    if (p.n_fin_sets == 1) {
+        const PartSet& ps = p.fin_set[0];
+        const long long g = ps.grid;
+        const long long t_lo = static_cast<long long>(rb) * ps.n_col_tiles, t_hi = t_lo + ps.n_col_tiles;
+        const int k_first = static_cast<int>(((t_lo + 1) * g - 1) / ps.total_tiles);
+        const int k_last = static_cast<int>((t_hi * g - 1) / ps.total_tiles);
+        const long long c_first = (ps.total_tiles * k_first) / g;
+        seg_first = rb - static_cast<int>(c_first / ps.n_col_tiles);
+        stride_k = static_cast<size_t>(ps.max_segs) * (kFwdFields * kBlockM);
+        base = ps.part + static_cast<size_t>(k_first) * stride_k + tid;
+        nk = k_last - k_first + 1;
+    }
     if (nk <= kFast) {
         // common case: issue every load up front (one L2 round trip), then merge from registers
         float sv[kFast], mv[kFast];
@@ -507,21 +542,19 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
         for (int i = 0; i < kFast; ++i)
             if (mv[i] > kNegBig) total += sv[i] * exp2f(exact_logit2<kLoss>(p, mv[i]) - top);
     } else {
-        // many small CTAs per row block (tiny problems): two passes
-        for (int i = 0; i < nk; ++i) {
-            const float* src = base + i * stride_k + (i == 0 ? seg_first * (kFwdFields * kBlockM) : 0);
+        // many small CTAs per row block (tiny problems) or two launches: two passes
+        visit([&](const float* src) {
             vmax = fmaxf(vmax, __ldcg(src + 1 * kBlockM));
             max_prec = fmaxf(max_prec, __ldcg(src + 2 * kBlockM));
             max_foll = fmaxf(max_foll, __ldcg(src + 3 * kBlockM));
             pos_mma = fmaxf(pos_mma, __ldcg(src + 4 * kBlockM));
-        }
+        });
         const float top = exact_logit2<kLoss>(p, vmax);
         total = exp2f(exact_logit2<kLoss>(p, v_pos) - top);
-        for (int i = 0; i < nk; ++i) {
-            const float* src = base + i * stride_k + (i == 0 ? seg_first * (kFwdFields * kBlockM) : 0);
+        visit([&](const float* src) {
             const float mk = __ldcg(src + 1 * kBlockM);
             if (mk > kNegBig) total += __ldcg(src + 0 * kBlockM) * exp2f(exact_logit2<kLoss>(p, mk) - top);
-        }
+        });
     }
     const float top = exact_logit2<kLoss>(p, vmax);
     float l2 = 0.f, loss_r = 0.f, w = 0.f, hit = 0.f;

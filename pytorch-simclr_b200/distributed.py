@@ -181,15 +181,16 @@ class PeerBatch:
                                       rowvec[0].data_ptr(), rowvec[1].data_ptr(), ws.data_ptr(), self.world, self.rank,
                                       tab["operand"], self._mc[gen], stream),
               "simclr_prepare_peer")
-        check(lib.simclr_peer_barrier(self.world, self.rank, self._flags, self.epoch.data_ptr(), None, None, None, stream),
-              "simclr_peer_barrier")
+        # the barrier between the operand push and its consumers is issued inside simclr_forward_peer, after the tiles
+        # of this rank's own columns (they overlap the NVLink transfer of everybody else's rows)
         check(lib.simclr_forward_peer(loss_kind, operand.data_ptr(), view["operand"].data_ptr(), self.b_local,
                                       self.b_global, self.row_offset, self.d, float(temperature), int(bool(normalize)),
                                       _lib.PRECISION_BF16, rowvec[1].data_ptr(), None, rowvec[2].data_ptr(),
                                       rowvec[3].data_ptr(),
                                       stats_local.data_ptr(), None, ws.data_ptr(), ws_bytes,
                                       None if bwd_ws is None else bwd_ws.data_ptr(), 0 if bwd_ws is None else bwd_ws.numel(),
-                                      self.world, self.rank, tab["colvec"], tab["stats"], stream), "simclr_forward_peer")
+                                      self.world, self.rank, tab["colvec"], tab["stats"], self._flags,
+                                      self.epoch.data_ptr(), stream), "simclr_forward_peer")
         check(lib.simclr_peer_barrier(self.world, self.rank, self._flags, self.epoch.data_ptr(), view["stats"].data_ptr(),
                                       stats_global.data_ptr(), loss.data_ptr(), stream), "simclr_peer_barrier")
         self.generation += 1

@@ -153,7 +153,7 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
                                       _ptr(w_local),
                                       rowvec[2].data_ptr(), rowvec[3].data_ptr(), stats.data_ptr(), loss.data_ptr(),
                                       ws.data_ptr(), ws_bytes, _ptr(bwd_ws), 0 if bwd_ws is None else bwd_ws.numel(), 0, 0,
-                                      None, None, stream), "simclr_forward")
+                                      None, None, None, None, stream), "simclr_forward")
     saved = _Saved()
     saved.operand_rows, saved.operand_cols = operand, operand_cols
     saved.inv_norm, saved.pos_dot = rowvec[0], rowvec[1]

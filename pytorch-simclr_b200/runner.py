@@ -65,7 +65,8 @@ class ContrastiveStep:
                                       self.temperature, int(self.normalize), self.precision, self.rowvec[1].data_ptr(), None,
                                       self.rowvec[2].data_ptr(), self.rowvec[3].data_ptr(), self.stats.data_ptr(),
                                       self.loss.data_ptr(), self.fwd_ws.data_ptr(), self.fwd_ws_bytes,
-                                      self.bwd_ws.data_ptr(), self.bwd_ws_bytes, 0, 0, None, None, st), "simclr_forward")
+                                      self.bwd_ws.data_ptr(), self.bwd_ws_bytes, 0, 0, None, None, None, None, st),
+              "simclr_forward")
 
     def backward(self, grad_out: Optional[torch.Tensor] = None) -> None:
         lib, st = self.lib, self._stream()
