@@ -112,7 +112,8 @@ class PeerBatch:
     peer = True
     GENERATIONS = 2
 
-    def __init__(self, b_local: int, d: int, group=None, device=None, use_multicast: bool = True):
+    def __init__(self, b_local: int, d: int, group=None, device=None, use_multicast: bool = True,
+                 overlap_local_first: bool = False):
         import torch.distributed._symmetric_memory as symm
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
@@ -165,6 +166,11 @@ class PeerBatch:
                 "colvec": local[base + op_bytes: base + op_bytes + 2 * 2 * self.bg_pad * 4].view(torch.float32),
                 "stats": local[base + op_bytes + lse_bytes: base + op_bytes + lse_bytes + self.world * 16].view(torch.float32),
             })
+        # overlap_local_first: run the tiles of this rank's own columns before the barrier that waits for the peers'
+        # operand rows (two tile-kernel launches).  Measured on 2/4/8 B200 at 2N = 65536: 1.444 / 0.7445 / 0.4132 ms
+        # against 1.422 / 0.7396 / 0.4111 ms without -- the NVLS push is not what limits the step, the second launch's
+        # fixed cost is slightly more than the hidden transfer -- hence off by default.
+        self.overlap = bool(overlap_local_first)
         self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.generation = 0                    # number of forwards issued so far
         self.lib = _lib.load()
@@ -181,16 +187,20 @@ class PeerBatch:
                                       rowvec[0].data_ptr(), rowvec[1].data_ptr(), ws.data_ptr(), self.world, self.rank,
                                       tab["operand"], self._mc[gen], stream),
               "simclr_prepare_peer")
-        # the barrier between the operand push and its consumers is issued inside simclr_forward_peer, after the tiles
-        # of this rank's own columns (they overlap the NVLink transfer of everybody else's rows)
+        if not self.overlap:
+            check(lib.simclr_peer_barrier(self.world, self.rank, self._flags, self.epoch.data_ptr(), None, None, None,
+                                          stream), "simclr_peer_barrier")
+        # (overlap: the barrier between the operand push and its consumers is issued inside simclr_forward_peer, after
+        # the tiles of this rank's own columns, which overlap the NVLink transfer of everybody else's rows)
         check(lib.simclr_forward_peer(loss_kind, operand.data_ptr(), view["operand"].data_ptr(), self.b_local,
                                       self.b_global, self.row_offset, self.d, float(temperature), int(bool(normalize)),
                                       _lib.PRECISION_BF16, rowvec[1].data_ptr(), None, rowvec[2].data_ptr(),
                                       rowvec[3].data_ptr(),
                                       stats_local.data_ptr(), None, ws.data_ptr(), ws_bytes,
                                       None if bwd_ws is None else bwd_ws.data_ptr(), 0 if bwd_ws is None else bwd_ws.numel(),
-                                      self.world, self.rank, tab["colvec"], tab["stats"], self._flags,
-                                      self.epoch.data_ptr(), stream), "simclr_forward_peer")
+                                      self.world, self.rank, tab["colvec"], tab["stats"],
+                                      self._flags if self.overlap else None,
+                                      self.epoch.data_ptr() if self.overlap else None, stream), "simclr_forward_peer")
         check(lib.simclr_peer_barrier(self.world, self.rank, self._flags, self.epoch.data_ptr(), view["stats"].data_ptr(),
                                       stats_global.data_ptr(), loss.data_ptr(), stream), "simclr_peer_barrier")
         self.generation += 1

@@ -35,6 +35,7 @@ ok = True
 for name, fn, ref_fn, use_weight, transport in (
         ("ntxent/peer", global_contrastive_loss, oracle.ntxent_closed_form, False, "peer"),
         ("ntxent/peer again", global_contrastive_loss, oracle.ntxent_closed_form, False, "peer"),
+        ("ntxent/peer overlap", global_contrastive_loss, oracle.ntxent_closed_form, False, "peer-overlap"),
         ("ntxent/nccl", global_contrastive_loss, oracle.ntxent_closed_form, False, "nccl"),
         ("ntxent+weight/nccl", global_contrastive_loss, oracle.ntxent_closed_form, True, "nccl"),
         ("modified/peer", global_modified_contrastive_loss, oracle.modified_closed_form, False, "peer"),
@@ -47,6 +48,16 @@ for name, fn, ref_fn, use_weight, transport in (
     a = z1[off:off + bl].cuda().requires_grad_(True)
     c = z2[off:off + bl].cuda().requires_grad_(True)
     kw = dict(temperature=args.tau, transport=transport)
+    if transport == "peer-overlap":
+        # the overlapped schedule (local-column tiles, barrier, remote-column tiles) through its own PeerBatch
+        from pytorch_simclr_b200 import distributed as D
+        from pytorch_simclr_b200.functional import ContrastiveLossFunction, LOSS_NTXENT
+        if "ov" not in globals():
+            ov = D.PeerBatch(args.b // world, args.d, None, torch.device("cuda", local), overlap_local_first=True)
+
+        def fn(x1, x2, temperature, transport):      # noqa: F811
+            loss, stats = ContrastiveLossFunction.apply(x1, x2, LOSS_NTXENT, float(temperature), True, None, ov)
+            return loss, 100.0 * stats[2].item() / (2 * x1.shape[0] * world)
     if use_weight:
         kw["weight"] = torch.cat((w[off:off + bl], w[args.b + off:args.b + off + bl])).cuda()
     loss, acc = fn(a, c, **kw)
