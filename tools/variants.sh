@@ -1,4 +1,4 @@
-for v in b200 v_nopp v_poly8 v_poly2 v_nopoly; do
+for v in b200 v_nopp v_poly8 v_nopp_poly8 b200; do
   echo "== $v"
   SIMCLR_B200_LIB=$PWD/pytorch-simclr_b200/lib/libsimclr_$v.so python - <<'PY'
 import sys, torch
@@ -18,13 +18,13 @@ with torch.cuda.graph(gb, stream=side): step.backward()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 def t(gr):
     for _ in range(5): flush.zero_(); gr.replay()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(40)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(200)]
     torch.cuda.synchronize()
     for a, b in ev:
         flush.zero_(); a.record(); gr.replay(); b.record()
     torch.cuda.synchronize()
-    ms = sorted(a.elapsed_time(b) for a, b in ev)
-    return ms[len(ms)//2] * 1e3
+    ms = [a.elapsed_time(b) for a, b in ev]
+    return sum(ms) / len(ms) * 1e3
 print("fwd stage %.1f us   bwd stage %.1f us   loss %.6f" % (t(gf), t(gb), float(step.loss)))
 PY
 done
