@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIMCLR_ABI_VERSION 7
+#define SIMCLR_ABI_VERSION 8
 
 /* loss kinds */
 #define SIMCLR_LOSS_NTXENT 0   /* objective.py:6-55  */
@@ -127,6 +127,25 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
                     void* workspace, size_t workspace_bytes, const float* primed_colvec, void* stream);
 
 /*
+ * Fused training-step form of the three stages for one GPU and an unweighted loss: what the reference's
+ *     loss, acc = loss_fn(z1, z2, temperature=t); loss /= accum_steps; loss.backward()      utils/model_utils.py:115-120
+ * enqueues when the upstream gradient (`grad_out`, device f32 [1], or NULL for 1.0 -- the reference's 1/accum_steps) is
+ * known up front.  Five launches (prepare, forward tile, forward finalize, backward tile, backward finalize).  Because
+ * the library sees the whole sequence it takes two things off the path between the tile kernels that the separate
+ * calls cannot: the reduction of the loss statistics moves into the backward finalize kernel, and the backward tile
+ * kernel loads its operands and issues its first score MMAs while the forward finalize kernel is still running.
+ *   rowvec   f32 [4][2*Bpad]   inv_norm | pos_dot | lse2 | row_loss (outputs / saved state, as in the staged calls)
+ *   stats    f32 [4], loss_out f32 [1] or NULL: as simclr_forward; valid when the whole call has completed
+ *   operand  bf16, simclr_operand_bytes(b, d, precision) bytes
+ * Workspaces as for simclr_forward / simclr_backward with b_local == b_global == b.
+ */
+int simclr_forward_backward(int loss, const void* x_batch1, const void* x_batch2, int64_t b, int64_t d, int in_dtype,
+                            int normalize, float temperature, int precision, const float* grad_out, void* operand,
+                            float* rowvec, float* stats, float* loss_out, void* grad1, void* grad2,
+                            void* forward_workspace, size_t forward_workspace_bytes, void* backward_workspace,
+                            size_t backward_workspace_bytes, void* stream);
+
+/*
  * Row-sharded global batch over peer memory (one process per GPU of one NVLink / NVSwitch node; not in the reference,
  * whose only batch-scaling device is gradient accumulation, utils/model_utils.py:113-123).  Buffers named *_peers are
  * arrays of `world` device pointers: entry r is THIS process's mapping of rank r's copy of a symmetric allocation
@@ -173,6 +192,12 @@ int simclr_peer_barrier(int world, int rank, void* const* flag_peers, unsigned i
  * device_buffer: int64[6 roles][64 iterations][4] or NULL to switch tracing off. */
 int simclr_debug_set_trace(void* device_buffer, int cta);
 
+/* Measurement: restrict the staged calls of this process to a subset of their kernels, so that bench.py can time ONE
+ * kernel of the step by itself (a CUDA graph of back-to-back launches of it between two events).  Bits: 1 prepare,
+ * 2 forward tile, 4 forward finalize, 8 backward tile, 16 backward finalize, 32 backward prepare; ~0 (default) = all.
+ * Results are only meaningful with the full mask. */
+int simclr_debug_set_stage_mask(unsigned int mask);
+
 /* Diagnostics: kernel-level %globaltimer timeline (tools/kernel_timeline.py).  device_buffer: uint64[8][2]
  * (min start / max end in ns per kernel id: 0 prepare, 1 forward tile, 2 backward prepare, 3 backward tile),
  * start slots initialised to ~0, end slots to 0; NULL switches it off.  Captured into graphs at capture time. */
@@ -186,7 +211,7 @@ int simclr_debug_mma_rate(long long* out_device, int batches, int grid, int mode
  * out: int64[10 variants][32 warps] cycles per 32-column chunk (CTA 0); sink: float[640] scratch. */
 int simclr_debug_chunk_rate(long long* out_device, int iters, int grid, int nwarps, float k2, float* sink, void* stream);
 
-/* Diagnostics: issue rate of single SASS opcodes with 1..16 warps per SM (tools/pipe_rate.py). out: int64[16]. */
+/* Diagnostics: issue rate of single SASS opcodes with 1..16 warps per SM (tools/pipe_rate.py). out: int64[32]. */
 int simclr_debug_pipe_rate(long long* out_device, int iters, int grid, int nwarps, float* sink, void* stream);
 
 /* Diagnostics: UMMA/TMA primitive self-test (tests/test_primitives.py). out_f32 receives 3*128*128 floats. */

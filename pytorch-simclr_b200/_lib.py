@@ -15,7 +15,7 @@ DTYPE_F32 = 0
 DTYPE_BF16 = 1
 PRECISION_BF16 = 0
 PRECISION_SPLIT = 1
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _lock = threading.Lock()
 _lib = None
@@ -40,6 +40,8 @@ SIGNATURES = {
     "simclr_operand_bytes": (_sz, [_i64, _i64, _int]),
     "simclr_backward": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp,
                                _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "simclr_forward_backward": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                       _vp, _sz, _vp, _sz, _vp]),
     "simclr_prepare_peer": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _int, _int, _vp,
                                    _vp, _vp]),
     "simclr_forward_peer": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -48,6 +50,7 @@ SIGNATURES = {
     "simclr_selftest_umma": (_int, [_vp, _vp, _vp, _vp]),
     "simclr_debug_set_trace": (_int, [_vp, _int]),
     "simclr_debug_set_kernel_trace": (_int, [_vp]),
+    "simclr_debug_set_stage_mask": (_int, [ctypes.c_uint]),
     "simclr_debug_chunk_rate": (_int, [_vp, _int, _int, _int, _f32, _vp, _vp]),
     "simclr_debug_pipe_rate": (_int, [_vp, _int, _int, _int, _vp, _vp]),
     "simclr_debug_mma_rate": (_int, [_vp, _int, _int, _int, _vp, _vp]),

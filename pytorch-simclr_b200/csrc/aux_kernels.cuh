@@ -60,16 +60,45 @@ __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x
                                float* __restrict__ pos_dot, unsigned int* __restrict__ zero_ptr, int zero_words,
                                unsigned long long* ktrace, PeerTable peers) {
     pdl_launch_dependents();
+    // The input rows are loaded BEFORE griddepcontrol.wait (they are the caller's tensors: no kernel of this library
+    // writes them, and a foreign producer never lets this kernel start early); every store comes after it, because the
+    // previous step's kernels may still be reading the buffers this kernel overwrites.
+    const int warps_per_block = blockDim.x >> 5;
+    const int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5);   // local image slot
+    const int lane = threadIdx.x & 31;
+    constexpr int kWords = kPer / 2;
+    float v1[kPer], v2[kPer];
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) v1[u] = v2[u] = 0.f;
+    if (i < a.b_loc) {
+        const T* r1 = x1 + static_cast<size_t>(i) * a.d;
+        const T* r2 = x2 + static_cast<size_t>(i) * a.d;
+        bool vec = false;
+        if constexpr (sizeof(T) == 4 && kPer == 4) {
+            // fp32 rows of exactly 128 columns at 16-byte aligned addresses: one float4 per lane
+            vec = a.d == a.d_pad && ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(x2)) & 15u) == 0;
+            if (vec) {
+                const float4 p4 = __ldg(reinterpret_cast<const float4*>(r1) + lane);
+                const float4 q4 = __ldg(reinterpret_cast<const float4*>(r2) + lane);
+                v1[0] = p4.x; v1[1] = p4.y; v1[2] = p4.z; v1[3] = p4.w;
+                v2[0] = q4.x; v2[1] = q4.y; v2[2] = q4.z; v2[3] = q4.w;
+            }
+        }
+        if (!vec) {
+#pragma unroll
+            for (int u = 0; u < kPer; ++u) {
+                const int k = lane * kPer + u;
+                v1[u] = k < a.d ? load_as_float(r1 + k) : 0.f;
+                v2[u] = k < a.d ? load_as_float(r2 + k) : 0.f;
+            }
+        }
+    }
     pdl_wait();
     ktrace_begin(ktrace, 0);
     struct End { unsigned long long* k; __device__ ~End() { ktrace_end(k, 0); } } end_guard{ktrace};
     if (zero_ptr != nullptr && blockIdx.x == 0)
-        for (int i = threadIdx.x; i < zero_words; i += blockDim.x) zero_ptr[i] = 0u;
-    const int warps_per_block = blockDim.x >> 5;
-    const int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5);   // local image slot
-    const int lane = threadIdx.x & 31;
+        for (int j = threadIdx.x; j < zero_words; j += blockDim.x) zero_ptr[j] = 0u;
     if (i >= a.bl_pad) return;
-    constexpr int kWords = kPer / 2;
     __nv_bfloat16* o1 = operand + static_cast<size_t>(i) * a.d_pad;
     __nv_bfloat16* o2 = operand + static_cast<size_t>(a.bl_pad + i) * a.d_pad;
     uint32_t w1[4] = {0u, 0u, 0u, 0u}, w2[4] = {0u, 0u, 0u, 0u};
@@ -88,28 +117,6 @@ __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x
             pos_dot[a.bl_pad + i] = 0.f;
         }
         return;
-    }
-    float v1[kPer], v2[kPer];
-    const T* r1 = x1 + static_cast<size_t>(i) * a.d;
-    const T* r2 = x2 + static_cast<size_t>(i) * a.d;
-    bool vec = false;
-    if constexpr (sizeof(T) == 4 && kPer == 4) {
-        // fp32 rows of exactly 128 columns at 16-byte aligned addresses: one float4 per lane
-        vec = a.d == a.d_pad && ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(x2)) & 15u) == 0;
-        if (vec) {
-            const float4 p4 = __ldg(reinterpret_cast<const float4*>(r1) + lane);
-            const float4 q4 = __ldg(reinterpret_cast<const float4*>(r2) + lane);
-            v1[0] = p4.x; v1[1] = p4.y; v1[2] = p4.z; v1[3] = p4.w;
-            v2[0] = q4.x; v2[1] = q4.y; v2[2] = q4.z; v2[3] = q4.w;
-        }
-    }
-    if (!vec) {
-#pragma unroll
-        for (int u = 0; u < kPer; ++u) {
-            const int k = lane * kPer + u;
-            v1[u] = k < a.d ? load_as_float(r1 + k) : 0.f;
-            v2[u] = k < a.d ? load_as_float(r2 + k) : 0.f;
-        }
     }
     float n1 = 0.f, n2 = 0.f, dot = 0.f;
 #pragma unroll
@@ -273,9 +280,19 @@ __global__ void __launch_bounds__(kBlockM) forward_finalize_kernel(const TilePar
     __shared__ float red[16];
     __shared__ int flags[4];
     pdl_launch_dependents();
+    // parameter arithmetic (64-bit divisions) and the caller's row weight: before the wait, i.e. under the tile kernel
+    const int rb = blockIdx.x, tid = threadIdx.x;
+    const FinIndex ix = fin_index(p, rb, tid);
+    float w_row = 1.f;
+    if (p.row_weight != nullptr) {
+        const int blocks_per_view = p.bl_pad / kBlockM;
+        const int vr = rb / blocks_per_view;
+        const int img = (rb - vr * blocks_per_view) * kBlockM + tid;
+        if (img < p.b_loc) w_row = __ldg(p.row_weight + vr * p.b_loc + img);
+    }
     pdl_wait();
     ktrace_begin(p.ktrace, 4);
-    forward_finalize_rowblock<kLoss>(p, blockIdx.x, threadIdx.x, red, flags);
+    forward_finalize_rowblock<kLoss>(p, rb, tid, ix, w_row, red, flags);
     ktrace_end(p.ktrace, 4);
 }
 
@@ -286,13 +303,20 @@ __global__ void __launch_bounds__(kBlockM) forward_finalize_kernel(const TilePar
 constexpr int kBwdFinBlocksPerRowBlock = 8;
 template <int D, int kLoss>
 __global__ void __launch_bounds__(512) backward_finalize_kernel(const TileParams p) {
+    static_assert(16 * kBwdFinBlocksPerRowBlock == kBlockM, "one warp per row");
     pdl_launch_dependents();
-    pdl_wait();
-    ktrace_begin(p.ktrace, 5);
     const int rb = blockIdx.x / kBwdFinBlocksPerRowBlock;
     const int sub = blockIdx.x % kBwdFinBlocksPerRowBlock;
-    backward_finalize_rowblock<D, kLoss>(p, rb, sub * 16 + (threadIdx.x >> 5), threadIdx.x & 31,
-                                         16 * kBwdFinBlocksPerRowBlock);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (p.ktrace != nullptr && threadIdx.x == 0) {
+        pdl_wait();
+        ktrace_begin(p.ktrace, 5);
+    }
+    backward_finalize_row<D, kLoss>(p, rb, sub * 16 + warp, lane);      // waits for the tile kernel inside
+    if (p.finish_stats && blockIdx.x == gridDim.x - 1 && warp == 15) {
+        pdl_wait();
+        finish_forward_stats(p, lane);
+    }
     ktrace_end(p.ktrace, 5);
 }
 

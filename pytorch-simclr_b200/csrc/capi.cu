@@ -19,6 +19,10 @@ namespace {
 long long* g_trace_ptr = nullptr;
 int g_trace_cta = 0;
 unsigned long long* g_ktrace_ptr = nullptr;
+// debug / measurement: which kernels the staged calls actually launch (simclr_debug_set_stage_mask)
+enum StageBit : unsigned { kStagePrepare = 1, kStageFwdTile = 2, kStageFwdFin = 4, kStageBwdTile = 8, kStageBwdFin = 16,
+                           kStageBwdPrepare = 32 };
+unsigned g_stage_mask = ~0u;
 
 // ------------------------------------------------------------------------------------------
 // cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
@@ -438,6 +442,7 @@ int simclr_prepare_peer(int loss, const void* x_batch1, const void* x_batch2, in
     const int blocks = static_cast<int>((g.bl_pad + warps - 1) / warps);
     auto* op = static_cast<__nv_bfloat16*>(operand);
     cudaError_t launch_rc = cudaSuccess;
+    if (!(g_stage_mask & kStagePrepare)) return SIMCLR_OK;
 #define SIMCLR_PREP2(T, LOSS, PER) \
     launch_rc = launch_pdl(prepare_kernel<T, LOSS, PER>, dim3(blocks), dim3(warps * 32), 0, st, static_cast<const T*>(x_batch1), static_cast<const T*>(x_batch2), a, op, inv_norm, pos_dot, zero_ptr, zero_words, g_ktrace_ptr, peers)
 #define SIMCLR_PREP(T, LOSS)                          \
@@ -479,22 +484,17 @@ int simclr_peer_barrier(int world, int rank, void* const* flag_peers, unsigned i
                                        epoch_local, stats_all, stats_out, loss_out));
 }
 
-int simclr_forward(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
-                   int64_t row_offset, int64_t d, float temperature, int normalize, const float* pos_dot,
-                   const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out, void* workspace,
-                   size_t workspace_bytes, void* stream) {
-    return simclr_forward_peer(loss, operand_rows, operand_cols, b_local, b_global, row_offset, d, temperature, normalize,
-                               SIMCLR_PRECISION_BF16, pos_dot, row_weight, lse2, row_loss, stats, loss_out, workspace,
-                               workspace_bytes, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, stream);
-}
+}  // extern "C"
 
-int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
-                        int64_t row_offset, int64_t d, float temperature, int normalize, int precision,
-                        const float* pos_dot,
-                        const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out,
-                        void* workspace, size_t workspace_bytes, void* backward_workspace,
-                        size_t backward_workspace_bytes, int world, int rank, void* const* colvec_peers,
-                        void* const* stats_peers, void* const* flag_peers, unsigned int* epoch_local, void* stream) {
+namespace {
+
+// defer_stats: the backward of the same fused step finishes the loss statistics (simclr_forward_backward)
+int forward_impl(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
+                 int64_t row_offset, int64_t d, float temperature, int normalize, int precision, const float* pos_dot,
+                 const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out, void* workspace,
+                 size_t workspace_bytes, void* backward_workspace, size_t backward_workspace_bytes, int world, int rank,
+                 void* const* colvec_peers, void* const* stats_peers, void* const* flag_peers, unsigned int* epoch_local,
+                 void* stream, bool defer_stats) {
     if (!operand_rows || !operand_cols || !pos_dot || !lse2 || !row_loss || !stats || !workspace)
         return SIMCLR_ERR_NULL_POINTER;
     if (!(temperature > 0.f) || !std::isfinite(temperature)) return SIMCLR_ERR_BAD_TEMPERATURE;
@@ -525,6 +525,7 @@ int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_
     p.block_part = w.block_part;
     p.stats = stats;
     p.loss_out = loss_out;
+    p.defer_stats = defer_stats ? 1 : 0;
     if ((rc = make_peer_table(world, rank, colvec_peers, &p.colvec_peers))) return rc;
     if ((rc = make_peer_table(world, rank, stats_peers, &p.stats_peers))) return rc;
     if (p.colvec_peers.world > 0 && (b_global != b_local * world || row_offset != b_local * rank)) return SIMCLR_ERR_BAD_PEERS;
@@ -552,7 +553,7 @@ int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_
     if (!overlap) {
         p.fin_set[0] = PartSet{w.part, g.total_tiles, g.n_col_tiles, g.max_segs, g.grid};
         p.n_fin_sets = 1;
-        if ((rc = dispatch_tile<false>(loss, g.d_pad, precision, map_rows, map_cols, map_rows, p, g.grid, st))) return rc;
+        if ((g_stage_mask & kStageFwdTile) && (rc = dispatch_tile<false>(loss, g.d_pad, precision, map_rows, map_cols, map_rows, p, g.grid, st))) return rc;
     } else {
         // Overlapped exchange: the columns this rank produced itself need no peer, so their tiles run while the other
         // ranks' operand rows are still crossing NVLink; the barrier follows, then the remote columns.
@@ -583,16 +584,19 @@ int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_
         p.n_fin_sets = 2;
     }
     cudaError_t e;
+    if (!(g_stage_mask & kStageFwdFin)) return SIMCLR_OK;
     if (loss == SIMCLR_LOSS_NTXENT) e = launch_pdl(forward_finalize_kernel<kNtXent>, dim3(g.n_row_blocks), dim3(kBlockM), 0, st, p);
     else e = launch_pdl(forward_finalize_kernel<kModified>, dim3(g.n_row_blocks), dim3(kBlockM), 0, st, p);
     return static_cast<int>(e);
 }
 
-int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t b_global,
-                    int64_t row_offset, int64_t d, int in_dtype, int normalize, float temperature, int precision,
-                    const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,
-                    const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
-                    void* workspace, size_t workspace_bytes, const float* primed_colvec, void* stream) {
+// finish_ws: forward workspace of the same fused step whose finalize kernel deferred the loss statistics, or nullptr
+int backward_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t b_global,
+                  int64_t row_offset, int64_t d, int in_dtype, int normalize, float temperature, int precision,
+                  const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,
+                  const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
+                  void* workspace, size_t workspace_bytes, const float* primed_colvec, void* stream, void* finish_ws,
+                  float* finish_stats, float* finish_loss) {
     if (!x_batch1 || !x_batch2 || !operand_rows || !operand_cols || !inv_norm || !pos_dot || !grad1 || !grad2 || !workspace)
         return SIMCLR_ERR_NULL_POINTER;
     if (!lse2_cols && !primed_colvec) return SIMCLR_ERR_NULL_POINTER;
@@ -619,7 +623,7 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
     AuxParams a = make_aux(g, s, b_local, b_global, row_offset, d, normalize);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-    if (primed_colvec == nullptr) {
+    if (primed_colvec == nullptr && (g_stage_mask & kStageBwdPrepare)) {
         if ((rc = static_cast<int>(launch_pdl(backward_prepare_kernel, dim3(device_info().sm_count * 2), dim3(256), 0, st, a,
                                               lse2_cols, col_scale, w.colvec, reinterpret_cast<float4*>(w.dacc),
                                               w.dacc_floats / 4, g_ktrace_ptr))))
@@ -640,8 +644,26 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
     p.pos_dot = pos_dot;
     p.col_scale = col_scale;
     p.grad_out = grad_out;
-    if ((rc = dispatch_tile<true>(loss, g.d_pad, precision, map_rows, map_cols, map_dacc, p, g.grid, st))) return rc;
+    // A primed backward follows the forward of the same operands; when the tile kernels fill the device (1 CTA per SM
+    // by shared memory and TMEM), no CTA of this launch can become resident before a forward tile CTA -- which waited
+    // for the complete operand matrix -- has exited: the operand loads and score MMAs need not wait for the finalize
+    // kernel in between (TileParams::early_operand).
+    p.early_operand = (primed_colvec != nullptr && g.grid == device_info().sm_count) ? 1 : 0;
+#ifdef SIMCLR_NO_EARLY_OPERAND
+    p.early_operand = 0;
+#endif
+    if (finish_ws != nullptr) {
+        FwdWorkspace fw = carve_forward(g, finish_ws);
+        p.block_part = fw.block_part;
+        p.stats = finish_stats;
+        p.loss_out = finish_loss;
+        p.finish_stats = 1;
+    }
+    if ((g_stage_mask & kStageBwdTile) &&
+        (rc = dispatch_tile<true>(loss, g.d_pad, precision, map_rows, map_cols, map_dacc, p, g.grid, st)))
+        return rc;
     cudaError_t fin_rc = cudaSuccess;
+    if (!(g_stage_mask & kStageBwdFin)) return SIMCLR_OK;
 #define SIMCLR_BFIN(DV)                                                                                  \
     case DV:                                                                                             \
         if (loss == SIMCLR_LOSS_NTXENT) fin_rc = launch_pdl(backward_finalize_kernel<DV, kNtXent>, dim3(g.n_row_blocks * kBwdFinBlocksPerRowBlock), dim3(512), 0, st, p); \
@@ -656,9 +678,77 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
     return static_cast<int>(fin_rc);
 }
 
+}  // namespace
+
+extern "C" {
+
+int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
+                        int64_t row_offset, int64_t d, float temperature, int normalize, int precision,
+                        const float* pos_dot,
+                        const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out,
+                        void* workspace, size_t workspace_bytes, void* backward_workspace,
+                        size_t backward_workspace_bytes, int world, int rank, void* const* colvec_peers,
+                        void* const* stats_peers, void* const* flag_peers, unsigned int* epoch_local, void* stream) {
+    return forward_impl(loss, operand_rows, operand_cols, b_local, b_global, row_offset, d, temperature, normalize, precision,
+                        pos_dot, row_weight, lse2, row_loss, stats, loss_out, workspace, workspace_bytes, backward_workspace,
+                        backward_workspace_bytes, world, rank, colvec_peers, stats_peers, flag_peers, epoch_local, stream,
+                        false);
+}
+
+int simclr_forward(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
+                   int64_t row_offset, int64_t d, float temperature, int normalize, const float* pos_dot,
+                   const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+    return simclr_forward_peer(loss, operand_rows, operand_cols, b_local, b_global, row_offset, d, temperature, normalize,
+                               SIMCLR_PRECISION_BF16, pos_dot, row_weight, lse2, row_loss, stats, loss_out, workspace,
+                               workspace_bytes, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t b_global,
+                    int64_t row_offset, int64_t d, int in_dtype, int normalize, float temperature, int precision,
+                    const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,
+                    const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
+                    void* workspace, size_t workspace_bytes, const float* primed_colvec, void* stream) {
+    return backward_impl(loss, x_batch1, x_batch2, b_local, b_global, row_offset, d, in_dtype, normalize, temperature,
+                         precision, operand_rows, operand_cols, inv_norm, pos_dot, lse2_cols, col_scale, grad_out, grad1,
+                         grad2, workspace, workspace_bytes, primed_colvec, stream, nullptr, nullptr, nullptr);
+}
+
+int simclr_forward_backward(int loss, const void* x_batch1, const void* x_batch2, int64_t b, int64_t d, int in_dtype,
+                            int normalize, float temperature, int precision, const float* grad_out, void* operand,
+                            float* rowvec, float* stats, float* loss_out, void* grad1, void* grad2,
+                            void* forward_workspace, size_t forward_workspace_bytes, void* backward_workspace,
+                            size_t backward_workspace_bytes, void* stream) {
+    if (!rowvec || !stats || !backward_workspace) return SIMCLR_ERR_NULL_POINTER;
+    const int64_t bp = simclr_pad_rows(b);
+    if (bp == 0) return SIMCLR_ERR_BAD_SHAPE;
+    float* inv_norm = rowvec;
+    float* pos_dot = rowvec + 2 * bp;
+    float* lse2 = rowvec + 4 * bp;
+    float* row_loss = rowvec + 6 * bp;
+    int rc = simclr_prepare_peer(loss, x_batch1, x_batch2, b, d, in_dtype, normalize, temperature, precision, operand,
+                                 inv_norm, pos_dot, forward_workspace, 0, 0, nullptr, nullptr, stream);
+    if (rc) return rc;
+    // the forward primes the backward workspace and leaves the reduction of the loss statistics to the backward finalize
+    // kernel: five launches, and nothing but the column vectors between the two tile kernels
+    rc = forward_impl(loss, operand, operand, b, b, 0, d, temperature, normalize, precision, pos_dot, nullptr, lse2, row_loss,
+                      stats, loss_out, forward_workspace, forward_workspace_bytes, backward_workspace,
+                      backward_workspace_bytes, 0, 0, nullptr, nullptr, nullptr, nullptr, stream, true);
+    if (rc) return rc;
+    return backward_impl(loss, x_batch1, x_batch2, b, b, 0, d, in_dtype, normalize, temperature, precision, operand, operand,
+                         inv_norm, pos_dot, nullptr, nullptr, grad_out, grad1, grad2, backward_workspace,
+                         backward_workspace_bytes, static_cast<const float*>(backward_workspace), stream, forward_workspace,
+                         stats, loss_out);
+}
+
 int simclr_debug_set_trace(void* device_buffer, int cta) {
     g_trace_ptr = static_cast<long long*>(device_buffer);
     g_trace_cta = cta;
+    return SIMCLR_OK;
+}
+
+int simclr_debug_set_stage_mask(unsigned int mask) {
+    g_stage_mask = mask;
     return SIMCLR_OK;
 }
 
@@ -697,6 +787,7 @@ int simclr_debug_pipe_rate(long long* out_device, int iters, int grid, int nwarp
 #define SIMCLR_PIPE(V) pipe_rate_kernel<V><<<grid, kThreadsForward, 0, st>>>(out_device, iters, nwarps, 1.0f, sink);
     SIMCLR_PIPE(0) SIMCLR_PIPE(1) SIMCLR_PIPE(2) SIMCLR_PIPE(3) SIMCLR_PIPE(4) SIMCLR_PIPE(5) SIMCLR_PIPE(6) SIMCLR_PIPE(7)
     SIMCLR_PIPE(8) SIMCLR_PIPE(9) SIMCLR_PIPE(10) SIMCLR_PIPE(11) SIMCLR_PIPE(12) SIMCLR_PIPE(13) SIMCLR_PIPE(14) SIMCLR_PIPE(15)
+    SIMCLR_PIPE(16) SIMCLR_PIPE(17) SIMCLR_PIPE(18) SIMCLR_PIPE(19) SIMCLR_PIPE(20)
 #undef SIMCLR_PIPE
     return static_cast<int>(cudaGetLastError());
 }

@@ -159,6 +159,17 @@ struct TileParams {
     PartSet fin_set[2];    // forward finalize: the launches whose partials it merges
     int n_fin_sets;
     unsigned long long* ktrace;   // optional (debug): kernel-level %globaltimer stamps
+    // Backward tile kernel: the operand matrix was complete before the kernel's predecessors started (it is written by
+    // the prepare kernel, two or more programmatic launches upstream, and the tile kernel of the forward -- which
+    // waited for it -- occupied every SM), so the TMA producer and the score-MMA issuers need not wait for the
+    // predecessor grid: the pipeline fill overlaps the forward finalize kernel.  Only the column vectors (softmax
+    // warps) and the accumulation buffer (flush warps) are behind griddepcontrol.wait.
+    int early_operand;
+    // Forward finalize: 1 -> write the per-row-block sums only and leave the reduction into `stats` / `loss_out` to the
+    // backward finalize kernel of the same step (finish_stats), which takes the ticket / last-block tail off the path
+    // between the two tile kernels.
+    int defer_stats;
+    int finish_stats;
 };
 
 // Debug timeline: trace[(role * kTraceIters + it) * 4 + k].  Roles: 0 TMA producer, 1 MMA issuer,
@@ -187,8 +198,9 @@ struct SmemLayout {
     static constexpr int kOffB = kTileBytes;
     static constexpr int kOffCv = kOffB + kStages * kTileBytes;
     static constexpr int kOffBar = kOffCv + kStages * kColvecBytes;
-    // barriers: a_full, a_empty, acc_full, acc_empty, b_full[S], b_empty[S], s_full[8], s_free[8], w_full[8], w_done[8]
-    static constexpr int kNumBars = 4 + 2 * kStages + 4 * kMaxSlots;   // kMaxSlots = 8
+    // barriers: a_full, a_empty, acc_full, acc_empty, b_full[S], b_empty[S], s_full[8], s_free[8], w_full[8], w_done[8],
+    // cv_full[S] (backward: the column vectors that travel with a column tile)
+    static constexpr int kNumBars = 4 + 3 * kStages + 4 * kMaxSlots;   // kMaxSlots = 8
     static constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
     static constexpr int kOffFlags = kOffTmemPtr + 16;                 // 16 ints of CTA-wide scratch
     static constexpr int kOffMerge = kOffFlags + 64;                   // forward: [2][4 WG][5][128] floats
@@ -245,6 +257,13 @@ struct RowCtx {
 struct FwdState {
     float run_max = kNegBig, sum = 0.f, max_prec = kNegBig, max_foll = kNegBig, pos_mma = kNegBig;
     float s1 = 0.f, s2 = 0.f, s3 = 0.f;   // constant-shift path: three more independent partial sums (folded at segment end)
+    f32x2 acc01 = 0ull, acc23 = 0ull;     // packed form of the same four partial sums (SIMCLR_PACKED)
+    SIMCLR_DEVICE float total() const {
+        float a, b, c, d;
+        unpack2(acc01, a, b);
+        unpack2(acc23, c, d);
+        return ((sum + s1) + (s2 + s3)) + ((a + b) + (c + d));
+    }
 };
 
 struct BwdRow {
@@ -278,9 +297,44 @@ SIMCLR_DEVICE float ex2_poly(float x) {
     }
     return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
 }
+// Two exponentials at once with packed fp32x2 instructions (degree 3): 6 packed + 2 integer instructions for the pair
+// instead of 2 x 7.
+SIMCLR_DEVICE void ex2_poly3_pair(float xa, float xb, float& ea, float& eb) {
+    constexpr f32x2 kMagic = splat2_bits(0x4B400000u);       // 12582912.0f
+    const f32x2 x = pack2(xa, xb);
+    const f32x2 t = add2(x, kMagic);
+    const f32x2 f = sub2(x, sub2(t, kMagic));
+    f32x2 q = fma2(f, splat2_bits(0x3D61FBB0u), splat2_bits(0x3E786F0Du));   // 0.0551716685, 0.2426111251
+    q = fma2(f, q, splat2_bits(0x3F31798Du));                                  // 0.6932609677
+    q = fma2(f, q, splat2_bits(0x3F7FFB49u));                                  // 0.9999280572
+    float qa, qb, ta, tb;
+    unpack2(q, qa, qb);
+    unpack2(t, ta, tb);
+    ea = __int_as_float(__float_as_int(qa) + (__float_as_int(ta) << 23));
+    eb = __int_as_float(__float_as_int(qb) + (__float_as_int(tb) << 23));
+}
+#ifndef SIMCLR_PACKED
+#define SIMCLR_PACKED 1               // fp32x2 instructions in the softmax warps' inner loops (0: scalar forms)
+#endif
+// Packed path: how many PAIRS of the 16 exponentials of a chunk run on the FMA pipe (the rest on MUFU: 8 pipe cycles
+// per warp instruction against 2 x 6 for a packed polynomial pair).
+#ifndef SIMCLR_POLY_PAIRS_FWD
+#define SIMCLR_POLY_PAIRS_FWD 3
+#endif
+#ifndef SIMCLR_POLY_PAIRS_BWD
+#define SIMCLR_POLY_PAIRS_BWD 1
+#endif
+// pairs of the 8-column round `round` (0 / 1) of a chunk: the odd pair, if any, goes to the second round
+SIMCLR_DEVICE constexpr int poly_pairs_in_round(int pairs, int round) { return round == 0 ? pairs / 2 : pairs - pairs / 2; }
 // element i of a 32-column chunk goes to the FMA-pipe exponential
 #ifndef SIMCLR_POLY_MASK
 #define SIMCLR_POLY_MASK 3            // element i of a chunk is a polynomial lane when (i & mask) == mask (3: every fourth)
+#endif
+#ifndef SIMCLR_FLUSH_WAIT_READ
+#define SIMCLR_FLUSH_WAIT_READ 1      // last flush of a CTA: wait for the TMA engine's reads only (0: for the adds to be performed)
+#endif
+#ifndef SIMCLR_BWD_DELAY_ST
+#define SIMCLR_BWD_DELAY_ST 0         // 1: store W of chunk k after the arithmetic of chunk k+1 (measured: slower)
 #endif
 #ifndef SIMCLR_PINGPONG
 #define SIMCLR_PINGPONG 1             // softmax pairs take turns (named-barrier token) instead of running freely
@@ -322,12 +376,31 @@ SIMCLR_DEVICE void fwd_chunk_fast(const Hot& h, const uint32_t (&r)[kChunk], flo
     if constexpr (kConst) {
         static_assert(kLoss == kNtXent, "constant shift is an NT-Xent fast path");
         cm = fmaxf(cm, c2);
+        if constexpr (SIMCLR_PACKED && kPoly && SIMCLR_POLY_MASK == 3) {
+            // eight columns per round: MUFU exponentials, the last pair(s) on the FMA pipe, four packed additions
 #pragma unroll
-        for (int i = 0; i < kChunk; i += 4) {
-            st.sum += (kPoly && poly_lane(i + 0)) ? ex2_poly<3>(v[i + 0]) : ex2_approx(v[i + 0]);
-            st.s1 += (kPoly && poly_lane(i + 1)) ? ex2_poly<3>(v[i + 1]) : ex2_approx(v[i + 1]);
-            st.s2 += (kPoly && poly_lane(i + 2)) ? ex2_poly<3>(v[i + 2]) : ex2_approx(v[i + 2]);
-            st.s3 += (kPoly && poly_lane(i + 3)) ? ex2_poly<3>(v[i + 3]) : ex2_approx(v[i + 3]);
+            for (int i = 0; i < kChunk; i += 8) {
+                float e[8];
+                const int np = poly_pairs_in_round(SIMCLR_POLY_PAIRS_FWD, i / 8);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (u < 8 - 2 * np) e[u] = ex2_approx(v[i + u]);
+#pragma unroll
+                for (int u = 0; u < 8; u += 2)      // adjacent columns: an aligned register pair
+                    if (u >= 8 - 2 * np) ex2_poly3_pair(v[i + u], v[i + u + 1], e[u], e[u + 1]);
+                st.acc01 = add2(st.acc01, pack2(e[0], e[1]));
+                st.acc23 = add2(st.acc23, pack2(e[2], e[3]));
+                st.acc01 = add2(st.acc01, pack2(e[4], e[5]));
+                st.acc23 = add2(st.acc23, pack2(e[6], e[7]));
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kChunk; i += 4) {
+                st.sum += (kPoly && poly_lane(i + 0)) ? ex2_poly<3>(v[i + 0]) : ex2_approx(v[i + 0]);
+                st.s1 += (kPoly && poly_lane(i + 1)) ? ex2_poly<3>(v[i + 1]) : ex2_approx(v[i + 1]);
+                st.s2 += (kPoly && poly_lane(i + 2)) ? ex2_poly<3>(v[i + 2]) : ex2_approx(v[i + 2]);
+                st.s3 += (kPoly && poly_lane(i + 3)) ? ex2_poly<3>(v[i + 3]) : ex2_approx(v[i + 3]);
+            }
         }
     } else {
         cm = fmaxf(cm, c2);
@@ -418,6 +491,38 @@ template <int kLoss, bool kConst, bool kSpecial, bool kSplit = false>
 SIMCLR_DEVICE void bwd_chunk(const Hot& h, const uint32_t (&r)[kChunk], uint32_t cv_addr, int cq, const RowCtx& rc,
                              const BwdRow& br, uint32_t (&w)[kChunk / 2], uint32_t (&wlo)[kChunk / 2]) {
     const int i_diag = rc.diag_col - cq, i_pos = rc.pos_col - cq;
+    if constexpr (SIMCLR_PACKED && kLoss == kNtXent && kConst && !kSplit && SIMCLR_POLY_MASK == 3) {
+        // W = exp2(S') * (a_r + a_c) with packed additions / multiplications; eight columns per round
+        const f32x2 row_a2 = pack2(br.row_a, br.row_a);
+#pragma unroll
+        for (int i = 0; i < kChunk; i += 8) {
+            const float4 a0 = lds_f4(cv_addr + i * 4), a1 = lds_f4(cv_addr + i * 4 + 16);
+            float e[8];
+            const int np = poly_pairs_in_round(SIMCLR_POLY_PAIRS_BWD, i / 8);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (u < 8 - 2 * np) e[u] = ex2_approx(__uint_as_float(r[i + u]));
+#pragma unroll
+            for (int u = 0; u < 8; u += 2)
+                if (u >= 8 - 2 * np)
+                    ex2_poly3_pair(__uint_as_float(r[i + u]), __uint_as_float(r[i + u + 1]), e[u], e[u + 1]);
+            const f32x2 w01 = mul2(pack2(e[0], e[1]), add2(pack2(a0.x, a0.y), row_a2));
+            const f32x2 w23 = mul2(pack2(e[2], e[3]), add2(pack2(a0.z, a0.w), row_a2));
+            const f32x2 w45 = mul2(pack2(e[4], e[5]), add2(pack2(a1.x, a1.y), row_a2));
+            const f32x2 w67 = mul2(pack2(e[6], e[7]), add2(pack2(a1.z, a1.w), row_a2));
+            float wv[8];
+            unpack2(w01, wv[0], wv[1]);
+            unpack2(w23, wv[2], wv[3]);
+            unpack2(w45, wv[4], wv[5]);
+            unpack2(w67, wv[6], wv[7]);
+            if constexpr (kSpecial) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) wv[u] = ((i + u == i_diag) | (i + u == i_pos)) ? 0.f : wv[u];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) w[(i + u) >> 1] = pack_bf16x2(wv[u], wv[u + 1]);
+        }
+    } else {
 #pragma unroll
     for (int i = 0; i < kChunk; i += 4) {
         const float4 ac = lds_f4(cv_addr + i * 4);
@@ -459,6 +564,7 @@ SIMCLR_DEVICE void bwd_chunk(const Hot& h, const uint32_t (&r)[kChunk], uint32_t
         }
     }
 }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Fused finalize steps.  A row block's tiles are spread over a few CTAs (contiguous tile ranges); the CTA that
@@ -472,20 +578,51 @@ SIMCLR_DEVICE float exact_logit2(const TileParams& p, float v) {
 
 // Forward: merge the per-CTA partials of row block rb, add the exact positive term, emit lse2 / row_loss and the
 // block's contribution to the loss statistics.  Called by the 128 threads of softmax warpgroup 0 (tid = row).
+// Where the partials of row block rb live when ONE tile-kernel launch produced them (pure parameter arithmetic: the
+// finalize kernel evaluates it before griddepcontrol.wait, i.e. while the tile kernel is still running).
+struct FinIndex {
+    const float* base;     // first contributing CTA's partial of this row (already offset by tid)
+    size_t stride_k;       // distance between consecutive CTAs' partials
+    int seg_first;         // segment index of the row block inside the first contributing CTA
+    int nk;                // number of contributing CTAs (kFinFast + 1: use the generic two-pass path)
+};
+constexpr int kFinFast = 6;
+SIMCLR_DEVICE FinIndex fin_index(const TileParams& p, int rb, int tid) {
+    FinIndex ix;
+    ix.base = nullptr;
+    ix.stride_k = 0;
+    ix.seg_first = 0;
+    ix.nk = kFinFast + 1;
+    if (p.n_fin_sets == 1) {
+        // CTAs whose range [T*k/G, T*(k+1)/G) overlaps row block rb: owner(t) = ((t+1)*G - 1) / T.  The partial of CTA k
+        // lives at part[(k * max_segs + seg_k)]: the first contributing CTA may have started in an earlier row block
+        // (seg_k = rb - its first row block); every later one starts inside this row block (seg 0).
+        const PartSet& ps = p.fin_set[0];
+        const long long g = ps.grid;
+        const long long t_lo = static_cast<long long>(rb) * ps.n_col_tiles, t_hi = t_lo + ps.n_col_tiles;
+        const int k_first = static_cast<int>(((t_lo + 1) * g - 1) / ps.total_tiles);
+        const int k_last = static_cast<int>((t_hi * g - 1) / ps.total_tiles);
+        const long long c_first = (ps.total_tiles * k_first) / g;
+        ix.seg_first = rb - static_cast<int>(c_first / ps.n_col_tiles);
+        ix.stride_k = static_cast<size_t>(ps.max_segs) * (kFwdFields * kBlockM);
+        ix.base = ps.part + static_cast<size_t>(k_first) * ix.stride_k + tid;
+        ix.nk = k_last - k_first + 1;
+    }
+    return ix;
+}
+
 template <int kLoss>
-SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int tid, float* red /*smem, 16 floats*/,
-                                             int* flags /*smem*/) {
+SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int tid, const FinIndex& ix, float w_row,
+                                             float* red /*smem, 16 floats*/, int* flags /*smem*/) {
     const int blocks_per_view = p.bl_pad / kBlockM;
     const int vr = rb / blocks_per_view;
     const int img = (rb - vr * blocks_per_view) * kBlockM + tid;
     const bool row_ok = img < p.b_loc;
     const int slot = rb * kBlockM + tid;
-    float v_pos = __ldg(p.pos_dot + slot);
+    float v_pos = __ldcg(p.pos_dot + slot);
     if constexpr (kLoss == kModified) v_pos = fmaxf(v_pos * p.qscale, kClampMin);
     else v_pos *= p.k2;               // exact fp32 positive logit in the log2 domain of the MMA scores
-    // Partials of CTA k of a launch live at part[(k * max_segs + seg_k)]: the first contributing CTA may have started
-    // in an earlier row block (seg_k = rb - its first row block); every later one starts inside this row block (seg 0).
-    // CTAs whose range [T*k/G, T*(k+1)/G) overlaps row block rb: owner(t) = ((t+1)*G - 1) / T.
+    // generic path (several launches, or many small CTAs per row block): visit every contributing partial
     auto visit = [&](auto&& f) {
         for (int s = 0; s < p.n_fin_sets; ++s) {
             const PartSet& ps = p.fin_set[s];
@@ -501,23 +638,11 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
         }
     };
     float vmax = v_pos, max_prec = kNegBig, max_foll = kNegBig, pos_mma = kNegBig, total;
-    constexpr int kFast = 6;
-    int nk = kFast + 1;
-    const float* base = nullptr;
-    size_t stride_k = 0;
-    int seg_first = 0;
-    if (p.n_fin_sets == 1) {
-        const PartSet& ps = p.fin_set[0];
-        const long long g = ps.grid;
-        const long long t_lo = static_cast<long long>(rb) * ps.n_col_tiles, t_hi = t_lo + ps.n_col_tiles;
-        const int k_first = static_cast<int>(((t_lo + 1) * g - 1) / ps.total_tiles);
-        const int k_last = static_cast<int>((t_hi * g - 1) / ps.total_tiles);
-        const long long c_first = (ps.total_tiles * k_first) / g;
-        seg_first = rb - static_cast<int>(c_first / ps.n_col_tiles);
-        stride_k = static_cast<size_t>(ps.max_segs) * (kFwdFields * kBlockM);
-        base = ps.part + static_cast<size_t>(k_first) * stride_k + tid;
-        nk = k_last - k_first + 1;
-    }
+    constexpr int kFast = kFinFast;
+    const int nk = ix.nk;
+    const float* base = ix.base;
+    const size_t stride_k = ix.stride_k;
+    const int seg_first = ix.seg_first;
     if (nk <= kFast) {
         // common case: issue every load up front (one L2 round trip), then merge from registers
         float sv[kFast], mv[kFast];
@@ -561,7 +686,7 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
     if (row_ok) {
         l2 = top + log2f(total);
         loss_r = (l2 - exact_logit2<kLoss>(p, v_pos)) * kLn2;
-        w = p.row_weight ? __ldg(p.row_weight + vr * p.b_loc + img) : 1.f;
+        w = w_row;
         // reference objective.py:51 -- Tensor.max returns the first maximal index
         hit = (max_prec < pos_mma && max_foll <= pos_mma) ? 1.f : 0.f;
     }
@@ -600,10 +725,15 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
         p.block_part[rb * 4 + 0] = (red[0] + red[1]) + (red[2] + red[3]);
         p.block_part[rb * 4 + 1] = (red[4] + red[5]) + (red[6] + red[7]);
         p.block_part[rb * 4 + 2] = (red[8] + red[9]) + (red[10] + red[11]);
-        __threadfence();
-        const unsigned int prev = atomicAdd(p.ticket, 1u);
-        flags[1] = (prev == static_cast<unsigned int>(p.n_row_blocks) - 1u) ? 1 : 0;
+        if (p.defer_stats) {
+            flags[1] = 0;                 // the backward finalize kernel of this step reduces block_part (finish_stats)
+        } else {
+            __threadfence();
+            const unsigned int prev = atomicAdd(p.ticket, 1u);
+            flags[1] = (prev == static_cast<unsigned int>(p.n_row_blocks) - 1u) ? 1 : 0;
+        }
     }
+    if (p.defer_stats) return;
     named_bar_sync(2, kBlockM);
     if (flags[1] && tid < 32) {
         __threadfence();
@@ -633,15 +763,16 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
     }
 }
 
-// Backward: rows of row block rb are complete in dacc.  Adds the exact positive-pair term and applies the
-// backward of the row normalisation (NT-Xent: L2, objective.py:26-27; modified: softplus + L1, :70-78).
-// Body of backward_finalize_kernel: one block per row block, warp w handles rows w, w+nwarps, ...
+// Backward finalize of ONE row (a warp): the tile kernel left W * operand of the row in dacc.  Adds the exact
+// positive-pair term and applies the backward of the row normalisation (NT-Xent: L2, objective.py:26-27; modified:
+// softplus + L1, :70-78).  The two input rows (x_self, x_other: caller inputs, never written by this library) are
+// loaded BEFORE griddepcontrol.wait, i.e. while the tile kernel drains; everything the step produced comes after it.
 template <int D, int kLoss>
-SIMCLR_DEVICE void backward_finalize_rowblock(const TileParams& p, int rb, int warp, int lane, int nwarps) {
+SIMCLR_DEVICE void backward_finalize_row(const TileParams& p, int rb, int r, int lane) {
     const int blocks_per_view = p.bl_pad / kBlockM;
     const int vr = rb / blocks_per_view;
-    const int img0 = (rb - vr * blocks_per_view) * kBlockM;
-    const float go = p.grad_out ? __ldg(p.grad_out) : 1.f;
+    const int img = (rb - vr * blocks_per_view) * kBlockM + r;
+    if (img >= p.b_loc) return;
     const void* x_self = vr == 0 ? p.x1 : p.x2;
     const void* x_other = vr == 0 ? p.x2 : p.x1;
     void* g_self = vr == 0 ? p.g1 : p.g2;
@@ -649,99 +780,124 @@ SIMCLR_DEVICE void backward_finalize_rowblock(const TileParams& p, int rb, int w
     const bool vec4 = kPerLane == 4 && p.d == D && !p.in_bf16 &&
                       ((reinterpret_cast<uintptr_t>(p.x1) | reinterpret_cast<uintptr_t>(p.x2) |
                         reinterpret_cast<uintptr_t>(p.g1) | reinterpret_cast<uintptr_t>(p.g2)) & 15u) == 0;
-    for (int r = warp; r < kBlockM; r += nwarps) {
-        const int img = img0 + r;
-        if (img >= p.b_loc) break;
-        const int slot_self = rb * kBlockM + r;
-        const int slot_other = (1 - vr) * p.bl_pad + img;
-        const int c_self = vr * p.bg_pad + p.row_off + img;
-        const int c_other = (1 - vr) * p.bg_pad + p.row_off + img;
-        const float inv_s = __ldg(p.inv_norm + slot_self), inv_o = __ldg(p.inv_norm + slot_other);
-        const float sc_s = p.col_scale ? __ldg(p.col_scale + c_self) : 0.5f / static_cast<float>(p.b_glob);
-        const float sc_o = p.col_scale ? __ldg(p.col_scale + c_other) : 0.5f / static_cast<float>(p.b_glob);
-        const float l2_s = __ldg(p.colvec + 2 * p.bg_pad + c_self), l2_o = __ldg(p.colvec + 2 * p.bg_pad + c_other);
-        const float pd = __ldg(p.pos_dot + slot_self);
-        float coef, outer;
-        if constexpr (kLoss == kNtXent) {
-            // (g_r P[r,pos] + g_pos P[pos,r] - g_r - g_pos) * zhat_pos in exact fp32
-            const float y = pd * p.k2;
-            coef = sc_s * (exp2f(y - l2_s) - 1.f) + sc_o * (exp2f(y - l2_o) - 1.f);
-            outer = p.inv_tau * go;
-        } else {
-            const float qv = pd * p.qscale;
-            const float lq = log2f(fmaxf(qv, kClampMin));
-            const float y = lq * (p.k2 - 1.f);
-            coef = (qv >= kClampMin) ? (sc_s * exp2f(y - l2_s) + sc_o * exp2f(y - l2_o) - (sc_s + sc_o) * exp2f(-lq)) : 0.f;
-            outer = p.inv_tau * p.qscale * go;
+    // Lane l owns the kPerLane consecutive columns [l * kPerLane, (l + 1) * kPerLane).  `vec4`: fp32 rows of exactly
+    // D = 128 columns at 16-byte aligned addresses move as one float4 per array and lane.
+    float xs[kPerLane], xo[kPerLane], ac[kPerLane];
+    if (vec4) {
+        if constexpr (kPerLane == 4) {
+            const float4 a4 = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(x_self) + static_cast<size_t>(img) * D) + lane);
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(x_other) + static_cast<size_t>(img) * D) + lane);
+            xs[0] = a4.x; xs[1] = a4.y; xs[2] = a4.z; xs[3] = a4.w;
+            xo[0] = b4.x; xo[1] = b4.y; xo[2] = b4.z; xo[3] = b4.w;
         }
-        const bool scaled = (kLoss == kModified) || p.normalize;
-        const float mul_s = scaled ? (inv_s == kInvNormClamped ? 1.f / kNormEps : inv_s) : 1.f;
-        const float mul_o = scaled ? (inv_o == kInvNormClamped ? 1.f / kNormEps : inv_o) : 1.f;
-        float raw[kPerLane], hs[kPerLane], dv[kPerLane];
-        float t = 0.f;
-        // Lane l owns the kPerLane consecutive columns [l * kPerLane, (l + 1) * kPerLane).  `vec4`: fp32 rows of exactly
-        // D = 128 columns at 16-byte aligned addresses move as one float4 per array and lane.
-        float xs[kPerLane], xo[kPerLane], ac[kPerLane];
-        if (vec4) {
-            if constexpr (kPerLane == 4) {
-                const float4 a4 = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(x_self) + static_cast<size_t>(img) * D) + lane);
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(x_other) + static_cast<size_t>(img) * D) + lane);
-                const float4 c4 = __ldcg(reinterpret_cast<const float4*>(p.dacc + static_cast<size_t>(slot_self) * D) + lane);
-                xs[0] = a4.x; xs[1] = a4.y; xs[2] = a4.z; xs[3] = a4.w;
-                xo[0] = b4.x; xo[1] = b4.y; xo[2] = b4.z; xo[3] = b4.w;
-                ac[0] = c4.x; ac[1] = c4.y; ac[2] = c4.z; ac[3] = c4.w;
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < kPerLane; ++u) {
-                const int k = lane * kPerLane + u;
-                const bool in = k < p.d;
-                xs[u] = in ? load_elem(x_self, static_cast<size_t>(img) * p.d + k, p.in_bf16) : 0.f;
-                xo[u] = in ? load_elem(x_other, static_cast<size_t>(img) * p.d + k, p.in_bf16) : 0.f;
-                ac[u] = __ldcg(p.dacc + static_cast<size_t>(slot_self) * D + k);
-            }
-        }
+    } else {
 #pragma unroll
         for (int u = 0; u < kPerLane; ++u) {
             const int k = lane * kPerLane + u;
             const bool in = k < p.d;
-            float es = xs[u], eo = xo[u];
-            raw[u] = es;
-            if constexpr (kLoss == kModified) {
-                es = in ? softplus_beta(es) : 0.f;
-                eo = in ? softplus_beta(eo) : 0.f;
-            }
-            hs[u] = es * mul_s;
-            const float ho = eo * mul_o;
-            dv[u] = (ac[u] * p.acc_scale + coef * ho) * outer;
-            t = fmaf(dv[u], hs[u], t);
+            xs[u] = in ? load_elem(x_self, static_cast<size_t>(img) * p.d + k, p.in_bf16) : 0.f;
+            xo[u] = in ? load_elem(x_other, static_cast<size_t>(img) * p.d + k, p.in_bf16) : 0.f;
         }
-        t = warp_sum(t);
-        float out[kPerLane];
+    }
+    pdl_wait();
+    const int slot_self = rb * kBlockM + r;
+    const int slot_other = (1 - vr) * p.bl_pad + img;
+    const int c_self = vr * p.bg_pad + p.row_off + img;
+    const int c_other = (1 - vr) * p.bg_pad + p.row_off + img;
+    if (vec4) {
+        if constexpr (kPerLane == 4) {
+            const float4 c4 = __ldcg(reinterpret_cast<const float4*>(p.dacc + static_cast<size_t>(slot_self) * D) + lane);
+            ac[0] = c4.x; ac[1] = c4.y; ac[2] = c4.z; ac[3] = c4.w;
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < kPerLane; ++u) ac[u] = __ldcg(p.dacc + static_cast<size_t>(slot_self) * D + lane * kPerLane + u);
+    }
+    const float go = p.grad_out ? __ldg(p.grad_out) : 1.f;
+    const float inv_s = __ldcg(p.inv_norm + slot_self), inv_o = __ldcg(p.inv_norm + slot_other);
+    const float sc_s = p.col_scale ? __ldcg(p.col_scale + c_self) : 0.5f / static_cast<float>(p.b_glob);
+    const float sc_o = p.col_scale ? __ldcg(p.col_scale + c_other) : 0.5f / static_cast<float>(p.b_glob);
+    const float l2_s = __ldcg(p.colvec + 2 * p.bg_pad + c_self), l2_o = __ldcg(p.colvec + 2 * p.bg_pad + c_other);
+    const float pd = __ldcg(p.pos_dot + slot_self);
+    float coef, outer;
+    if constexpr (kLoss == kNtXent) {
+        // (g_r P[r,pos] + g_pos P[pos,r] - g_r - g_pos) * zhat_pos in exact fp32
+        const float y = pd * p.k2;
+        coef = sc_s * (exp2f(y - l2_s) - 1.f) + sc_o * (exp2f(y - l2_o) - 1.f);
+        outer = p.inv_tau * go;
+    } else {
+        const float qv = pd * p.qscale;
+        const float lq = log2f(fmaxf(qv, kClampMin));
+        const float y = lq * (p.k2 - 1.f);
+        coef = (qv >= kClampMin) ? (sc_s * exp2f(y - l2_s) + sc_o * exp2f(y - l2_o) - (sc_s + sc_o) * exp2f(-lq)) : 0.f;
+        outer = p.inv_tau * p.qscale * go;
+    }
+    const bool scaled = (kLoss == kModified) || p.normalize;
+    const float mul_s = scaled ? (inv_s == kInvNormClamped ? 1.f / kNormEps : inv_s) : 1.f;
+    const float mul_o = scaled ? (inv_o == kInvNormClamped ? 1.f / kNormEps : inv_o) : 1.f;
+    float raw[kPerLane], hs[kPerLane], dv[kPerLane];
+    float t = 0.f;
+#pragma unroll
+    for (int u = 0; u < kPerLane; ++u) {
+        const int k = lane * kPerLane + u;
+        const bool in = k < p.d;
+        float es = xs[u], eo = xo[u];
+        raw[u] = es;
+        if constexpr (kLoss == kModified) {
+            es = in ? softplus_beta(es) : 0.f;
+            eo = in ? softplus_beta(eo) : 0.f;
+        }
+        hs[u] = es * mul_s;
+        const float ho = eo * mul_o;
+        dv[u] = (ac[u] * p.acc_scale + coef * ho) * outer;
+        t = fmaf(dv[u], hs[u], t);
+    }
+    t = warp_sum(t);
+    float out[kPerLane];
+#pragma unroll
+    for (int u = 0; u < kPerLane; ++u) {
+        float o = dv[u];
+        if constexpr (kLoss == kNtXent) {
+            // d/dz of z / max(||z||, eps): projection unless the clamp was active
+            if (p.normalize) o = (inv_s == kInvNormClamped) ? o / kNormEps : (o - hs[u] * t) * inv_s;
+        } else {
+            // L1 normalisation of a positive vector, then softplus'(x) = sigmoid(beta x)
+            o = (inv_s == kInvNormClamped) ? o / kNormEps : (o - t) * inv_s;
+            o *= softplus_beta_grad(raw[u]);
+        }
+        out[u] = o;
+    }
+    if (vec4) {
+        if constexpr (kPerLane == 4)
+            reinterpret_cast<float4*>(static_cast<float*>(g_self) + static_cast<size_t>(img) * D)[lane] =
+                make_float4(out[0], out[1], out[2], out[3]);
+    } else {
 #pragma unroll
         for (int u = 0; u < kPerLane; ++u) {
-            float o = dv[u];
-            if constexpr (kLoss == kNtXent) {
-                // d/dz of z / max(||z||, eps): projection unless the clamp was active
-                if (p.normalize) o = (inv_s == kInvNormClamped) ? o / kNormEps : (o - hs[u] * t) * inv_s;
-            } else {
-                // L1 normalisation of a positive vector, then softplus'(x) = sigmoid(beta x)
-                o = (inv_s == kInvNormClamped) ? o / kNormEps : (o - t) * inv_s;
-                o *= softplus_beta_grad(raw[u]);
-            }
-            out[u] = o;
+            const int k = lane * kPerLane + u;
+            if (k < p.d) store_elem(g_self, static_cast<size_t>(img) * p.d + k, p.in_bf16, out[u]);
         }
-        if (vec4) {
-            if constexpr (kPerLane == 4)
-                reinterpret_cast<float4*>(static_cast<float*>(g_self) + static_cast<size_t>(img) * D)[lane] =
-                    make_float4(out[0], out[1], out[2], out[3]);
-        } else {
-#pragma unroll
-            for (int u = 0; u < kPerLane; ++u) {
-                const int k = lane * kPerLane + u;
-                if (k < p.d) store_elem(g_self, static_cast<size_t>(img) * p.d + k, p.in_bf16, out[u]);
-            }
-        }
+    }
+}
+
+// Deferred loss statistics (TileParams::finish_stats): one warp adds up the per-row-block sums the forward finalize
+// kernel left in block_part, in a fixed order (deterministic).
+SIMCLR_DEVICE void finish_forward_stats(const TileParams& p, int lane) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int i = lane; i < p.n_row_blocks; i += 32) {
+        s0 += __ldcg(p.block_part + i * 4 + 0);
+        s1 += __ldcg(p.block_part + i * 4 + 1);
+        s2 += __ldcg(p.block_part + i * 4 + 2);
+    }
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+        p.stats[0] = s0;
+        p.stats[1] = s1;
+        p.stats[2] = s2;
+        p.stats[3] = s0 / s1;
+        if (p.loss_out) *p.loss_out = s0 / s1;
     }
 }
 
@@ -826,6 +982,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
     const uint32_t s_free = s_full + kMaxSlots * 8;        // [kSlots] forward only: softmax finished reading the score tile
     const uint32_t w_full = s_free + kMaxSlots * 8;        // [kSlots] backward only: W written to TMEM
     const uint32_t w_done = w_full + kMaxSlots * 8;        // [kSlots] backward only: gradient MMAs finished reading W
+    const uint32_t cv_full = w_done + kMaxSlots * 8;       // [S] backward only: column vectors of the stage's tile landed
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + L::kOffTmemPtr);
     float* smem_merge = reinterpret_cast<float*>(smem + L::kOffMerge);
 
@@ -854,6 +1011,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         for (int i = 0; i < S; ++i) {
             mbar_init(b_full + 8 * i, 1);
             mbar_init(b_empty + 8 * i, 1);
+            mbar_init(cv_full + 8 * i, 1);
         }
         for (int i = 0; i < kMaxSlots; ++i) {
             mbar_init(s_full + 8 * i, 1);
@@ -872,7 +1030,10 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr_smem;
     // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the predecessor's tail
-    pdl_wait();
+    // (early_operand: the producer waits later, after its first operand loads; the score issuers touch no global memory)
+    const bool runs_ahead = kBackward && p.early_operand != 0 &&
+                            (warp == kProducerWarp || (warp >= kScoreWarp0 && warp < kScoreWarp0 + kNumIssuers));
+    if (!runs_ahead) pdl_wait();
     ktrace_begin(p.ktrace, kBackward ? 3 : 1);
     if (threadIdx.x == 0) {
         cta_stamp(p, 0);
@@ -882,46 +1043,68 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
     if (warp == kProducerWarp) {
         // ================================ TMA producer ================================
         if (elect_one()) {
+            auto load_rows = [&](int rb_) {
+                mbar_arrive_expect_tx(a_full, L::kTileBytes);
+#pragma unroll
+                for (int pl = 0; pl < kPlanes; ++pl)
+#pragma unroll
+                    for (int ka = 0; ka < L::kAtoms; ++ka)
+                        tma_load_2d(sa_addr + pl * L::kPlaneBytes + ka * kAtomBytes, &tmap_rows, a_full, ka * kAtomK,
+                                    pl * 2 * p.bl_pad + rb_ * kBlockM);
+            };
+            auto load_cols = [&](int stage, int c0) {
+                mbar_arrive_expect_tx(b_full + 8 * stage, L::kTileBytes);
+#pragma unroll
+                for (int pl = 0; pl < kPlanes; ++pl)
+#pragma unroll
+                    for (int ka = 0; ka < L::kAtoms; ++ka)
+                        tma_load_2d(sb_addr + stage * L::kTileBytes + pl * L::kPlaneBytes + ka * kAtomBytes, &tmap_cols,
+                                    b_full + 8 * stage, ka * kAtomK, pl * 2 * p.bg_pad + c0);
+            };
+            // Early operand loads (backward, see TileParams::early_operand): the row-block tile and the column tiles of
+            // the first positions of the first segment leave before griddepcontrol.wait; their column vectors follow it.
+            int early = 0;
+            if (kBackward && p.early_operand != 0) {
+                for (TileWalker w(t_begin, t_end, nct); w.valid() && early < S; w.next()) {
+                    if (early == 0) load_rows(w.rb);
+                    load_cols(early, tile_col0<kLoss>(p, w.rb / blocks_per_view, w.j));
+                    ++early;
+                    if (w.seg_last()) break;
+                }
+                pdl_wait();
+            }
             RingPos<S> ring;
             bool wrapped = false;
             int seg = 0;
             for (TileWalker w(t_begin, t_end, nct); w.valid(); w.next()) {
                 const int it = w.idx;
                 if (w.seg_first()) {
-                    if (seg > 0) mbar_wait(a_empty, (seg - 1) & 1, 100);
-                    mbar_arrive_expect_tx(a_full, L::kTileBytes);
-#pragma unroll
-                    for (int pl = 0; pl < kPlanes; ++pl)
-#pragma unroll
-                        for (int ka = 0; ka < L::kAtoms; ++ka)
-                            tma_load_2d(sa_addr + pl * L::kPlaneBytes + ka * kAtomBytes, &tmap_rows, a_full, ka * kAtomK,
-                                        pl * 2 * p.bl_pad + w.rb * kBlockM);
+                    if (it >= early) {
+                        if (seg > 0) mbar_wait(a_empty, (seg - 1) & 1, 100);
+                        load_rows(w.rb);
+                    }
                     ++seg;
                 }
                 trace_event(p, 0, it, 0);
                 if (wrapped) mbar_wait(b_empty + 8 * ring.idx, ring.par ^ 1, 101);   // previous use of the stage released
                 trace_event(p, 0, it, 1);
                 const int c0 = tile_col0<kLoss>(p, w.rb / blocks_per_view, w.j);
-                mbar_arrive_expect_tx(b_full + 8 * ring.idx, L::kTileBytes + (kBackward ? L::kColvecBytes : 0));
-#pragma unroll
-                for (int pl = 0; pl < kPlanes; ++pl)
-#pragma unroll
-                    for (int ka = 0; ka < L::kAtoms; ++ka)
-                        tma_load_2d(sb_addr + ring.idx * L::kTileBytes + pl * L::kPlaneBytes + ka * kAtomBytes, &tmap_cols,
-                                    b_full + 8 * ring.idx, ka * kAtomK, pl * 2 * p.bg_pad + c0);
+                if (it >= early) load_cols(ring.idx, c0);
                 if constexpr (kBackward) {
                     const uint32_t cv = smem_base + L::kOffCv + ring.idx * (2 * kBlockN * 4);
-                    bulk_load_1d(cv, p.colvec + c0, kBlockN * 4, b_full + 8 * ring.idx);
-                    bulk_load_1d(cv + kBlockN * 4, p.colvec + 2 * p.bg_pad + c0, kBlockN * 4, b_full + 8 * ring.idx);
+                    mbar_arrive_expect_tx(cv_full + 8 * ring.idx, L::kColvecBytes);
+                    bulk_load_1d(cv, p.colvec + c0, kBlockN * 4, cv_full + 8 * ring.idx);
+                    bulk_load_1d(cv + kBlockN * 4, p.colvec + 2 * p.bg_pad + c0, kBlockN * 4, cv_full + 8 * ring.idx);
                 }
                 if (ring.idx == S - 1) wrapped = true;
                 ring.advance();
                 if (kBackward && w.seg_last()) {
-                    // hand two empty stages to the softmax warps: staging space of the accumulator flush
+                    // hand two empty stages to the flush warpgroup: staging space of the accumulator flush
 #pragma unroll 1
                     for (int k = 0; k < 2; ++k) {
                         if (wrapped) mbar_wait(b_empty + 8 * ring.idx, ring.par ^ 1, 102);
                         mbar_arrive(b_full + 8 * ring.idx);
+                        mbar_arrive(cv_full + 8 * ring.idx);      // keeps the phase of cv_full in step with the ring position
                         if (ring.idx == S - 1) wrapped = true;
                         ring.advance();
                     }
@@ -1008,7 +1191,6 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         const int row_in_block = quarter * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
         const uint32_t b_addr0 = sb_addr;
-        constexpr int kLogS = S == 2 ? 1 : (S == 4 ? 2 : 3);
 
         if (flusher) {
             // zero the gradient accumulator (TMEM is not cleared by the allocation); phase 0 of acc_empty
@@ -1069,11 +1251,15 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 mbar_wait(b_full + 8 * ring.idx, ring.par, 303);   // the two staging stages are ours
                 mbar_wait(b_full + 8 * st1.idx, st1.par, 304);
                 tc_fence_after_sync();
-#pragma unroll 1
+                // two 32-column TMEM loads in flight: the load of box q+1 overlaps the shared-memory stores of box q
+                uint32_t ra[32], rb2[32];
+                tmem_ld32(tmem_base + lane_addr + kTmemAcc, ra);
+#pragma unroll
                 for (int q = 0; q < D / 32; ++q) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + lane_addr + kTmemAcc + q * 32, r);
+                    uint32_t (&r)[32] = (q & 1) ? rb2 : ra;
+                    uint32_t (&nxt)[32] = (q & 1) ? ra : rb2;
                     tmem_ld_wait();
+                    if (q + 1 < D / 32) tmem_ld32(tmem_base + lane_addr + kTmemAcc + (q + 1) * 32, nxt);
                     tmem_st32_fill(tmem_base + lane_addr + kTmemAcc + q * 32, 0u);     // zero for the next segment
                     const int stage = (q / kBoxesPerStage) == 0 ? ring.idx : st1.idx;
                     const uint32_t row_addr = sb_addr + stage * L::kTileBytes + (q % kBoxesPerStage) * kAtomBytes +
@@ -1095,8 +1281,15 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                                           q * 32, w.rb * kBlockM);
                     }
                     bulk_commit_group();
-                    if (idx == w.n - 1) bulk_wait_group0();    // last segment: the adds are performed before exit
-                    else bulk_wait_group_read0();              // staging space may be reused
+                    // The staging space may be reused (or the CTA may exit) once the TMA engine has read it; the adds
+                    // themselves are performed by the time the grid completes, which is what the finalize kernel's
+                    // griddepcontrol.wait observes.
+#if SIMCLR_FLUSH_WAIT_READ
+                    bulk_wait_group_read0();
+#else
+                    if (idx == w.n - 1) bulk_wait_group0();
+                    else bulk_wait_group_read0();
+#endif
                     mbar_arrive(b_empty + 8 * ring.idx);
                     mbar_arrive(b_empty + 8 * st1.idx);
                 }
@@ -1166,8 +1359,8 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             br.row_l2 = 0.f;
             if constexpr (kBackward) {
                 if (rc.row_ok) {
-                    br.row_a = __ldg(p.colvec + rc.vr * h.bg_pad + rc.g);
-                    br.row_l2 = __ldg(p.colvec + 2 * h.bg_pad + rc.vr * h.bg_pad + rc.g);
+                    br.row_a = __ldcg(p.colvec + rc.vr * h.bg_pad + rc.g);
+                    br.row_l2 = __ldcg(p.colvec + 2 * h.bg_pad + rc.vr * h.bg_pad + rc.g);
                 }
             }
             const int pos_off = kBackward ? 2 * seg : 0;
@@ -1199,7 +1392,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 if (tracing) trace_event(p, 2 + wg, it, 0);
                 mbar_wait(s_full + 8 * slot, slot_par, 300);
                 if (tracing) trace_event(p, 2 + wg, it, 1);
-                if constexpr (kBackward) mbar_wait(b_full + 8 * stage, stage_par, 301);   // colvec visibility
+                if constexpr (kBackward) mbar_wait(cv_full + 8 * stage, stage_par, 301);  // column vectors landed
                 tc_fence_after_sync();
 
                 // This warpgroup's 64 columns in four 16-column chunks; the TMEM load of chunk k+1 is in flight while
@@ -1216,6 +1409,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 // address arithmetic, fences: ~800 cycles) now hides behind the other pair's maths instead of both
                 // pairs idling together (they otherwise drift into lock step).
                 if (SIMCLR_PINGPONG && it > 0) named_bar_sync(kTokenBar0 + pair, 32 * kNumSoftmaxWarps);
+                if (tracing) trace_event(p, 2 + wg, it, 3);
                 if constexpr (kBackward && kPrec != 0) {
                     // Split mode: W_hi goes where it always goes, W_lo into the upper half [64h+32, 64h+64) of this
                     // warpgroup's region -- over scores of chunks 2 and 3, so the W_lo words are held in registers until
@@ -1249,6 +1443,9 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                     // Common case: no masked element anywhere in the tile for this warp.  One straight-line block over
                     // the four chunks, so that the tail of chunk k overlaps the head of chunk k+1.
                     float cm = kNegBig;
+#if SIMCLR_BWD_DELAY_ST
+                    uint32_t wprev[kChunk / 2];           // backward: W of the previous chunk (stored one chunk late)
+#endif
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         uint32_t (&cur)[kChunk] = (k & 1) ? rb2 : ra;
@@ -1263,7 +1460,17 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         } else if constexpr (kPrec == 0) {
                             uint32_t wq[kChunk / 2], unused[kChunk / 2];
                             bwd_chunk<kLoss, kConst, false>(h, cur, cv_tile + k * kChunk * 4, 0, rc, br, wq, unused);
+#if SIMCLR_BWD_DELAY_ST
+                            // The store of chunk k-1 follows the arithmetic of chunk k in program order, so that the
+                            // exponentials of chunk k need not queue behind the pack / store tail of chunk k-1
+                            // (tcgen05 instructions are scheduling fences for each other, plain arithmetic is not).
+                            if (k > 0) tmem_st8(t0 + (k - 1) * (kChunk / 2), wprev);
+#pragma unroll
+                            for (int i = 0; i < kChunk / 2; ++i) wprev[i] = wq[i];
+                            if (k == 3) tmem_st8(t0 + 3 * (kChunk / 2), wprev);
+#else
                             tmem_st8(t0 + k * (kChunk / 2), wq);
+#endif
                         }
                     }
                     if constexpr (!kBackward) {
@@ -1330,7 +1537,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 // merge the four warpgroups' partial (max, sum, argmax bookkeeping) through shared memory ...
                 float* mg = smem_merge + (seg & 1) * (kNumSoftmaxWG * kFwdFields * kBlockM);
                 float* mine = mg + wg * (kFwdFields * kBlockM) + row_in_block;
-                mine[0 * kBlockM] = (fs.sum + fs.s1) + (fs.s2 + fs.s3);
+                mine[0 * kBlockM] = fs.total();
                 mine[1 * kBlockM] = fs.run_max;
                 mine[2 * kBlockM] = fs.max_prec;
                 mine[3 * kBlockM] = fs.max_foll;

@@ -120,11 +120,14 @@ SIMCLR_DEVICE bool mbar_try_wait_parked(uint32_t bar, uint32_t parity, uint32_t 
 // instructions (a waiting warp shares its sub-partition's issue slots with the softmax warps: ten-instruction spins of
 // five control warps were a quarter of all instructions the backward kernel executed); the clock is only read every
 // 4096 polls.
+#ifndef SIMCLR_PARK_NS
+#define SIMCLR_PARK_NS 2000u
+#endif
 SIMCLR_DEVICE void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
     if (mbar_try_wait(bar, parity)) return;
     long long t0 = 0;
     uint32_t polls = 0;
-    while (!mbar_try_wait_parked(bar, parity, 2000u)) {
+    while (!mbar_try_wait_parked(bar, parity, SIMCLR_PARK_NS)) {
         if ((++polls & 4095u) == 0u) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
@@ -343,6 +346,41 @@ SIMCLR_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+// Packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 work on an aligned register pair): one issue slot for two
+// results.  The softmax warps are bound by issue slots, not by the FMA pipe, so every pair of independent fp32
+// operations that can share an instruction is a slot gained.  A 64-bit value holds {lo, hi}.
+using f32x2 = unsigned long long;
+SIMCLR_DEVICE f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+SIMCLR_DEVICE void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+SIMCLR_DEVICE f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+SIMCLR_DEVICE f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+SIMCLR_DEVICE f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+SIMCLR_DEVICE f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// the same fp32 constant in both halves (ptxas folds it into the instruction as a 32-bit immediate)
+SIMCLR_DEVICE constexpr f32x2 splat2_bits(unsigned int bits) {
+    return (static_cast<f32x2>(bits) << 32) | static_cast<f32x2>(bits);
+}
+
 SIMCLR_DEVICE float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -77,7 +77,24 @@ class ContrastiveStep:
                                   self.grad1.data_ptr(), self.grad2.data_ptr(), self.bwd_ws.data_ptr(),
                                   self.bwd_ws_bytes, self.bwd_ws.data_ptr(), st), "simclr_backward")
 
-    def step(self) -> None:
+    def step(self, grad_out: Optional[torch.Tensor] = None, x1: Optional[torch.Tensor] = None,
+             x2: Optional[torch.Tensor] = None, grad1: Optional[torch.Tensor] = None,
+             grad2: Optional[torch.Tensor] = None) -> None:
+        """Fused forward+backward (simclr_forward_backward): five launches; the loss statistics are complete when the
+        backward finalize kernel has run.  x1 / x2 / grad1 / grad2 default to the runner's own buffers."""
+        x1 = self.x1 if x1 is None else x1
+        x2 = self.x2 if x2 is None else x2
+        grad1 = self.grad1 if grad1 is None else grad1
+        grad2 = self.grad2 if grad2 is None else grad2
+        check(self.lib.simclr_forward_backward(self.kind, x1.data_ptr(), x2.data_ptr(), self.b, self.d, self.code,
+                                               int(self.normalize), self.temperature, self.precision,
+                                               None if grad_out is None else grad_out.data_ptr(), self.operand.data_ptr(),
+                                               self.rowvec.data_ptr(), self.stats.data_ptr(), self.loss.data_ptr(),
+                                               grad1.data_ptr(), grad2.data_ptr(), self.fwd_ws.data_ptr(),
+                                               self.fwd_ws_bytes, self.bwd_ws.data_ptr(), self.bwd_ws_bytes, self._stream()),
+              "simclr_forward_backward")
+
+    def step_staged(self) -> None:
         self.forward()
         self.backward()
 

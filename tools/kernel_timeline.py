@@ -53,6 +53,7 @@ for label, do_flush in (("warm L2", False), ("after L2 flush", True)):
         torch.cuda.synchronize()
         t = buf.cpu().view(8, 2)[:6]
         t0 = int(t[0, 0])
-        line = " | ".join(f"{n} {int(a) - t0:6d}..{int(b) - t0:6d} ({int(b) - int(a):6d})" for n, (a, b) in zip(names, t.tolist()))
+        line = " | ".join(f"{n} {int(a) - t0:6d}..{int(b) - t0:6d} ({int(b) - int(a):6d})" for n, (a, b) in zip(names, t.tolist())
+                          if 0 < int(b) and int(a) < torch.iinfo(torch.int64).max)
         print(f"[{label}] events {ev0.elapsed_time(ev1) * 1e3:7.1f} us | {line}")
 lib.simclr_debug_set_kernel_trace(None)

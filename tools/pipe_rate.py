@@ -10,7 +10,8 @@ from pytorch_simclr_b200 import _lib  # noqa: E402
 
 lib = _lib.load()
 names = ["FFMA reg,reg,reg", "FFMA reg,imm,reg", "FADD reg,reg", "FADD reg,imm", "FMUL reg,reg", "MUFU.EX2", "FMNMX reg,reg",
-         "IMAD x*2^23+y", "SHL+IADD", "3 FFMA : 1 MUFU", "F2FP bf16x2", "FMNMX3", "LDS.128", "FSETP+FSEL", "HFMA2.BF16", "PRMT"]
+         "IMAD x*2^23+y", "SHL+IADD", "3 FFMA : 1 MUFU", "F2FP bf16x2", "FMNMX3", "LDS.128", "FSETP+FSEL", "HFMA2.BF16", "PRMT",
+         "FADD2", "FFMA2", "FADD2 : FMNMX 1:1", "3 FFMA2 : 1 MUFU", "FADD2 : FADD 1:1"]
 sink = torch.zeros(640, device="cuda")
 iters = 2000
 for nwarps in (4, 8, 16):
@@ -24,4 +25,6 @@ for nwarps in (4, 8, 16):
         ninstr = iters * 4 * 16 * (nwarps / 4)          # warp instructions issued on one sub-partition
         if i in (8, 13):
             ninstr *= 2
+        if i >= 16:
+            ninstr /= 2                                 # eight (packed or scalar) instructions per 16-chain round
         print(f"{nwarps // 4} warps/SMSP | {n:18s}: {o[i].item() / ninstr:6.2f} cycles per warp instruction per sub-partition")

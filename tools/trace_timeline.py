@@ -41,7 +41,7 @@ for phase in ("forward", "backward"):
     nz = t[t > 0]
     t0 = int(nz.min())
     print(f"==== {phase}: CTA {args.cta}, cycles relative to first event; span {int(nz.max()) - t0} cycles")
-    print("it | tma: wait_b_empty issue | mma: enter issue [wait_w gradissue] | wgX: wait_s got_s done")
+    print("it | tma: wait_b_empty issue | mma: enter issue [wait_w gradissue] | wgX: wait_s got_s done token")
     for it in range(ITERS):
         if not (t[:, it] > 0).any():
             break
