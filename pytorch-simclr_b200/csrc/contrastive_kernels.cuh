@@ -333,6 +333,9 @@ SIMCLR_DEVICE constexpr int poly_pairs_in_round(int pairs, int round) { return r
 #ifndef SIMCLR_FLUSH_WAIT_READ
 #define SIMCLR_FLUSH_WAIT_READ 1      // last flush of a CTA: wait for the TMA engine's reads only (0: for the adds to be performed)
 #endif
+#ifndef SIMCLR_FLUSH_ALTERNATE
+#define SIMCLR_FLUSH_ALTERNATE 1
+#endif
 #ifndef SIMCLR_BWD_DELAY_ST
 #define SIMCLR_BWD_DELAY_ST 0         // 1: store W of chunk k after the arithmetic of chunk k+1 (measured: slower)
 #endif
@@ -1274,8 +1277,11 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 fence_proxy_async_smem();                     // generic-proxy stores -> visible to the TMA engine
                 named_bar_sync(kFlushBar, 128);
                 if (warp == kFlushIssueWarp && elect_one()) {
+                    // Two or three CTAs share a row block and the ones that END in it flush at the same time: odd CTAs
+                    // walk the 32-column boxes backwards so that simultaneous reductions start on different lines.
 #pragma unroll 1
-                    for (int q = 0; q < D / 32; ++q) {
+                    for (int qq = 0; qq < D / 32; ++qq) {
+                        const int q = (SIMCLR_FLUSH_ALTERNATE && (blockIdx.x & 1)) ? D / 32 - 1 - qq : qq;
                         const int stage = (q / kBoxesPerStage) == 0 ? ring.idx : st1.idx;
                         tma_reduce_add_2d(&tmap_dacc, sb_addr + stage * L::kTileBytes + (q % kBoxesPerStage) * kAtomBytes,
                                           q * 32, w.rb * kBlockM);
@@ -1487,10 +1493,16 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                             if (special) {
                                 fwd_chunk_special<kLoss, kConst>(h, r, cq, vc, rc, fs);
                             } else {
+                                // an unmasked chunk of a tile that overlaps the warp's own images lies entirely before or
+                                // entirely after them: classify it by itself (the tile as a whole straddles the positive)
+                                const bool before = icq + kChunk - 1 < g_lo;
+                                bool prec;
+                                if constexpr (kLoss == kNtXent) prec = (rc.vr == 0) ? (vc == 1 && before) : (vc == 1 || before);
+                                else prec = before;
                                 float cm = kNegBig;
                                 fwd_chunk_fast<kLoss, kConst, kPrec == 0>(h, r, cm, fs);
-                                fs.max_prec = fmaxf(fs.max_prec, tile_prec ? cm : kNegBig);
-                                fs.max_foll = fmaxf(fs.max_foll, tile_prec ? kNegBig : cm);
+                                fs.max_prec = fmaxf(fs.max_prec, prec ? cm : kNegBig);
+                                fs.max_foll = fmaxf(fs.max_foll, prec ? kNegBig : cm);
                             }
                         } else {
                             uint32_t wq[kChunk / 2], unused[kChunk / 2];
@@ -1502,17 +1514,18 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                             tmem_st8(t0 + k * (kChunk / 2), wq);
                         }
                     };
-#pragma unroll 1
-                    for (int kk = 0; kk < 2; ++kk) {
-                        tmem_ld_wait16(ra);
-                        tmem_ld16(t0 + (2 * kk + 1) * kChunk, rb2);
-                        process(ra, 2 * kk);
-                        tmem_ld_wait16(rb2);
-                        if (kk == 0) tmem_ld16(t0 + 2 * kChunk, ra);
-                        process(rb2, 2 * kk + 1);
+                    // same shape as the common case (loads one chunk ahead, token passed at the same chunk)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t (&cur)[kChunk] = (k & 1) ? rb2 : ra;
+                        uint32_t (&nxt)[kChunk] = (k & 1) ? ra : rb2;
+                        tmem_ld_wait16(cur);
+                        if (k < 3) tmem_ld16(t0 + (k + 1) * kChunk, nxt);
+                        if (SIMCLR_PINGPONG && k == SIMCLR_TOKEN_CHUNK && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
+                        process(cur, k);
                     }
                 }
-                if (SIMCLR_PINGPONG && !(kBackward && kPrec != 0) && (tile_special || SIMCLR_TOKEN_CHUNK > 3) && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
+                if (SIMCLR_PINGPONG && !(kBackward && kPrec != 0) && SIMCLR_TOKEN_CHUNK > 3 && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
                 if constexpr (!kBackward) {
                     tc_fence_before_sync();
                     mbar_arrive(s_free + 8 * slot);
