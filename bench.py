@@ -530,7 +530,24 @@ def bench_multi(args):
     dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """stdout carries exactly one JSON line: everything else that writes to file descriptor 1 (NCCL's version banner,
+    library chatter of any rank) is sent to stderr; returns the stream for the JSON line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    global print
+    out = _claim_stdout()
+    _print = print
+
+    def print(*a, **k):          # noqa: A001  (the JSON line goes to the real stdout)
+        k.setdefault("file", out)
+        k.setdefault("flush", True)
+        _print(*a, **k)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

@@ -14,7 +14,8 @@ from . import _lib
 from ._lib import DTYPE_BF16, DTYPE_F32, LOSS_MODIFIED, LOSS_NTXENT, PRECISION_BF16, PRECISION_SPLIT, check
 
 __all__ = ["contrastive_forward_backward", "ContrastiveLossFunction", "LOSS_NTXENT", "LOSS_MODIFIED", "pad_rows",
-           "pad_dim", "compact_to_padded", "padded_to_compact", "set_precision", "get_precision", "resolve_precision"]
+           "pad_dim", "compact_to_padded", "padded_to_compact", "set_precision", "get_precision", "resolve_precision",
+           "set_eager_backward", "get_eager_backward", "run_fused"]
 
 BLOCK = 128
 
@@ -23,6 +24,24 @@ BLOCK = 128
 #   "fp32"  hi + lo bf16 operand planes, three products each -- fp32-grade (loss 1e-5, gradients 1e-4), d <= 128
 #   "auto"  fp32-grade for float32 inputs of d <= 128 on one GPU (what the fp32 reference delivers), bf16 otherwise
 _PRECISION = "auto"
+
+
+# When a single-GPU, unweighted loss is evaluated with gradients enabled, the autograd Function can run the FUSED
+# five-kernel step (simclr_forward_backward) at forward time and keep the unit-upstream gradients; backward() then only
+# scales them by grad_output.  The reference's call pattern (loss, acc = loss_fn(...); loss /= k; loss.backward(),
+# utils/model_utils.py:115-120) always follows a training forward by its backward, and the accuracy read-back it forces
+# (objective.py:52) otherwise splits the step into two launch sequences with a host round trip in between.
+_EAGER_BACKWARD = True
+
+
+def set_eager_backward(flag: bool) -> None:
+    """True (default): training forwards of the single-GPU unweighted losses compute their gradients at once."""
+    global _EAGER_BACKWARD
+    _EAGER_BACKWARD = bool(flag)
+
+
+def get_eager_backward() -> bool:
+    return _EAGER_BACKWARD
 
 
 def set_precision(mode: str) -> None:
@@ -173,6 +192,42 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
     return loss, stats, rowvec, saved
 
 
+def run_fused(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature: float, normalize: bool,
+              grad_out: Optional[torch.Tensor] = None, precision: Optional[int] = None):
+    """The fused five-kernel step through simclr_forward_backward (one GPU, unweighted): returns
+    (loss, stats, grad1, grad2), gradients of grad_out * loss (grad_out: device scalar or None for 1)."""
+    lib = _lib.load()
+    b, d = _validate(x1, x2)
+    x1 = x1.contiguous()
+    x2 = x2.contiguous()
+    dev = x1.device
+    bp, dp = pad_rows(b), pad_dim(d)
+    code = _dtype_code(x1)
+    if precision is None:
+        precision = resolve_precision(x1, False)
+    planes = 2 if precision == PRECISION_SPLIT else 1
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        operand = torch.empty((planes * 2 * bp, dp), dtype=torch.bfloat16, device=dev)
+        rowvec = torch.empty((4, 2 * bp), dtype=torch.float32, device=dev)
+        stats = torch.empty(4, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        g1 = torch.empty_like(x1)
+        g2 = torch.empty_like(x2)
+        fwd_bytes = lib.simclr_forward_workspace_bytes(loss_kind, b, b, d)
+        bwd_bytes = lib.simclr_backward_workspace_bytes(loss_kind, b, b, d)
+        ws = torch.empty(fwd_bytes + bwd_bytes, dtype=torch.uint8, device=dev)      # both workspaces, 256-byte aligned sizes
+        go = None
+        if grad_out is not None:
+            go = grad_out.to(device=dev, dtype=torch.float32).contiguous()
+        check(lib.simclr_forward_backward(loss_kind, x1.data_ptr(), x2.data_ptr(), b, d, code, int(bool(normalize)),
+                                          float(temperature), precision, _ptr(go), operand.data_ptr(), rowvec.data_ptr(),
+                                          stats.data_ptr(), loss.data_ptr(), g1.data_ptr(), g2.data_ptr(), ws.data_ptr(),
+                                          fwd_bytes, ws.data_ptr() + fwd_bytes, bwd_bytes, stream),
+              "simclr_forward_backward")
+    return loss, stats, g1, g2
+
+
 def run_backward(saved: "_Saved", x1: torch.Tensor, x2: torch.Tensor, grad_out: Optional[torch.Tensor]):
     lib = _lib.load()
     dev = x1.device
@@ -199,6 +254,9 @@ def run_backward(saved: "_Saved", x1: torch.Tensor, x2: torch.Tensor, grad_out: 
                                   saved.inv_norm.data_ptr(), saved.pos_dot.data_ptr(), saved.lse2_cols.data_ptr(),
                                   _ptr(saved.col_scale), _ptr(go), g1.data_ptr(), g2.data_ptr(), ws.data_ptr(),
                                   ws_bytes, primed, stream), "simclr_backward")
+        # the primed state (zeroed accumulation buffer) is consumed: a second backward over a retained graph takes
+        # the unprimed route (its backward-prepare kernel zeroes the buffer again)
+        saved.primed_colvec = None
     return g1, g2
 
 
@@ -217,7 +275,14 @@ class ContrastiveLossFunction(torch.autograd.Function):
                                                            any(ctx.needs_input_grad[:2]))
         else:
             want_grad = any(ctx.needs_input_grad[:2])
+            if want_grad and _EAGER_BACKWARD and gather is None and weight is None:
+                # fused step now, unit upstream gradient; backward() scales
+                loss, stats, g1, g2 = run_fused(loss_kind, x1, x2, temperature, normalize)
+                ctx.eager_grads = (g1, g2)
+                ctx.mark_non_differentiable(stats)
+                return loss, stats
             loss, stats, _rowvec, saved = run_forward(loss_kind, x1, x2, temperature, normalize, weight, gather, want_grad)
+        ctx.eager_grads = None
         ctx.saved_state = saved
         ctx.save_for_backward(x1, x2)
         ctx.mark_non_differentiable(stats)
@@ -225,6 +290,10 @@ class ContrastiveLossFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_stats):
+        if ctx.eager_grads is not None:
+            g1, g2 = ctx.eager_grads
+            scale = grad_loss.to(g1.dtype)
+            return g1 * scale, g2 * scale, None, None, None, None, None
         x1, x2 = ctx.saved_tensors
         g1, g2 = run_backward(ctx.saved_state, x1.contiguous(), x2.contiguous(), grad_loss)
         return g1, g2, None, None, None, None, None
@@ -235,6 +304,8 @@ def contrastive_forward_backward(loss_kind: int, x1: torch.Tensor, x2: torch.Ten
                                  grad_out: Optional[torch.Tensor] = None, precision: Optional[str] = None):
     """Autograd-free fused call: returns (loss, stats, grad1, grad2), all on the device."""
     prec = None if precision is None else resolve_precision(x1, False, precision)
+    if weight is None:
+        return run_fused(loss_kind, x1, x2, temperature, normalize, grad_out, prec)
     loss, stats, _rowvec, saved = run_forward(loss_kind, x1, x2, temperature, normalize, weight, None, True, prec)
     g1, g2 = run_backward(saved, x1.contiguous(), x2.contiguous(), grad_out)
     return loss, stats, g1, g2

@@ -34,6 +34,7 @@ PRECISIONS = ["bf16", "fp32"]
 def _restore_precision():
     yield
     sb.set_precision("auto")
+    sb.set_eager_backward(True)
 
 
 def _mode_for(precision, dtype, d):
@@ -300,7 +301,9 @@ def test_fused_step_equals_staged_calls_over_changing_inputs(kind, b, d, precisi
     torch.cuda.synchronize()
     for i in range(2 * n_sets):
         x1, x2 = xs[i % n_sets]
-        loss, stats, g1, g2 = F.contrastive_forward_backward(kind, x1, x2, tau, True, None, go, precision)
+        prec = F.resolve_precision(x1, False, precision)
+        loss, stats, _rv, saved = F.run_forward(kind, x1, x2, tau, True, None, None, True, prec)      # staged calls
+        g1, g2 = F.run_backward(saved, x1, x2, go)
         torch.cuda.synchronize()
         assert torch.equal(outs[i][2][:3], stats[:3]), f"step {i}: statistics differ"
         scale = float(g1.abs().max())
@@ -312,3 +315,51 @@ def test_fused_step_equals_staged_calls_over_changing_inputs(kind, b, d, precisi
     ltol, gtol = TOL[precision]
     assert float(outs[0][2][3]) == pytest.approx(ref.loss, rel=ltol)
     assert _grad_err(outs[0][0].cpu().numpy(), ref.grad1) < gtol
+
+
+@pytest.mark.parametrize("kind", ["ntxent", "modified"])
+@pytest.mark.parametrize("b,d,precision", [(512, 128, "fp32"), (4096, 128, "bf16"), (777, 100, "bf16")])
+def test_eager_and_staged_autograd_paths_agree(kind, b, d, precision):
+    """The autograd Function either runs the fused step at forward time and scales the kept gradients in backward()
+    (default) or the staged forward / backward calls: same loss, accuracy and gradients, including the in-place
+    division of the loss (utils/model_utils.py:116) and a second backward() over a retained graph."""
+    fn = sb.contrastive_loss if kind == "ntxent" else sb.modified_contrastive_loss
+    z1, z2 = oracle.make_embeddings(b, d, seed=31 + b, kind="correlated", noise=1.0)
+    sb.set_precision(precision)
+    res = {}
+    for eager in (True, False):
+        sb.set_eager_backward(eager)
+        a = z1.cuda().requires_grad_(True)
+        c = z2.cuda().requires_grad_(True)
+        loss, acc = fn(a, c, temperature=0.5)
+        loss /= 8
+        loss.backward(retain_graph=True)
+        g1 = a.grad.clone()
+        loss.backward()                      # accumulates a second, identical contribution
+        torch.cuda.synchronize()
+        assert float((a.grad - 2 * g1).abs().max()) <= 1e-5 * float(g1.abs().max())     # staged: a recomputation
+        res[eager] = (float(loss.detach()), acc, g1.cpu(), c.grad.cpu() / 2)
+    assert res[True][0] == pytest.approx(res[False][0], rel=1e-7)
+    assert res[True][1] == res[False][1]
+    scale = float(res[False][2].abs().max())
+    assert float((res[True][2] - res[False][2]).abs().max()) <= 3e-6 * scale
+    assert float((res[True][3] - res[False][3]).abs().max()) <= 3e-6 * scale
+    ref = (oracle.ntxent_closed_form if kind == "ntxent" else oracle.modified_closed_form)(z1, z2, temperature=0.5,
+                                                                                            grad_output=1.0 / 8)
+    assert _grad_err(res[True][2].numpy(), ref.grad1) < TOL[precision][1]
+
+
+def test_first_argmax_tie_with_an_earlier_column_of_the_positive_tile():
+    """objective.py:51 -- Tensor.max returns the FIRST maximal index.  A view-2 row identical to the positive, placed in
+    the same 128-column tile as the positive but in an earlier 16-column chunk, wins the tie (the row is NOT counted as
+    correct); placed later it loses (the row IS counted).  The oracle applies the reference rule exactly."""
+    b, d = 256, 128
+    z1, z2 = oracle.make_embeddings(b, d, seed=77, kind="correlated", noise=0.05)
+    z2 = z2.clone()
+    z2[130] = z2[200]          # duplicate BEFORE the positive of row 200 (same tile 128..255, chunk 0 vs chunk 4)
+    z2[250] = z2[140]          # duplicate AFTER the positive of row 140
+    ref = oracle.ntxent_closed_form(z1, z2, temperature=0.5)
+    for precision in PRECISIONS:
+        loss, acc, g1, g2 = _run(sb.contrastive_loss, z1, z2, precision=precision, temperature=0.5)
+        assert acc == ref.acc, precision
+        assert loss == pytest.approx(ref.loss, rel=TOL[precision][0])
