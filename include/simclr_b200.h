@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIMCLR_ABI_VERSION 8
+#define SIMCLR_ABI_VERSION 9
 
 /* loss kinds */
 #define SIMCLR_LOSS_NTXENT 0   /* objective.py:6-55  */
@@ -187,6 +187,26 @@ int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_
                         void* const* stats_peers, void* const* flag_peers, unsigned int* epoch_local, void* stream);
 int simclr_peer_barrier(int world, int rank, void* const* flag_peers, unsigned int* epoch_local, const float* stats_all,
                         float* stats_out, float* loss_out, void* stream);
+
+/*
+ * Fused row-sharded step: simclr_prepare_peer + simclr_forward_peer + simclr_backward of one rank in five launches,
+ * with the two cross-GPU barriers executed INSIDE the tile kernels instead of by simclr_peer_barrier launches: the
+ * prepare kernel bumps `epoch_local`, CTA 0 of the forward tile kernel publishes it to every rank's flags and the TMA
+ * producer of every CTA waits for all ranks before its first column-tile load (the row-block tile of local rows is
+ * already in flight); the forward finalize kernel bumps the epoch again and the backward tile kernel -- whose operand
+ * loads and first score MMAs run ahead of it -- does the same before it loads the peers' column vectors.  The backward
+ * finalize kernel adds up the ranks' statistics into stats_global / loss_out (the GLOBAL loss, identical on all ranks).
+ * Buffers as in the separate calls; operand / colvec / stats *_peers[rank] are this rank's own copies.  Every rank must
+ * issue the same sequence of fused steps and barrier calls (they share the flags and the epoch counter).
+ */
+int simclr_forward_backward_peer(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d,
+                                 int in_dtype, int normalize, float temperature, const float* grad_out, void* operand,
+                                 float* rowvec, float* stats_local, float* stats_global, float* loss_out, void* grad1,
+                                 void* grad2, void* forward_workspace, size_t forward_workspace_bytes,
+                                 void* backward_workspace, size_t backward_workspace_bytes, int world, int rank,
+                                 void* const* operand_global_peers, void* operand_global_multicast,
+                                 void* const* colvec_peers, void* const* stats_peers, void* const* flag_peers,
+                                 unsigned int* epoch_local, void* stream);
 
 /* Diagnostics: per-role clock64() timeline of one CTA of the tile kernels (tools/trace_timeline.py).
  * device_buffer: int64[6 roles][64 iterations][4] or NULL to switch tracing off. */

@@ -15,7 +15,7 @@ DTYPE_F32 = 0
 DTYPE_BF16 = 1
 PRECISION_BF16 = 0
 PRECISION_SPLIT = 1
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 _lock = threading.Lock()
 _lib = None
@@ -42,6 +42,8 @@ SIGNATURES = {
                                _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "simclr_forward_backward": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                        _vp, _sz, _vp, _sz, _vp]),
+    "simclr_forward_backward_peer": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                            _vp, _vp, _sz, _vp, _sz, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "simclr_prepare_peer": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _int, _int, _vp,
                                    _vp, _vp]),
     "simclr_forward_peer": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -58,7 +58,7 @@ template <typename T, int kLoss, int kPer /* d_pad / 32: 2, 4 or 8 */>
 __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x2, AuxParams a,
                                __nv_bfloat16* __restrict__ operand, float* __restrict__ inv_norm,
                                float* __restrict__ pos_dot, unsigned int* __restrict__ zero_ptr, int zero_words,
-                               unsigned long long* ktrace, PeerTable peers) {
+                               unsigned long long* ktrace, PeerTable peers, unsigned int* bump_epoch) {
     pdl_launch_dependents();
     // The input rows are loaded BEFORE griddepcontrol.wait (they are the caller's tensors: no kernel of this library
     // writes them, and a foreign producer never lets this kernel start early); every store comes after it, because the
@@ -98,6 +98,8 @@ __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x
     struct End { unsigned long long* k; __device__ ~End() { ktrace_end(k, 0); } } end_guard{ktrace};
     if (zero_ptr != nullptr && blockIdx.x == 0)
         for (int j = threadIdx.x; j < zero_words; j += blockDim.x) zero_ptr[j] = 0u;
+    // fused row-sharded step: the epoch of the barrier that the forward tile kernel executes (TileParams::sync_epoch)
+    if (bump_epoch != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *bump_epoch += 1u;
     if (i >= a.bl_pad) return;
     __nv_bfloat16* o1 = operand + static_cast<size_t>(i) * a.d_pad;
     __nv_bfloat16* o2 = operand + static_cast<size_t>(a.bl_pad + i) * a.d_pad;

@@ -409,10 +409,22 @@ size_t simclr_operand_bytes(int64_t b, int64_t d, int precision) {
     return static_cast<size_t>(precision == SIMCLR_PRECISION_SPLIT ? 2 : 1) * 2 * bp * dp * sizeof(__nv_bfloat16);
 }
 
-int simclr_prepare_peer(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
-                        int normalize, float temperature, int precision, void* operand, float* inv_norm, float* pos_dot,
-                        void* forward_workspace, int world, int rank, void* const* operand_global_peers,
-                        void* operand_global_multicast, void* stream) {
+}  // extern "C"
+
+namespace {
+
+// In-kernel barriers of the fused row-sharded step (TileParams::sync_flags)
+struct FusedSync {
+    int world, rank;
+    void* const* flag_peers;
+    unsigned int* epoch;
+    const float* stats_all;
+};
+
+int prepare_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
+                 int normalize, float temperature, int precision, void* operand, float* inv_norm, float* pos_dot,
+                 void* forward_workspace, int world, int rank, void* const* operand_global_peers,
+                 void* operand_global_multicast, void* stream, unsigned int* bump_epoch) {
     if (bad_precision(precision)) return SIMCLR_ERR_BAD_DTYPE;
     if (!x_batch1 || !x_batch2 || !operand || !inv_norm || !pos_dot) return SIMCLR_ERR_NULL_POINTER;
     if (in_dtype != SIMCLR_DTYPE_F32 && in_dtype != SIMCLR_DTYPE_BF16) return SIMCLR_ERR_BAD_DTYPE;
@@ -444,7 +456,7 @@ int simclr_prepare_peer(int loss, const void* x_batch1, const void* x_batch2, in
     cudaError_t launch_rc = cudaSuccess;
     if (!(g_stage_mask & kStagePrepare)) return SIMCLR_OK;
 #define SIMCLR_PREP2(T, LOSS, PER) \
-    launch_rc = launch_pdl(prepare_kernel<T, LOSS, PER>, dim3(blocks), dim3(warps * 32), 0, st, static_cast<const T*>(x_batch1), static_cast<const T*>(x_batch2), a, op, inv_norm, pos_dot, zero_ptr, zero_words, g_ktrace_ptr, peers)
+    launch_rc = launch_pdl(prepare_kernel<T, LOSS, PER>, dim3(blocks), dim3(warps * 32), 0, st, static_cast<const T*>(x_batch1), static_cast<const T*>(x_batch2), a, op, inv_norm, pos_dot, zero_ptr, zero_words, g_ktrace_ptr, peers, bump_epoch)
 #define SIMCLR_PREP(T, LOSS)                          \
     switch (g.d_pad) {                                \
         case 64: SIMCLR_PREP2(T, LOSS, 2); break;     \
@@ -461,6 +473,19 @@ int simclr_prepare_peer(int loss, const void* x_batch1, const void* x_batch2, in
 #undef SIMCLR_PREP
 #undef SIMCLR_PREP2
     return static_cast<int>(launch_rc);
+}
+
+}  // namespace
+
+extern "C" {
+
+int simclr_prepare_peer(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
+                        int normalize, float temperature, int precision, void* operand, float* inv_norm, float* pos_dot,
+                        void* forward_workspace, int world, int rank, void* const* operand_global_peers,
+                        void* operand_global_multicast, void* stream) {
+    return prepare_impl(loss, x_batch1, x_batch2, b_local, d, in_dtype, normalize, temperature, precision, operand, inv_norm,
+                        pos_dot, forward_workspace, world, rank, operand_global_peers, operand_global_multicast, stream,
+                        nullptr);
 }
 
 int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
@@ -494,7 +519,7 @@ int forward_impl(int loss, const void* operand_rows, const void* operand_cols, i
                  const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out, void* workspace,
                  size_t workspace_bytes, void* backward_workspace, size_t backward_workspace_bytes, int world, int rank,
                  void* const* colvec_peers, void* const* stats_peers, void* const* flag_peers, unsigned int* epoch_local,
-                 void* stream, bool defer_stats) {
+                 void* stream, bool defer_stats, const FusedSync* fused = nullptr) {
     if (!operand_rows || !operand_cols || !pos_dot || !lse2 || !row_loss || !stats || !workspace)
         return SIMCLR_ERR_NULL_POINTER;
     if (!(temperature > 0.f) || !std::isfinite(temperature)) return SIMCLR_ERR_BAD_TEMPERATURE;
@@ -526,6 +551,14 @@ int forward_impl(int loss, const void* operand_rows, const void* operand_cols, i
     p.stats = stats;
     p.loss_out = loss_out;
     p.defer_stats = defer_stats ? 1 : 0;
+    if (fused != nullptr) {
+        // the barrier after the operand push runs inside the tile kernel; the finalize kernel bumps the epoch for the
+        // barrier inside the backward tile kernel
+        if ((rc = make_peer_table(fused->world, fused->rank, fused->flag_peers, &p.sync_flags))) return rc;
+        if (p.sync_flags.world < 1 || fused->epoch == nullptr) return SIMCLR_ERR_BAD_PEERS;
+        p.sync_epoch = fused->epoch;
+        p.bump_epoch = fused->epoch;
+    }
     if ((rc = make_peer_table(world, rank, colvec_peers, &p.colvec_peers))) return rc;
     if ((rc = make_peer_table(world, rank, stats_peers, &p.stats_peers))) return rc;
     if (p.colvec_peers.world > 0 && (b_global != b_local * world || row_offset != b_local * rank)) return SIMCLR_ERR_BAD_PEERS;
@@ -596,7 +629,7 @@ int backward_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t 
                   const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,
                   const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
                   void* workspace, size_t workspace_bytes, const float* primed_colvec, void* stream, void* finish_ws,
-                  float* finish_stats, float* finish_loss) {
+                  float* finish_stats, float* finish_loss, const FusedSync* fused = nullptr) {
     if (!x_batch1 || !x_batch2 || !operand_rows || !operand_cols || !inv_norm || !pos_dot || !grad1 || !grad2 || !workspace)
         return SIMCLR_ERR_NULL_POINTER;
     if (!lse2_cols && !primed_colvec) return SIMCLR_ERR_NULL_POINTER;
@@ -655,6 +688,17 @@ int backward_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t 
     if (finish_ws != nullptr) {
         FwdWorkspace fw = carve_forward(g, finish_ws);
         p.block_part = fw.block_part;
+        p.stats = finish_stats;
+        p.loss_out = finish_loss;
+        p.finish_stats = 1;
+    }
+    if (fused != nullptr) {
+        if ((rc = make_peer_table(fused->world, fused->rank, fused->flag_peers, &p.sync_flags))) return rc;
+        if (p.sync_flags.world < 1 || fused->epoch == nullptr || fused->stats_all == nullptr || finish_stats == nullptr)
+            return SIMCLR_ERR_BAD_PEERS;
+        p.sync_epoch = fused->epoch;
+        p.stats_all = fused->stats_all;
+        p.stats_world = fused->world;
         p.stats = finish_stats;
         p.loss_out = finish_loss;
         p.finish_stats = 1;
@@ -739,6 +783,44 @@ int simclr_forward_backward(int loss, const void* x_batch1, const void* x_batch2
                          inv_norm, pos_dot, nullptr, nullptr, grad_out, grad1, grad2, backward_workspace,
                          backward_workspace_bytes, static_cast<const float*>(backward_workspace), stream, forward_workspace,
                          stats, loss_out);
+}
+
+int simclr_forward_backward_peer(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d,
+                                 int in_dtype, int normalize, float temperature, const float* grad_out, void* operand,
+                                 float* rowvec, float* stats_local, float* stats_global, float* loss_out, void* grad1,
+                                 void* grad2, void* forward_workspace, size_t forward_workspace_bytes,
+                                 void* backward_workspace, size_t backward_workspace_bytes, int world, int rank,
+                                 void* const* operand_global_peers, void* operand_global_multicast,
+                                 void* const* colvec_peers, void* const* stats_peers, void* const* flag_peers,
+                                 unsigned int* epoch_local, void* stream) {
+    if (!rowvec || !stats_local || !stats_global || !backward_workspace || !operand_global_peers || !colvec_peers ||
+        !stats_peers || !flag_peers || !epoch_local)
+        return SIMCLR_ERR_NULL_POINTER;
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return SIMCLR_ERR_BAD_PEERS;
+    const int64_t bp = simclr_pad_rows(b_local);
+    if (bp == 0) return SIMCLR_ERR_BAD_SHAPE;
+    float* inv_norm = rowvec;
+    float* pos_dot = rowvec + 2 * bp;
+    float* lse2 = rowvec + 4 * bp;
+    float* row_loss = rowvec + 6 * bp;
+    const int64_t b_global = b_local * world, row_offset = b_local * rank;
+    const void* operand_cols = operand_global_peers[rank];
+    const float* colvec_local = static_cast<const float*>(colvec_peers[rank]);
+    FusedSync fs{world, rank, flag_peers, epoch_local, static_cast<const float*>(stats_peers[rank])};
+    // prepare pushes the operand rows and bumps the epoch; the forward tile kernel signals / waits on it
+    int rc = prepare_impl(loss, x_batch1, x_batch2, b_local, d, in_dtype, normalize, temperature, SIMCLR_PRECISION_BF16,
+                          operand, inv_norm, pos_dot, forward_workspace, world, rank, operand_global_peers,
+                          operand_global_multicast, stream, epoch_local);
+    if (rc) return rc;
+    rc = forward_impl(loss, operand, operand_cols, b_local, b_global, row_offset, d, temperature, normalize,
+                      SIMCLR_PRECISION_BF16, pos_dot, nullptr, lse2, row_loss, stats_local, nullptr, forward_workspace,
+                      forward_workspace_bytes, backward_workspace, backward_workspace_bytes, world, rank, colvec_peers,
+                      stats_peers, nullptr, nullptr, stream, false, &fs);
+    if (rc) return rc;
+    return backward_impl(loss, x_batch1, x_batch2, b_local, b_global, row_offset, d, in_dtype, normalize, temperature,
+                         SIMCLR_PRECISION_BF16, operand, operand_cols, inv_norm, pos_dot, nullptr, nullptr, grad_out, grad1,
+                         grad2, backward_workspace, backward_workspace_bytes, colvec_local, stream, nullptr, stats_global,
+                         loss_out, &fs);
 }
 
 int simclr_debug_set_trace(void* device_buffer, int cta) {

@@ -170,7 +170,47 @@ struct TileParams {
     // between the two tile kernels.
     int defer_stats;
     int finish_stats;
+    // Row-sharded batch, fused step (simclr_forward_backward_peer): the cross-GPU barrier in front of this launch is
+    // executed INSIDE it -- CTA 0 signals, the TMA producer of every CTA waits before it touches what the peers pushed
+    // (sync_flags.world > 0).  *sync_epoch is the value to signal / wait for; the preceding kernel of the stream bumped it
+    // (bump_epoch of the prepare / forward finalize kernel).  No barrier kernel, no collective call.
+    PeerTable sync_flags;
+    const unsigned int* sync_epoch;
+    unsigned int* bump_epoch;
+    // backward finalize, row-sharded fused step: add up the ranks' statistics [world][4] (fixed order) into stats / loss_out
+    const float* stats_all;
+    int stats_world;
 };
+
+// Cross-GPU barrier executed by one thread of a kernel (see TileParams::sync_flags).  `signal`: this thread also
+// publishes the epoch to every rank -- everything this GPU pushed before is complete, because the pushing kernels
+// completed before the caller passed griddepcontrol.wait.  Returns when all ranks have published the epoch.
+SIMCLR_DEVICE void peer_sync_thread(const PeerTable& flags, const unsigned int* epoch, bool signal) {
+    const unsigned int target = __ldcg(epoch);
+    if (signal) {
+        __threadfence_system();
+        for (int r = 0; r < flags.world; ++r) {
+            unsigned int* remote = static_cast<unsigned int*>(flags.ptr[r]) + flags.rank;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(target) : "memory");
+        }
+    }
+    const unsigned int* mine = static_cast<const unsigned int*>(flags.ptr[flags.rank]);
+    for (int r = 0; r < flags.world; ++r) {
+        unsigned int seen;
+        long long spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine + r) : "memory");
+            if (static_cast<int>(seen - target) >= 0) break;
+            if (++spins > (1ll << 27)) {
+                printf("[simclr_b200] in-kernel peer barrier watchdog: rank %d waits for rank %d (epoch %u, seen %u)\n",
+                       flags.rank, r, target, seen);
+                __trap();
+            }
+        } while (true);
+    }
+    // what the peers stored before their signal is read next by the TMA engine (async proxy)
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
 
 // Debug timeline: trace[(role * kTraceIters + it) * 4 + k].  Roles: 0 TMA producer, 1 MMA issuer,
 // 2 + wg softmax warpgroup wg (lane 0 of its quarter-0 warp).
@@ -762,6 +802,7 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
                 dst[2] = s2;
             }
             *p.ticket = 0u;                        // leave the workspace header clean for the next call
+            if (p.bump_epoch != nullptr) *p.bump_epoch += 1u;   // the epoch the backward tile kernel's barrier uses
         }
     }
 }
@@ -887,14 +928,24 @@ SIMCLR_DEVICE void backward_finalize_row(const TileParams& p, int rb, int r, int
 // kernel left in block_part, in a fixed order (deterministic).
 SIMCLR_DEVICE void finish_forward_stats(const TileParams& p, int lane) {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    for (int i = lane; i < p.n_row_blocks; i += 32) {
-        s0 += __ldcg(p.block_part + i * 4 + 0);
-        s1 += __ldcg(p.block_part + i * 4 + 1);
-        s2 += __ldcg(p.block_part + i * 4 + 2);
+    if (p.stats_all != nullptr) {
+        // row-sharded batch: the ranks' sums, pushed by their forward finalize kernels and ordered by the barrier inside
+        // the backward tile kernel; lane 0 adds them in rank order (the same value on every rank)
+        for (int r = 0; r < p.stats_world; ++r) {
+            s0 += __ldcv(p.stats_all + 4 * r + 0);
+            s1 += __ldcv(p.stats_all + 4 * r + 1);
+            s2 += __ldcv(p.stats_all + 4 * r + 2);
+        }
+    } else {
+        for (int i = lane; i < p.n_row_blocks; i += 32) {
+            s0 += __ldcg(p.block_part + i * 4 + 0);
+            s1 += __ldcg(p.block_part + i * 4 + 1);
+            s2 += __ldcg(p.block_part + i * 4 + 2);
+        }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
     }
-    s0 = warp_sum(s0);
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
     if (lane == 0) {
         p.stats[0] = s0;
         p.stats[1] = s1;
@@ -1076,6 +1127,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 }
                 pdl_wait();
             }
+            bool synced = p.sync_flags.world == 0;
             RingPos<S> ring;
             bool wrapped = false;
             int seg = 0;
@@ -1091,6 +1143,13 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 trace_event(p, 0, it, 0);
                 if (wrapped) mbar_wait(b_empty + 8 * ring.idx, ring.par ^ 1, 101);   // previous use of the stage released
                 trace_event(p, 0, it, 1);
+                if (!synced) {
+                    // In-kernel cross-GPU barrier.  Forward: the row-block tile (local rows) is already in flight, the
+                    // column tiles are what the peers pushed.  Backward: the operands were complete before this kernel
+                    // started (early loads above), the peers' column vectors are what the barrier protects.
+                    peer_sync_thread(p.sync_flags, p.sync_epoch, blockIdx.x == 0);
+                    synced = true;
+                }
                 const int c0 = tile_col0<kLoss>(p, w.rb / blocks_per_view, w.j);
                 if (it >= early) load_cols(ring.idx, c0);
                 if constexpr (kBackward) {

@@ -207,6 +207,23 @@ class PeerBatch:
         return view["operand"], view["colvec"], self.generation
 
 
+    def fused_step(self, loss_kind, x1, x2, temperature, normalize, operand, rowvec, stats_local, stats_global, loss,
+                   grad1, grad2, fwd_ws, fwd_ws_bytes, bwd_ws, bwd_ws_bytes, stream, grad_out=None):
+        """The whole row-sharded step of this rank in five launches (simclr_forward_backward_peer): the two cross-GPU
+        barriers run inside the tile kernels.  Enqueue only; uses the next buffer generation like forward()."""
+        gen = self.generation % self.GENERATIONS
+        tab = self._tables[gen]
+        check(self.lib.simclr_forward_backward_peer(
+            loss_kind, x1.data_ptr(), x2.data_ptr(), self.b_local, self.d, _dtype_code(x1), int(bool(normalize)),
+            float(temperature), None if grad_out is None else grad_out.data_ptr(), operand.data_ptr(), rowvec.data_ptr(),
+            stats_local.data_ptr(), stats_global.data_ptr(), loss.data_ptr(), grad1.data_ptr(), grad2.data_ptr(),
+            fwd_ws.data_ptr(), fwd_ws_bytes, bwd_ws.data_ptr(), bwd_ws_bytes, self.world, self.rank, tab["operand"],
+            self._mc[gen], tab["colvec"], tab["stats"], self._flags, self.epoch.data_ptr(), stream),
+            "simclr_forward_backward_peer")
+        self.generation += 1
+        return self.generation
+
+
 def run_forward_peer(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature: float, normalize: bool,
                      peer: PeerBatch, prime_backward: bool = True):
     """Peer-memory counterpart of functional.run_forward (same return tuple)."""

@@ -103,8 +103,9 @@ class PeerStep:
     """Allocation-free step of the row-sharded global batch over peer memory (distributed.PeerBatch): what bench.py
     captures into one CUDA graph per rank at N > 1.  No collective call inside: the exchange is NVLink stores from the
     prepare / forward-finalize kernels plus two device-side barriers."""
-    KERNELS_FORWARD = 5     # prepare(+push), barrier, tile kernel, finalize(+push), barrier(+statistics)
+    KERNELS_FORWARD = 5     # staged: prepare(+push), barrier, tile kernel, finalize(+push), barrier(+statistics)
     KERNELS_BACKWARD = 2    # tile kernel, finalize (the forward primed the workspace)
+    KERNELS_FUSED = 5       # step(): prepare(+push), tile kernel(+barrier), finalize(+push), tile kernel(+barrier), finalize
 
     def __init__(self, loss_kind: int, b_local: int, dim: int, temperature: float, group=None, normalize: bool = True,
                  dtype: torch.dtype = torch.float32, device="cuda"):
@@ -151,6 +152,24 @@ class PeerStep:
                                        self.grad1.data_ptr(), self.grad2.data_ptr(), self.bwd_ws.data_ptr(),
                                        self.bwd_ws_bytes, colvec.data_ptr(), self._stream()), "simclr_backward")
 
-    def step(self) -> None:
+    def step(self, grad_out: Optional[torch.Tensor] = None, x1: Optional[torch.Tensor] = None,
+             x2: Optional[torch.Tensor] = None, grad1: Optional[torch.Tensor] = None,
+             grad2: Optional[torch.Tensor] = None) -> None:
+        """Fused step (simclr_forward_backward_peer): five launches, the cross-GPU barriers inside the tile kernels.
+        Consecutive steps alternate between the two buffer generations of the PeerBatch: a CUDA graph that is replayed
+        must therefore hold an EVEN number of steps (or end with ``barrier()``)."""
+        self.peer.fused_step(self.kind, self.x1 if x1 is None else x1, self.x2 if x2 is None else x2, self.temperature,
+                             self.normalize, self.operand, self.rowvec, self.stats_local, self.stats, self.loss,
+                             self.grad1 if grad1 is None else grad1, self.grad2 if grad2 is None else grad2, self.fwd_ws,
+                             self.fwd_ws_bytes, self.bwd_ws, self.bwd_ws_bytes, self._stream(), grad_out)
+
+    def barrier(self) -> None:
+        """A stand-alone device-side barrier over the ranks (same flags / epoch as the steps)."""
+        p = self.peer
+        check(self.lib.simclr_peer_barrier(p.world, p.rank, p._flags, p.epoch.data_ptr(), None, None, None, self._stream()),
+              "simclr_peer_barrier")
+
+    def step_staged(self) -> None:
+        """prepare / barrier / forward / barrier / backward as separate calls (seven launches)."""
         self.forward()
         self.backward()

@@ -36,7 +36,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_abi_version_and_error_strings(lib):
-    assert lib.simclr_abi_version() == 8
+    assert lib.simclr_abi_version() == 9
     assert lib.simclr_error_string(0) == b"ok"
     for code in range(-11, 0):
         assert lib.simclr_error_string(code) not in (b"", b"unknown error")
