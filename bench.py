@@ -461,7 +461,7 @@ def bench_multi(args):
     torch.cuda.synchronize()
     dist.barrier()
 
-    def capture(n, first, fused=True):
+    def capture(n, first, fused=True, tail_barrier=True):
         """n steps of this rank in one CUDA graph (5 launches each, the cross-GPU barriers inside the tile kernels; no
         collective call).  Steps alternate between the two buffer generations: an odd graph ends with a barrier so
         that it can be replayed.  Every rank captures and replays the same sequence."""
@@ -474,14 +474,17 @@ def bench_multi(args):
                 else:
                     step.x1, step.x2, step.grad1, step.grad2 = x1, x2, g1, g2
                     step.step_staged()
-            if n % 2:
+            if n % 2 and tail_barrier:
                 step.barrier()          # an odd number of steps: a trailing barrier makes the graph safe to replay
         return g
 
     k_timed = args.steps
-    g_warm = capture(max(4, args.warmup + args.warmup % 2), 0)
-    g_timed = capture(k_timed, args.warmup)
-    g_staged = capture(2, 0, fused=False)
+    # one step per graph, one graph per buffer generation: replayed alternately (a, b, a, b, ...)
+    g_a = capture(1, 0, tail_barrier=False)
+    g_b = capture(1, 1, tail_barrier=False)
+    g_b2b = capture(k_timed + k_timed % 2, 3)               # an even number of steps back to back (reported next to the headline)
+    g_sa = capture(1, 0, fused=False, tail_barrier=False)
+    g_sb = capture(1, 1, fused=False, tail_barrier=False)
     torch.cuda.synchronize()
     dist.barrier()
 
@@ -489,30 +492,63 @@ def bench_multi(args):
     if rank == 0:
         sampler.start()
 
-    def timed_ms(g, reps=1):
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    def isolated_ms(plan, warm):
+        """Sum of the CUDA-event times of the replays in `plan` (graphs), the L2 flushed (256 MiB memset, outside the
+        event pair) before each; every rank replays the same sequence (the in-kernel barriers pair up across ranks)."""
+        for g in warm:
+            flush.zero_()
+            g.replay()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in plan]
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        for g, (a, z) in zip(plan, ev):
+            flush.zero_()
+            a.record()
+            g.replay()
+            z.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        # a step ends on each rank when its own backward is done; the in-kernel barriers make every rank wait for the
+        # slowest one twice per step, so the per-rank sums differ only by the last backward: take the MAX over ranks
+        return max_over_ranks(sum(a.elapsed_time(z) for a, z in ev))
+
+    def fence_ranks():
+        """A stand-alone device barrier between measurement phases: whatever generation the next phase starts with, no
+        rank is still reading it."""
+        with torch.cuda.stream(side):
+            step.barrier()
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    n_warm = max(4, args.warmup + args.warmup % 2)
+    plan = ([g_a, g_b] * ((k_timed + 1) // 2))[:k_timed]
+    ms_step = isolated_ms(plan, [g_a, g_b] * (n_warm // 2)) / k_timed
+    fence_ranks()
+    n_st = max(4, min(16, k_timed - k_timed % 2))
+    ms_staged = isolated_ms([g_sa, g_sb] * (n_st // 2), [g_sa, g_sb]) / n_st
+    fence_ranks()
+
+    def b2b_ms():
         a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
         a.record()
-        for _ in range(reps):
-            g.replay()
+        g_b2b.replay()
         z.record()
         torch.cuda.synchronize()
         dist.barrier()
-        # a step ends on each rank when its own backward is done; the in-kernel barriers make every rank wait for the
-        # slowest one twice per step: take the MAX over ranks
-        t = torch.tensor([a.elapsed_time(z)], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t)
+        return max_over_ranks(a.elapsed_time(z))
 
-    flush.zero_()
-    timed_ms(g_warm)
-    timed_ms(g_timed)                                       # untimed pass: graph upload
-    ms_step = timed_ms(g_timed) / k_timed
-    ms_best = min(ms_step, min(timed_ms(g_timed) for _ in range(3)) / k_timed)
-    timed_ms(g_staged, 2)
-    ms_staged = timed_ms(g_staged, 8) / 16
+    b2b_ms()                                                # untimed pass: graph upload
+    ms_b2b = b2b_ms() / (k_timed + k_timed % 2)
+    fence_ranks()
 
     def e2e_step():
         a = h1.to(dev, non_blocking=True).requires_grad_(True)
@@ -544,20 +580,22 @@ def bench_multi(args):
             "config": {"workload": "ntxent_fwd_bwd global 2N=65536 d=128 tau=0.5 row-sharded", "global_batch": b,
                        "parallelism": f"rows/{world}; operands, lse2 and loss statistics pushed over NVLink by the prepare / "
                                       "finalize kernels (symmetric memory), 2 device-side barriers per step",
-                       "l2": f"inputs larger than L2: step i reads input set i mod {n_sets} of this rank "
-                             f"({n_sets} x {set_bytes >> 20} MB embeddings + gradients); the timed steps run back to back "
-                             "between one pair of CUDA events per rank, max over ranks",
-                       "launch": "one CUDA graph per rank holding the timed steps, 5 kernels per step "
-                                 "(simclr_forward_backward_peer: the two cross-GPU barriers run inside the tile kernels), "
-                                 "no collective call inside",
+                       "l2": "flushed before every step (256 MiB memset outside the event pair); one event pair = one CUDA "
+                             "graph of one step, two graphs (the two buffer generations of the symmetric buffers) replayed "
+                             "alternately; per-rank sums, max over ranks",
+                       "launch": "5 kernels per step and rank (simclr_forward_backward_peer: the two cross-GPU barriers run "
+                                 "inside the tile kernels), no collective call inside",
                        "timed_steps": k_timed,
                        "operand_push": "multimem.st (NVLS multicast)" if step.peer.multicast else "per-peer st.global",
                        "scaling_base": "the N=1 line's scaling_base (same 2N=65536 problem on one GPU)"},
             "e2e": {"value": m / (e2e_ms * 1e-3), "unit": "views/s", "h2d_bytes_per_step": 2 * bl * d * 4 * world,
                     "d2h_bytes_per_step": 8 * world, "ms_per_step": e2e_ms},
-            "ms_per_step_best_of_4": ms_best,
+            "ms_per_step_back_to_back": ms_b2b,
+            "back_to_back_protocol": "all K steps in one CUDA graph between one event pair per rank, no flush (inputs "
+                                     "rotate through more than L2): sustained clocks -- these GPUs report sw_power_cap "
+                                     "under continuous load, see `clocks`",
             "ms_per_step_staged": ms_staged,
-            "staged_protocol": "the same step as seven launches (separate barrier kernels), two-step graph replayed 8 times",
+            "staged_protocol": "the same step as seven launches (separate barrier kernels), same timing protocol",
             "gpu_launches": 5 * k_timed * world,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

@@ -75,6 +75,38 @@ for name, fn, ref_fn, use_weight, transport in (
     ok = ok and good
     print(f"[rank {rank}/{world}] {name}: loss {float(loss.detach()):.6f} (oracle {ref.loss:.6f}, rel {lrel:.1e}) "
           f"acc {acc:.3f} (oracle {ref.acc:.3f}) grad err {e1:.1e} {e2:.1e} -> {'OK' if good else 'FAIL'}", flush=True)
+# ---- the fused row-sharded step (PeerStep.step: five launches, cross-GPU barriers inside the tile kernels): four steps
+# over two different global batches, enqueued back to back without any host synchronisation in between ----
+from pytorch_simclr_b200.runner import PeerStep  # noqa: E402
+from pytorch_simclr_b200.functional import LOSS_MODIFIED, LOSS_NTXENT  # noqa: E402
+
+for kind, ref_fn, label in ((LOSS_NTXENT, oracle.ntxent_closed_form, "ntxent"), (LOSS_MODIFIED, oracle.modified_closed_form, "modified")):
+    off, bl = shard_rows(args.b, world, rank)
+    ps = PeerStep(kind, bl, args.d, args.tau, None, True, torch.float32, torch.device("cuda", local))
+    batches = [oracle.make_embeddings(args.b, args.d, seed=40 + s, kind="correlated" if s else "iid", noise=1.0) for s in range(2)]
+    go = torch.tensor([0.25], device="cuda")
+    outs = []
+    for i in range(4):
+        z1, z2 = batches[i % 2]
+        x1, x2 = z1[off:off + bl].cuda(), z2[off:off + bl].cuda()
+        g1, g2 = torch.empty_like(x1), torch.empty_like(x2)
+        ps.step(go, x1, x2, g1, g2)
+        outs.append((x1, x2, g1, g2, ps.stats.clone(), ps.loss.clone()))
+    torch.cuda.synchronize()
+    for i, (x1, x2, g1, g2, st, ls) in enumerate(outs):
+        z1, z2 = batches[i % 2]
+        ref = ref_fn(z1, z2, temperature=args.tau, grad_output=0.25)
+        gmax = max(np.abs(ref.grad1).max(), np.abs(ref.grad2).max())
+        e1 = np.abs(g1.cpu().numpy() - ref.grad1[off:off + bl]).max() / gmax
+        e2 = np.abs(g2.cpu().numpy() - ref.grad2[off:off + bl]).max() / gmax
+        lrel = abs(float(ls) - ref.loss) / abs(ref.loss)
+        acc = 100.0 * float(st[2]) / (2 * args.b)
+        acc_rows = 2.5 if label == "ntxent" else 6.5
+        good = lrel < 2e-3 and e1 < 1e-2 and e2 < 1e-2 and abs(acc - ref.acc) * 2 * args.b / 100.0 <= acc_rows
+        ok = ok and good
+        print(f"[rank {rank}/{world}] {label}/fused step {i}: loss {float(ls):.6f} (oracle {ref.loss:.6f}, rel {lrel:.1e}) "
+              f"acc {acc:.3f} (oracle {ref.acc:.3f}) grad err {e1:.1e} {e2:.1e} -> {'OK' if good else 'FAIL'}", flush=True)
+    del ps
 flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()
