@@ -1,0 +1,70 @@
+"""Read-back of the loss statistics without a stream synchronisation.
+
+The reference API returns the auxiliary-task accuracy as a python float (objective.py:52 / :96), i.e. every call ends
+with a device->host read.  ``tensor.item()`` costs a D2H copy plus a stream synchronisation (~45 us on the bench box);
+here the finalize kernel writes its four statistics straight into pinned, device-mapped host memory and the caller
+polls the last element (written after a system-scope fence) -- the data is there a PCIe write after the kernel ends.
+
+A ring of slots; a slot is reused only after the event recorded behind its previous user has completed.  If polling
+does not see the value within a few milliseconds (e.g. a NaN loss, which is indistinguishable from the sentinel), the
+event is synchronised instead, which is always correct.
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import torch
+
+_SLOTS = 64
+
+
+class _Ring:
+    def __init__(self):
+        self.buf = torch.empty((_SLOTS, 4), dtype=torch.float32).pin_memory()
+        self.np = self.buf.numpy()
+        self.events = [None] * _SLOTS
+        self.next = 0
+
+    def acquire(self):
+        i = self.next
+        self.next = (i + 1) % _SLOTS
+        ev = self.events[i]
+        if ev is not None:
+            ev.synchronize()              # the previous user of the slot has written it (normally long ago)
+        self.np[i, 3] = math.nan          # sentinel: the kernel overwrites it last
+        return i
+
+    def pointer(self, i: int) -> int:
+        return self.buf.data_ptr() + 16 * i          # pinned memory is device-accessible at the same address (UVA)
+
+    def launched(self, i: int) -> None:
+        ev = self.events[i]
+        if ev is None:
+            ev = self.events[i] = torch.cuda.Event()
+        ev.record()
+
+    def wait(self, i: int):
+        row = self.np[i]
+        deadline = None
+        spins = 0
+        while row[3] != row[3]:           # NaN until the kernel's last store lands
+            spins += 1
+            if (spins & 255) == 0:
+                now = time.perf_counter()
+                if deadline is None:
+                    deadline = now + 5e-3
+                elif now > deadline:
+                    self.events[i].synchronize()
+                    break
+        return float(row[0]), float(row[1]), float(row[2]), float(row[3])
+
+
+_ring = None
+
+
+def ring() -> _Ring:
+    global _ring
+    if _ring is None:
+        _ring = _Ring()
+    return _ring

@@ -793,6 +793,8 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
             p.stats[0] = s0;
             p.stats[1] = s1;
             p.stats[2] = s2;
+            // `stats` may be host-mapped memory that the caller polls on element 3 (pytorch_simclr_b200/_hoststats.py)
+            __threadfence_system();
             p.stats[3] = s0 / s1;
             if (p.loss_out) *p.loss_out = s0 / s1;
             for (int r = 0; r < p.stats_peers.world; ++r) {
@@ -950,6 +952,7 @@ SIMCLR_DEVICE void finish_forward_stats(const TileParams& p, int lane) {
         p.stats[0] = s0;
         p.stats[1] = s1;
         p.stats[2] = s2;
+        __threadfence_system();           // host-mapped `stats`: element 3 is what the caller polls on
         p.stats[3] = s0 / s1;
         if (p.loss_out) *p.loss_out = s0 / s1;
     }

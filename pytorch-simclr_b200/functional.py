@@ -10,7 +10,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from . import _lib
+from . import _hoststats, _lib
 from ._lib import DTYPE_BF16, DTYPE_F32, LOSS_MODIFIED, LOSS_NTXENT, PRECISION_BF16, PRECISION_SPLIT, check
 
 __all__ = ["contrastive_forward_backward", "ContrastiveLossFunction", "LOSS_NTXENT", "LOSS_MODIFIED", "pad_rows",
@@ -127,7 +127,7 @@ class _Saved:
 
 def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature: float, normalize: bool,
                 weight: Optional[torch.Tensor], gather=None, prime_backward: bool = False,
-                precision: Optional[int] = None):
+                precision: Optional[int] = None, host_slot: Optional[int] = None):
     """prepare + forward through the C ABI.  ``gather`` (distributed.py) turns the local operand / lse2 into
     their global-batch counterparts and returns (operand_cols, b_global, row_offset, reducer)."""
     lib = _lib.load()
@@ -167,12 +167,18 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
         if prime_backward and gather is None and weight is None:
             bwd_bytes = lib.simclr_backward_workspace_bytes(loss_kind, b, b, d)
             bwd_ws = torch.empty(bwd_bytes, dtype=torch.uint8, device=dev)
+        stats_ptr = stats.data_ptr()
+        if host_slot is not None and gather is None:
+            stats_ptr = _hoststats.ring().pointer(host_slot)
+            stats = _hoststats.ring().buf[host_slot]
         check(lib.simclr_forward_peer(loss_kind, operand.data_ptr(), operand_cols.data_ptr(), b, b_global, row_offset, d,
                                       float(temperature), int(bool(normalize)), precision, rowvec[1].data_ptr(),
                                       _ptr(w_local),
-                                      rowvec[2].data_ptr(), rowvec[3].data_ptr(), stats.data_ptr(), loss.data_ptr(),
+                                      rowvec[2].data_ptr(), rowvec[3].data_ptr(), stats_ptr, loss.data_ptr(),
                                       ws.data_ptr(), ws_bytes, _ptr(bwd_ws), 0 if bwd_ws is None else bwd_ws.numel(), 0, 0,
                                       None, None, None, None, stream), "simclr_forward")
+        if host_slot is not None and gather is None:
+            _hoststats.ring().launched(host_slot)
     saved = _Saved()
     saved.operand_rows, saved.operand_cols = operand, operand_cols
     saved.inv_norm, saved.pos_dot = rowvec[0], rowvec[1]
@@ -192,39 +198,70 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
     return loss, stats, rowvec, saved
 
 
+_FUSED_PLAN = {}      # (loss, b, d, precision) -> byte offsets of the scratch carved out of one allocation
+
+
+def _fused_plan(lib, loss_kind: int, b: int, d: int, precision: int):
+    key = (loss_kind, b, d, precision)
+    plan = _FUSED_PLAN.get(key)
+    if plan is None:
+        bp = pad_rows(b)
+        al = lambda n: (n + 255) // 256 * 256      # noqa: E731
+        op_bytes = lib.simclr_operand_bytes(b, d, precision)
+        if not op_bytes:
+            raise ValueError("unsupported shape / precision (fp32-grade operands need d <= 128)")
+        fwd_bytes = lib.simclr_forward_workspace_bytes(loss_kind, b, b, d)
+        bwd_bytes = lib.simclr_backward_workspace_bytes(loss_kind, b, b, d)
+        off, plan = 0, {}
+        for name, n in (("operand", op_bytes), ("rowvec", 4 * 2 * bp * 4), ("stats", 16), ("fwd", fwd_bytes),
+                        ("bwd", bwd_bytes)):
+            plan[name] = (off, n)
+            off += al(n)
+        plan["total"] = off
+        _FUSED_PLAN[key] = plan
+    return plan
+
+
 def run_fused(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature: float, normalize: bool,
-              grad_out: Optional[torch.Tensor] = None, precision: Optional[int] = None):
+              grad_out: Optional[torch.Tensor] = None, precision: Optional[int] = None, host_slot: Optional[int] = None):
     """The fused five-kernel step through simclr_forward_backward (one GPU, unweighted): returns
-    (loss, stats, grad1, grad2), gradients of grad_out * loss (grad_out: device scalar or None for 1)."""
+    (loss, stats, grad1, grad2), gradients of grad_out * loss (grad_out: device scalar or None for 1).
+    One scratch allocation per call (operand, row vectors, statistics and both workspaces are carved out of it)."""
     lib = _lib.load()
     b, d = _validate(x1, x2)
     x1 = x1.contiguous()
     x2 = x2.contiguous()
     dev = x1.device
-    bp, dp = pad_rows(b), pad_dim(d)
     code = _dtype_code(x1)
     if precision is None:
         precision = resolve_precision(x1, False)
-    planes = 2 if precision == PRECISION_SPLIT else 1
+    plan = _fused_plan(lib, loss_kind, b, d, precision)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream().cuda_stream
-        operand = torch.empty((planes * 2 * bp, dp), dtype=torch.bfloat16, device=dev)
-        rowvec = torch.empty((4, 2 * bp), dtype=torch.float32, device=dev)
-        stats = torch.empty(4, dtype=torch.float32, device=dev)
+        scratch = torch.empty(plan["total"], dtype=torch.uint8, device=dev)
+        base = scratch.data_ptr()
         loss = torch.empty((), dtype=torch.float32, device=dev)
         g1 = torch.empty_like(x1)
         g2 = torch.empty_like(x2)
-        fwd_bytes = lib.simclr_forward_workspace_bytes(loss_kind, b, b, d)
-        bwd_bytes = lib.simclr_backward_workspace_bytes(loss_kind, b, b, d)
-        ws = torch.empty(fwd_bytes + bwd_bytes, dtype=torch.uint8, device=dev)      # both workspaces, 256-byte aligned sizes
         go = None
         if grad_out is not None:
             go = grad_out.to(device=dev, dtype=torch.float32).contiguous()
+        if host_slot is not None:
+            # the statistics go straight to pinned host memory (see _hoststats.py); `stats` is then that host row
+            stats_ptr = _hoststats.ring().pointer(host_slot)
+            stats = _hoststats.ring().buf[host_slot]
+        else:
+            so = plan["stats"][0]
+            stats = scratch[so:so + 16].view(torch.float32)
+            stats_ptr = base + so
         check(lib.simclr_forward_backward(loss_kind, x1.data_ptr(), x2.data_ptr(), b, d, code, int(bool(normalize)),
-                                          float(temperature), precision, _ptr(go), operand.data_ptr(), rowvec.data_ptr(),
-                                          stats.data_ptr(), loss.data_ptr(), g1.data_ptr(), g2.data_ptr(), ws.data_ptr(),
-                                          fwd_bytes, ws.data_ptr() + fwd_bytes, bwd_bytes, stream),
+                                          float(temperature), precision, _ptr(go), base + plan["operand"][0],
+                                          base + plan["rowvec"][0], stats_ptr, loss.data_ptr(), g1.data_ptr(),
+                                          g2.data_ptr(), base + plan["fwd"][0], plan["fwd"][1], base + plan["bwd"][0],
+                                          plan["bwd"][1], stream),
               "simclr_forward_backward")
+        if host_slot is not None:
+            _hoststats.ring().launched(host_slot)
     return loss, stats, g1, g2
 
 
@@ -268,7 +305,7 @@ class ContrastiveLossFunction(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x1, x2, loss_kind, temperature, normalize, weight, gather):
+    def forward(ctx, x1, x2, loss_kind, temperature, normalize, weight, gather, host_slot=None):
         if getattr(gather, "peer", False):
             from .distributed import run_forward_peer
             loss, stats, _rowvec, saved = run_forward_peer(loss_kind, x1, x2, temperature, normalize, gather,
@@ -277,11 +314,12 @@ class ContrastiveLossFunction(torch.autograd.Function):
             want_grad = any(ctx.needs_input_grad[:2])
             if want_grad and _EAGER_BACKWARD and gather is None and weight is None:
                 # fused step now, unit upstream gradient; backward() scales
-                loss, stats, g1, g2 = run_fused(loss_kind, x1, x2, temperature, normalize)
+                loss, stats, g1, g2 = run_fused(loss_kind, x1, x2, temperature, normalize, host_slot=host_slot)
                 ctx.eager_grads = (g1, g2)
                 ctx.mark_non_differentiable(stats)
                 return loss, stats
-            loss, stats, _rowvec, saved = run_forward(loss_kind, x1, x2, temperature, normalize, weight, gather, want_grad)
+            loss, stats, _rowvec, saved = run_forward(loss_kind, x1, x2, temperature, normalize, weight, gather, want_grad,
+                                                      host_slot=host_slot if weight is None else None)
         ctx.eager_grads = None
         ctx.saved_state = saved
         ctx.save_for_backward(x1, x2)
@@ -293,10 +331,10 @@ class ContrastiveLossFunction(torch.autograd.Function):
         if ctx.eager_grads is not None:
             g1, g2 = ctx.eager_grads
             scale = grad_loss.to(g1.dtype)
-            return g1 * scale, g2 * scale, None, None, None, None, None
+            return g1 * scale, g2 * scale, None, None, None, None, None, None
         x1, x2 = ctx.saved_tensors
         g1, g2 = run_backward(ctx.saved_state, x1.contiguous(), x2.contiguous(), grad_loss)
-        return g1, g2, None, None, None, None, None
+        return g1, g2, None, None, None, None, None, None
 
 
 def contrastive_forward_backward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature: float,

@@ -11,8 +11,11 @@ The arithmetic runs in the sm_100a extension; CPU tensors raise ``ValueError``.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
+from . import _hoststats
 from .functional import LOSS_MODIFIED, LOSS_NTXENT, ContrastiveLossFunction
 
 __all__ = ["contrastive_loss", "modified_contrastive_loss"]
@@ -23,18 +26,33 @@ def _as_supported(x: torch.Tensor) -> torch.Tensor:
     return x if x.dtype in (torch.float32, torch.bfloat16) else x.float()
 
 
+# SIMCLR_B200_HOST_STATS=0 falls back to tensor.item() for the accuracy read-back (measurement / debugging)
+_HOST_STATS = os.environ.get("SIMCLR_B200_HOST_STATS", "1") != "0"
+
+
+def _loss_and_accuracy(x1, x2, kind, temperature, normalize, weight):
+    """(loss tensor, accuracy float).  The accuracy forces a device->host read (reference objective.py:52 / :96); for the
+    unweighted losses the finalize kernel writes the statistics into pinned host memory and this thread polls it
+    (_hoststats.py) instead of paying a stream synchronisation."""
+    if weight is None and x1.is_cuda and _HOST_STATS:
+        ring = _hoststats.ring()
+        slot = ring.acquire()
+        loss, _stats = ContrastiveLossFunction.apply(x1, x2, kind, temperature, normalize, None, None, slot)
+        correct = ring.wait(slot)[2]
+    else:
+        loss, stats = ContrastiveLossFunction.apply(x1, x2, kind, temperature, normalize, weight, None)
+        correct = stats[2].item()
+    return loss, 100.0 * correct / (2 * x1.shape[0])
+
+
 def contrastive_loss(x_batch1, x_batch2, temperature=1.0, normalize=True, weight=None):
     """NT-Xent loss and auxiliary-task top-1 accuracy (reference objective.py:6-55)."""
     x1, x2 = _as_supported(x_batch1), _as_supported(x_batch2)
-    loss, stats = ContrastiveLossFunction.apply(x1, x2, LOSS_NTXENT, float(temperature), bool(normalize), weight, None)
-    correct = stats[2].item()                    # host sync, as reference objective.py:52
-    return loss, 100.0 * correct / (2 * x1.shape[0])
+    return _loss_and_accuracy(x1, x2, LOSS_NTXENT, float(temperature), bool(normalize), weight)
 
 
 def modified_contrastive_loss(x_batch1, x_batch2, **kwargs):
     """Probabilistic ("--new_loss" / --modified_loss) variant (reference objective.py:58-98)."""
     temperature = kwargs.get("temperature", 1.0)   # objective.py:68: every other kwarg is ignored
     x1, x2 = _as_supported(x_batch1), _as_supported(x_batch2)
-    loss, stats = ContrastiveLossFunction.apply(x1, x2, LOSS_MODIFIED, float(temperature), True, None, None)
-    correct = stats[2].item()                    # host sync, as reference objective.py:96
-    return loss, 100.0 * correct / (2 * x1.shape[0])
+    return _loss_and_accuracy(x1, x2, LOSS_MODIFIED, float(temperature), True, None)
