@@ -119,6 +119,8 @@ struct TileParams {
     float acc_scale;   // backward finalize: 1/sqrt(k2) undoes the operand factor in dacc = W * operand (modified: 1)
     float m2;          // constant log2-domain shift of the one-exp backward form
     int const_shift;   // backward: 1 -> one exp per element (bounded scores), 0 -> general two-exp form
+    int pow;           // modified loss: 1 / 2 when 1/tau is exactly 1 / 2 (exp(A) = (B P)^(1/tau) is then a plain power: no
+                       // transcendental at all), else 0
     float qscale;      // modified loss: (float) b_glob, the factor inside the clamp
     float inv_tau;
     int d;             // true embedding dimension (<= D)
@@ -392,6 +394,8 @@ struct Hot {
     float k2, m2, qscale;
     int bg_pad, b_glob;
     bool const_shift;
+    int pow;           // TileParams::pow
+    float qc, clampc;  // modified backward, power path: qscale * 2^-m2 and 1e-4 * 2^-m2 (pow 2);  2^-m2 in qc for pow 1
 };
 
 template <int kLoss>
@@ -416,8 +420,17 @@ SIMCLR_DEVICE void fwd_chunk_fast(const Hot& h, const uint32_t (&r)[kChunk], flo
     float c2 = fmaxf(v[0], v[1]);
 #pragma unroll
     for (int i = 2; i < kChunk; i += 2) c2 = fmaxf(c2, fmaxf(v[i], v[i + 1]));     // FMNMX3
-    if constexpr (kConst) {
-        static_assert(kLoss == kNtXent, "constant shift is an NT-Xent fast path");
+    if constexpr (kConst && kLoss == kModified) {
+        // power path (1/tau = 1 or 2): exp(A) = v or v * v, no transcendental; bounded sums, no running maximum
+        cm = fmaxf(cm, c2);
+        const bool square = h.pow == 2;
+#pragma unroll
+        for (int i = 0; i < kChunk; i += 4) {
+            const f32x2 v01 = pack2(v[i + 0], v[i + 1]), v23 = pack2(v[i + 2], v[i + 3]);
+            st.acc01 = add2(st.acc01, square ? mul2(v01, v01) : v01);
+            st.acc23 = add2(st.acc23, square ? mul2(v23, v23) : v23);
+        }
+    } else if constexpr (kConst) {
         cm = fmaxf(cm, c2);
         if constexpr (SIMCLR_PACKED && kPoly && SIMCLR_POLY_MASK == 3) {
             // eight columns per round: MUFU exponentials, the last pair(s) on the FMA pipe, four packed additions
@@ -493,7 +506,24 @@ SIMCLR_DEVICE void fwd_chunk_special(const Hot& h, const uint32_t (&r)[kChunk], 
     st.max_prec = fmaxf(st.max_prec, cp);
     st.max_foll = fmaxf(st.max_foll, cf);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    if constexpr (kConst) {
+    if constexpr (kConst && kLoss == kModified) {
+        // power path: masked elements (kNegBig) contribute nothing
+        const bool square = h.pow == 2;
+#pragma unroll
+        for (int i = 0; i < kChunk; i += 4) {
+            float e[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float x = v[i + u];
+                e[u] = (x == kNegBig) ? 0.f : (square ? x * x : x);
+            }
+            a0 += e[0];
+            a1 += e[1];
+            a2 += e[2];
+            a3 += e[3];
+        }
+        st.sum += (a0 + a1) + (a2 + a3);
+    } else if constexpr (kConst) {
         // exp2(-3e38) = 0: masked elements drop out by themselves
 #pragma unroll
         for (int i = 0; i < kChunk; i += 4) {
@@ -534,6 +564,34 @@ template <int kLoss, bool kConst, bool kSpecial, bool kSplit = false>
 SIMCLR_DEVICE void bwd_chunk(const Hot& h, const uint32_t (&r)[kChunk], uint32_t cv_addr, int cq, const RowCtx& rc,
                              const BwdRow& br, uint32_t (&w)[kChunk / 2], uint32_t (&wlo)[kChunk / 2]) {
     const int i_diag = rc.diag_col - cq, i_pos = rc.pos_col - cq;
+    if (kLoss == kModified && kConst && !kSplit && h.pow != 0) {
+        // Power path of the modified loss (1/tau = 1 or 2): e^A / P = B (B P)^(1/tau - 1) is 1 or B P itself, so
+        // W = t (a_r + a_c) with t = [B P >= 1e-4] * (B P or 1) * 2^-m2 -- no transcendental (warp-uniform branch).
+        const f32x2 row_a2 = pack2(br.row_a, br.row_a);
+        const f32x2 qc2 = pack2(h.qc, h.qc);
+        const bool square = h.pow == 2;
+        const float thr = square ? h.clampc : kClampMin;
+        const f32x2 sc2 = square ? qc2 : pack2(h.qscale, h.qscale);
+#pragma unroll
+        for (int i = 0; i < kChunk; i += 4) {
+            const float4 ac = lds_f4(cv_addr + i * 4);
+            float q0, q1, q2, q3;
+            unpack2(mul2(pack2(__uint_as_float(r[i + 0]), __uint_as_float(r[i + 1])), sc2), q0, q1);
+            unpack2(mul2(pack2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), sc2), q2, q3);
+            const float t0 = (q0 >= thr) ? (square ? q0 : h.qc) : 0.f, t1 = (q1 >= thr) ? (square ? q1 : h.qc) : 0.f;
+            const float t2 = (q2 >= thr) ? (square ? q2 : h.qc) : 0.f, t3 = (q3 >= thr) ? (square ? q3 : h.qc) : 0.f;
+            float wv[4];
+            unpack2(mul2(pack2(t0, t1), add2(pack2(ac.x, ac.y), row_a2)), wv[0], wv[1]);
+            unpack2(mul2(pack2(t2, t3), add2(pack2(ac.z, ac.w), row_a2)), wv[2], wv[3]);
+            if constexpr (kSpecial) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) wv[u] = ((i + u == i_diag) | (i + u == i_pos)) ? 0.f : wv[u];
+            }
+            w[(i >> 1) + 0] = pack_bf16x2(wv[0], wv[1]);
+            w[(i >> 1) + 1] = pack_bf16x2(wv[2], wv[3]);
+        }
+        return;
+    }
     if constexpr (SIMCLR_PACKED && kLoss == kNtXent && kConst && !kSplit && SIMCLR_POLY_MASK == 3) {
         // W = exp2(S') * (a_r + a_c) with packed additions / multiplications; eight columns per round
         const f32x2 row_a2 = pack2(br.row_a, br.row_a);
@@ -1393,6 +1451,12 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         h.bg_pad = p.bg_pad;
         h.b_glob = p.b_glob;
         h.const_shift = kConst;
+        h.pow = p.pow;
+        {
+            const float c0 = exp2f(-p.m2);
+            h.qc = p.pow == 2 ? p.qscale * c0 : c0;
+            h.clampc = kClampMin * c0;
+        }
         const int b_loc = p.b_loc, row_off = p.row_off;
         const bool tracing = p.trace != nullptr && static_cast<int>(blockIdx.x) == p.trace_cta && quarter == 0 && lane == 0;
         constexpr int kLogS = S == 2 ? 1 : (S == 4 ? 2 : 3);
@@ -1421,7 +1485,8 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             const bool warp_rows_ok = img_lo + 31 < b_loc;
             const int g_lo = row_off + img_lo, g_hi = g_lo + 31;
             FwdState fs;
-            if (!kBackward && kConst) fs.run_max = kConstShiftRaw;
+            // constant-shift forward: the "running maximum" is the fixed raw value whose logit is 0
+            if (!kBackward && kConst) fs.run_max = (kLoss == kNtXent) ? kConstShiftRaw : 1.0f;
             BwdRow br;
             br.row_a = 0.f;
             br.row_l2 = 0.f;
