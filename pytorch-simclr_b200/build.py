@@ -17,6 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsimclr_b200.so")
+TRACE_LIB_PATH = os.path.join(LIB_DIR, "libsimclr_b200_trace.so")      # the same library with the debug stamps compiled in
 STAMP = LIB_PATH + ".stamp"
 SOURCES = ["capi.cu"]
 DEPS = ["capi.cu", "contrastive_kernels.cuh", "aux_kernels.cuh", "selftest.cuh", "probes.cuh", "sm100_ptx.cuh", "row_math.cuh",
@@ -49,11 +50,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.isfile(LIB_PATH) and os.path.isfile(STAMP) and open(STAMP).read().strip() == digest:
         return LIB_PATH
     cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    # the tracing variant for tools/trace_timeline.py and tools/cta_timeline.py, built alongside
+    trace_cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")] + ["-DSIMCLR_TRACE=1", "-o", TRACE_LIB_PATH] + \
+                [os.path.join(CSRC, s) for s in SOURCES]
+    trace_proc = subprocess.Popen(trace_cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     proc = subprocess.run(cmd, capture_output=True, text=True)
+    trace_out, _ = trace_proc.communicate()
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed building libsimclr_b200.so")
+    if trace_proc.returncode != 0:
+        sys.stderr.write(trace_out)
+        raise RuntimeError("nvcc failed building libsimclr_b200_trace.so")
     with open(os.path.join(LIB_DIR, "ptxas.log"), "w") as f:
         f.write(proc.stdout + proc.stderr)
     with open(STAMP, "w") as f:

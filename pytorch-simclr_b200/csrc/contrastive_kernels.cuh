@@ -218,9 +218,18 @@ SIMCLR_DEVICE void peer_sync_thread(const PeerTable& flags, const unsigned int* 
 // 2 + wg softmax warpgroup wg (lane 0 of its quarter-0 warp).
 constexpr int kTraceIters = 64;
 constexpr int kTraceRoles = 2 + 4;
+// Per-role / per-CTA debug stamps of the tile kernels (tools/trace_timeline.py, tools/cta_timeline.py).  Compiled OUT of
+// the product library: the predicated stamp code (constant loads, CTA-id compares) sits in the single-thread producer /
+// issuer loops whose per-hop latency bounds the pipeline -- measured 67.0 -> 64.0 us per step without it
+// (profiles/r01b_notes.md).  build.py builds lib/libsimclr_b200_trace.so with -DSIMCLR_TRACE=1 for the tools.
+#ifndef SIMCLR_TRACE
+#define SIMCLR_TRACE 0
+#endif
 SIMCLR_DEVICE void trace_event(const TileParams& p, int role, int it, int k) {
+#if SIMCLR_TRACE
     if (p.trace != nullptr && static_cast<int>(blockIdx.x) == p.trace_cta && it < kTraceIters)
         p.trace[(role * kTraceIters + it) * 4 + k] = clock64();
+#endif
 }
 
 // kPrec = 0: bf16 operands.  kPrec = 1 ("split", fp32-grade): every operand row is stored as hi = bf16(x) and
@@ -1019,7 +1028,9 @@ SIMCLR_DEVICE void finish_forward_stats(const TileParams& p, int lane) {
 // Debug: per-CTA %globaltimer stamps, ktrace[64 + cta*8 + k]  (k: 0 start, 1/3 segment 0/1 tiles done,
 // 2/4 segment 0/1 finalize done, 5 end).
 SIMCLR_DEVICE void cta_stamp(const TileParams& p, int k) {
+#if SIMCLR_TRACE
     if (p.ktrace != nullptr) p.ktrace[64 + blockIdx.x * 8 + k] = global_timer_ns();
+#endif
 }
 
 // Walks a CTA's contiguous tile range without per-tile 64-bit divisions.
@@ -1150,10 +1161,12 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                             (warp == kProducerWarp || (warp >= kScoreWarp0 && warp < kScoreWarp0 + kNumIssuers));
     if (!runs_ahead) pdl_wait();
     ktrace_begin(p.ktrace, kBackward ? 3 : 1);
+#if SIMCLR_TRACE
     if (threadIdx.x == 0) {
         cta_stamp(p, 0);
         if (p.ktrace != nullptr) p.ktrace[64 + blockIdx.x * 8 + 6] = clock64();
     }
+#endif
 
     if (warp == kProducerWarp) {
         // ================================ TMA producer ================================
@@ -1458,7 +1471,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             h.clampc = kClampMin * c0;
         }
         const int b_loc = p.b_loc, row_off = p.row_off;
-        const bool tracing = p.trace != nullptr && static_cast<int>(blockIdx.x) == p.trace_cta && quarter == 0 && lane == 0;
+        const bool tracing = SIMCLR_TRACE && p.trace != nullptr && static_cast<int>(blockIdx.x) == p.trace_cta && quarter == 0 && lane == 0;
         constexpr int kLogS = S == 2 ? 1 : (S == 4 ? 2 : 3);
         static_assert((1 << kLogS) == S, "ring size must be 2, 4 or 8");
 
@@ -1725,10 +1738,12 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
     tc_fence_before_sync();
     __syncthreads();
     ktrace_end(p.ktrace, kBackward ? 3 : 1);
+#if SIMCLR_TRACE
     if (threadIdx.x == 0) {
         cta_stamp(p, 5);
         if (p.ktrace != nullptr) p.ktrace[64 + blockIdx.x * 8 + 7] = clock64();
     }
+#endif
     if (warp == kAllocWarp) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, kTmemCols);

@@ -4,6 +4,9 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+# the stamps are compiled out of the product library: use the tracing build (pytorch-simclr_b200/build.py makes both)
+os.environ.setdefault("SIMCLR_B200_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                      "pytorch-simclr_b200", "lib", "libsimclr_b200_trace.so"))
 import torch  # noqa: E402
 
 from pytorch_simclr_b200 import _lib  # noqa: E402
