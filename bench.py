@@ -43,7 +43,7 @@ L2_FLUSH_BYTES = 256 << 20
 N_INPUT_SETS = 48        # 48 x (2 x 4096 x 128 fp32) = 192 MB of inputs > 126 MB L2
 KERNEL_CHAIN = 20        # launches of one kernel per event pair in the per-kernel timing
 STAGE_FWD_TILE, STAGE_BWD_TILE = 2, 8
-NCU_DRAM_BYTES_BWD_TILE = 6416384     # ncu --set full, backward tile kernel, per launch (profiles/r01b_ncu_full_tile_kernels.csv)
+NCU_DRAM_BYTES_BWD_TILE = 6418688     # ncu --set full, backward tile kernel, per launch (profiles/r01c_ncu_full_tile_kernels.csv)
 
 
 def algorithmic_flops(m, d):
@@ -392,7 +392,7 @@ def bench_single(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_BWD_TILE,
-                     "traffic_source": "profiles/r01b_ncu_full_tile_kernels.csv (dram__bytes_read.sum + dram__bytes_write.sum"
+                     "traffic_source": "profiles/r01c_ncu_full_tile_kernels.csv (dram__bytes_read.sum + dram__bytes_write.sum"
                                        " of one launch; algorithmic minimum 2 MB operand read: the rest is dacc/colvec"
                                        " first touch, everything else is L2 resident)",
                      "kernel": "contrastive_tile_kernel<128,0,true> (backward)",
