@@ -63,9 +63,15 @@ constexpr int kScoreWarp0 = kNumSoftmaxWarps + 1;       // warps 17, 18
 constexpr int kAllocWarp = kScoreWarp0 + 1;             // warp 18 allocates TMEM before it starts issuing
 constexpr int kGradWarp0 = kScoreWarp0 + kNumIssuers;   // warps 19, 20 (backward)
 constexpr int kThreadsForward = 32 * (kNumSoftmaxWarps + 4);                    // 640 (warp 19 idles)
-constexpr int kFlushWarp0 = kGradWarp0 + kNumIssuers - 1;   // warps 20..23: TMEM lane quarters 0..3
-constexpr int kFlushIssueWarp = kFlushWarp0 + 1;            // warp 21 issues the TMA reductions
-constexpr int kThreadsBackward = 32 * (kFlushWarp0 + 4);    // 768 (registers are allocated in units of four warps anyway)
+// One gradient issuer (warp 20) doubles as a flush warp; sharing BOTH (23 warps, 736 threads) compiles and runs but buys
+// no registers: ptxas allocates per warp in units of 512, so 80 registers per thread is the limit down to 22 warps and
+// 96 needs <= 21 warps (which would take the score issuers off the tensor pipe during a flush).
+#ifndef SIMCLR_BWD_SHARED_FLUSH_WARPS
+#define SIMCLR_BWD_SHARED_FLUSH_WARPS 1
+#endif
+constexpr int kFlushWarp0 = kGradWarp0 + kNumIssuers - SIMCLR_BWD_SHARED_FLUSH_WARPS;   // warps 20..23: TMEM lane quarters 0..3
+constexpr int kFlushIssueWarp = kFlushWarp0 + 2;            // a flush warp that is not a gradient issuer issues the TMA reductions
+constexpr int kThreadsBackward = 32 * (kFlushWarp0 + 4);    // 768
 constexpr int kFlushBar = 4;                                // named barrier of the flush warpgroup
 constexpr int kMaxScoreBufs = 4;
 constexpr int kNumPairs = kNumSoftmaxWG / 2;             // a tile is shared by a pair of warpgroups
