@@ -67,3 +67,54 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.SimclrLibraryError, match="no CPU or eager fallback"):
         _lib.load()
+
+
+def test_fused_call_scratch_plan_is_aligned_and_sized_by_the_library():
+    """functional._fused_plan carves operand, row vectors, statistics and both workspaces out of one allocation."""
+    from pytorch_simclr_b200 import _lib
+    lib = _lib.load()
+    for kind, b, d, prec in ((0, 4096, 128, _lib.PRECISION_BF16), (1, 300, 100, _lib.PRECISION_SPLIT), (0, 777, 256, _lib.PRECISION_BF16)):
+        plan = F._fused_plan(lib, kind, b, d, prec)
+        names = ["operand", "rowvec", "stats", "fwd", "bwd"]
+        end = 0
+        for n in names:
+            off, size = plan[n]
+            assert off % 256 == 0 and off >= end and size > 0
+            end = off + size
+        assert plan["total"] >= end
+        assert plan["operand"][1] == lib.simclr_operand_bytes(b, d, prec)
+        assert plan["fwd"][1] == lib.simclr_forward_workspace_bytes(kind, b, b, d)
+        assert plan["bwd"][1] == lib.simclr_backward_workspace_bytes(kind, b, b, d)
+        assert plan["rowvec"][1] == 4 * 2 * F.pad_rows(b) * 4
+    with pytest.raises(ValueError):
+        F._fused_plan(lib, 0, 64, 256, _lib.PRECISION_SPLIT)          # split operands need d <= 128
+
+
+def test_eager_backward_and_precision_switches():
+    assert sb.get_eager_backward() is True
+    sb.set_eager_backward(False)
+    assert sb.get_eager_backward() is False
+    sb.set_eager_backward(True)
+    with pytest.raises(ValueError):
+        sb.set_precision("fp8")
+    x = torch.zeros(4, 128)
+    assert F.resolve_precision(x, False, "bf16") == 0 and F.resolve_precision(x, False, "fp32") == 1
+    assert F.resolve_precision(x, True, "auto") == 0                   # the sharded batch runs bf16 operands
+    with pytest.raises(ValueError):
+        F.resolve_precision(torch.zeros(4, 200), False, "fp32")
+
+
+def test_fused_entry_points_reject_bad_arguments_without_a_gpu():
+    """simclr_forward_backward / _peer validate before they touch the device."""
+    import ctypes
+    from pytorch_simclr_b200 import _lib
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(1 << 12)
+    p = (ctypes.addressof(buf) + 255) & ~255
+    assert lib.simclr_forward_backward(0, p, p, 4, 8, 0, 1, 0.5, 0, None, p, None, p, None, p, p, p, 1 << 20, p, 1 << 20, None) == -1
+    assert lib.simclr_forward_backward(0, p, p, 0, 8, 0, 1, 0.5, 0, None, p, p, p, None, p, p, p, 1 << 20, p, 1 << 20, None) == -2
+    arr = (ctypes.c_void_p * 2)(p, p)
+    assert lib.simclr_forward_backward_peer(0, p, p, 4, 8, 0, 1, 0.5, None, p, p, p, p, None, p, p, p, 1 << 20, p, 1 << 20, 2, 5,
+                                            arr, None, arr, arr, arr, p, None) == -12      # rank outside the world
+    assert lib.simclr_forward_backward_peer(0, p, p, 4, 8, 0, 1, 0.5, None, p, p, p, p, None, p, p, p, 1 << 20, p, 1 << 20, 2, 0,
+                                            None, None, arr, arr, arr, p, None) == -1
