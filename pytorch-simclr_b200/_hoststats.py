@@ -23,6 +23,7 @@ class _Ring:
     def __init__(self):
         self.buf = torch.empty((_SLOTS, 4), dtype=torch.float32).pin_memory()
         self.np = self.buf.numpy()
+        self.base = self.buf.data_ptr()
         self.events = [None] * _SLOTS
         self.next = 0
 
@@ -30,13 +31,13 @@ class _Ring:
         i = self.next
         self.next = (i + 1) % _SLOTS
         ev = self.events[i]
-        if ev is not None:
+        if ev is not None and not ev.query():
             ev.synchronize()              # the previous user of the slot has written it (normally long ago)
         self.np[i, 3] = math.nan          # sentinel: the kernel overwrites it last
         return i
 
     def pointer(self, i: int) -> int:
-        return self.buf.data_ptr() + 16 * i          # pinned memory is device-accessible at the same address (UVA)
+        return self.base + 16 * i                    # pinned memory is device-accessible at the same address (UVA)
 
     def launched(self, i: int) -> None:
         ev = self.events[i]

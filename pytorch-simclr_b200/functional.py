@@ -68,6 +68,26 @@ def resolve_precision(x: torch.Tensor, distributed: bool = False, mode: Optional
     return PRECISION_SPLIT if (x.dtype == torch.float32 and fits and not distributed) else PRECISION_BF16
 
 
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _device_guard(dev: torch.device):
+    """torch.cuda.device(dev) only when dev is not already the current device (the context manager costs microseconds
+    on a path whose whole host side is a few tens of them)."""
+    idx = dev.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(dev)
+
+
 def pad_rows(b: int) -> int:
     return (b + BLOCK - 1) // BLOCK * BLOCK
 
@@ -140,7 +160,7 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
     if precision is None:
         precision = resolve_precision(x1, gather is not None)
     planes = 2 if precision == PRECISION_SPLIT else 1
-    with torch.cuda.device(dev):
+    with _device_guard(dev):
         stream = torch.cuda.current_stream().cuda_stream
         operand = torch.empty((planes * 2 * bp, dp), dtype=torch.bfloat16, device=dev)
         rowvec = torch.empty((4, 2 * bp), dtype=torch.float32, device=dev)   # inv_norm, pos_dot, lse2, row_loss
@@ -236,7 +256,7 @@ def run_fused(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature: f
     if precision is None:
         precision = resolve_precision(x1, False)
     plan = _fused_plan(lib, loss_kind, b, d, precision)
-    with torch.cuda.device(dev):
+    with _device_guard(dev):
         stream = torch.cuda.current_stream().cuda_stream
         scratch = torch.empty(plan["total"], dtype=torch.uint8, device=dev)
         base = scratch.data_ptr()
@@ -272,7 +292,7 @@ def run_backward(saved: "_Saved", x1: torch.Tensor, x2: torch.Tensor, grad_out: 
     if peer is not None and peer.generation - saved.generation >= peer.GENERATIONS:
         raise RuntimeError("the peer-memory buffers of this forward have been reused: call backward before the "
                            f"{peer.GENERATIONS}nd following global forward (or use transport='nccl')")
-    with torch.cuda.device(dev):
+    with _device_guard(dev):
         stream = torch.cuda.current_stream().cuda_stream
         g1 = torch.empty_like(x1)
         g2 = torch.empty_like(x2)
@@ -330,8 +350,8 @@ class ContrastiveLossFunction(torch.autograd.Function):
     def backward(ctx, grad_loss, _grad_stats):
         if ctx.eager_grads is not None:
             g1, g2 = ctx.eager_grads
-            scale = grad_loss.to(g1.dtype)
-            return g1 * scale, g2 * scale, None, None, None, None, None, None
+            s1, s2 = torch._foreach_mul((g1, g2), grad_loss.to(g1.dtype))      # one launch for both (kept grads stay intact)
+            return s1, s2, None, None, None, None, None, None
         x1, x2 = ctx.saved_tensors
         g1, g2 = run_backward(ctx.saved_state, x1.contiguous(), x2.contiguous(), grad_loss)
         return g1, g2, None, None, None, None, None, None
