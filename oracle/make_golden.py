@@ -99,6 +99,19 @@ def main():
                         normalize=True, weight=np.zeros(0), grad_output=1.0, loss=loss, acc=acc, grad1=g1, grad2=g2,
                         bf16=False)
     print(f"ntxent_ties: loss={loss:.6f} acc={acc:.3f}")
+    # exact ties INSIDE the positive's 128-column tile, earlier and later than the positive (two image blocks, so that the
+    # sm_100a kernels see the tie in an ordinary chunk of a masked tile): view-2 row 130 duplicates row 200 (the
+    # duplicate precedes the positive of row 200 -> the reference's first-argmax picks it), row 250 duplicates row 140
+    # (the duplicate follows the positive of row 140 -> the positive wins)
+    z1, z2 = make_embeddings(256, 128, seed=77, kind="correlated", noise=0.05)
+    z2 = z2.clone()
+    z2[130] = z2[200]
+    z2[250] = z2[140]
+    loss, acc, g1, g2 = _run(ref.contrastive_loss, z1, z2, 1.0, temperature=0.5, normalize=True)
+    np.savez_compressed(os.path.join(OUT, "ntxent_ties_b256_d128_same_tile.npz"), z1=z1.numpy(), z2=z2.numpy(),
+                        temperature=0.5, normalize=True, weight=np.zeros(0), grad_output=1.0, loss=loss, acc=acc, grad1=g1,
+                        grad2=g2, bf16=False)
+    print(f"ntxent_ties_same_tile: loss={loss:.6f} acc={acc:.3f}")
 
     for i, (name, n, d, tau, kind, noise, go, bf16) in enumerate(MODIFIED_CASES):
         z1, z2 = make_embeddings(n, d, seed=300 + i, kind=kind, noise=noise, bf16_representable=bf16)
