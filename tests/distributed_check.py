@@ -1,7 +1,7 @@
 """Row-sharded global-batch check, launched with torchrun (one process per GPU, NCCL):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
-        tools/distributed_check.py [--batch 2048] [--dim 128]
+        tests/distributed_check.py [--batch 2048] [--dim 128]
 
 Every rank compares the global loss / accuracy and its local gradients with the single-process fp64 oracle
 evaluated on the gathered batch (test infrastructure: imports oracle/)."""

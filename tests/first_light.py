@@ -1,8 +1,8 @@
 """GPU bring-up diagnostics (run on the B200 box through gpurun).  Each stage runs in its own process so a
 trapped kernel cannot poison the next stage.  Everything is logged to gpurun_out/first_light.log.
 
-    python tools/first_light.py            # all stages
-    python tools/first_light.py STAGE ...  # selected stages
+    python tests/first_light.py            # all stages
+    python tests/first_light.py STAGE ...  # selected stages
 """
 import os
 import subprocess

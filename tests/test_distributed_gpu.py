@@ -24,6 +24,6 @@ def test_global_batch_matches_single_process_oracle(world):
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(REPO, "tools", "distributed_check.py"), "--batch", "2048", "--dim", "128"]
+           os.path.join(REPO, "tests", "distributed_check.py"), "--batch", "2048", "--dim", "128"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
