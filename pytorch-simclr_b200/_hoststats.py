@@ -12,6 +12,7 @@ event is synchronised instead, which is always correct.
 from __future__ import annotations
 
 import math
+import threading
 import time
 
 import torch
@@ -26,10 +27,12 @@ class _Ring:
         self.base = self.buf.data_ptr()
         self.events = [None] * _SLOTS
         self.next = 0
+        self.lock = threading.Lock()      # slot hand-out only; a slot is used by the thread that acquired it
 
     def acquire(self):
-        i = self.next
-        self.next = (i + 1) % _SLOTS
+        with self.lock:
+            i = self.next
+            self.next = (i + 1) % _SLOTS
         ev = self.events[i]
         if ev is not None and not ev.query():
             ev.synchronize()              # the previous user of the slot has written it (normally long ago)
