@@ -1160,7 +1160,14 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const uint32_t tmem_base = *tmem_ptr_smem;
+    // Every role re-reads the TMEM base address from shared memory through an opaque load: the value is then local to the
+    // role's branch instead of being live (and, in the 80-register backward build, spilled to local memory) across the
+    // role split -- the issuers' per-tile path no longer starts with a local-memory load.
+    auto load_tmem_base = [&]() {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_base + L::kOffTmemPtr) : "memory");
+        return v;
+    };
     // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the predecessor's tail
     // (early_operand: the producer waits later, after its first operand loads; the score issuers touch no global memory)
     const bool runs_ahead = kBackward && p.early_operand != 0 &&
@@ -1258,6 +1265,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         // S[buf] = A * B_stage^T (both operands K-major).  The whole warp walks the loop and waits on the
         // barriers; one elected lane issues the tcgen05 ops (operands stay in uniform registers).
         const int me = warp - kScoreWarp0;
+        const uint32_t tmem_base = load_tmem_base();
         const uint32_t a_addr = sa_addr;
         const uint32_t b_addr0 = sb_addr;
         RingPos<S> ring;
@@ -1328,6 +1336,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         // mutual ordering.
         const bool issuer = warp < kGradWarp0 + kNumIssuers;
         const bool flusher = warp >= kFlushWarp0;
+        const uint32_t tmem_base = load_tmem_base();
         const int me = warp - kGradWarp0;
         const int quarter = warp & 3;
         const int row_in_block = quarter * 32 + lane;
@@ -1454,6 +1463,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         }
     } else if (warp < kNumSoftmaxWarps) {
         // ================================ softmax warpgroups ================================
+        const uint32_t tmem_base = load_tmem_base();
         const int wg = (warp - kSoftmaxWarp0) >> 2;          // 0 .. kNumSoftmaxWG-1
         const int pair = wg >> 1;                             // which tiles (it % 2)
         const int half = wg & 1;                              // which 64 columns of the tile
@@ -1752,7 +1762,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
 #endif
     if (warp == kAllocWarp) {
         tc_fence_after_sync();
-        tmem_dealloc(tmem_base, kTmemCols);
+        tmem_dealloc(load_tmem_base(), kTmemCols);
     }
 }
 
