@@ -125,7 +125,7 @@ def time_loss_only(loss_fn, b, d, tau, steps=30):
     return (time.perf_counter() - t0) * 1e3 / steps
 
 
-def run(name, batch, res, cifar_stem, steps, warmup, tau=0.5):
+def run(name, batch, res, cifar_stem, steps, warmup, tau=0.5, quiet=False):
     from objective import contrastive_loss           # the drop-in module at the repository root
     torch.manual_seed(0)
     out = {"config": name, "batch": batch, "resolution": res, "stem": "cifar 3x3 s1, no maxpool" if cifar_stem else "7x7 s2 + maxpool",
@@ -143,7 +143,9 @@ def run(name, batch, res, cifar_stem, steps, warmup, tau=0.5):
         del model, opt
         torch.cuda.empty_cache()
     out["step_ratio_ours_over_reference"] = out["ours"]["ms_per_step"] / out["reference_arithmetic"]["ms_per_step"]
-    print(json.dumps(out), flush=True)
+    if not quiet:
+        print(json.dumps(out), flush=True)
+    return out
 
 
 if __name__ == "__main__":

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIMCLR_ABI_VERSION 9
+#define SIMCLR_ABI_VERSION 10
 
 /* loss kinds */
 #define SIMCLR_LOSS_NTXENT 0   /* objective.py:6-55  */
@@ -146,6 +146,26 @@ int simclr_forward_backward(int loss, const void* x_batch1, const void* x_batch2
                             size_t backward_workspace_bytes, void* stream);
 
 /*
+ * The same fused step split around its last kernel, for callers that learn the upstream gradient only after they have
+ * seen the loss (torch.autograd: forward() returns, the caller scales the loss -- utils/model_utils.py:116 divides it by
+ * the accumulation steps in place -- and backward() delivers grad_output):
+ *   simclr_forward_backward_begin   prepare, forward tile, forward finalize (loss statistics complete here: `stats` /
+ *                                   `loss_out` are valid as soon as that kernel has run, while the backward tile kernel --
+ *                                   launched by the same call -- is still running), backward tile: four launches;
+ *   simclr_forward_backward_finish  the backward finalize kernel alone: grad1 / grad2 = grad_out * dloss/dx.  May be
+ *                                   repeated (a second backward over a retained graph): it only reads the workspace.
+ * Buffers as in simclr_forward_backward; `operand`, `rowvec` and `backward_workspace` must be kept between the calls.
+ */
+int simclr_forward_backward_begin(int loss, const void* x_batch1, const void* x_batch2, int64_t b, int64_t d, int in_dtype,
+                                  int normalize, float temperature, int precision, void* operand, float* rowvec,
+                                  float* stats, float* loss_out, void* forward_workspace, size_t forward_workspace_bytes,
+                                  void* backward_workspace, size_t backward_workspace_bytes, void* stream);
+int simclr_forward_backward_finish(int loss, const void* x_batch1, const void* x_batch2, int64_t b, int64_t d, int in_dtype,
+                                   int normalize, float temperature, int precision, const float* grad_out,
+                                   const void* operand, const float* rowvec, void* grad1, void* grad2,
+                                   void* backward_workspace, size_t backward_workspace_bytes, void* stream);
+
+/*
  * Row-sharded global batch over peer memory (one process per GPU of one NVLink / NVSwitch node; not in the reference,
  * whose only batch-scaling device is gradient accumulation, utils/model_utils.py:113-123).  Buffers named *_peers are
  * arrays of `world` device pointers: entry r is THIS process's mapping of rank r's copy of a symmetric allocation
@@ -208,34 +228,31 @@ int simclr_forward_backward_peer(int loss, const void* x_batch1, const void* x_b
                                  void* const* colvec_peers, void* const* stats_peers, void* const* flag_peers,
                                  unsigned int* epoch_local, void* stream);
 
-/* Diagnostics: per-role clock64() timeline of one CTA of the tile kernels (tools/trace_timeline.py).
- * device_buffer: int64[6 roles][64 iterations][4] or NULL to switch tracing off. */
-int simclr_debug_set_trace(void* device_buffer, int cta);
-
-/* Measurement: restrict the staged calls of this process to a subset of their kernels, so that bench.py can time ONE
- * kernel of the step by itself (a CUDA graph of back-to-back launches of it between two events).  Bits: 1 prepare,
- * 2 forward tile, 4 forward finalize, 8 backward tile, 16 backward finalize, 32 backward prepare; ~0 (default) = all.
- * Results are only meaningful with the full mask. */
-int simclr_debug_set_stage_mask(unsigned int mask);
-
-/* Diagnostics: kernel-level %globaltimer timeline (tools/kernel_timeline.py).  device_buffer: uint64[8][2]
- * (min start / max end in ns per kernel id: 0 prepare, 1 forward tile, 2 backward prepare, 3 backward tile),
- * start slots initialised to ~0, end slots to 0; NULL switches it off.  Captured into graphs at capture time. */
-int simclr_debug_set_kernel_trace(void* device_buffer);
-
-/* Diagnostics: tcgen05.mma issue / execution rate probe under contention (tools/mma_rate.py).
- * out: int64[4 configs][4]; mode 0 idle, 1 tcgen05.ld, 2 MUFU, 3 FFMA, 4 all; sink: float[640] scratch. */
-int simclr_debug_mma_rate(long long* out_device, int batches, int grid, int mode, float* sink, void* stream);
-
-/* Diagnostics: throughput of the softmax warps' per-chunk arithmetic without MMA/TMA (tools/chunk_rate.py).
- * out: int64[10 variants][32 warps] cycles per 32-column chunk (CTA 0); sink: float[640] scratch. */
-int simclr_debug_chunk_rate(long long* out_device, int iters, int grid, int nwarps, float k2, float* sink, void* stream);
-
-/* Diagnostics: issue rate of single SASS opcodes with 1..16 warps per SM (tools/pipe_rate.py). out: int64[32]. */
-int simclr_debug_pipe_rate(long long* out_device, int iters, int grid, int nwarps, float* sink, void* stream);
-
-/* Diagnostics: UMMA/TMA primitive self-test (tests/test_primitives.py). out_f32 receives 3*128*128 floats. */
-int simclr_selftest_umma(const void* a_bf16_128x128, const void* b_bf16_128x128, float* out_f32, void* stream);
+/*
+ * Measurement entry points (bench.py): simclr_forward_peer on one GPU / simclr_backward restricted to a subset of their
+ * kernels, so that ONE kernel of the step can be timed by itself (a CUDA graph of back-to-back launches of it between
+ * two events, reading the state the last full call left).  `stage_mask` is a per-call argument -- there is no process
+ * state; results are only meaningful with SIMCLR_STAGE_ALL.  Arguments as in simclr_forward_peer (world == 0) and
+ * simclr_backward.
+ */
+#define SIMCLR_STAGE_PREPARE 1u
+#define SIMCLR_STAGE_FORWARD_TILE 2u
+#define SIMCLR_STAGE_FORWARD_FINALIZE 4u
+#define SIMCLR_STAGE_BACKWARD_TILE 8u
+#define SIMCLR_STAGE_BACKWARD_FINALIZE 16u
+#define SIMCLR_STAGE_BACKWARD_PREPARE 32u
+#define SIMCLR_STAGE_ALL 0xFFFFFFFFu
+int simclr_forward_stages(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
+                          int64_t row_offset, int64_t d, float temperature, int normalize, int precision,
+                          const float* pos_dot, const float* row_weight, float* lse2, float* row_loss, float* stats,
+                          float* loss_out, void* workspace, size_t workspace_bytes, void* backward_workspace,
+                          size_t backward_workspace_bytes, void* stream, unsigned int stage_mask);
+int simclr_backward_stages(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t b_global,
+                           int64_t row_offset, int64_t d, int in_dtype, int normalize, float temperature, int precision,
+                           const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,
+                           const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
+                           void* workspace, size_t workspace_bytes, const float* primed_colvec, void* stream,
+                           unsigned int stage_mask);
 
 #ifdef __cplusplus
 }

@@ -191,6 +191,55 @@ def ntxent_closed_form(x_batch1, x_batch2, temperature: float = 1.0, normalize: 
     return OracleResult(loss, correct, 100.0 * correct / m, g1, g2, lse, row_loss)
 
 
+def ntxent_row_sample_check(x_batch1, x_batch2, temperature: float, sample_rows, grad_output: float = 1.0,
+                            block: int = 2048, threads: Optional[int] = None):
+    """Blockwise fp64 NT-Xent at sizes where nothing M x M can exist (2N = 65536): the exact global loss, the
+    first-argmax count over ALL rows, and the input gradients of the rows in ``sample_rows`` (indices into
+    Z = [x_batch1; x_batch2]).  Same closed forms as ``ntxent_closed_form`` (reference objective.py:23-53, normalised,
+    unweighted); torch CPU float64 so that the elementwise passes use every host core.
+
+    Returns (loss, correct, grads[len(sample_rows), d]).
+    """
+    if threads:
+        torch.set_num_threads(threads)
+    z = torch.cat((torch.as_tensor(_as_f64(x_batch1)), torch.as_tensor(_as_f64(x_batch2))), 0)
+    m, d = z.shape
+    n = m // 2
+    nrm = z.norm(dim=1).clamp_min(L2_EPS)                          # objective.py:26-27
+    zh = z / nrm[:, None]
+    inv_tau = 1.0 / temperature
+    lse = torch.empty(m, dtype=torch.float64)
+    s_pos = torch.empty(m, dtype=torch.float64)
+    correct = 0
+    perm = torch.cat((torch.arange(n, m), torch.arange(0, n)))     # objective.py:48-49 column order
+    for r0 in range(0, m, block):
+        r1 = min(m, r0 + block)
+        rows = torch.arange(r0, r1)
+        s = (zh[r0:r1] @ zh.T) * inv_tau                            # objective.py:35-36,42-43
+        pos = (rows + n) % m
+        s_pos[r0:r1] = s[torch.arange(r1 - r0), pos]
+        s[torch.arange(r1 - r0), rows] = -float("inf")              # objective.py:39-40
+        lse[r0:r1] = torch.logsumexp(s, dim=1)
+        # first maximal index in the reference's permuted order; the label of row r is r in that frame
+        pred = s[:, perm].argmax(dim=1)
+        correct += int((pred == rows).sum())
+    loss = float((lse - s_pos).mean())                              # objective.py:47,50
+    sample = torch.as_tensor(np.asarray(sample_rows, dtype=np.int64))
+    g = grad_output / m
+    grads = torch.empty((len(sample), d), dtype=torch.float64)
+    for i0 in range(0, len(sample), 256):
+        rows = sample[i0:i0 + 256]
+        k = len(rows)
+        s = (zh[rows] @ zh.T) * inv_tau
+        w = g * (torch.exp(s - lse[rows][:, None]) + torch.exp(s - lse[None, :]))
+        w[torch.arange(k), rows] = 0.0
+        w[torch.arange(k), (rows + n) % m] -= 2.0 * g
+        dzh = (w @ zh) * inv_tau
+        zr = zh[rows]
+        grads[i0:i0 + k] = (dzh - zr * (zr * dzh).sum(dim=1, keepdim=True)) / nrm[rows][:, None]
+    return loss, correct, grads.numpy()
+
+
 def _softplus64(x: np.ndarray) -> np.ndarray:
     bx = SOFTPLUS_BETA * x
     out = np.where(bx > SOFTPLUS_THRESHOLD, x, np.log1p(np.exp(np.minimum(bx, SOFTPLUS_THRESHOLD))) / SOFTPLUS_BETA)

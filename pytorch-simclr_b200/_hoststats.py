@@ -21,7 +21,11 @@ _SLOTS = 64
 
 
 class _Ring:
-    def __init__(self):
+    """One ring per device: a CUDA event is bound to the device of its first record, and a slot's event orders the
+    slot's reuse against the stream of THAT device."""
+
+    def __init__(self, device: int):
+        self.device = device
         self.buf = torch.empty((_SLOTS, 4), dtype=torch.float32).pin_memory()
         self.np = self.buf.numpy()
         self.base = self.buf.data_ptr()
@@ -43,10 +47,16 @@ class _Ring:
         return self.base + 16 * i                    # pinned memory is device-accessible at the same address (UVA)
 
     def launched(self, i: int) -> None:
+        """Record the slot's event behind the launch, on the current stream of the ring's device."""
         ev = self.events[i]
         if ev is None:
             ev = self.events[i] = torch.cuda.Event()
-        ev.record()
+        ev.record(torch.cuda.current_stream(self.device))
+
+    def abandon(self, i: int) -> None:
+        """The call that acquired the slot failed before (or while) launching: nothing will ever write the slot, and a
+        stale event of the previous user must not be waited on in its name."""
+        self.np[i, 3] = 0.0
 
     def wait(self, i: int):
         row = self.np[i]
@@ -59,16 +69,28 @@ class _Ring:
                 if deadline is None:
                     deadline = now + 5e-3
                 elif now > deadline:
-                    self.events[i].synchronize()
+                    if self.events[i] is not None:
+                        self.events[i].synchronize()
                     break
         return float(row[0]), float(row[1]), float(row[2]), float(row[3])
 
 
-_ring = None
+_rings = {}
+_rings_lock = threading.Lock()
 
 
-def ring() -> _Ring:
-    global _ring
-    if _ring is None:
-        _ring = _Ring()
-    return _ring
+def ring(device=None) -> _Ring:
+    """The ring of `device` (index or torch.device; default: the current CUDA device)."""
+    if device is None:
+        idx = torch.cuda.current_device()
+    elif isinstance(device, int):
+        idx = device
+    else:
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+    r = _rings.get(idx)
+    if r is None:
+        with _rings_lock:
+            r = _rings.get(idx)
+            if r is None:
+                r = _rings[idx] = _Ring(idx)
+    return r

@@ -15,7 +15,7 @@ DTYPE_F32 = 0
 DTYPE_BF16 = 1
 PRECISION_BF16 = 0
 PRECISION_SPLIT = 1
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _lock = threading.Lock()
 _lib = None
@@ -42,6 +42,10 @@ SIGNATURES = {
                                _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "simclr_forward_backward": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                        _vp, _sz, _vp, _sz, _vp]),
+    "simclr_forward_backward_begin": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp,
+                                             _sz, _vp, _sz, _vp]),
+    "simclr_forward_backward_finish": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp,
+                                              _vp, _sz, _vp]),
     "simclr_forward_backward_peer": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                             _vp, _vp, _sz, _vp, _sz, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "simclr_prepare_peer": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _int, _int, _vp,
@@ -49,14 +53,25 @@ SIGNATURES = {
     "simclr_forward_peer": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp,
                                    _vp, _sz, _vp, _sz, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "simclr_peer_barrier": (_int, [_int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "simclr_forward_stages": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp,
+                                     _vp, _sz, _vp, _sz, _vp, ctypes.c_uint]),
+    "simclr_backward_stages": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp,
+                                      _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, ctypes.c_uint]),
+}
+
+# include/simclr_b200_debug.h: exported by the tracing build (lib/libsimclr_b200_trace.so) only
+DEBUG_SIGNATURES = {
     "simclr_selftest_umma": (_int, [_vp, _vp, _vp, _vp]),
     "simclr_debug_set_trace": (_int, [_vp, _int]),
     "simclr_debug_set_kernel_trace": (_int, [_vp]),
-    "simclr_debug_set_stage_mask": (_int, [ctypes.c_uint]),
     "simclr_debug_chunk_rate": (_int, [_vp, _int, _int, _int, _f32, _vp, _vp]),
     "simclr_debug_pipe_rate": (_int, [_vp, _int, _int, _int, _vp, _vp]),
     "simclr_debug_mma_rate": (_int, [_vp, _int, _int, _int, _vp, _vp]),
 }
+TRACE_LIB_PATH = os.path.join(_HERE, "lib", "libsimclr_b200_trace.so")
+STAGE_PREPARE, STAGE_FORWARD_TILE, STAGE_FORWARD_FINALIZE, STAGE_BACKWARD_TILE, STAGE_BACKWARD_FINALIZE = 1, 2, 4, 8, 16
+STAGE_BACKWARD_PREPARE, STAGE_ALL = 32, 0xFFFFFFFF
+_debug_lib = None
 
 
 class SimclrLibraryError(RuntimeError):
@@ -82,8 +97,44 @@ def load():
             fn.argtypes = args
         if lib.simclr_abi_version() != ABI_VERSION:
             raise SimclrLibraryError(f"ABI mismatch: library {lib.simclr_abi_version()} vs binding {ABI_VERSION}")
+        _bind_debug(lib)
         _lib = lib
     return _lib
+
+
+def _bind_debug(lib) -> bool:
+    if not hasattr(lib, "simclr_debug_set_trace"):
+        return False
+    for name, (res, args) in DEBUG_SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return True
+
+
+def load_debug():
+    """The tracing build (diagnostics of include/simclr_b200_debug.h next to the whole product ABI).  The timeline tools
+    set SIMCLR_B200_LIB to it before importing the package, so that the kernels they trace come from the same library;
+    the rate probes and the primitive self-test are self-contained and may load it next to the product library."""
+    global _debug_lib
+    if _debug_lib is not None:
+        return _debug_lib
+    lib = load()
+    if hasattr(lib, "simclr_debug_set_trace"):
+        _debug_lib = lib
+        return lib
+    with _lock:
+        if _debug_lib is None:
+            if not os.path.isfile(TRACE_LIB_PATH):
+                raise SimclrLibraryError(f"{TRACE_LIB_PATH} is missing: python pytorch-simclr_b200/build.py builds it")
+            dbg = ctypes.CDLL(TRACE_LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(dbg, name)
+                fn.restype = res
+                fn.argtypes = args
+            _bind_debug(dbg)
+            _debug_lib = dbg
+    return _debug_lib
 
 
 def check(code: int, what: str) -> None:

@@ -203,7 +203,8 @@ __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerTable flags, unsigned int* __restrict__ epoch_local,
                                                           const float* __restrict__ stats_all,
-                                                          float* __restrict__ stats_out, float* __restrict__ loss_out) {
+                                                          float* __restrict__ stats_out, float* __restrict__ loss_out,
+                                                          unsigned long long timeout_ns) {
     pdl_launch_dependents();
     pdl_wait();
     const int t = threadIdx.x;
@@ -217,19 +218,7 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerTable flags, unsig
     if (t < flags.world) {
         unsigned int* remote = static_cast<unsigned int*>(flags.ptr[t]) + flags.rank;
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(target) : "memory");
-        const unsigned int* mine = static_cast<const unsigned int*>(flags.ptr[flags.rank]) + t;
-        unsigned int seen;
-        long long spins = 0;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-            if (static_cast<int>(seen - target) >= 0) break;
-            __nanosleep(64);
-            if (++spins > (1ll << 26)) {            // ~ seconds: a peer never arrived
-                printf("[simclr_b200] peer barrier watchdog: rank %d waits for rank %d (epoch %u, seen %u)\n", flags.rank, t,
-                       target, seen);
-                __trap();
-            }
-        } while (true);
+        peer_flag_wait(static_cast<const unsigned int*>(flags.ptr[flags.rank]) + t, target, timeout_ns, flags.rank, t);
     }
     __syncwarp();
     __threadfence_system();

@@ -2,27 +2,41 @@
 // TMA tensor-map encoding and kernel launches.  No host synchronisation, no allocation.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <utility>
 
 #include "../../include/simclr_b200.h"
 #include "aux_kernels.cuh"
+#if SIMCLR_TRACE
+// Diagnostics (timelines, rate probes, primitive self-test) exist only in the tracing build of the library
+// (lib/libsimclr_b200_trace.so, include/simclr_b200_debug.h); the product library carries none of it.
+#include "../../include/simclr_b200_debug.h"
 #include "probes.cuh"
 #include "selftest.cuh"
+#endif
 
 using namespace simclr;
 
 namespace {
 
+#if SIMCLR_TRACE
 // debug timeline target (simclr_debug_set_trace); applies to subsequent launches of this process
 long long* g_trace_ptr = nullptr;
 int g_trace_cta = 0;
 unsigned long long* g_ktrace_ptr = nullptr;
-// debug / measurement: which kernels the staged calls actually launch (simclr_debug_set_stage_mask)
-enum StageBit : unsigned { kStagePrepare = 1, kStageFwdTile = 2, kStageFwdFin = 4, kStageBwdTile = 8, kStageBwdFin = 16,
-                           kStageBwdPrepare = 32 };
-unsigned g_stage_mask = ~0u;
+#else
+constexpr long long* g_trace_ptr = nullptr;
+constexpr int g_trace_cta = 0;
+constexpr unsigned long long* g_ktrace_ptr = nullptr;
+#endif
+// Which kernels a staged call launches: a per-call argument of the measurement entry points simclr_forward_stages /
+// simclr_backward_stages (bench.py times ONE kernel of the step by itself); every other entry point passes kAllStages.
+enum StageBit : unsigned { kStagePrepare = SIMCLR_STAGE_PREPARE, kStageFwdTile = SIMCLR_STAGE_FORWARD_TILE,
+                           kStageFwdFin = SIMCLR_STAGE_FORWARD_FINALIZE, kStageBwdTile = SIMCLR_STAGE_BACKWARD_TILE,
+                           kStageBwdFin = SIMCLR_STAGE_BACKWARD_FINALIZE, kStageBwdPrepare = SIMCLR_STAGE_BACKWARD_PREPARE };
+constexpr unsigned kAllStages = ~0u;
 
 // ------------------------------------------------------------------------------------------
 // cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
@@ -44,8 +58,49 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+// A training loop calls with the same buffers step after step (and a CUDA graph is captured once), so the encoded maps
+// are kept in a small per-process cache keyed by everything that determines them; cuTensorMapEncodeTiled is a driver
+// call of a microsecond or two and a step needs five maps.  A CUtensorMap holds no reference to the memory it
+// describes: a stale entry (buffer freed and reallocated elsewhere) simply never matches again.
+struct MapKey {
+    const void* base;
+    int64_t rows, d_pad;
+    int kind;      // 0 operand (bf16), 1 accumulator (f32)
+    bool operator==(const MapKey& o) const { return base == o.base && rows == o.rows && d_pad == o.d_pad && kind == o.kind; }
+};
+constexpr int kMapCacheSize = 32;
+struct MapCache {
+    std::mutex mu;
+    MapKey key[kMapCacheSize] = {};
+    CUtensorMap map[kMapCacheSize];
+    bool used[kMapCacheSize] = {};
+    int next = 0;
+    bool find(const MapKey& k, CUtensorMap* out) {
+        std::lock_guard<std::mutex> lock(mu);
+        for (int i = 0; i < kMapCacheSize; ++i)
+            if (used[i] && key[i] == k) {
+                *out = map[i];
+                return true;
+            }
+        return false;
+    }
+    void put(const MapKey& k, const CUtensorMap& m) {
+        std::lock_guard<std::mutex> lock(mu);
+        key[next] = k;
+        map[next] = m;
+        used[next] = true;
+        next = (next + 1) % kMapCacheSize;
+    }
+};
+MapCache& map_cache() {
+    static MapCache c;
+    return c;
+}
+
 // bf16 [rows][d_pad] row-major, box = 128 rows x 64 elements (128 B), 128-byte swizzle
 int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, int64_t d_pad) {
+    const MapKey key{base, rows, d_pad, 0};
+    if (map_cache().find(key, map)) return SIMCLR_OK;
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return SIMCLR_ERR_DRIVER_ENTRY;
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d_pad), static_cast<cuuint64_t>(rows)};
@@ -55,7 +110,9 @@ int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, int64_t d
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? SIMCLR_OK : SIMCLR_ERR_TENSOR_MAP;
+    if (r != CUDA_SUCCESS) return SIMCLR_ERR_TENSOR_MAP;
+    map_cache().put(key, *map);
+    return SIMCLR_OK;
 }
 
 // Launch with the programmatic-stream-serialization attribute (see pdl_wait() in sm100_ptx.cuh): the kernel may be
@@ -82,19 +139,36 @@ struct DeviceInfo {
     bool valid = false;
 };
 
+constexpr int kMaxDevices = 64;
+
 const DeviceInfo& device_info() {
-    static DeviceInfo info[64];
+    static DeviceInfo info[kMaxDevices];
+    static std::once_flag once[kMaxDevices];
+    static const DeviceInfo fallback;
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
-        static DeviceInfo fallback;
-        return fallback;
-    }
-    if (!info[dev].valid) {
-        cudaDeviceGetAttribute(&info[dev].sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&info[dev].cc_major, cudaDevAttrComputeCapabilityMajor, dev);
-        info[dev].valid = true;
-    }
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return fallback;
+    std::call_once(once[dev], [dev] {
+        DeviceInfo d;
+        d.valid = cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+                  cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess;
+        info[dev] = d;
+    });
     return info[dev];
+}
+
+// Watchdog of the cross-GPU flag waits (peer_flag_wait): SIMCLR_B200_PEER_TIMEOUT_S seconds, default 600, 0 = none.
+// Read once per process.
+unsigned long long peer_timeout_ns() {
+    static const unsigned long long ns = [] {
+        double seconds = 600.0;
+        if (const char* env = std::getenv("SIMCLR_B200_PEER_TIMEOUT_S")) {
+            char* end = nullptr;
+            const double v = std::strtod(env, &end);
+            if (end != env && v >= 0.0) seconds = v;
+        }
+        return static_cast<unsigned long long>(seconds * 1e9);
+    }();
+    return ns;
 }
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
@@ -225,6 +299,8 @@ Scales make_scales(int loss, float temperature, int normalize, int64_t b_global)
 // fp32 [rows][d_pad] row-major (the gradient accumulation buffer), box = 128 rows x 32 floats (128 B), 128-byte
 // swizzle: target of the backward kernel's TMA reduce-add
 int make_dacc_map(CUtensorMap* map, const void* base, int64_t rows, int64_t d_pad) {
+    const MapKey key{base, rows, d_pad, 1};
+    if (map_cache().find(key, map)) return SIMCLR_OK;
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return SIMCLR_ERR_DRIVER_ENTRY;
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d_pad), static_cast<cuuint64_t>(rows)};
@@ -234,22 +310,25 @@ int make_dacc_map(CUtensorMap* map, const void* base, int64_t rows, int64_t d_pa
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estride,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? SIMCLR_OK : SIMCLR_ERR_TENSOR_MAP;
+    if (r != CUDA_SUCCESS) return SIMCLR_ERR_TENSOR_MAP;
+    map_cache().put(key, *map);
+    return SIMCLR_OK;
 }
 
 template <int D, int kLoss, bool kBackward, bool kConst, int kPrec>
 int launch_tile(const CUtensorMap& rows, const CUtensorMap& cols, const CUtensorMap& dacc, const TileParams& p, int grid,
                 cudaStream_t st) {
     auto kern = contrastive_tile_kernel<D, kLoss, kBackward, kConst, kPrec>;
-    static bool configured[64] = {};
+    static std::once_flag configured[kMaxDevices];
+    static cudaError_t configure_rc[kMaxDevices];
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             SmemLayout<D, kPrec>::kDynamicBytes);
-        if (e != cudaSuccess) return static_cast<int>(e);
-        configured[dev & 63] = true;
-    }
+    dev &= kMaxDevices - 1;
+    std::call_once(configured[dev], [&] {
+        configure_rc[dev] = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 SmemLayout<D, kPrec>::kDynamicBytes);
+    });
+    if (configure_rc[dev] != cudaSuccess) return static_cast<int>(configure_rc[dev]);
     return static_cast<int>(launch_pdl(kern, dim3(grid), dim3(kBackward ? kThreadsBackward : kThreadsForward),
                                        SmemLayout<D, kPrec>::kDynamicBytes, st, rows, cols, dacc, p));
 }
@@ -340,6 +419,7 @@ TileParams make_tile_params(const Geometry& g, const Scales& s, int64_t b_local,
     p.trace_cta = g_trace_cta;
     p.ktrace = g_ktrace_ptr;
     p.tile_grid = g.grid;
+    p.peer_timeout_ns = peer_timeout_ns();
     return p;
 }
 
@@ -465,7 +545,6 @@ int prepare_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t b
     const int blocks = static_cast<int>((g.bl_pad + warps - 1) / warps);
     auto* op = static_cast<__nv_bfloat16*>(operand);
     cudaError_t launch_rc = cudaSuccess;
-    if (!(g_stage_mask & kStagePrepare)) return SIMCLR_OK;
 #define SIMCLR_PREP2(T, LOSS, PER) \
     launch_rc = launch_pdl(prepare_kernel<T, LOSS, PER>, dim3(blocks), dim3(warps * 32), 0, st, static_cast<const T*>(x_batch1), static_cast<const T*>(x_batch2), a, op, inv_norm, pos_dot, zero_ptr, zero_words, g_ktrace_ptr, peers, bump_epoch)
 #define SIMCLR_PREP(T, LOSS)                          \
@@ -517,7 +596,7 @@ int simclr_peer_barrier(int world, int rank, void* const* flag_peers, unsigned i
     if (rc) return rc;
     if ((rc = check_device())) return rc;
     return static_cast<int>(launch_pdl(peer_barrier_kernel, dim3(1), dim3(32), 0, static_cast<cudaStream_t>(stream), flags,
-                                       epoch_local, stats_all, stats_out, loss_out));
+                                       epoch_local, stats_all, stats_out, loss_out, peer_timeout_ns()));
 }
 
 }  // extern "C"
@@ -530,7 +609,7 @@ int forward_impl(int loss, const void* operand_rows, const void* operand_cols, i
                  const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out, void* workspace,
                  size_t workspace_bytes, void* backward_workspace, size_t backward_workspace_bytes, int world, int rank,
                  void* const* colvec_peers, void* const* stats_peers, void* const* flag_peers, unsigned int* epoch_local,
-                 void* stream, bool defer_stats, const FusedSync* fused = nullptr) {
+                 void* stream, bool defer_stats, const FusedSync* fused = nullptr, unsigned stages = kAllStages) {
     if (!operand_rows || !operand_cols || !pos_dot || !lse2 || !row_loss || !stats || !workspace)
         return SIMCLR_ERR_NULL_POINTER;
     if (!(temperature > 0.f) || !std::isfinite(temperature)) return SIMCLR_ERR_BAD_TEMPERATURE;
@@ -597,7 +676,7 @@ int forward_impl(int loss, const void* operand_rows, const void* operand_cols, i
     if (!overlap) {
         p.fin_set[0] = PartSet{w.part, g.total_tiles, g.n_col_tiles, g.max_segs, g.grid};
         p.n_fin_sets = 1;
-        if ((g_stage_mask & kStageFwdTile) && (rc = dispatch_tile<false>(loss, g.d_pad, precision, map_rows, map_cols, map_rows, p, g.grid, st))) return rc;
+        if ((stages & kStageFwdTile) && (rc = dispatch_tile<false>(loss, g.d_pad, precision, map_rows, map_cols, map_rows, p, g.grid, st))) return rc;
     } else {
         // Overlapped exchange: the columns this rank produced itself need no peer, so their tiles run while the other
         // ranks' operand rows are still crossing NVLink; the barrier follows, then the remote columns.
@@ -628,7 +707,7 @@ int forward_impl(int loss, const void* operand_rows, const void* operand_cols, i
         p.n_fin_sets = 2;
     }
     cudaError_t e;
-    if (!(g_stage_mask & kStageFwdFin)) return SIMCLR_OK;
+    if (!(stages & kStageFwdFin)) return SIMCLR_OK;
     if (loss == SIMCLR_LOSS_NTXENT) e = launch_pdl(forward_finalize_kernel<kNtXent>, dim3(g.n_row_blocks), dim3(kBlockM), 0, st, p);
     else e = launch_pdl(forward_finalize_kernel<kModified>, dim3(g.n_row_blocks), dim3(kBlockM), 0, st, p);
     return static_cast<int>(e);
@@ -640,7 +719,7 @@ int backward_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t 
                   const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,
                   const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
                   void* workspace, size_t workspace_bytes, const float* primed_colvec, void* stream, void* finish_ws,
-                  float* finish_stats, float* finish_loss, const FusedSync* fused = nullptr) {
+                  float* finish_stats, float* finish_loss, const FusedSync* fused = nullptr, unsigned stages = kAllStages) {
     if (!x_batch1 || !x_batch2 || !operand_rows || !operand_cols || !inv_norm || !pos_dot || !grad1 || !grad2 || !workspace)
         return SIMCLR_ERR_NULL_POINTER;
     if (!lse2_cols && !primed_colvec) return SIMCLR_ERR_NULL_POINTER;
@@ -667,7 +746,7 @@ int backward_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t 
     AuxParams a = make_aux(g, s, b_local, b_global, row_offset, d, normalize);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-    if (primed_colvec == nullptr && (g_stage_mask & kStageBwdPrepare)) {
+    if (primed_colvec == nullptr && (stages & kStageBwdPrepare)) {
         if ((rc = static_cast<int>(launch_pdl(backward_prepare_kernel, dim3(device_info().sm_count * 2), dim3(256), 0, st, a,
                                               lse2_cols, col_scale, w.colvec, reinterpret_cast<float4*>(w.dacc),
                                               w.dacc_floats / 4, g_ktrace_ptr))))
@@ -714,11 +793,11 @@ int backward_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t 
         p.loss_out = finish_loss;
         p.finish_stats = 1;
     }
-    if ((g_stage_mask & kStageBwdTile) &&
+    if ((stages & kStageBwdTile) &&
         (rc = dispatch_tile<true>(loss, g.d_pad, precision, map_rows, map_cols, map_dacc, p, g.grid, st)))
         return rc;
     cudaError_t fin_rc = cudaSuccess;
-    if (!(g_stage_mask & kStageBwdFin)) return SIMCLR_OK;
+    if (!(stages & kStageBwdFin)) return SIMCLR_OK;
 #define SIMCLR_BFIN(DV)                                                                                  \
     case DV:                                                                                             \
         if (loss == SIMCLR_LOSS_NTXENT) fin_rc = launch_pdl(backward_finalize_kernel<DV, kNtXent>, dim3(g.n_row_blocks * kBwdFinBlocksPerRowBlock), dim3(512), 0, st, p); \
@@ -769,31 +848,95 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
                          grad2, workspace, workspace_bytes, primed_colvec, stream, nullptr, nullptr, nullptr);
 }
 
-int simclr_forward_backward(int loss, const void* x_batch1, const void* x_batch2, int64_t b, int64_t d, int in_dtype,
-                            int normalize, float temperature, int precision, const float* grad_out, void* operand,
-                            float* rowvec, float* stats, float* loss_out, void* grad1, void* grad2,
-                            void* forward_workspace, size_t forward_workspace_bytes, void* backward_workspace,
-                            size_t backward_workspace_bytes, void* stream) {
-    if (!rowvec || !stats || !backward_workspace) return SIMCLR_ERR_NULL_POINTER;
+int simclr_forward_stages(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
+                          int64_t row_offset, int64_t d, float temperature, int normalize, int precision,
+                          const float* pos_dot, const float* row_weight, float* lse2, float* row_loss, float* stats,
+                          float* loss_out, void* workspace, size_t workspace_bytes, void* backward_workspace,
+                          size_t backward_workspace_bytes, void* stream, unsigned int stage_mask) {
+    return forward_impl(loss, operand_rows, operand_cols, b_local, b_global, row_offset, d, temperature, normalize, precision,
+                        pos_dot, row_weight, lse2, row_loss, stats, loss_out, workspace, workspace_bytes, backward_workspace,
+                        backward_workspace_bytes, 0, 0, nullptr, nullptr, nullptr, nullptr, stream, false, nullptr,
+                        stage_mask);
+}
+
+int simclr_backward_stages(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t b_global,
+                           int64_t row_offset, int64_t d, int in_dtype, int normalize, float temperature, int precision,
+                           const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,
+                           const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
+                           void* workspace, size_t workspace_bytes, const float* primed_colvec, void* stream,
+                           unsigned int stage_mask) {
+    return backward_impl(loss, x_batch1, x_batch2, b_local, b_global, row_offset, d, in_dtype, normalize, temperature,
+                         precision, operand_rows, operand_cols, inv_norm, pos_dot, lse2_cols, col_scale, grad_out, grad1,
+                         grad2, workspace, workspace_bytes, primed_colvec, stream, nullptr, nullptr, nullptr, nullptr,
+                         stage_mask);
+}
+
+namespace {
+// The fused single-GPU step, whole (begin && finish) or split in two calls around the backward finalize kernel.
+int fused_step_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t b, int64_t d, int in_dtype, int normalize,
+                    float temperature, int precision, const float* grad_out, void* operand, float* rowvec, float* stats,
+                    float* loss_out, void* grad1, void* grad2, void* forward_workspace, size_t forward_workspace_bytes,
+                    void* backward_workspace, size_t backward_workspace_bytes, void* stream, bool begin, bool finish) {
+    if (!rowvec || !backward_workspace) return SIMCLR_ERR_NULL_POINTER;
+    if (begin && !stats) return SIMCLR_ERR_NULL_POINTER;
     const int64_t bp = simclr_pad_rows(b);
     if (bp == 0) return SIMCLR_ERR_BAD_SHAPE;
     float* inv_norm = rowvec;
     float* pos_dot = rowvec + 2 * bp;
     float* lse2 = rowvec + 4 * bp;
     float* row_loss = rowvec + 6 * bp;
-    int rc = simclr_prepare_peer(loss, x_batch1, x_batch2, b, d, in_dtype, normalize, temperature, precision, operand,
+    int rc;
+    if (begin) {
+        rc = simclr_prepare_peer(loss, x_batch1, x_batch2, b, d, in_dtype, normalize, temperature, precision, operand,
                                  inv_norm, pos_dot, forward_workspace, 0, 0, nullptr, nullptr, stream);
-    if (rc) return rc;
-    // the forward primes the backward workspace and leaves the reduction of the loss statistics to the backward finalize
-    // kernel: five launches, and nothing but the column vectors between the two tile kernels
-    rc = forward_impl(loss, operand, operand, b, b, 0, d, temperature, normalize, precision, pos_dot, nullptr, lse2, row_loss,
-                      stats, loss_out, forward_workspace, forward_workspace_bytes, backward_workspace,
-                      backward_workspace_bytes, 0, 0, nullptr, nullptr, nullptr, nullptr, stream, true);
-    if (rc) return rc;
+        if (rc) return rc;
+        // The forward primes the backward workspace.  Whole step: the reduction of the loss statistics is left to the
+        // backward finalize kernel (five launches, nothing but the column vectors between the two tile kernels).  Split
+        // step: the forward finalize kernel completes them, so that the caller can read loss / accuracy while the
+        // backward tile kernel is still running.
+        rc = forward_impl(loss, operand, operand, b, b, 0, d, temperature, normalize, precision, pos_dot, nullptr, lse2,
+                          row_loss, stats, loss_out, forward_workspace, forward_workspace_bytes, backward_workspace,
+                          backward_workspace_bytes, 0, 0, nullptr, nullptr, nullptr, nullptr, stream, finish);
+        if (rc) return rc;
+    }
+    const unsigned stages = (begin ? kStageBwdTile : 0u) | (finish ? kStageBwdFin : 0u);
+    // grad1 / grad2 are only written by the finalize kernel; a `begin` call may pass NULL
+    void* g1 = grad1 ? grad1 : const_cast<void*>(x_batch1);
+    void* g2 = grad2 ? grad2 : const_cast<void*>(x_batch2);
+    if (finish && (!grad1 || !grad2)) return SIMCLR_ERR_NULL_POINTER;
     return backward_impl(loss, x_batch1, x_batch2, b, b, 0, d, in_dtype, normalize, temperature, precision, operand, operand,
-                         inv_norm, pos_dot, nullptr, nullptr, grad_out, grad1, grad2, backward_workspace,
-                         backward_workspace_bytes, static_cast<const float*>(backward_workspace), stream, forward_workspace,
-                         stats, loss_out);
+                         inv_norm, pos_dot, nullptr, nullptr, grad_out, g1, g2, backward_workspace,
+                         backward_workspace_bytes, static_cast<const float*>(backward_workspace), stream,
+                         (begin && finish) ? forward_workspace : nullptr, stats, loss_out, nullptr, stages);
+}
+}  // namespace
+
+int simclr_forward_backward(int loss, const void* x_batch1, const void* x_batch2, int64_t b, int64_t d, int in_dtype,
+                            int normalize, float temperature, int precision, const float* grad_out, void* operand,
+                            float* rowvec, float* stats, float* loss_out, void* grad1, void* grad2,
+                            void* forward_workspace, size_t forward_workspace_bytes, void* backward_workspace,
+                            size_t backward_workspace_bytes, void* stream) {
+    return fused_step_impl(loss, x_batch1, x_batch2, b, d, in_dtype, normalize, temperature, precision, grad_out, operand,
+                           rowvec, stats, loss_out, grad1, grad2, forward_workspace, forward_workspace_bytes,
+                           backward_workspace, backward_workspace_bytes, stream, true, true);
+}
+
+int simclr_forward_backward_begin(int loss, const void* x_batch1, const void* x_batch2, int64_t b, int64_t d, int in_dtype,
+                                  int normalize, float temperature, int precision, void* operand, float* rowvec,
+                                  float* stats, float* loss_out, void* forward_workspace, size_t forward_workspace_bytes,
+                                  void* backward_workspace, size_t backward_workspace_bytes, void* stream) {
+    return fused_step_impl(loss, x_batch1, x_batch2, b, d, in_dtype, normalize, temperature, precision, nullptr, operand,
+                           rowvec, stats, loss_out, nullptr, nullptr, forward_workspace, forward_workspace_bytes,
+                           backward_workspace, backward_workspace_bytes, stream, true, false);
+}
+
+int simclr_forward_backward_finish(int loss, const void* x_batch1, const void* x_batch2, int64_t b, int64_t d, int in_dtype,
+                                   int normalize, float temperature, int precision, const float* grad_out,
+                                   const void* operand, const float* rowvec, void* grad1, void* grad2,
+                                   void* backward_workspace, size_t backward_workspace_bytes, void* stream) {
+    return fused_step_impl(loss, x_batch1, x_batch2, b, d, in_dtype, normalize, temperature, precision, grad_out,
+                           const_cast<void*>(operand), const_cast<float*>(rowvec), nullptr, nullptr, grad1, grad2, nullptr, 0,
+                           backward_workspace, backward_workspace_bytes, stream, false, true);
 }
 
 int simclr_forward_backward_peer(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d,
@@ -834,14 +977,10 @@ int simclr_forward_backward_peer(int loss, const void* x_batch1, const void* x_b
                          loss_out, &fs);
 }
 
+#if SIMCLR_TRACE
 int simclr_debug_set_trace(void* device_buffer, int cta) {
     g_trace_ptr = static_cast<long long*>(device_buffer);
     g_trace_cta = cta;
-    return SIMCLR_OK;
-}
-
-int simclr_debug_set_stage_mask(unsigned int mask) {
-    g_stage_mask = mask;
     return SIMCLR_OK;
 }
 
@@ -880,7 +1019,7 @@ int simclr_debug_pipe_rate(long long* out_device, int iters, int grid, int nwarp
 #define SIMCLR_PIPE(V) pipe_rate_kernel<V><<<grid, kThreadsForward, 0, st>>>(out_device, iters, nwarps, 1.0f, sink);
     SIMCLR_PIPE(0) SIMCLR_PIPE(1) SIMCLR_PIPE(2) SIMCLR_PIPE(3) SIMCLR_PIPE(4) SIMCLR_PIPE(5) SIMCLR_PIPE(6) SIMCLR_PIPE(7)
     SIMCLR_PIPE(8) SIMCLR_PIPE(9) SIMCLR_PIPE(10) SIMCLR_PIPE(11) SIMCLR_PIPE(12) SIMCLR_PIPE(13) SIMCLR_PIPE(14) SIMCLR_PIPE(15)
-    SIMCLR_PIPE(16) SIMCLR_PIPE(17) SIMCLR_PIPE(18) SIMCLR_PIPE(19) SIMCLR_PIPE(20)
+    SIMCLR_PIPE(16) SIMCLR_PIPE(17) SIMCLR_PIPE(18) SIMCLR_PIPE(19) SIMCLR_PIPE(20) SIMCLR_PIPE(21) SIMCLR_PIPE(22) SIMCLR_PIPE(23)
 #undef SIMCLR_PIPE
     return static_cast<int>(cudaGetLastError());
 }
@@ -902,5 +1041,7 @@ int simclr_selftest_umma(const void* a_bf16, const void* b_bf16, float* out_f32,
     selftest_umma_kernel<<<1, 128, kSelftestSmemBytes, static_cast<cudaStream_t>(stream)>>>(map_a, map_b, out_f32);
     return static_cast<int>(cudaGetLastError());
 }
+
+#endif  // SIMCLR_TRACE
 
 }  // extern "C"

@@ -185,15 +185,46 @@ struct TileParams {
     PeerTable sync_flags;
     const unsigned int* sync_epoch;
     unsigned int* bump_epoch;
+    unsigned long long peer_timeout_ns;   // watchdog of the cross-GPU waits (0 = none)
     // backward finalize, row-sharded fused step: add up the ranks' statistics [world][4] (fixed order) into stats / loss_out
     const float* stats_all;
     int stats_world;
 };
 
+// Waits until *flag (system scope) has reached `target`.  Polls with an exponential __nanosleep back-off (the waiting
+// thread shares its SM with working warps and its loads cross NVLink-coherent memory) and a %globaltimer watchdog:
+// ranks of a training job legitimately skew by seconds to minutes (a checkpoint, a validation pass on rank 0, a
+// dataloader stall), so the limit is minutes by default and configurable (SIMCLR_B200_PEER_TIMEOUT_S, 0 = wait
+// for ever; see capi.cu peer_timeout_ns()) -- NCCL's comparable watchdog is host-side and also minutes.
+SIMCLR_DEVICE void peer_flag_wait(const unsigned int* flag, unsigned int target, unsigned long long timeout_ns, int rank,
+                                  int peer) {
+    unsigned int seen;
+    unsigned int backoff = 32, polls = 0;
+    unsigned long long t0 = 0;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        if (static_cast<int>(seen - target) >= 0) return;
+        __nanosleep(backoff);
+        if (backoff < 256) {
+            backoff <<= 1;             // short waits (the common case: ranks arrive within microseconds) stay responsive
+        } else if (timeout_ns != 0 && (++polls & 1023u) == 0u) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > timeout_ns) {
+                printf("[simclr_b200] peer barrier timeout after %llu s: rank %d waits for rank %d (epoch %u, seen %u); "
+                       "SIMCLR_B200_PEER_TIMEOUT_S sets the limit (0 = none)\n",
+                       timeout_ns / 1000000000ull, rank, peer, target, seen);
+                __trap();
+            }
+        }
+    } while (true);
+}
+
 // Cross-GPU barrier executed by one thread of a kernel (see TileParams::sync_flags).  `signal`: this thread also
 // publishes the epoch to every rank -- everything this GPU pushed before is complete, because the pushing kernels
 // completed before the caller passed griddepcontrol.wait.  Returns when all ranks have published the epoch.
-SIMCLR_DEVICE void peer_sync_thread(const PeerTable& flags, const unsigned int* epoch, bool signal) {
+SIMCLR_DEVICE void peer_sync_thread(const PeerTable& flags, const unsigned int* epoch, bool signal,
+                                    unsigned long long timeout_ns) {
     const unsigned int target = __ldcg(epoch);
     if (signal) {
         __threadfence_system();
@@ -203,19 +234,7 @@ SIMCLR_DEVICE void peer_sync_thread(const PeerTable& flags, const unsigned int* 
         }
     }
     const unsigned int* mine = static_cast<const unsigned int*>(flags.ptr[flags.rank]);
-    for (int r = 0; r < flags.world; ++r) {
-        unsigned int seen;
-        long long spins = 0;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine + r) : "memory");
-            if (static_cast<int>(seen - target) >= 0) break;
-            if (++spins > (1ll << 27)) {
-                printf("[simclr_b200] in-kernel peer barrier watchdog: rank %d waits for rank %d (epoch %u, seen %u)\n",
-                       flags.rank, r, target, seen);
-                __trap();
-            }
-        } while (true);
-    }
+    for (int r = 0; r < flags.world; ++r) peer_flag_wait(mine + r, target, timeout_ns, flags.rank, r);
     // what the peers stored before their signal is read next by the TMA engine (async proxy)
     asm volatile("fence.proxy.async.global;" ::: "memory");
 }
@@ -1234,7 +1253,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                     // In-kernel cross-GPU barrier.  Forward: the row-block tile (local rows) is already in flight, the
                     // column tiles are what the peers pushed.  Backward: the operands were complete before this kernel
                     // started (early loads above), the peers' column vectors are what the barrier protects.
-                    peer_sync_thread(p.sync_flags, p.sync_epoch, blockIdx.x == 0);
+                    peer_sync_thread(p.sync_flags, p.sync_epoch, blockIdx.x == 0, p.peer_timeout_ns);
                     synced = true;
                 }
                 const int c0 = tile_col0<kLoss>(p, w.rb / blocks_per_view, w.j);

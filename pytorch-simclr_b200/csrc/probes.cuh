@@ -174,8 +174,9 @@ chunk_rate_kernel(long long* __restrict__ out, int iters, int nwarps, float k2, 
 //   6 FMNMX reg,reg   7 IMAD (shl-add form)   8 LEA-style shl+add (integer)   9 FFMA 3-reg + MUFU interleaved 3:1
 //   10 F2FP (cvt.rn.bf16x2.f32)   11 FMNMX3 (max of three)   12 LDS.128   13 FSETP+FSEL   14 HFMA2.BF16 (fma.rn.bf16x2)
 //   15 PRMT   16 FADD2   17 FFMA2   18 FADD2 : FMNMX 1:1   19 FFMA2 : MUFU 3:1   20 FADD2 : FADD 1:1
+//   21 ex2.approx.ftz.f16x2   22 ex2.approx.ftz.bf16x2   23 cvt.rn.f16x2.f32 (F2FP.F16)
 // ---------------------------------------------------------------------------------------------
-constexpr int kPipeOps = 21;
+constexpr int kPipeOps = 24;
 constexpr int kPipeChains = 16;
 constexpr int kPipeUnroll = 4;      // instructions per chain per loop iteration
 
@@ -225,6 +226,9 @@ pipe_rate_kernel(long long* __restrict__ out, int iters, int nwarps, float seed,
                 } else if constexpr (kOp == 13) asm volatile("{ .reg .pred q; setp.gt.f32 q, %1, 0f00000000; selp.f32 %0, %0, %2, q; }" : "+f"(a[c]) : "f"(b), "f"(d));
                 else if constexpr (kOp == 14) asm volatile("fma.rn.bf16x2 %0, %0, %1, %2;" : "+r"(ia[c]) : "r"(ib), "r"(ib));
                 else if constexpr (kOp == 15) asm volatile("prmt.b32 %0, %0, %1, 0x5410;" : "+r"(ia[c]) : "r"(ib));
+                else if constexpr (kOp == 21) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(ia[c]));
+                else if constexpr (kOp == 22) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(ia[c]));
+                else if constexpr (kOp == 23) asm volatile("{ .reg .f32 t; mov.b32 t, %0; cvt.rn.f16x2.f32 %0, t, %1; }" : "+r"(ia[c]) : "f"(b));
                 else if constexpr (kOp >= 16) {
                     // packed chains: chain c pairs a[c] with a[c ^ 8] (8 packed chains of two floats)
                     const bool packed_slot = kOp == 16 || kOp == 17 || ((kOp == 18 || kOp == 20) && (c & 1) == 0) || (kOp == 19 && (c & 3) != 3);

@@ -12,7 +12,14 @@ enlarge the set of negatives (utils/model_utils.py:113-123).  Here the 2B x 2B p
             loss with respect to its own rows -- there is no column-partial reduce-scatter to do.
 
 Every rank must hold the same number of images.  The returned loss is the global loss (identical on all
-ranks); its gradient w.r.t. the local inputs is exact, so DDP-style parameter all-reduce composes as usual.
+ranks) and each rank receives the COMPLETE gradient of that global loss with respect to its own rows.
+
+Composition with DistributedDataParallel: DDP AVERAGES parameter gradients over the ranks.  Here every rank already
+back-propagates the gradient of the whole global loss through its own rows, so the sum over ranks -- not the mean --
+is the single-process global-batch gradient; under DDP the effective gradient would be 1/world of it.  Pass
+``ddp_scale=True`` (multiplies the returned loss by the world size, so that DDP's mean is the exact gradient; the
+value reported to the caller is then world x the global loss) or scale the loss yourself.
+tests/distributed_check.py checks this against a single-process run.
 
 Two transports:
   * ``PeerBatch`` (default on GPUs): the exchange is fused into our own kernels over peer memory.  The operand rows
@@ -272,27 +279,44 @@ def _peer_for(x1: torch.Tensor, group) -> PeerBatch:
     return _PEER_CACHE[key]
 
 
-def _global_loss(kind, x1, x2, temperature, normalize, weight, group, transport="auto"):
-    use_peer = transport == "peer" or (transport == "auto" and weight is None and x1.is_cuda)
+def _global_loss(kind, x1, x2, temperature, normalize, weight, group, transport="auto", ddp_scale=False):
+    from .functional import get_precision
+    if transport not in ("auto", "peer", "nccl"):
+        raise ValueError("transport must be 'auto', 'peer' or 'nccl'")
+    # The peer-memory transport carries bf16 operands and the unweighted loss only: anything else must not be dropped
+    # silently.  "auto" routes such calls through the collectives; an explicit "peer" is an error.
+    peer_ok = weight is None and get_precision() != "fp32" and x1.is_cuda
+    if transport == "peer" and not peer_ok:
+        if weight is not None:
+            raise ValueError("transport='peer' does not support per-row weights: use transport='nccl' (or 'auto')")
+        if not x1.is_cuda:
+            raise ValueError("transport='peer' needs CUDA tensors")
+        raise ValueError("transport='peer' computes with bf16 tensor-core operands; precision 'fp32' was requested "
+                         "(set_precision): use transport='nccl' (or 'auto')")
+    use_peer = transport == "peer" or (transport == "auto" and peer_ok)
     if use_peer:
         gather = _peer_for(x1, group)
-        loss, stats = ContrastiveLossFunction.apply(x1, x2, kind, float(temperature), bool(normalize), None, gather)
-        correct = stats[2].item()
-        return loss, 100.0 * correct / (2 * x1.shape[0] * gather.world)
-    gather = RowShardGather(group)
+        weight = None
+    else:
+        gather = RowShardGather(group)
     loss, stats = ContrastiveLossFunction.apply(x1, x2, kind, float(temperature), bool(normalize), weight, gather)
     correct = stats[2].item()
+    if ddp_scale:
+        loss = loss * gather.world
     return loss, 100.0 * correct / (2 * x1.shape[0] * gather.world)
 
 
 def global_contrastive_loss(x_batch1, x_batch2, temperature=1.0, normalize=True, weight: Optional[torch.Tensor] = None,
-                            group=None, transport: str = "auto"):
+                            group=None, transport: str = "auto", ddp_scale: bool = False):
     """NT-Xent over the union of all ranks' batches.  Same signature and return convention as
     ``contrastive_loss`` (reference objective.py:6-10,55); ``weight`` is this rank's [2*B_local] slice.
-    ``transport``: "peer" (fused NVLink stores + device barriers), "nccl" (collectives) or "auto"."""
-    return _global_loss(LOSS_NTXENT, x_batch1, x_batch2, temperature, normalize, weight, group, transport)
+    ``transport``: "peer" (fused NVLink stores + device barriers; unweighted, bf16 operands -- anything else raises),
+    "nccl" (collectives) or "auto".  ``ddp_scale``: see the module docstring (gradient averaging under DDP)."""
+    return _global_loss(LOSS_NTXENT, x_batch1, x_batch2, temperature, normalize, weight, group, transport, ddp_scale)
 
 
-def global_modified_contrastive_loss(x_batch1, x_batch2, group=None, transport: str = "auto", **kwargs):
+def global_modified_contrastive_loss(x_batch1, x_batch2, group=None, transport: str = "auto", ddp_scale: bool = False,
+                                     **kwargs):
     """Probabilistic loss over the union of all ranks' batches (reference objective.py:58-98)."""
-    return _global_loss(LOSS_MODIFIED, x_batch1, x_batch2, kwargs.get("temperature", 1.0), True, None, group, transport)
+    return _global_loss(LOSS_MODIFIED, x_batch1, x_batch2, kwargs.get("temperature", 1.0), True, None, group, transport,
+                        ddp_scale)

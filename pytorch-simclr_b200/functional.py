@@ -15,7 +15,7 @@ from ._lib import DTYPE_BF16, DTYPE_F32, LOSS_MODIFIED, LOSS_NTXENT, PRECISION_B
 
 __all__ = ["contrastive_forward_backward", "ContrastiveLossFunction", "LOSS_NTXENT", "LOSS_MODIFIED", "pad_rows",
            "pad_dim", "compact_to_padded", "padded_to_compact", "set_precision", "get_precision", "resolve_precision",
-           "set_eager_backward", "get_eager_backward", "run_fused"]
+           "set_eager_backward", "get_eager_backward", "run_fused", "run_fused_begin", "run_fused_finish"]
 
 BLOCK = 128
 
@@ -26,9 +26,10 @@ BLOCK = 128
 _PRECISION = "auto"
 
 
-# When a single-GPU, unweighted loss is evaluated with gradients enabled, the autograd Function can run the FUSED
-# five-kernel step (simclr_forward_backward) at forward time and keep the unit-upstream gradients; backward() then only
-# scales them by grad_output.  The reference's call pattern (loss, acc = loss_fn(...); loss /= k; loss.backward(),
+# When a single-GPU, unweighted loss is evaluated with gradients enabled, the autograd Function runs the first FOUR
+# kernels of the fused step at forward time (simclr_forward_backward_begin: the backward tile kernel is already in flight
+# when forward() returns) and backward() launches the last one with grad_output as its device scalar
+# (simclr_forward_backward_finish).  The reference's call pattern (loss, acc = loss_fn(...); loss /= k; loss.backward(),
 # utils/model_utils.py:115-120) always follows a training forward by its backward, and the accuracy read-back it forces
 # (objective.py:52) otherwise splits the step into two launch sequences with a host round trip in between.
 _EAGER_BACKWARD = True
@@ -189,8 +190,8 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
             bwd_ws = torch.empty(bwd_bytes, dtype=torch.uint8, device=dev)
         stats_ptr = stats.data_ptr()
         if host_slot is not None and gather is None:
-            stats_ptr = _hoststats.ring().pointer(host_slot)
-            stats = _hoststats.ring().buf[host_slot]
+            stats_ptr = _hoststats.ring(dev).pointer(host_slot)
+            stats = _hoststats.ring(dev).buf[host_slot]
         check(lib.simclr_forward_peer(loss_kind, operand.data_ptr(), operand_cols.data_ptr(), b, b_global, row_offset, d,
                                       float(temperature), int(bool(normalize)), precision, rowvec[1].data_ptr(),
                                       _ptr(w_local),
@@ -198,7 +199,7 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
                                       ws.data_ptr(), ws_bytes, _ptr(bwd_ws), 0 if bwd_ws is None else bwd_ws.numel(), 0, 0,
                                       None, None, None, None, stream), "simclr_forward")
         if host_slot is not None and gather is None:
-            _hoststats.ring().launched(host_slot)
+            _hoststats.ring(dev).launched(host_slot)
     saved = _Saved()
     saved.operand_rows, saved.operand_cols = operand, operand_cols
     saved.inv_norm, saved.pos_dot = rowvec[0], rowvec[1]
@@ -268,8 +269,8 @@ def run_fused(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature: f
             go = grad_out.to(device=dev, dtype=torch.float32).contiguous()
         if host_slot is not None:
             # the statistics go straight to pinned host memory (see _hoststats.py); `stats` is then that host row
-            stats_ptr = _hoststats.ring().pointer(host_slot)
-            stats = _hoststats.ring().buf[host_slot]
+            stats_ptr = _hoststats.ring(dev).pointer(host_slot)
+            stats = _hoststats.ring(dev).buf[host_slot]
         else:
             so = plan["stats"][0]
             stats = scratch[so:so + 16].view(torch.float32)
@@ -281,8 +282,72 @@ def run_fused(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature: f
                                           plan["bwd"][1], stream),
               "simclr_forward_backward")
         if host_slot is not None:
-            _hoststats.ring().launched(host_slot)
+            _hoststats.ring(dev).launched(host_slot)
     return loss, stats, g1, g2
+
+
+class _FusedState:
+    """What simclr_forward_backward_begin leaves for simclr_forward_backward_finish (device buffers + call constants)."""
+    __slots__ = ("scratch", "plan", "loss", "b", "d", "code", "normalize", "temperature", "precision")
+
+
+def run_fused_begin(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature: float, normalize: bool,
+                    precision: Optional[int] = None, host_slot: Optional[int] = None):
+    """First four kernels of the fused step (simclr_forward_backward_begin): returns (loss, stats, state).  The loss
+    statistics are complete when the forward finalize kernel has run -- the backward tile kernel, launched by the same
+    call, is still running then; ``run_fused_finish`` launches the last kernel once the upstream gradient is known."""
+    lib = _lib.load()
+    b, d = _validate(x1, x2)
+    dev = x1.device
+    if precision is None:
+        precision = resolve_precision(x1, False)
+    plan = _fused_plan(lib, loss_kind, b, d, precision)
+    st = _FusedState()
+    st.plan, st.loss, st.b, st.d, st.code = plan, loss_kind, b, d, _dtype_code(x1)
+    st.normalize, st.temperature, st.precision = int(bool(normalize)), float(temperature), precision
+    with _device_guard(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        st.scratch = scratch = torch.empty(plan["total"], dtype=torch.uint8, device=dev)
+        base = scratch.data_ptr()
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        if host_slot is not None:
+            ring = _hoststats.ring(dev)
+            stats_ptr, stats = ring.pointer(host_slot), ring.buf[host_slot]
+        else:
+            so = plan["stats"][0]
+            stats = scratch[so:so + 16].view(torch.float32)
+            stats_ptr = base + so
+        check(lib.simclr_forward_backward_begin(loss_kind, x1.data_ptr(), x2.data_ptr(), b, d, st.code, st.normalize,
+                                                st.temperature, precision, base + plan["operand"][0],
+                                                base + plan["rowvec"][0], stats_ptr, loss.data_ptr(),
+                                                base + plan["fwd"][0], plan["fwd"][1], base + plan["bwd"][0],
+                                                plan["bwd"][1], stream), "simclr_forward_backward_begin")
+        if host_slot is not None:
+            ring.launched(host_slot)
+    return loss, stats, st
+
+
+def run_fused_finish(st: "_FusedState", x1: torch.Tensor, x2: torch.Tensor, grad_out: Optional[torch.Tensor]):
+    """The backward finalize kernel (simclr_forward_backward_finish): gradients of grad_out * loss.  Repeatable."""
+    lib = _lib.load()
+    dev = x1.device
+    plan = st.plan
+    with _device_guard(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        g1 = torch.empty_like(x1)
+        g2 = torch.empty_like(x2)
+        go = None
+        if grad_out is not None:
+            go = grad_out
+            if go.dtype != torch.float32 or go.device != dev or not go.is_contiguous():
+                go = go.to(device=dev, dtype=torch.float32).contiguous()
+        base = st.scratch.data_ptr()
+        check(lib.simclr_forward_backward_finish(st.loss, x1.data_ptr(), x2.data_ptr(), st.b, st.d, st.code, st.normalize,
+                                                 st.temperature, st.precision, _ptr(go), base + plan["operand"][0],
+                                                 base + plan["rowvec"][0], g1.data_ptr(), g2.data_ptr(),
+                                                 base + plan["bwd"][0], plan["bwd"][1], stream),
+              "simclr_forward_backward_finish")
+    return g1, g2
 
 
 def run_backward(saved: "_Saved", x1: torch.Tensor, x2: torch.Tensor, grad_out: Optional[torch.Tensor]):
@@ -333,14 +398,18 @@ class ContrastiveLossFunction(torch.autograd.Function):
         else:
             want_grad = any(ctx.needs_input_grad[:2])
             if want_grad and _EAGER_BACKWARD and gather is None and weight is None:
-                # fused step now, unit upstream gradient; backward() scales
-                loss, stats, g1, g2 = run_fused(loss_kind, x1, x2, temperature, normalize, host_slot=host_slot)
-                ctx.eager_grads = (g1, g2)
+                # Four of the five kernels of the fused step now (the loss / accuracy are complete after the third, so the
+                # caller reads them while the backward tile kernel runs); backward() launches the finalize kernel with
+                # grad_output as its device scalar -- no extra pass over the gradients.
+                x1, x2 = x1.contiguous(), x2.contiguous()
+                loss, stats, state = run_fused_begin(loss_kind, x1, x2, temperature, normalize, host_slot=host_slot)
+                ctx.fused_state = state
+                ctx.save_for_backward(x1, x2)
                 ctx.mark_non_differentiable(stats)
                 return loss, stats
             loss, stats, _rowvec, saved = run_forward(loss_kind, x1, x2, temperature, normalize, weight, gather, want_grad,
                                                       host_slot=host_slot if weight is None else None)
-        ctx.eager_grads = None
+        ctx.fused_state = None
         ctx.saved_state = saved
         ctx.save_for_backward(x1, x2)
         ctx.mark_non_differentiable(stats)
@@ -348,11 +417,10 @@ class ContrastiveLossFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_stats):
-        if ctx.eager_grads is not None:
-            g1, g2 = ctx.eager_grads
-            s1, s2 = torch._foreach_mul((g1, g2), grad_loss.to(g1.dtype))      # one launch for both (kept grads stay intact)
-            return s1, s2, None, None, None, None, None, None
         x1, x2 = ctx.saved_tensors
+        if ctx.fused_state is not None:
+            g1, g2 = run_fused_finish(ctx.fused_state, x1, x2, grad_loss)
+            return g1, g2, None, None, None, None, None, None
         g1, g2 = run_backward(ctx.saved_state, x1.contiguous(), x2.contiguous(), grad_loss)
         return g1, g2, None, None, None, None, None, None
 

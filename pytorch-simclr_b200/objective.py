@@ -35,9 +35,13 @@ def _loss_and_accuracy(x1, x2, kind, temperature, normalize, weight):
     unweighted losses the finalize kernel writes the statistics into pinned host memory and this thread polls it
     (_hoststats.py) instead of paying a stream synchronisation."""
     if weight is None and x1.is_cuda and _HOST_STATS:
-        ring = _hoststats.ring()
+        ring = _hoststats.ring(x1.device)
         slot = ring.acquire()
-        loss, _stats = ContrastiveLossFunction.apply(x1, x2, kind, temperature, normalize, None, None, slot)
+        try:
+            loss, _stats = ContrastiveLossFunction.apply(x1, x2, kind, temperature, normalize, None, None, slot)
+        except BaseException:
+            ring.abandon(slot)
+            raise
         correct = ring.wait(slot)[2]
     else:
         loss, stats = ContrastiveLossFunction.apply(x1, x2, kind, temperature, normalize, weight, None)

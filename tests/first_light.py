@@ -18,7 +18,7 @@ def stage_selftest():
     import numpy as np
     import torch
     from pytorch_simclr_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_debug()
     torch.manual_seed(0)
     a = torch.randn(128, 128).to(torch.bfloat16).cuda()
     b = torch.randn(128, 128).to(torch.bfloat16).cuda()

@@ -9,6 +9,7 @@ import pytest
 from conftest import REPO
 
 HEADER = os.path.join(REPO, "include", "simclr_b200.h")
+DEBUG_HEADER = os.path.join(REPO, "include", "simclr_b200_debug.h")
 
 
 @pytest.fixture(scope="module")
@@ -19,8 +20,8 @@ def lib():
     return _lib.load()
 
 
-def _declared_functions():
-    text = open(HEADER).read()
+def _declared_functions(header=HEADER):
+    text = open(header).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(simclr_[a-z0-9_]+)\s*\(", text)))
 
@@ -35,8 +36,23 @@ def test_header_symbols_are_exported(lib):
     assert sorted(_lib.SIGNATURES) == declared, "ctypes binding and header disagree"
 
 
+def test_diagnostics_live_in_the_tracing_build_only(lib):
+    """include/simclr_b200_debug.h: exported by libsimclr_b200_trace.so (next to the whole product ABI), absent from
+    the product library."""
+    from pytorch_simclr_b200 import _lib
+    debug = _declared_functions(DEBUG_HEADER)
+    assert sorted(_lib.DEBUG_SIGNATURES) == debug
+    product = ctypes.CDLL(_lib.LIB_PATH)
+    trace = ctypes.CDLL(_lib.TRACE_LIB_PATH)
+    for name in debug:
+        assert not hasattr(product, name), f"{name} must not ship in the product library"
+        assert hasattr(trace, name)
+    for name in _declared_functions():
+        assert hasattr(trace, name)
+
+
 def test_abi_version_and_error_strings(lib):
-    assert lib.simclr_abi_version() == 9
+    assert lib.simclr_abi_version() == 10
     assert lib.simclr_error_string(0) == b"ok"
     for code in range(-11, 0):
         assert lib.simclr_error_string(code) not in (b"", b"unknown error")

@@ -9,7 +9,7 @@ import torch  # noqa: E402
 
 from pytorch_simclr_b200 import _lib  # noqa: E402
 
-lib = _lib.load()
+lib = _lib.load_debug()
 names = ["fwd shipped (1/4 poly4)", "bwd shipped (1/4 poly3)", "fwd all-MUFU + max", "fwd all-MUFU no max", "fwd 1/2 poly4",
          "MUFU + FADD only", "FFMA only (4/elem)", "bwd all-MUFU", "tcgen05.ld only", "fwd 1/4 poly3"]
 sink = torch.zeros(640, device="cuda")

@@ -5,6 +5,9 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+# the stamps only exist in the tracing build: make it the library the whole package uses in this process
+os.environ.setdefault("SIMCLR_B200_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                     "pytorch-simclr_b200", "lib", "libsimclr_b200_trace.so"))
 import torch  # noqa: E402
 
 from pytorch_simclr_b200 import _lib  # noqa: E402

@@ -7,7 +7,7 @@ import torch  # noqa: E402
 
 from pytorch_simclr_b200 import _lib  # noqa: E402
 
-lib = _lib.load()
+lib = _lib.load_debug()
 names = ["SS N=128", "SS N=256", "TS N=128 (A in TMEM)", "SS/TS N=128 alternating"]
 modes = ["idle", "tcgen05.ld", "MUFU.EX2", "FFMA", "ld+MUFU+FFMA"]
 sink = torch.zeros(640, device="cuda")

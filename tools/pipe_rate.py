@@ -8,10 +8,10 @@ import torch  # noqa: E402
 
 from pytorch_simclr_b200 import _lib  # noqa: E402
 
-lib = _lib.load()
+lib = _lib.load_debug()
 names = ["FFMA reg,reg,reg", "FFMA reg,imm,reg", "FADD reg,reg", "FADD reg,imm", "FMUL reg,reg", "MUFU.EX2", "FMNMX reg,reg",
          "IMAD x*2^23+y", "SHL+IADD", "3 FFMA : 1 MUFU", "F2FP bf16x2", "FMNMX3", "LDS.128", "FSETP+FSEL", "HFMA2.BF16", "PRMT",
-         "FADD2", "FFMA2", "FADD2 : FMNMX 1:1", "3 FFMA2 : 1 MUFU", "FADD2 : FADD 1:1"]
+         "FADD2", "FFMA2", "FADD2 : FMNMX 1:1", "3 FFMA2 : 1 MUFU", "FADD2 : FADD 1:1", "EX2.F16x2", "EX2.BF16x2", "F2FP f16x2"]
 sink = torch.zeros(640, device="cuda")
 iters = 2000
 for nwarps in (4, 8, 16):
@@ -25,6 +25,6 @@ for nwarps in (4, 8, 16):
         ninstr = iters * 4 * 16 * (nwarps / 4)          # warp instructions issued on one sub-partition
         if i in (8, 13):
             ninstr *= 2
-        if i >= 16:
+        if 16 <= i <= 20:
             ninstr /= 2                                 # eight (packed or scalar) instructions per 16-chain round
         print(f"{nwarps // 4} warps/SMSP | {n:18s}: {o[i].item() / ninstr:6.2f} cycles per warp instruction per sub-partition")
