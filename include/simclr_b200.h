@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIMCLR_ABI_VERSION 10
+#define SIMCLR_ABI_VERSION 11
 
 /* loss kinds */
 #define SIMCLR_LOSS_NTXENT 0   /* objective.py:6-55  */
@@ -81,9 +81,9 @@ size_t simclr_backward_workspace_bytes(int loss, int64_t b_local, int64_t b_glob
  *                                  to simclr_forward / simclr_backward); the modified loss ignores `temperature`
  *   inv_norm f32  [2*Blpad]        1 / max(||z||, 1e-12)   (1 when normalize == 0)
  *   pos_dot  f32  [2*Blpad]        exact fp32 <op_r, op_pos(r)> of the positive pair
- * `forward_workspace` (may be NULL) is the workspace the following simclr_forward call will use; its counter
- * header is zeroed here so that no separate memset is needed.  simclr_forward requires that header (the first
- * 4 * (2*Blpad/128 + 4) bytes) to be zero on entry and leaves it zero on exit.
+ * `forward_workspace` (may be NULL) is the workspace the following simclr_forward call will use; its counters (the
+ * ticket header and the per-row candidate counters of the exact accuracy count) are zeroed here so that no separate
+ * memset is needed.  simclr_forward requires them to be zero on entry and leaves them zero on exit.
  */
 int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
                    int normalize, float temperature, void* operand, float* inv_norm, float* pos_dot,
@@ -103,11 +103,18 @@ int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t
  * reference's compact order (view-1 rows then view-2 rows), or NULL.
  * `normalize` must repeat the value given to simclr_prepare: normalised rows bound the scores (|S| <= 1), which
  * lets the NT-Xent kernel use a constant softmax shift instead of a running maximum.
+ * Accuracy count (stats[2], objective.py:51-53 / :95-97: first argmax == positive): with bf16 operands a tensor-core score
+ * is only known to within 2^-8 of the largest possible score, so rows whose best negative lies within that band of the
+ * exact positive are decided by re-scoring the (at most 8) negatives inside the band in exact fp32 -- which needs the
+ * exact rows: `x_batch1` / `x_batch2` / `in_dtype` / `inv_norm` as given to / produced by simclr_prepare (one GPU,
+ * b_local == b_global; or zrows_* of simclr_forward_peer).  All NULL, normalize == 0, or more than 8 negatives inside the
+ * band of a row: that row is decided on the tensor-core scores (exact ties between identical rows stay exact either way).
  */
 int simclr_forward(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
                    int64_t row_offset, int64_t d, float temperature, int normalize, const float* pos_dot,
                    const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out, void* workspace,
-                   size_t workspace_bytes, void* stream);
+                   size_t workspace_bytes, const void* x_batch1, const void* x_batch2, int in_dtype, const float* inv_norm,
+                   void* stream);
 
 /*
  * Stage 3 -- backward: gradients of  grad_out * loss  with respect to x_batch1 / x_batch2 of this rank.
@@ -193,18 +200,25 @@ int simclr_forward_backward_finish(int loss, const void* x_batch1, const void* x
  *                       rank, before the pushed data is consumed.  world == 0 / NULL peers degrade to the local calls
  *                       (these are also the entry points that take `precision`; simclr_prepare / simclr_forward are
  *                       their SIMCLR_PRECISION_BF16 single-rank forms).
+ * Exact accuracy count across ranks: simclr_prepare_peer additionally writes the exact fp32 normalised rows of this rank
+ * into `zrows_local` f32 [2*Blpad][Dpad] (may be NULL); simclr_forward_peer re-scores the candidates of a row from
+ * `zrows_peers` (world pointers: every rank's zrows_local in symmetric memory, read over NVLink for the few rows needed)
+ * or from `zrows_global` f32 [2*Bgpad][Dpad] (the ranks' zrows_local gathered by a collective); both NULL: from
+ * x_batch1 / x_batch2 / inv_norm as in simclr_forward when b_local == b_global, else on the tensor-core scores.
  */
 int simclr_prepare_peer(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
                         int normalize, float temperature, int precision, void* operand, float* inv_norm, float* pos_dot,
                         void* forward_workspace, int world, int rank, void* const* operand_global_peers,
-                        void* operand_global_multicast, void* stream);
+                        void* operand_global_multicast, float* zrows_local, void* stream);
 int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
                         int64_t row_offset, int64_t d, float temperature, int normalize, int precision,
                         const float* pos_dot,
                         const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out,
                         void* workspace, size_t workspace_bytes, void* backward_workspace,
                         size_t backward_workspace_bytes, int world, int rank, void* const* colvec_peers,
-                        void* const* stats_peers, void* const* flag_peers, unsigned int* epoch_local, void* stream);
+                        void* const* stats_peers, void* const* flag_peers, unsigned int* epoch_local,
+                        const void* x_batch1, const void* x_batch2, int in_dtype, const float* inv_norm,
+                        const float* zrows_global, void* const* zrows_peers, void* stream);
 int simclr_peer_barrier(int world, int rank, void* const* flag_peers, unsigned int* epoch_local, const float* stats_all,
                         float* stats_out, float* loss_out, void* stream);
 
@@ -226,7 +240,7 @@ int simclr_forward_backward_peer(int loss, const void* x_batch1, const void* x_b
                                  void* backward_workspace, size_t backward_workspace_bytes, int world, int rank,
                                  void* const* operand_global_peers, void* operand_global_multicast,
                                  void* const* colvec_peers, void* const* stats_peers, void* const* flag_peers,
-                                 unsigned int* epoch_local, void* stream);
+                                 unsigned int* epoch_local, void* const* zrows_peers, void* stream);
 
 /*
  * Measurement entry points (bench.py): simclr_forward_peer on one GPU / simclr_backward restricted to a subset of their
@@ -246,7 +260,8 @@ int simclr_forward_stages(int loss, const void* operand_rows, const void* operan
                           int64_t row_offset, int64_t d, float temperature, int normalize, int precision,
                           const float* pos_dot, const float* row_weight, float* lse2, float* row_loss, float* stats,
                           float* loss_out, void* workspace, size_t workspace_bytes, void* backward_workspace,
-                          size_t backward_workspace_bytes, void* stream, unsigned int stage_mask);
+                          size_t backward_workspace_bytes, const void* x_batch1, const void* x_batch2, int in_dtype,
+                          const float* inv_norm, void* stream, unsigned int stage_mask);
 int simclr_backward_stages(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t b_global,
                            int64_t row_offset, int64_t d, int in_dtype, int normalize, float temperature, int precision,
                            const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,

@@ -105,6 +105,7 @@ class OracleResult:
     grad2: Optional[np.ndarray]
     lse: np.ndarray        # per-row log-sum-exp (natural log), length M
     row_loss: np.ndarray   # per-row loss L_r, length M
+    margin: Optional[np.ndarray] = None   # per row: best negative logit - positive logit (how close the argmax decision is)
 
 
 def _as_f64(x) -> np.ndarray:
@@ -154,6 +155,7 @@ def ntxent_closed_form(x_batch1, x_batch2, temperature: float = 1.0, normalize: 
 
     lse = np.empty(m)
     s_pos = np.empty(m)
+    margin = np.empty(m)
     correct = 0
     for r0 in range(0, m, block):
         r1 = min(m, r0 + block)
@@ -164,6 +166,9 @@ def ntxent_closed_form(x_batch1, x_batch2, temperature: float = 1.0, normalize: 
         mx = s.max(axis=1)
         lse[r0:r1] = mx + np.log(np.exp(s - mx[:, None]).sum(axis=1))
         correct += int(first_argmax_is_positive(s, rows, n).sum())
+        neg = s.copy()
+        neg[np.arange(r1 - r0), pos[r0:r1]] = -np.inf
+        margin[r0:r1] = neg.max(axis=1) - s_pos[r0:r1] if m > 2 else -np.inf
     row_loss = lse - s_pos
     loss = float((w * row_loss).sum() / wsum)                         # objective.py:47,50
 
@@ -188,7 +193,7 @@ def ntxent_closed_form(x_batch1, x_batch2, temperature: float = 1.0, normalize: 
         else:
             dz = dzh
         g1, g2 = dz[:n], dz[n:]
-    return OracleResult(loss, correct, 100.0 * correct / m, g1, g2, lse, row_loss)
+    return OracleResult(loss, correct, 100.0 * correct / m, g1, g2, lse, row_loss, margin)
 
 
 def ntxent_row_sample_check(x_batch1, x_batch2, temperature: float, sample_rows, grad_output: float = 1.0,
@@ -266,6 +271,7 @@ def modified_closed_form(x_batch1, x_batch2, temperature: float = 1.0, grad_outp
 
     lse = np.empty(m)
     a_pos = np.empty(m)
+    margin = np.empty(m)
     correct = 0
     for view in (0, 1):
         mine, other = src[view], src[1 - view]
@@ -277,6 +283,9 @@ def modified_closed_form(x_batch1, x_batch2, temperature: float = 1.0, grad_outp
             lse[view * n + r0:view * n + r1] = mx + np.log(np.exp(a - mx[:, None]).sum(axis=1))
             a_pos[view * n + r0:view * n + r1] = a[np.arange(r1 - r0), np.arange(r0, r1)]
             correct += int((a.argmax(axis=1) == np.arange(r0, r1)).sum())  # objective.py:95-96
+            neg = a.copy()
+            neg[np.arange(r1 - r0), np.arange(r0, r1)] = -np.inf
+            margin[view * n + r0:view * n + r1] = neg.max(axis=1) - a_pos[view * n + r0:view * n + r1] if n > 1 else -np.inf
     row_loss = lse - a_pos
     loss = float(row_loss.mean())                                          # objective.py:92-94
 
@@ -304,7 +313,7 @@ def modified_closed_form(x_batch1, x_batch2, temperature: float = 1.0, grad_outp
             sig = 1.0 / (1.0 + np.exp(-SOFTPLUS_BETA * x))
             grads.append(ds * np.where(SOFTPLUS_BETA * x > SOFTPLUS_THRESHOLD, 1.0, sig))
         g1, g2 = grads
-    return OracleResult(loss, correct, 100.0 * correct / m, g1, g2, lse, row_loss)
+    return OracleResult(loss, correct, 100.0 * correct / m, g1, g2, lse, row_loss, margin)
 
 
 # --------------------------------------------------------------------------------------------

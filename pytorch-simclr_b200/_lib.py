@@ -15,7 +15,7 @@ DTYPE_F32 = 0
 DTYPE_BF16 = 1
 PRECISION_BF16 = 0
 PRECISION_SPLIT = 1
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 _lock = threading.Lock()
 _lib = None
@@ -36,7 +36,7 @@ SIGNATURES = {
     "simclr_backward_workspace_bytes": (_sz, [_int, _i64, _i64, _i64]),
     "simclr_prepare": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _vp, _vp, _vp, _vp, _vp]),
     "simclr_forward": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                              _sz, _vp]),
+                              _sz, _vp, _vp, _int, _vp, _vp]),
     "simclr_operand_bytes": (_sz, [_i64, _i64, _int]),
     "simclr_backward": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp,
                                _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
@@ -47,14 +47,14 @@ SIGNATURES = {
     "simclr_forward_backward_finish": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp,
                                               _vp, _sz, _vp]),
     "simclr_forward_backward_peer": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                            _vp, _vp, _sz, _vp, _sz, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                            _vp, _vp, _sz, _vp, _sz, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "simclr_prepare_peer": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _int, _int, _vp,
-                                   _vp, _vp]),
+                                   _vp, _vp, _vp]),
     "simclr_forward_peer": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp,
-                                   _vp, _sz, _vp, _sz, _int, _int, _vp, _vp, _vp, _vp, _vp]),
+                                   _vp, _sz, _vp, _sz, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp]),
     "simclr_peer_barrier": (_int, [_int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "simclr_forward_stages": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp,
-                                     _vp, _sz, _vp, _sz, _vp, ctypes.c_uint]),
+                                     _vp, _sz, _vp, _sz, _vp, _vp, _int, _vp, _vp, ctypes.c_uint]),
     "simclr_backward_stages": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp,
                                       _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, ctypes.c_uint]),
 }

@@ -58,7 +58,8 @@ template <typename T, int kLoss, int kPer /* d_pad / 32: 2, 4 or 8 */>
 __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x2, AuxParams a,
                                __nv_bfloat16* __restrict__ operand, float* __restrict__ inv_norm,
                                float* __restrict__ pos_dot, unsigned int* __restrict__ zero_ptr, int zero_words,
-                               unsigned long long* ktrace, PeerTable peers, unsigned int* bump_epoch) {
+                               unsigned long long* ktrace, PeerTable peers, unsigned int* bump_epoch,
+                               unsigned int* __restrict__ cand_cnt, float* __restrict__ zstash) {
     pdl_launch_dependents();
     // The input rows are loaded BEFORE griddepcontrol.wait (they are the caller's tensors: no kernel of this library
     // writes them, and a foreign producer never lets this kernel start early); every store comes after it, because the
@@ -101,6 +102,11 @@ __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x
     // fused row-sharded step: the epoch of the barrier that the forward tile kernel executes (TileParams::sync_epoch)
     if (bump_epoch != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *bump_epoch += 1u;
     if (i >= a.bl_pad) return;
+    // candidate counters of the exact accuracy count (forward workspace): zero for both views of this image slot
+    if (cand_cnt != nullptr && lane == 0) {
+        cand_cnt[i] = 0u;
+        cand_cnt[a.bl_pad + i] = 0u;
+    }
     __nv_bfloat16* o1 = operand + static_cast<size_t>(i) * a.d_pad;
     __nv_bfloat16* o2 = operand + static_cast<size_t>(a.bl_pad + i) * a.d_pad;
     uint32_t w1[4] = {0u, 0u, 0u, 0u}, w2[4] = {0u, 0u, 0u, 0u};
@@ -163,6 +169,17 @@ __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x
     }
     store_words<kWords>(o1, lane, w1);
     store_words<kWords>(o2, lane, w2);
+    if (zstash != nullptr) {
+        // exact fp32 normalised rows for the re-scoring of accuracy candidates by OTHER ranks (symmetric memory, read over
+        // NVLink only for the few candidates) or after a gather: [2*bl_pad][d_pad], lane l owns kPer consecutive columns
+        float* z1 = zstash + static_cast<size_t>(i) * a.d_pad + lane * kPer;
+        float* z2 = zstash + static_cast<size_t>(a.bl_pad + i) * a.d_pad + lane * kPer;
+#pragma unroll
+        for (int u = 0; u < kPer; u += 2) {
+            *reinterpret_cast<float2*>(z1 + u) = make_float2(v1[u] * s1, v1[u + 1] * s1);
+            *reinterpret_cast<float2*>(z2 + u) = make_float2(v2[u] * s2, v2[u + 1] * s2);
+        }
+    }
     if (a.split) {
         uint32_t l1[4] = {0u, 0u, 0u, 0u}, l2[4] = {0u, 0u, 0u, 0u};
 #pragma unroll

@@ -216,6 +216,8 @@ inline size_t header_bytes(const Geometry&) { return 256; }
 
 struct FwdWorkspace {
     unsigned int* ticket;
+    unsigned int* cand_cnt;   // [2*bl_pad] candidate counters of the exact accuracy count (zero between calls)
+    int* cand;                // [2*bl_pad][kCandMax]
     float* part;
     float* part2;      // partials of the second launch of the overlapped row-sharded forward
     float* block_part;
@@ -228,6 +230,12 @@ FwdWorkspace carve_forward(const Geometry& g, void* base) {
     off += header_bytes(g);
     w.block_part = reinterpret_cast<float*>(static_cast<char*>(base) + off);
     off += align256(static_cast<size_t>(g.n_row_blocks) * 4 * sizeof(float));
+    // (everything up to here depends on the LOCAL rows only: the prepare kernel, which does not know the window of the
+    // forward launch, zeroes the ticket header and the candidate counters)
+    w.cand_cnt = reinterpret_cast<unsigned int*>(static_cast<char*>(base) + off);
+    off += align256(static_cast<size_t>(2) * g.bl_pad * sizeof(unsigned int));
+    w.cand = reinterpret_cast<int*>(static_cast<char*>(base) + off);
+    off += align256(static_cast<size_t>(2) * g.bl_pad * kCandMax * sizeof(int));
     // sized for the full column window; a narrower window never needs more (fewer tiles per CTA, at most as many CTAs),
     // except that max_segs can grow by the row blocks a CTA additionally spans: bound it by n_row_blocks
     const int segs = g.n_row_blocks < 8 ? g.n_row_blocks : (g.max_segs + 6 < g.n_row_blocks ? g.max_segs + 6 : g.n_row_blocks);
@@ -260,13 +268,14 @@ BwdWorkspace carve_backward(const Geometry& g, void* base) {
 
 // log2-domain constants shared by forward and backward
 struct Scales {
-    float k2, inv_tau, m2, qscale, op_scale;
+    float k2, inv_tau, tau, m2, qscale, op_scale;
     int const_shift;
     int pow;       // modified loss: 1 / 2 when 1/tau is exactly that (plain-power path), else 0
 };
 Scales make_scales(int loss, float temperature, int normalize, int64_t b_global) {
     Scales s;
     s.inv_tau = 1.0f / temperature;
+    s.tau = temperature;
     s.qscale = static_cast<float>(b_global);
     if (loss == SIMCLR_LOSS_NTXENT) {
         s.k2 = 1.4426950408889634f * s.inv_tau;
@@ -414,6 +423,7 @@ TileParams make_tile_params(const Geometry& g, const Scales& s, int64_t b_local,
     p.pow = s.pow;
     p.qscale = s.qscale;
     p.inv_tau = s.inv_tau;
+    p.tau = s.tau;
     p.acc_scale = 1.0f / s.op_scale;
     p.trace = g_trace_ptr;
     p.trace_cta = g_trace_cta;
@@ -515,8 +525,9 @@ struct FusedSync {
 int prepare_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
                  int normalize, float temperature, int precision, void* operand, float* inv_norm, float* pos_dot,
                  void* forward_workspace, int world, int rank, void* const* operand_global_peers,
-                 void* operand_global_multicast, void* stream, unsigned int* bump_epoch) {
+                 void* operand_global_multicast, void* stream, unsigned int* bump_epoch, float* zrows_local) {
     if (bad_precision(precision)) return SIMCLR_ERR_BAD_DTYPE;
+    if (zrows_local != nullptr && misaligned(zrows_local)) return SIMCLR_ERR_MISALIGNED;
     if (!x_batch1 || !x_batch2 || !operand || !inv_norm || !pos_dot) return SIMCLR_ERR_NULL_POINTER;
     if (in_dtype != SIMCLR_DTYPE_F32 && in_dtype != SIMCLR_DTYPE_BF16) return SIMCLR_ERR_BAD_DTYPE;
     if (!(temperature > 0.f) || !std::isfinite(temperature)) return SIMCLR_ERR_BAD_TEMPERATURE;
@@ -537,6 +548,7 @@ int prepare_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t b
     Scales s = make_scales(loss, temperature, normalize, b_global);
     unsigned int* zero_ptr = static_cast<unsigned int*>(forward_workspace);
     const int zero_words = static_cast<int>(header_bytes(g) / 4);
+    unsigned int* cand_cnt = forward_workspace ? carve_forward(g, forward_workspace).cand_cnt : nullptr;
     if (precision == SIMCLR_PRECISION_SPLIT && g.d_pad > 128) return SIMCLR_ERR_UNSUPPORTED_DIM;
     AuxParams a = make_aux(g, s, b_local, b_global, row_offset, d, normalize);
     a.split = precision == SIMCLR_PRECISION_SPLIT ? 1 : 0;
@@ -546,7 +558,7 @@ int prepare_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t b
     auto* op = static_cast<__nv_bfloat16*>(operand);
     cudaError_t launch_rc = cudaSuccess;
 #define SIMCLR_PREP2(T, LOSS, PER) \
-    launch_rc = launch_pdl(prepare_kernel<T, LOSS, PER>, dim3(blocks), dim3(warps * 32), 0, st, static_cast<const T*>(x_batch1), static_cast<const T*>(x_batch2), a, op, inv_norm, pos_dot, zero_ptr, zero_words, g_ktrace_ptr, peers, bump_epoch)
+    launch_rc = launch_pdl(prepare_kernel<T, LOSS, PER>, dim3(blocks), dim3(warps * 32), 0, st, static_cast<const T*>(x_batch1), static_cast<const T*>(x_batch2), a, op, inv_norm, pos_dot, zero_ptr, zero_words, g_ktrace_ptr, peers, bump_epoch, cand_cnt, zrows_local)
 #define SIMCLR_PREP(T, LOSS)                          \
     switch (g.d_pad) {                                \
         case 64: SIMCLR_PREP2(T, LOSS, 2); break;     \
@@ -572,10 +584,10 @@ extern "C" {
 int simclr_prepare_peer(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
                         int normalize, float temperature, int precision, void* operand, float* inv_norm, float* pos_dot,
                         void* forward_workspace, int world, int rank, void* const* operand_global_peers,
-                        void* operand_global_multicast, void* stream) {
+                        void* operand_global_multicast, float* zrows_local, void* stream) {
     return prepare_impl(loss, x_batch1, x_batch2, b_local, d, in_dtype, normalize, temperature, precision, operand, inv_norm,
                         pos_dot, forward_workspace, world, rank, operand_global_peers, operand_global_multicast, stream,
-                        nullptr);
+                        nullptr, zrows_local);
 }
 
 int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
@@ -583,7 +595,7 @@ int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t
                    void* forward_workspace, void* stream) {
     return simclr_prepare_peer(loss, x_batch1, x_batch2, b_local, d, in_dtype, normalize, temperature,
                                SIMCLR_PRECISION_BF16, operand, inv_norm, pos_dot, forward_workspace, 0, 0, nullptr, nullptr,
-                               stream);
+                               nullptr, stream);
 }
 
 int simclr_peer_barrier(int world, int rank, void* const* flag_peers, unsigned int* epoch_local, const float* stats_all,
@@ -603,13 +615,25 @@ int simclr_peer_barrier(int world, int rank, void* const* flag_peers, unsigned i
 
 namespace {
 
+// Where the forward finalize kernel finds exact fp32 rows for the accuracy candidates (TileParams::cand_cnt): the caller's
+// inputs on one GPU, a gathered fp32 copy, or the ranks' symmetric copies.  All NULL: tensor-core decision.
+struct ExactSource {
+    const void* x1 = nullptr;
+    const void* x2 = nullptr;
+    int in_dtype = SIMCLR_DTYPE_F32;
+    const float* inv_norm = nullptr;
+    const float* zrows = nullptr;            // [2*Bgpad][Dpad]
+    void* const* zrows_peers = nullptr;      // world pointers to [2*Blpad][Dpad]
+};
+
 // defer_stats: the backward of the same fused step finishes the loss statistics (simclr_forward_backward)
 int forward_impl(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
                  int64_t row_offset, int64_t d, float temperature, int normalize, int precision, const float* pos_dot,
                  const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out, void* workspace,
                  size_t workspace_bytes, void* backward_workspace, size_t backward_workspace_bytes, int world, int rank,
                  void* const* colvec_peers, void* const* stats_peers, void* const* flag_peers, unsigned int* epoch_local,
-                 void* stream, bool defer_stats, const FusedSync* fused = nullptr, unsigned stages = kAllStages) {
+                 void* stream, bool defer_stats, const FusedSync* fused = nullptr, unsigned stages = kAllStages,
+                 const ExactSource& exact = ExactSource()) {
     if (!operand_rows || !operand_cols || !pos_dot || !lse2 || !row_loss || !stats || !workspace)
         return SIMCLR_ERR_NULL_POINTER;
     if (!(temperature > 0.f) || !std::isfinite(temperature)) return SIMCLR_ERR_BAD_TEMPERATURE;
@@ -641,6 +665,32 @@ int forward_impl(int loss, const void* operand_rows, const void* operand_cols, i
     p.stats = stats;
     p.loss_out = loss_out;
     p.defer_stats = defer_stats ? 1 : 0;
+    p.normalize = normalize;
+    // Exact accuracy count (bf16 operands; normalised rows bound the error of a tensor-core score): needs a source of
+    // exact fp32 rows for every column -- the inputs themselves when this call covers the whole batch
+    if (precision == SIMCLR_PRECISION_BF16 && (normalize || loss == SIMCLR_LOSS_MODIFIED)) {
+        if (exact.in_dtype != SIMCLR_DTYPE_F32 && exact.in_dtype != SIMCLR_DTYPE_BF16) return SIMCLR_ERR_BAD_DTYPE;
+        bool have = false;
+        if (exact.zrows_peers != nullptr && world > 0) {
+            if ((rc = make_peer_table(world, rank, exact.zrows_peers, &p.zrows_peers))) return rc;
+            have = true;
+        } else if (exact.zrows != nullptr) {
+            if (misaligned(exact.zrows)) return SIMCLR_ERR_MISALIGNED;
+            p.zrows = exact.zrows;
+            have = true;
+        } else if (exact.x1 && exact.x2 && exact.inv_norm && b_local == b_global) {
+            p.x1 = exact.x1;
+            p.x2 = exact.x2;
+            p.inv_norm = exact.inv_norm;
+            p.in_bf16 = exact.in_dtype == SIMCLR_DTYPE_BF16 ? 1 : 0;
+            have = true;
+        }
+        if (have) {
+            p.cand_cnt = w.cand_cnt;
+            p.cand = w.cand;
+            p.band = (loss == SIMCLR_LOSS_NTXENT ? s.k2 : 1.0f) * kBandRel;
+        }
+    }
     if (fused != nullptr) {
         // the barrier after the operand push runs inside the tile kernel; the finalize kernel bumps the epoch for the
         // barrier inside the backward tile kernel
@@ -822,20 +872,31 @@ int simclr_forward_peer(int loss, const void* operand_rows, const void* operand_
                         const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out,
                         void* workspace, size_t workspace_bytes, void* backward_workspace,
                         size_t backward_workspace_bytes, int world, int rank, void* const* colvec_peers,
-                        void* const* stats_peers, void* const* flag_peers, unsigned int* epoch_local, void* stream) {
+                        void* const* stats_peers, void* const* flag_peers, unsigned int* epoch_local,
+                        const void* x_batch1, const void* x_batch2, int in_dtype, const float* inv_norm,
+                        const float* zrows_global, void* const* zrows_peers, void* stream) {
+    ExactSource ex;
+    ex.x1 = x_batch1;
+    ex.x2 = x_batch2;
+    ex.in_dtype = in_dtype;
+    ex.inv_norm = inv_norm;
+    ex.zrows = zrows_global;
+    ex.zrows_peers = zrows_peers;
     return forward_impl(loss, operand_rows, operand_cols, b_local, b_global, row_offset, d, temperature, normalize, precision,
                         pos_dot, row_weight, lse2, row_loss, stats, loss_out, workspace, workspace_bytes, backward_workspace,
                         backward_workspace_bytes, world, rank, colvec_peers, stats_peers, flag_peers, epoch_local, stream,
-                        false);
+                        false, nullptr, kAllStages, ex);
 }
 
 int simclr_forward(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
                    int64_t row_offset, int64_t d, float temperature, int normalize, const float* pos_dot,
                    const float* row_weight, float* lse2, float* row_loss, float* stats, float* loss_out, void* workspace,
-                   size_t workspace_bytes, void* stream) {
+                   size_t workspace_bytes, const void* x_batch1, const void* x_batch2, int in_dtype, const float* inv_norm,
+                   void* stream) {
     return simclr_forward_peer(loss, operand_rows, operand_cols, b_local, b_global, row_offset, d, temperature, normalize,
                                SIMCLR_PRECISION_BF16, pos_dot, row_weight, lse2, row_loss, stats, loss_out, workspace,
-                               workspace_bytes, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, stream);
+                               workspace_bytes, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, x_batch1, x_batch2,
+                               in_dtype, inv_norm, nullptr, nullptr, stream);
 }
 
 int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t b_global,
@@ -852,11 +913,17 @@ int simclr_forward_stages(int loss, const void* operand_rows, const void* operan
                           int64_t row_offset, int64_t d, float temperature, int normalize, int precision,
                           const float* pos_dot, const float* row_weight, float* lse2, float* row_loss, float* stats,
                           float* loss_out, void* workspace, size_t workspace_bytes, void* backward_workspace,
-                          size_t backward_workspace_bytes, void* stream, unsigned int stage_mask) {
+                          size_t backward_workspace_bytes, const void* x_batch1, const void* x_batch2, int in_dtype,
+                          const float* inv_norm, void* stream, unsigned int stage_mask) {
+    ExactSource ex;
+    ex.x1 = x_batch1;
+    ex.x2 = x_batch2;
+    ex.in_dtype = in_dtype;
+    ex.inv_norm = inv_norm;
     return forward_impl(loss, operand_rows, operand_cols, b_local, b_global, row_offset, d, temperature, normalize, precision,
                         pos_dot, row_weight, lse2, row_loss, stats, loss_out, workspace, workspace_bytes, backward_workspace,
                         backward_workspace_bytes, 0, 0, nullptr, nullptr, nullptr, nullptr, stream, false, nullptr,
-                        stage_mask);
+                        stage_mask, ex);
 }
 
 int simclr_backward_stages(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t b_global,
@@ -888,15 +955,21 @@ int fused_step_impl(int loss, const void* x_batch1, const void* x_batch2, int64_
     int rc;
     if (begin) {
         rc = simclr_prepare_peer(loss, x_batch1, x_batch2, b, d, in_dtype, normalize, temperature, precision, operand,
-                                 inv_norm, pos_dot, forward_workspace, 0, 0, nullptr, nullptr, stream);
+                                 inv_norm, pos_dot, forward_workspace, 0, 0, nullptr, nullptr, nullptr, stream);
         if (rc) return rc;
+        ExactSource ex;
+        ex.x1 = x_batch1;
+        ex.x2 = x_batch2;
+        ex.in_dtype = in_dtype;
+        ex.inv_norm = inv_norm;
         // The forward primes the backward workspace.  Whole step: the reduction of the loss statistics is left to the
         // backward finalize kernel (five launches, nothing but the column vectors between the two tile kernels).  Split
         // step: the forward finalize kernel completes them, so that the caller can read loss / accuracy while the
         // backward tile kernel is still running.
         rc = forward_impl(loss, operand, operand, b, b, 0, d, temperature, normalize, precision, pos_dot, nullptr, lse2,
                           row_loss, stats, loss_out, forward_workspace, forward_workspace_bytes, backward_workspace,
-                          backward_workspace_bytes, 0, 0, nullptr, nullptr, nullptr, nullptr, stream, finish);
+                          backward_workspace_bytes, 0, 0, nullptr, nullptr, nullptr, nullptr, stream, finish, nullptr,
+                          kAllStages, ex);
         if (rc) return rc;
     }
     const unsigned stages = (begin ? kStageBwdTile : 0u) | (finish ? kStageBwdFin : 0u);
@@ -946,7 +1019,7 @@ int simclr_forward_backward_peer(int loss, const void* x_batch1, const void* x_b
                                  void* backward_workspace, size_t backward_workspace_bytes, int world, int rank,
                                  void* const* operand_global_peers, void* operand_global_multicast,
                                  void* const* colvec_peers, void* const* stats_peers, void* const* flag_peers,
-                                 unsigned int* epoch_local, void* stream) {
+                                 unsigned int* epoch_local, void* const* zrows_peers, void* stream) {
     if (!rowvec || !stats_local || !stats_global || !backward_workspace || !operand_global_peers || !colvec_peers ||
         !stats_peers || !flag_peers || !epoch_local)
         return SIMCLR_ERR_NULL_POINTER;
@@ -961,15 +1034,20 @@ int simclr_forward_backward_peer(int loss, const void* x_batch1, const void* x_b
     const void* operand_cols = operand_global_peers[rank];
     const float* colvec_local = static_cast<const float*>(colvec_peers[rank]);
     FusedSync fs{world, rank, flag_peers, epoch_local, static_cast<const float*>(stats_peers[rank])};
-    // prepare pushes the operand rows and bumps the epoch; the forward tile kernel signals / waits on it
+    // prepare pushes the operand rows and bumps the epoch; the forward tile kernel signals / waits on it.  The exact fp32
+    // rows for the accuracy candidates stay on the rank that owns them (zrows_peers[rank]); the finalize kernels of the
+    // other ranks read the few rows they need over NVLink
     int rc = prepare_impl(loss, x_batch1, x_batch2, b_local, d, in_dtype, normalize, temperature, SIMCLR_PRECISION_BF16,
                           operand, inv_norm, pos_dot, forward_workspace, world, rank, operand_global_peers,
-                          operand_global_multicast, stream, epoch_local);
+                          operand_global_multicast, stream, epoch_local,
+                          zrows_peers ? static_cast<float*>(zrows_peers[rank]) : nullptr);
     if (rc) return rc;
+    ExactSource ex;
+    ex.zrows_peers = zrows_peers;
     rc = forward_impl(loss, operand, operand_cols, b_local, b_global, row_offset, d, temperature, normalize,
                       SIMCLR_PRECISION_BF16, pos_dot, nullptr, lse2, row_loss, stats_local, nullptr, forward_workspace,
                       forward_workspace_bytes, backward_workspace, backward_workspace_bytes, world, rank, colvec_peers,
-                      stats_peers, nullptr, nullptr, stream, false, &fs);
+                      stats_peers, nullptr, nullptr, stream, false, &fs, kAllStages, ex);
     if (rc) return rc;
     return backward_impl(loss, x_batch1, x_batch2, b_local, b_global, row_offset, d, in_dtype, normalize, temperature,
                          SIMCLR_PRECISION_BF16, operand, operand_cols, inv_norm, pos_dot, nullptr, nullptr, grad_out, grad1,

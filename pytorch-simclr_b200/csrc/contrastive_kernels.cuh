@@ -84,6 +84,14 @@ constexpr int kTokenBar0 = 2;         // named barriers 2, 3: ping-pong tokens o
 constexpr int kFwdFields = 5;         // per-row partial: sum, run-max, max-preceding, max-following, pos(mma)
 constexpr float kNegBig = -3.0e38f;   // finite stand-in for -inf
 constexpr float kClampMin = 1e-4f;    // reference objective.py:87-88
+// Exact accuracy count in bf16 mode (reference objective.py:51-53 / :95-97): the tensor-core score of a negative differs
+// from its exact value by at most kBandRel * (largest possible |score|), so a row's first-argmax decision taken on
+// tensor-core scores is certain unless its best negative lies inside that band around the EXACT positive score; the
+// (few) negatives inside the band are recorded as candidates and re-scored in exact fp32 by the finalize kernel.
+// bf16 round-to-nearest operands: relative error 2^-9 each, so |sum a_i b_i - sum a~_i b~_i| <= (2^-8 + 2^-18) sum|a_i b_i|
+// <= 2^-8 (1 + 2^-10) |a||b| (Cauchy-Schwarz); fp32 accumulation of d <= 256 terms adds < 2^-15 of that.  2 % margin.
+constexpr float kBandRel = 1.02f / 256.0f;
+constexpr int kCandMax = 8;           // candidates kept per row; a row with more falls back to the tensor-core decision
 // NT-Xent with normalised rows: |S'| <= k2 (+ bf16 rounding) and k2 <= 40 is required for this path, so exp2(S') stays
 // far inside the fp32 range: no running maximum and no shift at all ("constant shift" of zero)
 constexpr float kConstShiftRaw = 0.f;
@@ -129,6 +137,7 @@ struct TileParams {
                        // transcendental at all), else 0
     float qscale;      // modified loss: (float) b_glob, the factor inside the clamp
     float inv_tau;
+    float tau;         // the caller's temperature
     int d;             // true embedding dimension (<= D)
     int in_bf16;       // element type of x_batch / grad: 0 = f32, 1 = bf16
     int normalize;
@@ -186,6 +195,17 @@ struct TileParams {
     const unsigned int* sync_epoch;
     unsigned int* bump_epoch;
     unsigned long long peer_timeout_ns;   // watchdog of the cross-GPU waits (0 = none)
+    // Exact accuracy count (bf16 mode, normalised rows): per-row candidate lists filled by the forward tile kernel and
+    // consumed (and reset) by the forward finalize kernel.  nullptr: the count is decided on the tensor-core scores.
+    unsigned int* cand_cnt;    // [2*bl_pad], zero on entry, left zero
+    int* cand;                 // [2*bl_pad][kCandMax] global column indices
+    float band;                // half-width of the uncertainty band: absolute in log2-domain logits (NT-Xent: k2 * kBandRel),
+                               // relative (modified: kBandRel, all terms of its products are positive)
+    // where the finalize kernel finds the exact fp32 normalised rows of the candidates' columns: the caller's inputs
+    // (x1 / x2 / inv_norm above, one GPU), a gathered copy [2*bg_pad][D] (collective transport) or the ranks' own copies
+    // [2*bl_pad][D] in symmetric memory (peer transport)
+    const float* zrows;
+    PeerTable zrows_peers;
     // backward finalize, row-sharded fused step: add up the ranks' statistics [world][4] (fixed order) into stats / loss_out
     const float* stats_all;
     int stats_world;
@@ -316,6 +336,57 @@ template <int kLoss>
 SIMCLR_DEVICE float logit2(const TileParams& p, float v) {
     if constexpr (kLoss == kNtXent) return v;
     else return lg2_approx(v) * p.k2;
+}
+
+// Uncertainty band [lo, hi] of the tracked raw value around the exact positive `v_pos` (same expression in the tile
+// kernel that records the candidates and in the finalize kernel that classifies the row).
+// (explicitly rounded operations: no FMA contraction, so that both kernels compute the same bits)
+template <int kLoss>
+SIMCLR_DEVICE void cand_band(float band, float v_pos, float& lo, float& hi) {
+    if constexpr (kLoss == kNtXent) {
+        lo = __fsub_rn(v_pos, band);
+        hi = __fadd_rn(v_pos, band);
+    } else {
+        lo = __fmul_rn(v_pos, __fsub_rn(1.0f, band));
+        hi = __fmul_rn(v_pos, __fadd_rn(1.0f, band));
+    }
+}
+// the exact positive in the units of the tracked raw value
+template <int kLoss>
+SIMCLR_DEVICE float pos_raw_value(float pos_dot, float k2, float qscale) {
+    if constexpr (kLoss == kNtXent) return __fmul_rn(pos_dot, k2);
+    else return fmaxf(__fmul_rn(pos_dot, qscale), kClampMin);
+}
+
+// Rare path of the forward tile kernel: the 64 columns of this warp's part of a score tile are read again from TMEM and
+// every valid negative inside the band of its row is appended to the row's candidate list.  Returns the largest valid
+// negative of the thread's row in this tile.  Whole warp (tcgen05.ld is warp-collective); rows that are not interested
+// pass lo = +3e38.
+template <int kLoss>
+__device__ __noinline__ float cand_rescan(uint32_t t0, int cbase, int icbase, int b_glob, float qscale, int diag_col, int pos_col,
+                                          float lo, float hi, unsigned int* cnt, int* list) {
+    float tile_max = kNegBig;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        uint32_t r[16];
+        tmem_ld16(t0 + k * 16, r);
+        tmem_ld_wait16(r);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int col = cbase + k * 16 + i;
+            float v = __uint_as_float(r[i]);
+            if constexpr (kLoss == kModified) v = fmaxf(v * qscale, kClampMin);
+            const bool dead = (col == diag_col) | (col == pos_col) | (icbase + k * 16 + i >= b_glob);
+            if (!dead) {
+                tile_max = fmaxf(tile_max, v);
+                if (v >= lo && v <= hi) {
+                    const unsigned int at = atomicAdd(cnt, 1u);
+                    if (at < static_cast<unsigned int>(kCandMax)) list[at] = col;
+                }
+            }
+        }
+    }
+    return tile_max;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -746,6 +817,78 @@ SIMCLR_DEVICE FinIndex fin_index(const TileParams& p, int rb, int tid) {
     return ix;
 }
 
+// ---- exact re-scoring of the candidates (forward finalize kernel, warp-cooperative) ----
+// Where the exact fp32 normalised row of global column (view, image) comes from: a stash (gathered, or a peer's
+// symmetric copy) or the caller's inputs, normalised on the fly exactly as the prepare kernel did.
+struct ZRow {
+    const float* stash;        // normalised fp32 row (d_pad elements) or nullptr
+    const void* x;             // raw input row (d elements of in_dtype) when stash == nullptr
+    float mul;                 // 1 / norm (L2 or L1), 1 when the loss was called with normalize = False
+};
+template <int kLoss>
+SIMCLR_DEVICE ZRow zrow_of(const TileParams& p, int view, int g_img) {
+    ZRow z;
+    z.x = nullptr;
+    z.mul = 1.f;
+    const int d_pad = p.d <= 64 ? 64 : (p.d <= 128 ? 128 : 256);
+    if (p.zrows_peers.world > 0) {
+        const int owner = g_img / p.b_loc, li = g_img - owner * p.b_loc;
+        z.stash = static_cast<const float*>(p.zrows_peers.ptr[owner]) + static_cast<size_t>(view * p.bl_pad + li) * d_pad;
+    } else if (p.zrows != nullptr) {
+        z.stash = p.zrows + static_cast<size_t>(view * p.bg_pad + g_img) * d_pad;
+    } else {
+        z.stash = nullptr;
+        const int li = g_img - p.row_off;        // one GPU: every column is a local row
+        const size_t off = static_cast<size_t>(li) * p.d;
+        const char* base = static_cast<const char*>(view == 0 ? p.x1 : p.x2);
+        z.x = base + off * (p.in_bf16 ? 2 : 4);
+        if (kLoss == kModified || p.normalize) {
+            const float inv = __ldcg(p.inv_norm + view * p.bl_pad + li);
+            z.mul = inv == kInvNormClamped ? 1.f / kNormEps : inv;
+        }
+    }
+    return z;
+}
+template <int kLoss>
+SIMCLR_DEVICE float zrow_elem(const TileParams& p, const ZRow& z, int k) {
+    if (z.stash != nullptr) return __ldcg(z.stash + k);
+    float e = load_elem(z.x, static_cast<size_t>(k), p.in_bf16);
+    if constexpr (kLoss == kModified) e = softplus_beta(e);
+    return e * z.mul;
+}
+// <z_a, z_b> by the whole warp: lane l adds the elements k = l, l + 32, ... in ascending order, then one xor butterfly:
+// the same two rows always give the same bits, whichever of them is "the positive" (exact ties stay exact).
+template <int kLoss>
+SIMCLR_DEVICE float zrow_dot(const TileParams& p, const ZRow& a, const ZRow& b, int lane) {
+    float acc = 0.f;
+    for (int k = lane; k < p.d; k += 32) acc = fmaf(zrow_elem<kLoss>(p, a, k), zrow_elem<kLoss>(p, b, k), acc);
+    return warp_sum(acc);
+}
+// the reference's fp32 logit of an exact similarity (objective.py:35-43: s / temperature; :87-90: log(clamp(B s)) / temperature)
+template <int kLoss>
+SIMCLR_DEVICE float reference_logit(const TileParams& p, float s) {
+    if constexpr (kLoss == kNtXent) return __fdiv_rn(s, p.tau);
+    else return __fdiv_rn(logf(fmaxf(s * p.qscale, kClampMin)), p.tau);
+}
+// Does the row (view vr, global image g) keep its positive as FIRST argmax among its recorded candidates?  Whole warp.
+template <int kLoss>
+SIMCLR_DEVICE bool exact_first_argmax(const TileParams& p, int vr, int g, const int* list, int n, int lane) {
+    const ZRow zr = zrow_of<kLoss>(p, vr, g);
+    const float l_pos = reference_logit<kLoss>(p, zrow_dot<kLoss>(p, zr, zrow_of<kLoss>(p, 1 - vr, g), lane));
+    bool ok = true;
+    for (int i = 0; i < n; ++i) {
+        const int col = __ldcg(list + i);
+        const int vc = col >= p.bg_pad ? 1 : 0, ic = col - vc * p.bg_pad;
+        const float l_c = reference_logit<kLoss>(p, zrow_dot<kLoss>(p, zr, zrow_of<kLoss>(p, vc, ic), lane));
+        // reference column order (objective.py:48-49 / :93): does column (vc, ic) come before the positive?
+        bool prec;
+        if constexpr (kLoss == kNtXent) prec = (vr == 0) ? (vc == 1 && ic < g) : (vc == 1 || ic < g);
+        else prec = ic < g;
+        ok = ok && (prec ? (l_c < l_pos) : (l_c <= l_pos));
+    }
+    return ok;
+}
+
 template <int kLoss>
 SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int tid, const FinIndex& ix, float w_row,
                                              float* red /*smem, 16 floats*/, int* flags /*smem*/) {
@@ -818,12 +961,40 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
     }
     const float top = exact_logit2<kLoss>(p, vmax);
     float l2 = 0.f, loss_r = 0.f, w = 0.f, hit = 0.f;
+    bool ambiguous = false;
+    unsigned int n_cand = 0;
     if (row_ok) {
         l2 = top + log2f(total);
         loss_r = (l2 - exact_logit2<kLoss>(p, v_pos)) * kLn2;
         w = w_row;
         // reference objective.py:51 -- Tensor.max returns the first maximal index
         hit = (max_prec < pos_mma && max_foll <= pos_mma) ? 1.f : 0.f;
+        if (p.cand_cnt != nullptr) {
+            // Exact count: certain unless the best negative lies in the band around the exact positive; then the
+            // recorded candidates decide (a row with more than kCandMax of them keeps the tensor-core decision)
+            n_cand = __ldcg(p.cand_cnt + slot);
+            float lo, hi;
+            cand_band<kLoss>(p.band, pos_raw_value<kLoss>(__ldcg(p.pos_dot + slot), p.k2, p.qscale), lo, hi);
+            const float best = fmaxf(max_prec, max_foll);
+            if (best > hi) hit = 0.f;
+            else if (best < lo) hit = 1.f;
+            else ambiguous = n_cand <= static_cast<unsigned int>(kCandMax);
+        }
+    }
+    if (p.cand_cnt != nullptr) {
+        if (n_cand != 0u) p.cand_cnt[slot] = 0u;              // left zero for the next call
+        unsigned int todo = __ballot_sync(0xffffffffu, ambiguous);
+        const int lane = tid & 31;
+        while (todo != 0u) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const int img_s = __shfl_sync(0xffffffffu, img, src);
+            const int n_s = static_cast<int>(__shfl_sync(0xffffffffu, n_cand, src));
+            const int slot_s = __shfl_sync(0xffffffffu, slot, src);
+            const bool ok = exact_first_argmax<kLoss>(p, vr, p.row_off + img_s, p.cand + static_cast<size_t>(slot_s) * kCandMax,
+                                                     n_s, lane);
+            if (lane == src) hit = ok ? 1.f : 0.f;
+        }
     }
     p.lse2[slot] = l2;
     p.row_loss[slot] = loss_r;
@@ -1506,6 +1677,9 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             h.clampc = kClampMin * c0;
         }
         const int b_loc = p.b_loc, row_off = p.row_off;
+        // candidates of the exact accuracy count are recorded by the bf16-mode forward kernel (the split mode's scores
+        // are fp32-grade already)
+        constexpr bool kRecord = !kBackward && kPrec == 0;
         const bool tracing = SIMCLR_TRACE && p.trace != nullptr && static_cast<int>(blockIdx.x) == p.trace_cta && quarter == 0 && lane == 0;
         constexpr int kLogS = S == 2 ? 1 : (S == 4 ? 2 : 3);
         static_assert((1 << kLogS) == S, "ring size must be 2, 4 or 8");
@@ -1545,6 +1719,17 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 }
             }
             const int pos_off = kBackward ? 2 * seg : 0;
+            // exact accuracy count: the band around this row's exact positive inside which a tensor-core score cannot
+            // decide (lo = +inf: not recording -- padding rows, rows already known to be wrong, feature switched off)
+            float band_lo = 3.0e38f, band_hi = 3.0e38f;
+            unsigned int* cand_cnt_row = nullptr;
+            if constexpr (kRecord) {
+                if (p.cand_cnt != nullptr && rc.row_ok) {
+                    const int slot_r = rb * kBlockM + row_in_block;
+                    cand_cnt_row = p.cand_cnt + slot_r;
+                    cand_band<kLoss>(p.band, pos_raw_value<kLoss>(__ldcg(p.pos_dot + slot_r), h.k2, h.qscale), band_lo, band_hi);
+                }
+            }
 
 #pragma unroll 1
             for (int s = (idx0 ^ pair) & 1; s < seg_len; s += 2) {
@@ -1658,6 +1843,15 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         fs.max_prec = fmaxf(fs.max_prec, tile_prec ? cm : kNegBig);
                         fs.max_foll = fmaxf(fs.max_foll, tile_prec ? kNegBig : cm);
                     }
+                    if constexpr (kRecord) {
+                        // a negative of this tile reaches the band of some row of the warp (rare): record the candidates
+                        if (__any_sync(0xffffffffu, cm >= band_lo)) {
+                            const float tm = cand_rescan<kLoss>(t0, cbase, cbase - vc * h.bg_pad, h.b_glob, h.qscale, -1, -1,
+                                                                band_lo, band_hi, cand_cnt_row,
+                                                                p.cand + static_cast<size_t>(rb * kBlockM + row_in_block) * kCandMax);
+                            if (tm > band_hi) band_lo = 3.0e38f;      // the row is wrong whatever the rest says
+                        }
+                    }
                 } else {
                     auto process = [&](const uint32_t (&r)[kChunk], int k) {
                         const int cq = cbase + k * kChunk;
@@ -1698,6 +1892,16 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         if (k < 3) tmem_ld16(t0 + (k + 1) * kChunk, nxt);
                         if (SIMCLR_PINGPONG && k == SIMCLR_TOKEN_CHUNK && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
                         process(cur, k);
+                    }
+                    if constexpr (kRecord) {
+                        // tiles with masked elements (diagonal, positive, padding: ~1.5 % of all tiles) are always rescanned
+                        // while a row of the warp is still undecided
+                        if (__any_sync(0xffffffffu, band_lo < 3.0e38f)) {
+                            const float tm = cand_rescan<kLoss>(t0, cbase, cbase - vc * h.bg_pad, h.b_glob, h.qscale, rc.diag_col,
+                                                                rc.pos_col, band_lo, band_hi, cand_cnt_row,
+                                                                p.cand + static_cast<size_t>(rb * kBlockM + row_in_block) * kCandMax);
+                            if (tm > band_hi) band_lo = 3.0e38f;
+                        }
                     }
                 }
                 if (SIMCLR_PINGPONG && !(kBackward && kPrec != 0) && SIMCLR_TOKEN_CHUNK > 3 && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);

@@ -88,6 +88,11 @@ class RowShardGather:
     def rowvec(self, vec_local: torch.Tensor, b: int) -> torch.Tensor:
         return self._gather_views(vec_local, b)
 
+    def zrows(self, zrows_local: torch.Tensor, b: int) -> torch.Tensor:
+        """The ranks' exact fp32 normalised rows [2*pad(b), Dpad] -> [2*pad(b*world), Dpad]: what the forward finalize
+        kernel re-scores accuracy candidates from (include/simclr_b200.h, zrows_global)."""
+        return self._gather_views(zrows_local, b)
+
     def reduce(self, stats: torch.Tensor, loss: torch.Tensor):
         """Sum the per-rank [sum w L, sum w, #correct]; the global loss is their ratio."""
         tot = stats[:3].clone()
@@ -136,7 +141,10 @@ class PeerBatch:
         op_bytes = _align(2 * self.bg_pad * self.dp * 2)
         lse_bytes = _align(2 * 2 * self.bg_pad * 4)
         st_bytes = _align(self.world * 4 * 4)
-        self._gen_bytes = op_bytes + lse_bytes + st_bytes
+        # this rank's exact fp32 normalised rows [2*Blpad][Dpad]: never pushed, read by the other ranks' finalize kernels
+        # for the few accuracy candidates they have to re-score
+        z_bytes = _align(2 * pad_rows(self.b_local) * self.dp * 4)
+        self._gen_bytes = op_bytes + lse_bytes + st_bytes + z_bytes
         flag_off = self.GENERATIONS * self._gen_bytes
         total = flag_off + _align(16 * 4)
         self.buf = symm.empty(total, dtype=torch.uint8, device=self.device)
@@ -153,6 +161,7 @@ class PeerBatch:
                 "operand": arr(*[p + base for p in ptrs]),
                 "colvec": arr(*[p + base + op_bytes for p in ptrs]),
                 "stats": arr(*[p + base + op_bytes + lse_bytes for p in ptrs]),
+                "zrows": arr(*[p + base + op_bytes + lse_bytes + st_bytes for p in ptrs]),
             })
         self._flags = arr(*[p + flag_off for p in ptrs])
         # NVLS multicast mapping of the same allocation (0 when the fabric has no multicast support)
@@ -192,7 +201,7 @@ class PeerBatch:
         check(lib.simclr_prepare_peer(loss_kind, x1.data_ptr(), x2.data_ptr(), self.b_local, self.d, code,
                                       int(bool(normalize)), float(temperature), _lib.PRECISION_BF16, operand.data_ptr(),
                                       rowvec[0].data_ptr(), rowvec[1].data_ptr(), ws.data_ptr(), self.world, self.rank,
-                                      tab["operand"], self._mc[gen], stream),
+                                      tab["operand"], self._mc[gen], tab["zrows"][self.rank], stream),
               "simclr_prepare_peer")
         if not self.overlap:
             check(lib.simclr_peer_barrier(self.world, self.rank, self._flags, self.epoch.data_ptr(), None, None, None,
@@ -207,7 +216,8 @@ class PeerBatch:
                                       None if bwd_ws is None else bwd_ws.data_ptr(), 0 if bwd_ws is None else bwd_ws.numel(),
                                       self.world, self.rank, tab["colvec"], tab["stats"],
                                       self._flags if self.overlap else None,
-                                      self.epoch.data_ptr() if self.overlap else None, stream), "simclr_forward_peer")
+                                      self.epoch.data_ptr() if self.overlap else None, None, None, code, None, None,
+                                      tab["zrows"], stream), "simclr_forward_peer")
         check(lib.simclr_peer_barrier(self.world, self.rank, self._flags, self.epoch.data_ptr(), view["stats"].data_ptr(),
                                       stats_global.data_ptr(), loss.data_ptr(), stream), "simclr_peer_barrier")
         self.generation += 1
@@ -225,7 +235,7 @@ class PeerBatch:
             float(temperature), None if grad_out is None else grad_out.data_ptr(), operand.data_ptr(), rowvec.data_ptr(),
             stats_local.data_ptr(), stats_global.data_ptr(), loss.data_ptr(), grad1.data_ptr(), grad2.data_ptr(),
             fwd_ws.data_ptr(), fwd_ws_bytes, bwd_ws.data_ptr(), bwd_ws_bytes, self.world, self.rank, tab["operand"],
-            self._mc[gen], tab["colvec"], tab["stats"], self._flags, self.epoch.data_ptr(), stream),
+            self._mc[gen], tab["colvec"], tab["stats"], self._flags, self.epoch.data_ptr(), tab["zrows"], stream),
             "simclr_forward_backward_peer")
         self.generation += 1
         return self.generation

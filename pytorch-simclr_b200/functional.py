@@ -170,13 +170,21 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
         b_global_hint = b if gather is None else b * gather.world
         ws_bytes = lib.simclr_forward_workspace_bytes(loss_kind, b, b_global_hint, d)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        # exact fp32 normalised rows for the accuracy candidates of OTHER ranks (collective transport: gathered below)
+        zrows_local = None
+        if gather is not None and precision == PRECISION_BF16 and hasattr(gather, "zrows"):
+            zrows_local = torch.empty((2 * bp, dp), dtype=torch.float32, device=dev)
         check(lib.simclr_prepare_peer(loss_kind, x1.data_ptr(), x2.data_ptr(), b, d, code, int(bool(normalize)),
                                       float(temperature), precision, operand.data_ptr(), rowvec[0].data_ptr(),
-                                      rowvec[1].data_ptr(), ws.data_ptr(), 0, 0, None, None, stream), "simclr_prepare")
+                                      rowvec[1].data_ptr(), ws.data_ptr(), 0, 0, None, None, _ptr(zrows_local), stream),
+              "simclr_prepare")
+        zrows_global = None
         if gather is None:
             operand_cols, b_global, row_offset = operand, b, 0
         else:
             operand_cols, b_global, row_offset = gather.operand(operand, b)
+            if zrows_local is not None:
+                zrows_global = gather.zrows(zrows_local, b)
         w_local = None
         if weight is not None:
             w_local = weight.to(device=dev, dtype=torch.float32).contiguous()
@@ -197,7 +205,8 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
                                       _ptr(w_local),
                                       rowvec[2].data_ptr(), rowvec[3].data_ptr(), stats_ptr, loss.data_ptr(),
                                       ws.data_ptr(), ws_bytes, _ptr(bwd_ws), 0 if bwd_ws is None else bwd_ws.numel(), 0, 0,
-                                      None, None, None, None, stream), "simclr_forward")
+                                      None, None, None, None, x1.data_ptr(), x2.data_ptr(), code, rowvec[0].data_ptr(),
+                                      _ptr(zrows_global), None, stream), "simclr_forward")
         if host_slot is not None and gather is None:
             _hoststats.ring(dev).launched(host_slot)
     saved = _Saved()

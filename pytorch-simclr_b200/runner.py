@@ -59,7 +59,7 @@ class ContrastiveStep:
         check(self.lib.simclr_prepare_peer(self.kind, self.x1.data_ptr(), self.x2.data_ptr(), self.b, self.d, self.code,
                                            int(self.normalize), self.temperature, self.precision, self.operand.data_ptr(),
                                            self.rowvec[0].data_ptr(), self.rowvec[1].data_ptr(), self.fwd_ws.data_ptr(), 0,
-                                           0, None, None, self._stream()), "simclr_prepare")
+                                           0, None, None, None, self._stream()), "simclr_prepare")
 
     def forward(self, stage_mask: Optional[int] = None) -> None:
         """prepare + forward.  ``stage_mask`` (measurement only, include/simclr_b200.h SIMCLR_STAGE_*): launch only the
@@ -69,14 +69,15 @@ class ContrastiveStep:
             check(lib.simclr_prepare_peer(self.kind, self.x1.data_ptr(), self.x2.data_ptr(), self.b, self.d, self.code,
                                           int(self.normalize), self.temperature, self.precision, self.operand.data_ptr(),
                                           self.rowvec[0].data_ptr(), self.rowvec[1].data_ptr(), self.fwd_ws.data_ptr(), 0, 0,
-                                          None, None, st), "simclr_prepare")
+                                          None, None, None, st), "simclr_prepare")
         # the forward primes the backward workspace (zeroed accumulation buffer, column vectors)
         check(lib.simclr_forward_stages(self.kind, self.operand.data_ptr(), self.operand.data_ptr(), self.b, self.b, 0,
                                         self.d, self.temperature, int(self.normalize), self.precision,
                                         self.rowvec[1].data_ptr(), None, self.rowvec[2].data_ptr(),
                                         self.rowvec[3].data_ptr(), self.stats.data_ptr(), self.loss.data_ptr(),
                                         self.fwd_ws.data_ptr(), self.fwd_ws_bytes, self.bwd_ws.data_ptr(),
-                                        self.bwd_ws_bytes, st, _lib.STAGE_ALL if stage_mask is None else stage_mask),
+                                        self.bwd_ws_bytes, self.x1.data_ptr(), self.x2.data_ptr(), self.code,
+                                        self.rowvec[0].data_ptr(), st, _lib.STAGE_ALL if stage_mask is None else stage_mask),
               "simclr_forward")
 
     def backward(self, grad_out: Optional[torch.Tensor] = None, stage_mask: Optional[int] = None) -> None:

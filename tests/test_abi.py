@@ -52,7 +52,7 @@ def test_diagnostics_live_in_the_tracing_build_only(lib):
 
 
 def test_abi_version_and_error_strings(lib):
-    assert lib.simclr_abi_version() == 10
+    assert lib.simclr_abi_version() == 11
     assert lib.simclr_error_string(0) == b"ok"
     for code in range(-11, 0):
         assert lib.simclr_error_string(code) not in (b"", b"unknown error")
@@ -83,16 +83,16 @@ def test_argument_validation_without_gpu(lib):
     p = (p + 255) & ~255
     # null pointers
     assert lib.simclr_prepare(0, None, p, 4, 8, 0, 1, 0.5, p, p, p, None, None) == -1
-    assert lib.simclr_forward(0, None, p, 4, 4, 0, 8, 0.5, 1, p, None, p, p, p, None, p, 1 << 15, None) == -1
+    assert lib.simclr_forward(0, None, p, 4, 4, 0, 8, 0.5, 1, p, None, p, p, p, None, p, 1 << 15, None, None, 0, None, None) == -1
     # bad dtype / shape / dim / loss / temperature / workspace
     assert lib.simclr_prepare(0, p, p, 4, 8, 9, 1, 0.5, p, p, p, None, None) == -4
     assert lib.simclr_prepare(0, p, p, 0, 8, 0, 1, 0.5, p, p, p, None, None) == -2
     assert lib.simclr_prepare(0, p, p, 4, 300, 0, 1, 0.5, p, p, p, None, None) == -3
     assert lib.simclr_prepare(5, p, p, 4, 8, 0, 1, 0.5, p, p, p, None, None) == -11
-    assert lib.simclr_forward(0, p, p, 4, 4, 0, 8, 0.0, 1, p, None, p, p, p, None, p, 1 << 15, None) == -7
-    assert lib.simclr_forward(0, p, p, 4, 2, 0, 8, 0.5, 1, p, None, p, p, p, None, p, 1 << 15, None) == -2   # b_glob < b_loc
-    assert lib.simclr_forward(0, p, p, 4, 8, 6, 8, 0.5, 1, p, None, p, p, p, None, p, 1 << 15, None) == -2   # shard outside
-    assert lib.simclr_forward(0, p, p, 4, 4, 0, 8, 0.5, 1, p, None, p, p, p, None, p, 16, None) == -5
-    assert lib.simclr_forward(0, p + 4, p, 4, 4, 0, 8, 0.5, 1, p, None, p, p, p, None, p, 1 << 15, None) == -6
+    assert lib.simclr_forward(0, p, p, 4, 4, 0, 8, 0.0, 1, p, None, p, p, p, None, p, 1 << 15, None, None, 0, None, None) == -7
+    assert lib.simclr_forward(0, p, p, 4, 2, 0, 8, 0.5, 1, p, None, p, p, p, None, p, 1 << 15, None, None, 0, None, None) == -2   # b_glob < b_loc
+    assert lib.simclr_forward(0, p, p, 4, 8, 6, 8, 0.5, 1, p, None, p, p, p, None, p, 1 << 15, None, None, 0, None, None) == -2   # shard outside
+    assert lib.simclr_forward(0, p, p, 4, 4, 0, 8, 0.5, 1, p, None, p, p, p, None, p, 16, None, None, 0, None, None) == -5
+    assert lib.simclr_forward(0, p + 4, p, 4, 4, 0, 8, 0.5, 1, p, None, p, p, p, None, p, 1 << 15, None, None, 0, None, None) == -6
     assert lib.simclr_backward(0, p, p, 4, 4, 0, 8, 0, 1, float("nan"), 0, p, p, p, p, p, None, None, p, p, p, 1 << 15,
                                None, None) == -7

@@ -9,8 +9,9 @@ Tolerances are BASELINE.json's north_star contracts, each test running in both a
                    max|reference gradient|;
   precision "fp32" (split hi+lo bf16 operands, the fp32/TF32-grade path): loss within 1e-5 relative, gradients within
                    1e-4 of max|reference gradient|;
-accuracy (an integer count) exact in the fp32-grade mode and on the fixtures; at 2N = 8192 the bf16 mode may flip a
-near-tie inside bf16 resolution (allowed: 1 row).
+accuracy (an integer count, objective.py:51-53 / :95-97) exact in BOTH modes: the bf16 mode re-scores in exact fp32 every
+negative whose tensor-core score lies within the bf16 error bound of the exact positive (candidates recorded by the
+forward tile kernel, decided by the forward finalize kernel).
 """
 import os
 
@@ -124,7 +125,7 @@ def test_ntxent_against_fp64_oracle(b, d, tau, kind, dtype, precision):
     ref = oracle.ntxent_closed_form(z1, z2, temperature=tau)
     loss, acc, g1, g2 = _run(sb.contrastive_loss, z1, z2, 1.0, dtype, precision, temperature=tau)
     assert loss == pytest.approx(ref.loss, rel=LOSS_RTOL)
-    assert abs(acc - ref.acc) * 2 * b / 100.0 <= (0.5 if precision == "fp32" or b < 4096 else 1.5)
+    assert acc == ref.acc                # the count is exact in both modes
     assert _grad_err(g1, ref.grad1) < GRAD_TOL and _grad_err(g2, ref.grad2) < GRAD_TOL
 
 
@@ -142,8 +143,9 @@ def test_modified_against_fp64_oracle(b, d, tau, kind, dtype, precision):
     ref = oracle.modified_closed_form(z1, z2, temperature=tau)
     loss, acc, g1, g2 = _run(sb.modified_contrastive_loss, z1, z2, 1.0, dtype, precision, temperature=tau)
     assert loss == pytest.approx(ref.loss, rel=LOSS_RTOL)
-    # the modified loss compares products of probabilities that agree to three digits: bf16 operands may flip a few
-    assert abs(acc - ref.acc) * 2 * b / 100.0 <= (0.5 if precision == "fp32" else 4.5)
+    # the modified loss compares products of probabilities that agree to three digits: only the exact re-scoring of the
+    # near-ties makes the bf16 mode's count exact
+    assert acc == ref.acc
     assert _grad_err(g1, ref.grad1) < GRAD_TOL and _grad_err(g2, ref.grad2) < GRAD_TOL
 
 
@@ -363,3 +365,62 @@ def test_first_argmax_tie_with_an_earlier_column_of_the_positive_tile():
         loss, acc, g1, g2 = _run(sb.contrastive_loss, z1, z2, precision=precision, temperature=0.5)
         assert acc == ref.acc, precision
         assert loss == pytest.approx(ref.loss, rel=TOL[precision][0])
+
+
+def _near_tie_batch(b, d, seed, ndup=96, sigma=0.08):
+    """Image ndup + i is a near-copy of image i (i < ndup): 4 * ndup rows whose best negative is within ~1e-3 of the
+    positive in cosine similarity, on either side of it -- far inside bf16 resolution (2^-8)."""
+    gen = torch.Generator().manual_seed(seed)
+    base = torch.randn(b, d, generator=gen)
+    base[ndup:2 * ndup] = base[:ndup]
+    return base + sigma * torch.randn(b, d, generator=gen), base + sigma * torch.randn(b, d, generator=gen)
+
+
+@pytest.mark.parametrize("kind", ["ntxent", "modified"])
+@pytest.mark.parametrize("b,d", [(1024, 128), (4096, 128), (777, 100)])
+def test_accuracy_count_is_exact_under_near_ties_in_bf16_mode(kind, b, d):
+    """Adversarial for the bf16 tensor-core scores: hundreds of rows whose best negative is inside bf16 resolution of the
+    positive.  The count must equal the fp64 oracle's (objective.py:51-53 / :95-97) in both arithmetic modes.  The batch
+    is chosen (first seed that qualifies) so that no decision is closer than 3e-6 -- below that the reference's own fp32
+    arithmetic is no longer order-stable against fp64 either."""
+    ref_fn = oracle.ntxent_closed_form if kind == "ntxent" else oracle.modified_closed_form
+    for seed in range(16):
+        z1, z2 = _near_tie_batch(b, d, seed)
+        ref = ref_fn(z1, z2, temperature=0.5, need_grad=False)
+        gap = np.abs(ref.margin * 0.5)                  # similarity units (NT-Xent) / log-ratio units (modified)
+        if gap.min() > 3e-6:
+            break
+    else:
+        pytest.fail("no seed gives a resolvable batch")
+    assert (gap < 2.0 ** -8).sum() >= 300              # the bf16 scores cannot decide these rows
+    assert 50.0 < ref.acc < 99.0
+    fn = sb.contrastive_loss if kind == "ntxent" else sb.modified_contrastive_loss
+    for precision in PRECISIONS:
+        sb.set_precision(precision)
+        with torch.no_grad():
+            loss, acc = fn(z1.cuda(), z2.cuda(), temperature=0.5)
+        assert acc == ref.acc, (precision, acc, ref.acc)
+        # and through the training path (fused begin / finish calls)
+        a = z1.cuda().requires_grad_(True)
+        c = z2.cuda().requires_grad_(True)
+        loss, acc = fn(a, c, temperature=0.5)
+        assert acc == ref.acc, (precision, "training path", acc, ref.acc)
+
+
+def test_more_near_ties_than_candidate_slots_falls_back_gracefully():
+    """Sixteen near-copies of every image: more negatives inside the band than the 8 candidate slots of a row.  Such
+    rows keep the tensor-core decision (documented in include/simclr_b200.h): the count stays within a few rows of the
+    oracle's and nothing overflows."""
+    b, d = 512, 128
+    gen = torch.Generator().manual_seed(5)
+    base = torch.randn(b // 16, d, generator=gen)
+    owner = torch.arange(b) % (b // 16)
+    z1 = base[owner] + 1e-3 * torch.randn(b, d, generator=gen)
+    z2 = base[owner] + 1e-3 * torch.randn(b, d, generator=gen)
+    ref = oracle.ntxent_closed_form(z1, z2, temperature=0.5, need_grad=False)
+    sb.set_precision("bf16")
+    for _ in range(2):                                          # twice: the candidate counters must be left clean
+        with torch.no_grad():
+            loss, acc = sb.contrastive_loss(z1.cuda(), z2.cuda(), temperature=0.5)
+        assert abs(acc - ref.acc) * 2 * b / 100.0 <= 0.25 * 2 * b
+        assert loss.item() == pytest.approx(ref.loss, rel=2e-3)
