@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIMCLR_ABI_VERSION 11
+#define SIMCLR_ABI_VERSION 12
 
 /* loss kinds */
 #define SIMCLR_LOSS_NTXENT 0   /* objective.py:6-55  */
@@ -41,6 +41,13 @@ extern "C" {
 #define SIMCLR_PRECISION_BF16 0  /* bf16 operands, fp32 accumulate: loss 2e-3, gradients 1e-2 (the fast path) */
 #define SIMCLR_PRECISION_SPLIT 1 /* hi + lo bf16 planes, three products each: fp32-grade, loss 1e-5, gradients 1e-4;
                                     d <= 128, single GPU or NCCL transport; operand buffers hold two planes */
+
+/* flags of the backward / fused entry points */
+#define SIMCLR_FLAG_DETERMINISTIC 1 /* bit-identical gradients from run to run: every (CTA, segment) of the backward tile kernel
+                                       stores its accumulator into its own slot and the finalize kernel adds the slots of a row
+                                       block in a fixed order, instead of TMA reduce-adds into one buffer in completion order
+                                       (the reference's cudnn.deterministic / manual_seed switch, pretrain.py:59-61).  Needs the
+                                       larger workspace of simclr_backward_workspace_bytes_flags. */
 
 /* error codes */
 #define SIMCLR_OK 0
@@ -71,6 +78,7 @@ size_t simclr_operand_bytes(int64_t b, int64_t d, int precision);
 /* Bytes of scratch each stage needs.  b_local == b_global on a single GPU. */
 size_t simclr_forward_workspace_bytes(int loss, int64_t b_local, int64_t b_global, int64_t d);
 size_t simclr_backward_workspace_bytes(int loss, int64_t b_local, int64_t b_global, int64_t d);
+size_t simclr_backward_workspace_bytes_flags(int loss, int64_t b_local, int64_t b_global, int64_t d, int flags);
 
 /*
  * Stage 1 -- prologue (objective.py:25-30 L2 normalise, or :70-78 softplus + L1 normalise).
@@ -131,7 +139,7 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
                     int64_t row_offset, int64_t d, int in_dtype, int normalize, float temperature, int precision,
                     const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,
                     const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
-                    void* workspace, size_t workspace_bytes, const float* primed_colvec, void* stream);
+                    void* workspace, size_t workspace_bytes, const float* primed_colvec, int flags, void* stream);
 
 /*
  * Fused training-step form of the three stages for one GPU and an unweighted loss: what the reference's
@@ -150,7 +158,7 @@ int simclr_forward_backward(int loss, const void* x_batch1, const void* x_batch2
                             int normalize, float temperature, int precision, const float* grad_out, void* operand,
                             float* rowvec, float* stats, float* loss_out, void* grad1, void* grad2,
                             void* forward_workspace, size_t forward_workspace_bytes, void* backward_workspace,
-                            size_t backward_workspace_bytes, void* stream);
+                            size_t backward_workspace_bytes, int flags, void* stream);
 
 /*
  * The same fused step split around its last kernel, for callers that learn the upstream gradient only after they have
@@ -166,11 +174,11 @@ int simclr_forward_backward(int loss, const void* x_batch1, const void* x_batch2
 int simclr_forward_backward_begin(int loss, const void* x_batch1, const void* x_batch2, int64_t b, int64_t d, int in_dtype,
                                   int normalize, float temperature, int precision, void* operand, float* rowvec,
                                   float* stats, float* loss_out, void* forward_workspace, size_t forward_workspace_bytes,
-                                  void* backward_workspace, size_t backward_workspace_bytes, void* stream);
+                                  void* backward_workspace, size_t backward_workspace_bytes, int flags, void* stream);
 int simclr_forward_backward_finish(int loss, const void* x_batch1, const void* x_batch2, int64_t b, int64_t d, int in_dtype,
                                    int normalize, float temperature, int precision, const float* grad_out,
                                    const void* operand, const float* rowvec, void* grad1, void* grad2,
-                                   void* backward_workspace, size_t backward_workspace_bytes, void* stream);
+                                   void* backward_workspace, size_t backward_workspace_bytes, int flags, void* stream);
 
 /*
  * Row-sharded global batch over peer memory (one process per GPU of one NVLink / NVSwitch node; not in the reference,
@@ -240,7 +248,7 @@ int simclr_forward_backward_peer(int loss, const void* x_batch1, const void* x_b
                                  void* backward_workspace, size_t backward_workspace_bytes, int world, int rank,
                                  void* const* operand_global_peers, void* operand_global_multicast,
                                  void* const* colvec_peers, void* const* stats_peers, void* const* flag_peers,
-                                 unsigned int* epoch_local, void* const* zrows_peers, void* stream);
+                                 unsigned int* epoch_local, void* const* zrows_peers, int flags, void* stream);
 
 /*
  * Measurement entry points (bench.py): simclr_forward_peer on one GPU / simclr_backward restricted to a subset of their
@@ -266,7 +274,7 @@ int simclr_backward_stages(int loss, const void* x_batch1, const void* x_batch2,
                            int64_t row_offset, int64_t d, int in_dtype, int normalize, float temperature, int precision,
                            const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,
                            const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
-                           void* workspace, size_t workspace_bytes, const float* primed_colvec, void* stream,
+                           void* workspace, size_t workspace_bytes, const float* primed_colvec, int flags, void* stream,
                            unsigned int stage_mask);
 
 #ifdef __cplusplus

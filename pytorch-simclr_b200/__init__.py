@@ -5,8 +5,9 @@ Import name: ``pytorch_simclr_b200`` (the directory is ``pytorch-simclr_b200/``;
 """
 from .objective import contrastive_loss, modified_contrastive_loss  # noqa: F401
 from .functional import (ContrastiveLossFunction, contrastive_forward_backward, LOSS_NTXENT,  # noqa: F401
-                         LOSS_MODIFIED, set_precision, get_precision, set_eager_backward, get_eager_backward)
+                         LOSS_MODIFIED, set_precision, get_precision, set_eager_backward, get_eager_backward,
+                         set_deterministic, get_deterministic)
 
 __all__ = ["contrastive_loss", "modified_contrastive_loss", "ContrastiveLossFunction",
            "contrastive_forward_backward", "LOSS_NTXENT", "LOSS_MODIFIED", "set_precision", "get_precision",
-           "set_eager_backward", "get_eager_backward"]
+           "set_eager_backward", "get_eager_backward", "set_deterministic", "get_deterministic"]

@@ -15,7 +15,8 @@ DTYPE_F32 = 0
 DTYPE_BF16 = 1
 PRECISION_BF16 = 0
 PRECISION_SPLIT = 1
-ABI_VERSION = 11
+FLAG_DETERMINISTIC = 1
+ABI_VERSION = 12
 
 _lock = threading.Lock()
 _lib = None
@@ -34,20 +35,24 @@ SIGNATURES = {
     "simclr_pad_dim": (_i64, [_i64]),
     "simclr_forward_workspace_bytes": (_sz, [_int, _i64, _i64, _i64]),
     "simclr_backward_workspace_bytes": (_sz, [_int, _i64, _i64, _i64]),
+    "simclr_backward_workspace_bytes_flags": (_sz, [_int, _i64, _i64, _i64, _int]),
     "simclr_prepare": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _vp, _vp, _vp, _vp, _vp]),
     "simclr_forward": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                               _sz, _vp, _vp, _int, _vp, _vp]),
     "simclr_operand_bytes": (_sz, [_i64, _i64, _int]),
     "simclr_backward": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp,
-                               _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+                               _vp, _vp, _vp, _vp, _sz, _vp, _int, _vp]),
     "simclr_forward_backward": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                       _vp, _sz, _vp, _sz, _vp]),
+                                       _vp, _sz, _vp, _sz, _int, _vp]),
     "simclr_forward_backward_begin": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp,
-                                             _sz, _vp, _sz, _vp]),
+                                             _sz, _vp, _sz, _int, _vp]),
     "simclr_forward_backward_finish": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp,
-                                              _vp, _sz, _vp]),
-    "simclr_forward_backward_peer": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                            _vp, _vp, _sz, _vp, _sz, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                              _vp, _sz, _int, _vp]),
+    "simclr_forward_backward_peer": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32,           # loss .. temperature
+                                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,                  # grad_out .. grad2
+                                            _vp, _sz, _vp, _sz, _int, _int,                          # workspaces, world, rank
+                                            _vp, _vp, _vp, _vp, _vp, _vp, _vp,                       # peers .. zrows_peers
+                                            _int, _vp]),
     "simclr_prepare_peer": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _int, _int, _vp,
                                    _vp, _vp, _vp]),
     "simclr_forward_peer": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -56,7 +61,7 @@ SIGNATURES = {
     "simclr_forward_stages": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp,
                                      _vp, _sz, _vp, _sz, _vp, _vp, _int, _vp, _vp, ctypes.c_uint]),
     "simclr_backward_stages": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp,
-                                      _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, ctypes.c_uint]),
+                                      _vp, _vp, _vp, _vp, _vp, _sz, _vp, _int, _vp, ctypes.c_uint]),
 }
 
 # include/simclr_b200_debug.h: exported by the tracing build (lib/libsimclr_b200_trace.so) only

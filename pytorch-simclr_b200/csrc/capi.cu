@@ -218,6 +218,7 @@ struct FwdWorkspace {
     unsigned int* ticket;
     unsigned int* cand_cnt;   // [2*bl_pad] candidate counters of the exact accuracy count (zero between calls)
     int* cand;                // [2*bl_pad][kCandMax]
+    int* amb_list;            // [2*bl_pad] rows whose accuracy decision is left to the backward tile kernel (fused step)
     float* part;
     float* part2;      // partials of the second launch of the overlapped row-sharded forward
     float* block_part;
@@ -236,6 +237,8 @@ FwdWorkspace carve_forward(const Geometry& g, void* base) {
     off += align256(static_cast<size_t>(2) * g.bl_pad * sizeof(unsigned int));
     w.cand = reinterpret_cast<int*>(static_cast<char*>(base) + off);
     off += align256(static_cast<size_t>(2) * g.bl_pad * kCandMax * sizeof(int));
+    w.amb_list = reinterpret_cast<int*>(static_cast<char*>(base) + off);
+    off += align256(static_cast<size_t>(2) * g.bl_pad * sizeof(int));
     // sized for the full column window; a narrower window never needs more (fewer tiles per CTA, at most as many CTAs),
     // except that max_segs can grow by the row blocks a CTA additionally spans: bound it by n_row_blocks
     const int segs = g.n_row_blocks < 8 ? g.n_row_blocks : (g.max_segs + 6 < g.n_row_blocks ? g.max_segs + 6 : g.n_row_blocks);
@@ -251,10 +254,12 @@ FwdWorkspace carve_forward(const Geometry& g, void* base) {
 struct BwdWorkspace {
     float* colvec;
     float* dacc;
+    float* det_part;       // deterministic mode: [grid * max_segs * 128][d_pad] per-(CTA, segment) accumulator slots
     size_t dacc_floats;
+    int64_t det_rows;
     size_t bytes;
 };
-BwdWorkspace carve_backward(const Geometry& g, void* base) {
+BwdWorkspace carve_backward(const Geometry& g, void* base, bool deterministic = false) {
     BwdWorkspace w;
     size_t off = 0;
     w.colvec = reinterpret_cast<float*>(static_cast<char*>(base) + off);
@@ -262,6 +267,13 @@ BwdWorkspace carve_backward(const Geometry& g, void* base) {
     w.dacc = reinterpret_cast<float*>(static_cast<char*>(base) + off);
     w.dacc_floats = static_cast<size_t>(2) * g.bl_pad * g.d_pad;
     off += align256(w.dacc_floats * sizeof(float));
+    w.det_part = nullptr;
+    w.det_rows = 0;
+    if (deterministic) {
+        w.det_part = reinterpret_cast<float*>(static_cast<char*>(base) + off);
+        w.det_rows = static_cast<int64_t>(g.grid) * g.max_segs * kBlockM;
+        off += align256(static_cast<size_t>(w.det_rows) * g.d_pad * sizeof(float));
+    }
     w.bytes = off;
     return w;
 }
@@ -498,9 +510,13 @@ size_t simclr_forward_workspace_bytes(int loss, int64_t b_local, int64_t b_globa
 }
 
 size_t simclr_backward_workspace_bytes(int loss, int64_t b_local, int64_t b_global, int64_t d) {
+    return simclr_backward_workspace_bytes_flags(loss, b_local, b_global, d, 0);
+}
+
+size_t simclr_backward_workspace_bytes_flags(int loss, int64_t b_local, int64_t b_global, int64_t d, int flags) {
     Geometry g;
     if (make_geometry(loss, b_local, b_global, 0, d, &g) != SIMCLR_OK) return 0;
-    return carve_backward(g, nullptr).bytes;
+    return carve_backward(g, nullptr, (flags & SIMCLR_FLAG_DETERMINISTIC) != 0).bytes;
 }
 
 size_t simclr_operand_bytes(int64_t b, int64_t d, int precision) {
@@ -689,6 +705,14 @@ int forward_impl(int loss, const void* operand_rows, const void* operand_cols, i
             p.cand_cnt = w.cand_cnt;
             p.cand = w.cand;
             p.band = (loss == SIMCLR_LOSS_NTXENT ? s.k2 : 1.0f) * kBandRel;
+            if (defer_stats && fused == nullptr && p.x1 != nullptr) {
+                // fused one-GPU step: the exact re-scoring is left to the backward tile kernel (header words 1, 2 of the
+                // workspace: zeroed by the prepare kernel with the ticket)
+                p.defer_accuracy = 1;
+                p.amb_cnt = w.ticket + 1;
+                p.amb_hits = w.ticket + 2;
+                p.amb_list = w.amb_list;
+            }
         }
     }
     if (fused != nullptr) {
@@ -769,7 +793,8 @@ int backward_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t 
                   const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,
                   const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
                   void* workspace, size_t workspace_bytes, const float* primed_colvec, void* stream, void* finish_ws,
-                  float* finish_stats, float* finish_loss, const FusedSync* fused = nullptr, unsigned stages = kAllStages) {
+                  float* finish_stats, float* finish_loss, const FusedSync* fused = nullptr, unsigned stages = kAllStages,
+                  int flags = 0) {
     if (!x_batch1 || !x_batch2 || !operand_rows || !operand_cols || !inv_norm || !pos_dot || !grad1 || !grad2 || !workspace)
         return SIMCLR_ERR_NULL_POINTER;
     if (!lse2_cols && !primed_colvec) return SIMCLR_ERR_NULL_POINTER;
@@ -780,7 +805,8 @@ int backward_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t 
     int rc = make_geometry(loss, b_local, b_global, row_offset, d, &g);
     if (rc) return rc;
     if (misaligned(operand_rows) || misaligned(operand_cols) || misaligned(workspace)) return SIMCLR_ERR_MISALIGNED;
-    BwdWorkspace w = carve_backward(g, workspace);
+    const bool deterministic = (flags & SIMCLR_FLAG_DETERMINISTIC) != 0;
+    BwdWorkspace w = carve_backward(g, workspace, deterministic);
     if (workspace_bytes < w.bytes) return SIMCLR_ERR_WORKSPACE_TOO_SMALL;
     if ((rc = check_device())) return rc;
 
@@ -789,8 +815,12 @@ int backward_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t 
     CUtensorMap map_rows, map_cols;
     if ((rc = make_operand_map(&map_rows, operand_rows, planes * 2 * g.bl_pad, g.d_pad))) return rc;
     if ((rc = make_operand_map(&map_cols, operand_cols, planes * 2 * g.bg_pad, g.d_pad))) return rc;
+    // the accumulator flush targets the shared accumulation buffer (TMA reduce-add) or, in deterministic mode, the
+    // (CTA, segment) slots (TMA store)
     CUtensorMap map_dacc;
-    if ((rc = make_dacc_map(&map_dacc, w.dacc, 2 * g.bl_pad, g.d_pad))) return rc;
+    if ((rc = deterministic ? make_dacc_map(&map_dacc, w.det_part, w.det_rows, g.d_pad)
+                            : make_dacc_map(&map_dacc, w.dacc, 2 * g.bl_pad, g.d_pad)))
+        return rc;
 
     Scales s = make_scales(loss, temperature, normalize, b_global);
     AuxParams a = make_aux(g, s, b_local, b_global, row_offset, d, normalize);
@@ -809,6 +839,8 @@ int backward_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t 
     p.normalize = normalize;
     p.colvec = primed_colvec ? primed_colvec : w.colvec;
     p.dacc = w.dacc;
+    p.det_part = w.det_part;
+    p.deterministic = deterministic ? 1 : 0;
     p.x1 = x_batch1;
     p.x2 = x_batch2;
     p.g1 = grad1;
@@ -831,6 +863,15 @@ int backward_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t 
         p.stats = finish_stats;
         p.loss_out = finish_loss;
         p.finish_stats = 1;
+        if (precision == SIMCLR_PRECISION_BF16 && (normalize || loss == SIMCLR_LOSS_MODIFIED) && b_local == b_global) {
+            // the forward finalize kernel of this fused step listed the rows it could not decide (forward_impl)
+            p.resolve_ambiguous = 1;
+            p.amb_cnt = fw.ticket + 1;
+            p.amb_hits = fw.ticket + 2;
+            p.amb_list = fw.amb_list;
+            p.cand_cnt = fw.cand_cnt;
+            p.cand = fw.cand;
+        }
     }
     if (fused != nullptr) {
         if ((rc = make_peer_table(fused->world, fused->rank, fused->flag_peers, &p.sync_flags))) return rc;
@@ -903,10 +944,11 @@ int simclr_backward(int loss, const void* x_batch1, const void* x_batch2, int64_
                     int64_t row_offset, int64_t d, int in_dtype, int normalize, float temperature, int precision,
                     const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,
                     const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
-                    void* workspace, size_t workspace_bytes, const float* primed_colvec, void* stream) {
+                    void* workspace, size_t workspace_bytes, const float* primed_colvec, int flags, void* stream) {
     return backward_impl(loss, x_batch1, x_batch2, b_local, b_global, row_offset, d, in_dtype, normalize, temperature,
                          precision, operand_rows, operand_cols, inv_norm, pos_dot, lse2_cols, col_scale, grad_out, grad1,
-                         grad2, workspace, workspace_bytes, primed_colvec, stream, nullptr, nullptr, nullptr);
+                         grad2, workspace, workspace_bytes, primed_colvec, stream, nullptr, nullptr, nullptr, nullptr,
+                         kAllStages, flags);
 }
 
 int simclr_forward_stages(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
@@ -930,12 +972,12 @@ int simclr_backward_stages(int loss, const void* x_batch1, const void* x_batch2,
                            int64_t row_offset, int64_t d, int in_dtype, int normalize, float temperature, int precision,
                            const void* operand_rows, const void* operand_cols, const float* inv_norm, const float* pos_dot,
                            const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
-                           void* workspace, size_t workspace_bytes, const float* primed_colvec, void* stream,
+                           void* workspace, size_t workspace_bytes, const float* primed_colvec, int flags, void* stream,
                            unsigned int stage_mask) {
     return backward_impl(loss, x_batch1, x_batch2, b_local, b_global, row_offset, d, in_dtype, normalize, temperature,
                          precision, operand_rows, operand_cols, inv_norm, pos_dot, lse2_cols, col_scale, grad_out, grad1,
                          grad2, workspace, workspace_bytes, primed_colvec, stream, nullptr, nullptr, nullptr, nullptr,
-                         stage_mask);
+                         stage_mask, flags);
 }
 
 namespace {
@@ -943,7 +985,8 @@ namespace {
 int fused_step_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t b, int64_t d, int in_dtype, int normalize,
                     float temperature, int precision, const float* grad_out, void* operand, float* rowvec, float* stats,
                     float* loss_out, void* grad1, void* grad2, void* forward_workspace, size_t forward_workspace_bytes,
-                    void* backward_workspace, size_t backward_workspace_bytes, void* stream, bool begin, bool finish) {
+                    void* backward_workspace, size_t backward_workspace_bytes, void* stream, bool begin, bool finish,
+                    int flags) {
     if (!rowvec || !backward_workspace) return SIMCLR_ERR_NULL_POINTER;
     if (begin && !stats) return SIMCLR_ERR_NULL_POINTER;
     const int64_t bp = simclr_pad_rows(b);
@@ -980,7 +1023,7 @@ int fused_step_impl(int loss, const void* x_batch1, const void* x_batch2, int64_
     return backward_impl(loss, x_batch1, x_batch2, b, b, 0, d, in_dtype, normalize, temperature, precision, operand, operand,
                          inv_norm, pos_dot, nullptr, nullptr, grad_out, g1, g2, backward_workspace,
                          backward_workspace_bytes, static_cast<const float*>(backward_workspace), stream,
-                         (begin && finish) ? forward_workspace : nullptr, stats, loss_out, nullptr, stages);
+                         (begin && finish) ? forward_workspace : nullptr, stats, loss_out, nullptr, stages, flags);
 }
 }  // namespace
 
@@ -988,28 +1031,28 @@ int simclr_forward_backward(int loss, const void* x_batch1, const void* x_batch2
                             int normalize, float temperature, int precision, const float* grad_out, void* operand,
                             float* rowvec, float* stats, float* loss_out, void* grad1, void* grad2,
                             void* forward_workspace, size_t forward_workspace_bytes, void* backward_workspace,
-                            size_t backward_workspace_bytes, void* stream) {
+                            size_t backward_workspace_bytes, int flags, void* stream) {
     return fused_step_impl(loss, x_batch1, x_batch2, b, d, in_dtype, normalize, temperature, precision, grad_out, operand,
                            rowvec, stats, loss_out, grad1, grad2, forward_workspace, forward_workspace_bytes,
-                           backward_workspace, backward_workspace_bytes, stream, true, true);
+                           backward_workspace, backward_workspace_bytes, stream, true, true, flags);
 }
 
 int simclr_forward_backward_begin(int loss, const void* x_batch1, const void* x_batch2, int64_t b, int64_t d, int in_dtype,
                                   int normalize, float temperature, int precision, void* operand, float* rowvec,
                                   float* stats, float* loss_out, void* forward_workspace, size_t forward_workspace_bytes,
-                                  void* backward_workspace, size_t backward_workspace_bytes, void* stream) {
+                                  void* backward_workspace, size_t backward_workspace_bytes, int flags, void* stream) {
     return fused_step_impl(loss, x_batch1, x_batch2, b, d, in_dtype, normalize, temperature, precision, nullptr, operand,
                            rowvec, stats, loss_out, nullptr, nullptr, forward_workspace, forward_workspace_bytes,
-                           backward_workspace, backward_workspace_bytes, stream, true, false);
+                           backward_workspace, backward_workspace_bytes, stream, true, false, flags);
 }
 
 int simclr_forward_backward_finish(int loss, const void* x_batch1, const void* x_batch2, int64_t b, int64_t d, int in_dtype,
                                    int normalize, float temperature, int precision, const float* grad_out,
                                    const void* operand, const float* rowvec, void* grad1, void* grad2,
-                                   void* backward_workspace, size_t backward_workspace_bytes, void* stream) {
+                                   void* backward_workspace, size_t backward_workspace_bytes, int flags, void* stream) {
     return fused_step_impl(loss, x_batch1, x_batch2, b, d, in_dtype, normalize, temperature, precision, grad_out,
                            const_cast<void*>(operand), const_cast<float*>(rowvec), nullptr, nullptr, grad1, grad2, nullptr, 0,
-                           backward_workspace, backward_workspace_bytes, stream, false, true);
+                           backward_workspace, backward_workspace_bytes, stream, false, true, flags);
 }
 
 int simclr_forward_backward_peer(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d,
@@ -1019,7 +1062,7 @@ int simclr_forward_backward_peer(int loss, const void* x_batch1, const void* x_b
                                  void* backward_workspace, size_t backward_workspace_bytes, int world, int rank,
                                  void* const* operand_global_peers, void* operand_global_multicast,
                                  void* const* colvec_peers, void* const* stats_peers, void* const* flag_peers,
-                                 unsigned int* epoch_local, void* const* zrows_peers, void* stream) {
+                                 unsigned int* epoch_local, void* const* zrows_peers, int flags, void* stream) {
     if (!rowvec || !stats_local || !stats_global || !backward_workspace || !operand_global_peers || !colvec_peers ||
         !stats_peers || !flag_peers || !epoch_local)
         return SIMCLR_ERR_NULL_POINTER;
@@ -1052,7 +1095,7 @@ int simclr_forward_backward_peer(int loss, const void* x_batch1, const void* x_b
     return backward_impl(loss, x_batch1, x_batch2, b_local, b_global, row_offset, d, in_dtype, normalize, temperature,
                          SIMCLR_PRECISION_BF16, operand, operand_cols, inv_norm, pos_dot, nullptr, nullptr, grad_out, grad1,
                          grad2, backward_workspace, backward_workspace_bytes, colvec_local, stream, nullptr, stats_global,
-                         loss_out, &fs);
+                         loss_out, &fs, kAllStages, flags);
 }
 
 #if SIMCLR_TRACE

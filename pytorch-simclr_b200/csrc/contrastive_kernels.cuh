@@ -86,12 +86,14 @@ constexpr float kNegBig = -3.0e38f;   // finite stand-in for -inf
 constexpr float kClampMin = 1e-4f;    // reference objective.py:87-88
 // Exact accuracy count in bf16 mode (reference objective.py:51-53 / :95-97): the tensor-core score of a negative differs
 // from its exact value by at most kBandRel * (largest possible |score|), so a row's first-argmax decision taken on
-// tensor-core scores is certain unless its best negative lies inside that band around the EXACT positive score; the
-// (few) negatives inside the band are recorded as candidates and re-scored in exact fp32 by the finalize kernel.
+// tensor-core scores is certain unless its best negative lies inside that band around the EXACT positive score.  The
+// forward tile kernel records, per row, the (few) 16-column chunks whose maximum fell inside the band while the row was
+// still undecided; the finalize kernel re-scores the columns of those chunks in exact fp32.
 // bf16 round-to-nearest operands: relative error 2^-9 each, so |sum a_i b_i - sum a~_i b~_i| <= (2^-8 + 2^-18) sum|a_i b_i|
 // <= 2^-8 (1 + 2^-10) |a||b| (Cauchy-Schwarz); fp32 accumulation of d <= 256 terms adds < 2^-15 of that.  2 % margin.
 constexpr float kBandRel = 1.02f / 256.0f;
-constexpr int kCandMax = 8;           // candidates kept per row; a row with more falls back to the tensor-core decision
+constexpr int kCandMax = 8;           // candidate ranges kept per row; a row with more falls back to the tensor-core decision
+constexpr int kCandRange = 16;        // columns per candidate range (one chunk of the softmax warps' tile walk)
 // NT-Xent with normalised rows: |S'| <= k2 (+ bf16 rounding) and k2 <= 40 is required for this path, so exp2(S') stays
 // far inside the fp32 range: no running maximum and no shift at all ("constant shift" of zero)
 constexpr float kConstShiftRaw = 0.f;
@@ -153,7 +155,14 @@ struct TileParams {
     float* loss_out;           // [1] or nullptr
     // backward
     const float* colvec;       // [2 planes][2*bg_pad]; plane 0 = a_c (or g_c), plane 1 = lse2_c
-    float* dacc;               // [2*bl_pad][D] fp32, zero on entry, accumulated with red.global.add
+    float* dacc;               // [2*bl_pad][D] fp32, zero on entry, accumulated with TMA reduce-add (the 2 - 3 CTAs that
+                               // share a row block add in the order they happen to finish: last-bit run-to-run noise)
+    // Deterministic mode (TileParams::deterministic): every (CTA, segment) instead STORES its accumulator into its own
+    // 128-row slot of det_part [grid * max_segs * 128][D] and the backward finalize kernel adds the slots of a row block
+    // in CTA order -- bit-identical gradients from run to run (the reference's cudnn.deterministic switch,
+    // pretrain.py:59-61), for ~2.3x the accumulator traffic.
+    const float* det_part;
+    int deterministic;
     const void* x1;            // inputs [b_loc][d]
     const void* x2;
     void* g1;                  // gradients [b_loc][d]
@@ -206,6 +215,15 @@ struct TileParams {
     // [2*bl_pad][D] in symmetric memory (peer transport)
     const float* zrows;
     PeerTable zrows_peers;
+    // Fused one-GPU step: the forward finalize kernel only LISTS the rows that need the exact re-scoring (amb_cnt /
+    // amb_list, defer_accuracy) and an otherwise idle flush warp of the backward tile kernel works the list off while the
+    // tile pipeline runs (resolve_ambiguous), adding the rows it confirms to amb_hits; the backward finalize kernel adds
+    // that to the count.  Nothing of the exact arithmetic then sits between the two tile kernels.
+    unsigned int* amb_cnt;     // [1] zero on entry (workspace header)
+    unsigned int* amb_hits;    // [1] zero on entry (workspace header)
+    int* amb_list;             // [2*bl_pad] row slots
+    int defer_accuracy;
+    int resolve_ambiguous;
     // backward finalize, row-sharded fused step: add up the ranks' statistics [world][4] (fixed order) into stats / loss_out
     const float* stats_all;
     int stats_world;
@@ -301,8 +319,14 @@ struct SmemLayout {
     static constexpr int kOffFlags = kOffTmemPtr + 16;                 // 16 ints of CTA-wide scratch
     static constexpr int kOffMerge = kOffFlags + 64;                   // forward: [2][4 WG][5][128] floats
     static constexpr int kMergeBytes = 2 * kNumSoftmaxWG * kFwdFields * kBlockM * 4;
-    static constexpr int kBytes = kOffMerge + kMergeBytes;
+    // forward, bf16 mode: candidates of the exact accuracy count, double-buffered by segment parity:
+    // [2] x { count u32 [128] | wrong u32 [128] | columns i32 [128][kCandMax] }
+    static constexpr int kOffCand = kOffMerge + kMergeBytes;
+    static constexpr int kCandWords = kBlockM * (2 + kCandMax);
+    static constexpr int kCandBytes = kPrec ? 0 : 2 * kCandWords * 4;
+    static constexpr int kBytes = kOffCand + kCandBytes;
     static constexpr int kDynamicBytes = kBytes + 1024;              // slack for manual 1024 B alignment
+    static_assert(kDynamicBytes <= 227 * 1024, "shared memory of one CTA");
 };
 
 
@@ -358,36 +382,9 @@ SIMCLR_DEVICE float pos_raw_value(float pos_dot, float k2, float qscale) {
     else return fmaxf(__fmul_rn(pos_dot, qscale), kClampMin);
 }
 
-// Rare path of the forward tile kernel: the 64 columns of this warp's part of a score tile are read again from TMEM and
-// every valid negative inside the band of its row is appended to the row's candidate list.  Returns the largest valid
-// negative of the thread's row in this tile.  Whole warp (tcgen05.ld is warp-collective); rows that are not interested
-// pass lo = +3e38.
-template <int kLoss>
-__device__ __noinline__ float cand_rescan(uint32_t t0, int cbase, int icbase, int b_glob, float qscale, int diag_col, int pos_col,
-                                          float lo, float hi, unsigned int* cnt, int* list) {
-    float tile_max = kNegBig;
-#pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
-        uint32_t r[16];
-        tmem_ld16(t0 + k * 16, r);
-        tmem_ld_wait16(r);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int col = cbase + k * 16 + i;
-            float v = __uint_as_float(r[i]);
-            if constexpr (kLoss == kModified) v = fmaxf(v * qscale, kClampMin);
-            const bool dead = (col == diag_col) | (col == pos_col) | (icbase + k * 16 + i >= b_glob);
-            if (!dead) {
-                tile_max = fmaxf(tile_max, v);
-                if (v >= lo && v <= hi) {
-                    const unsigned int at = atomicAdd(cnt, 1u);
-                    if (at < static_cast<unsigned int>(kCandMax)) list[at] = col;
-                }
-            }
-        }
-    }
-    return tile_max;
-}
+#ifndef SIMCLR_CAND_MODE
+#define SIMCLR_CAND_MODE 1            // 0: candidates of the exact accuracy count are never recorded (A/B measurements)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Softmax-warp helpers.  One thread owns one row (TMEM lane); a tile is consumed in four 32-column
@@ -485,6 +482,9 @@ SIMCLR_DEVICE constexpr int poly_pairs_in_round(int pairs, int round) { return r
 #endif
 #ifndef SIMCLR_BWD_DELAY_ST
 #define SIMCLR_BWD_DELAY_ST 0         // 1: store W of chunk k after the arithmetic of chunk k+1 (measured: slower)
+#endif
+#ifndef SIMCLR_TOKEN_FENCE
+#define SIMCLR_TOKEN_FENCE 1          // 1: a basic-block boundary pins the token hand-over in front of its chunk's arithmetic
 #endif
 #ifndef SIMCLR_PINGPONG
 #define SIMCLR_PINGPONG 1             // softmax pairs take turns (named-barrier token) instead of running freely
@@ -588,7 +588,7 @@ SIMCLR_DEVICE void fwd_chunk_fast(const Hot& h, const uint32_t (&r)[kChunk], flo
 // row's two special positions; `split` separates the columns that precede the positive in the reference's order.
 template <int kLoss, bool kConst>
 SIMCLR_DEVICE void fwd_chunk_special(const Hot& h, const uint32_t (&r)[kChunk], int cq, int vc, const RowCtx& rc,
-                                     FwdState& st) {
+                                     FwdState& st, float& cm) {
     const int icq = cq - vc * h.bg_pad;                          // image index of the chunk's first column
     const int n_valid = rc.row_ok ? h.b_glob - icq : 0;          // elements i >= n_valid are padding (or the row is)
     const int i_diag = rc.diag_col - cq;                         // outside [0, kChunk) when not in this chunk
@@ -610,6 +610,7 @@ SIMCLR_DEVICE void fwd_chunk_special(const Hot& h, const uint32_t (&r)[kChunk], 
     }
     st.max_prec = fmaxf(st.max_prec, cp);
     st.max_foll = fmaxf(st.max_foll, cf);
+    cm = fmaxf(cm, fmaxf(cp, cf));      // largest valid negative of the chunk (exact accuracy count)
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     if constexpr (kConst && kLoss == kModified) {
         // power path: masked elements (kNegBig) contribute nothing
@@ -849,19 +850,48 @@ SIMCLR_DEVICE ZRow zrow_of(const TileParams& p, int view, int g_img) {
     }
     return z;
 }
+// Lane l of the warp holds the elements [128 j + 4 l, 128 j + 4 l + 4) of a row, j < kVecs (kVecs = 1: d <= 128, 2: d <= 256),
+// normalised exactly as the prepare kernel normalised them; one 16-byte (f32) / 8-byte (bf16) load per j when the row
+// allows it.
 template <int kLoss>
-SIMCLR_DEVICE float zrow_elem(const TileParams& p, const ZRow& z, int k) {
-    if (z.stash != nullptr) return __ldcg(z.stash + k);
-    float e = load_elem(z.x, static_cast<size_t>(k), p.in_bf16);
-    if constexpr (kLoss == kModified) e = softplus_beta(e);
-    return e * z.mul;
+SIMCLR_DEVICE float4 zrow_vec(const TileParams& p, const ZRow& z, int lane, int j) {
+    const int k0 = 128 * j + 4 * lane;
+    float e[4] = {0.f, 0.f, 0.f, 0.f};
+    if (k0 >= p.d) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (z.stash != nullptr) return __ldcg(reinterpret_cast<const float4*>(z.stash + k0));   // d_pad floats, zero beyond d
+    const bool full = k0 + 4 <= p.d;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(z.x) + static_cast<uintptr_t>(k0) * (p.in_bf16 ? 2 : 4);
+    if (full && !p.in_bf16 && (addr & 15u) == 0) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(addr));
+        e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w;
+    } else if (full && p.in_bf16 && (addr & 7u) == 0) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(addr));
+        e[0] = __uint_as_float(v.x << 16); e[1] = __uint_as_float(v.x & 0xffff0000u);
+        e[2] = __uint_as_float(v.y << 16); e[3] = __uint_as_float(v.y & 0xffff0000u);
+    } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (k0 + u < p.d) e[u] = load_elem(z.x, static_cast<size_t>(k0 + u), p.in_bf16);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        if constexpr (kLoss == kModified) e[u] = (k0 + u < p.d) ? softplus_beta(e[u]) : 0.f;
+        e[u] *= z.mul;
+    }
+    return make_float4(e[0], e[1], e[2], e[3]);
 }
-// <z_a, z_b> by the whole warp: lane l adds the elements k = l, l + 32, ... in ascending order, then one xor butterfly:
-// the same two rows always give the same bits, whichever of them is "the positive" (exact ties stay exact).
-template <int kLoss>
-SIMCLR_DEVICE float zrow_dot(const TileParams& p, const ZRow& a, const ZRow& b, int lane) {
+// <z_r, z_c> by the whole warp from the lanes' vectors: fixed order of operations, then one xor butterfly -- the same
+// two rows always give the same bits, whichever column is "the positive" (exact ties stay exact).
+template <int kVecs>
+SIMCLR_DEVICE float zrow_dot(const float4 (&a)[kVecs], const float4 (&b)[kVecs]) {
     float acc = 0.f;
-    for (int k = lane; k < p.d; k += 32) acc = fmaf(zrow_elem<kLoss>(p, a, k), zrow_elem<kLoss>(p, b, k), acc);
+#pragma unroll
+    for (int j = 0; j < kVecs; ++j) {
+        acc = fmaf(a[j].x, b[j].x, acc);
+        acc = fmaf(a[j].y, b[j].y, acc);
+        acc = fmaf(a[j].z, b[j].z, acc);
+        acc = fmaf(a[j].w, b[j].w, acc);
+    }
     return warp_sum(acc);
 }
 // the reference's fp32 logit of an exact similarity (objective.py:35-43: s / temperature; :87-90: log(clamp(B s)) / temperature)
@@ -870,23 +900,74 @@ SIMCLR_DEVICE float reference_logit(const TileParams& p, float s) {
     if constexpr (kLoss == kNtXent) return __fdiv_rn(s, p.tau);
     else return __fdiv_rn(logf(fmaxf(s * p.qscale, kClampMin)), p.tau);
 }
-// Does the row (view vr, global image g) keep its positive as FIRST argmax among its recorded candidates?  Whole warp.
-template <int kLoss>
-SIMCLR_DEVICE bool exact_first_argmax(const TileParams& p, int vr, int g, const int* list, int n, int lane) {
-    const ZRow zr = zrow_of<kLoss>(p, vr, g);
-    const float l_pos = reference_logit<kLoss>(p, zrow_dot<kLoss>(p, zr, zrow_of<kLoss>(p, 1 - vr, g), lane));
+// Does the row (view vr, global image g) keep its positive as FIRST argmax among the columns of its recorded candidate
+// chunks (list[i] = first global column of a kCandRange-column chunk)?  Whole warp.  All columns of a chunk are in
+// flight at once: a chunk costs one memory latency.
+template <int kLoss, int kVecs, int kRound = kCandRange>
+SIMCLR_DEVICE bool exact_first_argmax_v(const TileParams& p, int vr, int g, const int* list, int n, int lane) {
+    static_assert(kCandRange % kRound == 0, "a chunk is re-scored in whole rounds");
+    const ZRow row = zrow_of<kLoss>(p, vr, g), pos = zrow_of<kLoss>(p, 1 - vr, g);
+    float4 zr[kVecs], zp[kVecs];
+#pragma unroll
+    for (int j = 0; j < kVecs; ++j) {
+        zr[j] = zrow_vec<kLoss>(p, row, lane, j);
+        zp[j] = zrow_vec<kLoss>(p, pos, lane, j);
+    }
+    const float l_pos = reference_logit<kLoss>(p, zrow_dot<kVecs>(zr, zp));
     bool ok = true;
-    for (int i = 0; i < n; ++i) {
-        const int col = __ldcg(list + i);
-        const int vc = col >= p.bg_pad ? 1 : 0, ic = col - vc * p.bg_pad;
-        const float l_c = reference_logit<kLoss>(p, zrow_dot<kLoss>(p, zr, zrow_of<kLoss>(p, vc, ic), lane));
-        // reference column order (objective.py:48-49 / :93): does column (vc, ic) come before the positive?
-        bool prec;
-        if constexpr (kLoss == kNtXent) prec = (vr == 0) ? (vc == 1 && ic < g) : (vc == 1 || ic < g);
-        else prec = ic < g;
-        ok = ok && (prec ? (l_c < l_pos) : (l_c <= l_pos));
+    for (int i = 0; i < n && ok; ++i) {
+        const int first = __ldcg(list + i);
+        const int vc = first >= p.bg_pad ? 1 : 0;            // a chunk never mixes views
+        for (int u0 = 0; u0 < kCandRange && ok; u0 += kRound) {
+            const int ic0 = first + u0 - vc * p.bg_pad;
+            float4 zc[kRound][kVecs];
+#pragma unroll
+            for (int v = 0; v < kRound; ++v) {
+                // masked columns (padding, the row itself, the positive: image g in either view) load row g instead
+                const bool live = ic0 + v < p.b_glob && ic0 + v != g && !(kLoss == kModified && vc == vr);
+                const ZRow col = zrow_of<kLoss>(p, vc, live ? ic0 + v : g);
+#pragma unroll
+                for (int j = 0; j < kVecs; ++j) zc[v][j] = zrow_vec<kLoss>(p, col, lane, j);
+            }
+#pragma unroll
+            for (int v = 0; v < kRound; ++v) {
+                const int ic = ic0 + v;
+                const bool live = ic < p.b_glob && ic != g && !(kLoss == kModified && vc == vr);
+                const float l_c = reference_logit<kLoss>(p, zrow_dot<kVecs>(zr, zc[v]));
+                // reference column order (objective.py:48-49 / :93): does column (vc, ic) come before the positive?
+                bool prec;
+                if constexpr (kLoss == kNtXent) prec = (vr == 0) ? (vc == 1 && ic < g) : (vc == 1 || ic < g);
+                else prec = ic < g;
+                if (live) ok = ok && (prec ? (l_c < l_pos) : (l_c <= l_pos));
+            }
+        }
     }
     return ok;
+}
+template <int kLoss>
+SIMCLR_DEVICE bool exact_first_argmax(const TileParams& p, int vr, int g, const int* list, int n, int lane) {
+    return p.d <= 128 ? exact_first_argmax_v<kLoss, 1>(p, vr, g, list, n, lane)
+                      : exact_first_argmax_v<kLoss, 2>(p, vr, g, list, n, lane);
+}
+
+// One warp of the backward tile kernel (fused one-GPU step): work off this CTA's share of the rows the forward finalize
+// kernel listed as undecided.  Not inlined: its registers must not count against the tile kernel's roles.
+template <int kLoss, int kVecs>
+__device__ __noinline__ void resolve_ambiguous_rows(const TileParams* pp, int lane) {
+    const TileParams& p = *pp;
+    const unsigned int n = __ldcg(p.amb_cnt);
+    for (unsigned int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int slot = __ldcg(p.amb_list + i);
+        const int vr = slot >= p.bl_pad ? 1 : 0;
+        const int g = p.row_off + slot - vr * p.bl_pad;
+        const int n_c = static_cast<int>(__ldcg(p.cand_cnt + slot));
+        // rounds of 8 / 4 columns: the routine lives in an 80-register kernel
+        const bool ok = exact_first_argmax_v<kLoss, kVecs, 8 / kVecs>(p, vr, g, p.cand + static_cast<size_t>(slot) * kCandMax, n_c, lane);
+        if (lane == 0) {
+            p.cand_cnt[slot] = 0u;                            // left zero for the next call
+            if (ok) atomicAdd(p.amb_hits, 1u);
+        }
+    }
 }
 
 template <int kLoss>
@@ -981,7 +1062,38 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
             else ambiguous = n_cand <= static_cast<unsigned int>(kCandMax);
         }
     }
-    if (p.cand_cnt != nullptr) {
+    if (p.cand_cnt != nullptr && p.defer_accuracy) {
+        // fused step: list the undecided rows (rare) for the backward tile kernel's idle flush warp; they count as
+        // misses here and are added back through amb_hits
+        if (ambiguous) {
+            p.amb_list[atomicAdd(p.amb_cnt, 1u)] = slot;
+            hit = 0.f;
+        } else if (n_cand != 0u) {
+            p.cand_cnt[slot] = 0u;
+        }
+        // ... and pull the input rows of their candidate ranges towards L2 (the inputs of a step are read once by the
+        // prepare kernel: by now they may only be in HBM), so that the re-scoring warp pays L2 latencies
+        unsigned int todo = __ballot_sync(0xffffffffu, ambiguous);
+        const int lane = tid & 31;
+        while (todo != 0u) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const int n_s = static_cast<int>(__shfl_sync(0xffffffffu, n_cand, src));
+            const int slot_s = __shfl_sync(0xffffffffu, slot, src);
+            for (int i = 0; i < n_s; ++i) {
+                const int first = __ldcg(p.cand + static_cast<size_t>(slot_s) * kCandMax + i);
+                const int vc = first >= p.bg_pad ? 1 : 0;
+                for (int u = lane; u < kCandRange; u += 32) {
+                    const int ic = first + u - vc * p.bg_pad;
+                    if (ic >= p.b_glob) continue;
+                    const ZRow z = zrow_of<kLoss>(p, vc, ic);
+                    const char* row_ptr = static_cast<const char*>(z.stash != nullptr ? static_cast<const void*>(z.stash) : z.x);
+                    const int bytes = p.d * (z.stash != nullptr || !p.in_bf16 ? 4 : 2);
+                    for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row_ptr + o));
+                }
+            }
+        }
+    } else if (p.cand_cnt != nullptr) {
         if (n_cand != 0u) p.cand_cnt[slot] = 0u;              // left zero for the next call
         unsigned int todo = __ballot_sync(0xffffffffu, ambiguous);
         const int lane = tid & 31;
@@ -1113,7 +1225,31 @@ SIMCLR_DEVICE void backward_finalize_row(const TileParams& p, int rb, int r, int
     const int slot_other = (1 - vr) * p.bl_pad + img;
     const int c_self = vr * p.bg_pad + p.row_off + img;
     const int c_other = (1 - vr) * p.bg_pad + p.row_off + img;
-    if (vec4) {
+    if (p.deterministic) {
+        // add the (CTA, segment) slots of this row block in CTA order: CTA k of the tile kernel owned the tiles
+        // [T k / G, T (k + 1) / G); the first contributing CTA may have started in an earlier row block
+        const long long grid = p.tile_grid;
+        const long long t_lo = static_cast<long long>(rb) * p.n_col_tiles, t_hi = t_lo + p.n_col_tiles;
+        const int k_first = static_cast<int>(((t_lo + 1) * grid - 1) / p.total_tiles);
+        const int k_last = static_cast<int>((t_hi * grid - 1) / p.total_tiles);
+        const int seg_first = rb - static_cast<int>(((p.total_tiles * k_first) / grid) / p.n_col_tiles);
+#pragma unroll
+        for (int u = 0; u < kPerLane; ++u) ac[u] = 0.f;
+        for (int k = k_first; k <= k_last; ++k) {
+            const size_t prow = (static_cast<size_t>(k) * p.max_segs + (k == k_first ? seg_first : 0)) * kBlockM + r;
+            const float* src = p.det_part + prow * D + lane * kPerLane;
+            if constexpr (kPerLane >= 4) {
+#pragma unroll
+                for (int u = 0; u < kPerLane; u += 4) {
+                    const float4 c4 = __ldcg(reinterpret_cast<const float4*>(src + u));
+                    ac[u] += c4.x; ac[u + 1] += c4.y; ac[u + 2] += c4.z; ac[u + 3] += c4.w;
+                }
+            } else {
+                const float2 c2 = __ldcg(reinterpret_cast<const float2*>(src));
+                ac[0] += c2.x; ac[1] += c2.y;
+            }
+        }
+    } else if (vec4) {
         if constexpr (kPerLane == 4) {
             const float4 c4 = __ldcg(reinterpret_cast<const float4*>(p.dacc + static_cast<size_t>(slot_self) * D) + lane);
             ac[0] = c4.x; ac[1] = c4.y; ac[2] = c4.z; ac[3] = c4.w;
@@ -1210,6 +1346,8 @@ SIMCLR_DEVICE void finish_forward_stats(const TileParams& p, int lane) {
         s0 = warp_sum(s0);
         s1 = warp_sum(s1);
         s2 = warp_sum(s2);
+        // rows the backward tile kernel re-scored exactly and confirmed (fused step, see TileParams::amb_hits)
+        if (p.amb_hits != nullptr) s2 += static_cast<float>(__ldcg(p.amb_hits));
     }
     if (lane == 0) {
         p.stats[0] = s0;
@@ -1271,7 +1409,7 @@ struct RingPos {
 template <int D, int kLoss, bool kBackward, bool kConst, int kPrec>
 __global__ void __launch_bounds__(kBackward ? kThreadsBackward : kThreadsForward, 1)
 contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
-                        const __grid_constant__ CUtensorMap tmap_dacc, const TileParams p) {
+                        const __grid_constant__ CUtensorMap tmap_dacc, const __grid_constant__ TileParams p) {
     using L = SmemLayout<D, kPrec>;
     constexpr int kPlanes = L::kPlanes;
     // split mode: the three operand-plane products that make up one fp32-grade product (lo*lo is below 2^-17)
@@ -1346,6 +1484,11 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
     if (warp == kAllocWarp) {
         tmem_alloc(tmem_ptr_smem, kTmemCols);
         tmem_relinquish();
+    }
+    if constexpr (!kBackward && kPrec == 0) {
+        // shared-memory candidate lists of the exact accuracy count start empty (both segment parities)
+        uint32_t* cz = reinterpret_cast<uint32_t*>(smem + L::kOffCand);
+        for (int i = threadIdx.x; i < 2 * L::kCandWords; i += blockDim.x) cz[i] = 0u;
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -1540,10 +1683,13 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             tmem_st_wait();
             tc_fence_before_sync();
             mbar_arrive(acc_empty);
+            // the last flush warp now has nothing to do until the first segment ends: it re-scores the rows whose
+            // accuracy decision the forward finalize kernel left open (fused step; usually none) under the tile pipeline
+            if (warp == kFlushWarp0 + 3 && p.resolve_ambiguous) resolve_ambiguous_rows<kLoss, (D <= 128 ? 1 : 2)>(&p, lane);
         }
 
         RingPos<S> ring;
-        RingPos<kSlots> slot;
+        RingPos<kSlots> slot, prev_slot;      // prev_slot: hand-off slot of tile idx - 1 (deterministic mode)
         int buf = 0;
         int seg = 0;
         for (TileWalker w(t_begin, t_end, nct); w.valid(); w.next()) {
@@ -1553,6 +1699,13 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 if (w.seg_first()) mbar_wait(acc_empty, seg & 1, 203);
                 if ((ring.idx & 1) == me) {
                     if (lane == 0) trace_event(p, 1, idx, 2);
+                    // Deterministic mode: the two issuers would otherwise feed the accumulator in whatever order their W
+                    // tiles become ready, and the fp32 accumulation order -- hence the last bit of the gradients -- would
+                    // depend on timing.  The gradient MMAs of tile idx are issued when those of tile idx - 1 (the other
+                    // issuer's) have COMPLETED; the score MMAs of later tiles keep the tensor pipe busy meanwhile.  Tile
+                    // idx - 1 used the previous hand-off slot; this warp is that barrier's second waiter and, like the
+                    // first, observes every one of its phases (the slot ring is even: a slot always meets the same issuer).
+                    if (p.deterministic && idx > 0) mbar_wait(w_done + 8 * prev_slot.idx, prev_slot.par, 206);
                     mbar_wait(w_full + 8 * slot.idx, slot.par, 204);
                     tc_fence_after_sync();
                     if (lane == 0) trace_event(p, 1, idx, 3);
@@ -1580,6 +1733,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 }
             }
             ring.advance();
+            prev_slot = slot;
             slot.advance();
             if (++buf == NB) buf = 0;
             if (!w.seg_last()) continue;
@@ -1621,8 +1775,11 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                     for (int qq = 0; qq < D / 32; ++qq) {
                         const int q = (SIMCLR_FLUSH_ALTERNATE && (blockIdx.x & 1)) ? D / 32 - 1 - qq : qq;
                         const int stage = (q / kBoxesPerStage) == 0 ? ring.idx : st1.idx;
-                        tma_reduce_add_2d(&tmap_dacc, sb_addr + stage * L::kTileBytes + (q % kBoxesPerStage) * kAtomBytes,
-                                          q * 32, w.rb * kBlockM);
+                        const uint32_t box = sb_addr + stage * L::kTileBytes + (q % kBoxesPerStage) * kAtomBytes;
+                        if (p.deterministic)      // tmap_dacc describes det_part: this (CTA, segment)'s private slot
+                            tma_store_2d(&tmap_dacc, box, q * 32, (static_cast<int>(blockIdx.x) * p.max_segs + seg) * kBlockM);
+                        else
+                            tma_reduce_add_2d(&tmap_dacc, box, q * 32, w.rb * kBlockM);
                     }
                     bulk_commit_group();
                     // The staging space may be reused (or the CTA may exit) once the TMA engine has read it; the adds
@@ -1677,9 +1834,10 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             h.clampc = kClampMin * c0;
         }
         const int b_loc = p.b_loc, row_off = p.row_off;
+        const bool token_fence = p.n_row_blocks != 0;      // always true, unknown to the compiler (see SIMCLR_TOKEN_FENCE)
         // candidates of the exact accuracy count are recorded by the bf16-mode forward kernel (the split mode's scores
         // are fp32-grade already)
-        constexpr bool kRecord = !kBackward && kPrec == 0;
+        constexpr bool kRecord = !kBackward && kPrec == 0 && SIMCLR_CAND_MODE != 0;
         const bool tracing = SIMCLR_TRACE && p.trace != nullptr && static_cast<int>(blockIdx.x) == p.trace_cta && quarter == 0 && lane == 0;
         constexpr int kLogS = S == 2 ? 1 : (S == 4 ? 2 : 3);
         static_assert((1 << kLogS) == S, "ring size must be 2, 4 or 8");
@@ -1722,11 +1880,24 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             // exact accuracy count: the band around this row's exact positive inside which a tensor-core score cannot
             // decide (lo = +inf: not recording -- padding rows, rows already known to be wrong, feature switched off)
             float band_lo = 3.0e38f, band_hi = 3.0e38f;
-            unsigned int* cand_cnt_row = nullptr;
+            // this row's slots in the shared-memory candidate buffer of the segment's parity: count | wrong flag | list
+            const uint32_t cand_base = smem_base + L::kOffCand + (seg & 1) * (L::kCandWords * 4);
+            const uint32_t cand_cnt_addr = cand_base + row_in_block * 4;
+            const uint32_t cand_wrong_addr = cand_base + (kBlockM + row_in_block) * 4;
+            const uint32_t cand_list_addr = cand_base + (2 * kBlockM + row_in_block * kCandMax) * 4;
+            int pending_range = -1;          // first global column of this thread's pending candidate range, or -1
+            auto publish_range = [&](int first_col) {
+                uint32_t at;
+                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(at) : "r"(cand_cnt_addr) : "memory");
+                if (at < static_cast<uint32_t>(kCandMax))
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(cand_list_addr + at * 4), "r"(first_col) : "memory");
+#if SIMCLR_TRACE
+                if (p.ktrace != nullptr) atomicAdd(p.ktrace + 33, 1ull);                       // diagnostics: published ranges
+#endif
+            };
             if constexpr (kRecord) {
                 if (p.cand_cnt != nullptr && rc.row_ok) {
                     const int slot_r = rb * kBlockM + row_in_block;
-                    cand_cnt_row = p.cand_cnt + slot_r;
                     cand_band<kLoss>(p.band, pos_raw_value<kLoss>(__ldcg(p.pos_dot + slot_r), h.k2, h.qscale), band_lo, band_hi);
                 }
             }
@@ -1767,6 +1938,40 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 const uint32_t t0 = tmem_base + lane_addr + buf * kBlockN + half * 64;
                 const int cbase = c0 + half * 64;
                 const uint32_t cv_tile = cv_base + stage * (2 * kBlockN * 4) + half * 64 * 4;
+                // Exact accuracy count.  `tile_max`: this thread's largest valid negative of the tile.  Hot path: one compare
+                // and one vote per tile.  Behind the vote (rare): a row whose negative exceeds the band is wrong whatever
+                // else happens and stops taking part (the four thread instances of a row -- two pairs x two column
+                // halves -- share that verdict through a flag in shared memory: a hint, plain stores); a tile maximum
+                // INSIDE the band of an undecided row makes its 16-column chunk(s) the thread's pending candidate.  Pending
+                // candidates are only published at the end of the segment, and only for rows that are still undecided
+                // then: with unrelated embeddings nearly every row is proven wrong one tile later and nothing is
+                // published at all (an immediate TMEM rescan cost ~5000 cycles per event, cold code, with both softmax
+                // pairs waiting for the warp that ran it: +3.4 us per forward launch on random inputs, profiles/r02_notes.md).
+                auto record_candidates = [&](float tile_max, const float (&cmk)[4]) {
+                    if (!__any_sync(0xffffffffu, tile_max >= band_lo)) return;
+#if SIMCLR_TRACE
+                    if (p.ktrace != nullptr && lane == 0) atomicAdd(p.ktrace + 32, 1ull);     // diagnostics: triggers
+#endif
+                    if (band_lo < 3.0e38f) {
+                        uint32_t known_wrong;
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(known_wrong) : "r"(cand_wrong_addr) : "memory");
+                        if (known_wrong != 0u) {
+                            band_lo = 3.0e38f;
+                        } else if (tile_max > band_hi) {
+                            band_lo = 3.0e38f;
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(cand_wrong_addr), "r"(1u) : "memory");
+                        } else {
+                            // every 16-column chunk whose maximum lies in the band (none exceeds it) is a candidate
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (cmk[k] >= band_lo) {
+                                    if (pending_range >= 0) publish_range(pending_range);   // a second near-tie chunk: very rare
+                                    pending_range = cbase + k * kChunk;
+                                }
+                            }
+                        }
+                    }
+                };
                 uint32_t ra[kChunk], rb2[kChunk];
                 tmem_ld16(t0, ra);
                 // Ping-pong: the arithmetic of tile `it` starts when the other pair has finished that of tile it-1.
@@ -1808,7 +2013,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 } else if (!tile_special) {
                     // Common case: no masked element anywhere in the tile for this warp.  One straight-line block over
                     // the four chunks, so that the tail of chunk k overlaps the head of chunk k+1.
-                    float cm = kNegBig;
+                    float cmk[4] = {kNegBig, kNegBig, kNegBig, kNegBig};      // forward: maximum of each 16-column chunk
 #if SIMCLR_BWD_DELAY_ST
                     uint32_t wprev[kChunk / 2];           // backward: W of the previous chunk (stored one chunk late)
 #endif
@@ -1820,9 +2025,13 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         if (k < 3) tmem_ld16(t0 + (k + 1) * kChunk, nxt);
                         // hand the token over one chunk early: the other pair's first chunk fills the pipes while this
                         // pair drains its last one (covers the bar.arrive -> bar.sync wake-up latency)
-                        if (SIMCLR_PINGPONG && k == SIMCLR_TOKEN_CHUNK && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
+                        if (SIMCLR_PINGPONG && k == SIMCLR_TOKEN_CHUNK && it + 1 < n) named_bar_arrive_pinned(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps, cur);
+                        // ptxas floats a bar.arrive (nothing depends on it) to the END of its basic block, i.e. behind the
+                        // arithmetic of the chunk it was written in front of -- the other pair then gets the token a chunk
+                        // late.  An always-true branch the compiler cannot see through ends the basic block right here.
+                        if (SIMCLR_TOKEN_FENCE && k == SIMCLR_TOKEN_CHUNK && !token_fence) continue;
                         if constexpr (!kBackward) {
-                            fwd_chunk_fast<kLoss, kConst, kPrec == 0>(h, cur, cm, fs);
+                            fwd_chunk_fast<kLoss, kConst, kPrec == 0>(h, cur, cmk[k], fs);
                         } else if constexpr (kPrec == 0) {
                             uint32_t wq[kChunk / 2], unused[kChunk / 2];
                             bwd_chunk<kLoss, kConst, false>(h, cur, cv_tile + k * kChunk * 4, 0, rc, br, wq, unused);
@@ -1840,19 +2049,13 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         }
                     }
                     if constexpr (!kBackward) {
+                        const float cm = fmaxf(fmaxf(cmk[0], cmk[1]), fmaxf(cmk[2], cmk[3]));
                         fs.max_prec = fmaxf(fs.max_prec, tile_prec ? cm : kNegBig);
                         fs.max_foll = fmaxf(fs.max_foll, tile_prec ? kNegBig : cm);
-                    }
-                    if constexpr (kRecord) {
-                        // a negative of this tile reaches the band of some row of the warp (rare): record the candidates
-                        if (__any_sync(0xffffffffu, cm >= band_lo)) {
-                            const float tm = cand_rescan<kLoss>(t0, cbase, cbase - vc * h.bg_pad, h.b_glob, h.qscale, -1, -1,
-                                                                band_lo, band_hi, cand_cnt_row,
-                                                                p.cand + static_cast<size_t>(rb * kBlockM + row_in_block) * kCandMax);
-                            if (tm > band_hi) band_lo = 3.0e38f;      // the row is wrong whatever the rest says
-                        }
+                        if constexpr (kRecord) record_candidates(cm, cmk);
                     }
                 } else {
+                    float cms[4] = {kNegBig, kNegBig, kNegBig, kNegBig};   // largest valid negative of this thread's row per chunk
                     auto process = [&](const uint32_t (&r)[kChunk], int k) {
                         const int cq = cbase + k * kChunk;
                         const int icq = cq - vc * h.bg_pad;
@@ -1860,7 +2063,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         if constexpr (!kBackward) special = special || !warp_rows_ok || (icq + kChunk - 1 >= h.b_glob);
                         if constexpr (!kBackward) {
                             if (special) {
-                                fwd_chunk_special<kLoss, kConst>(h, r, cq, vc, rc, fs);
+                                fwd_chunk_special<kLoss, kConst>(h, r, cq, vc, rc, fs, cms[k]);
                             } else {
                                 // an unmasked chunk of a tile that overlaps the warp's own images lies entirely before or
                                 // entirely after them: classify it by itself (the tile as a whole straddles the positive)
@@ -1872,6 +2075,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                                 fwd_chunk_fast<kLoss, kConst, kPrec == 0>(h, r, cm, fs);
                                 fs.max_prec = fmaxf(fs.max_prec, prec ? cm : kNegBig);
                                 fs.max_foll = fmaxf(fs.max_foll, prec ? kNegBig : cm);
+                                cms[k] = cm;
                             }
                         } else {
                             uint32_t wq[kChunk / 2], unused[kChunk / 2];
@@ -1890,19 +2094,10 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         uint32_t (&nxt)[kChunk] = (k & 1) ? ra : rb2;
                         tmem_ld_wait16(cur);
                         if (k < 3) tmem_ld16(t0 + (k + 1) * kChunk, nxt);
-                        if (SIMCLR_PINGPONG && k == SIMCLR_TOKEN_CHUNK && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
+                        if (SIMCLR_PINGPONG && k == SIMCLR_TOKEN_CHUNK && it + 1 < n) named_bar_arrive_pinned(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps, cur);
                         process(cur, k);
                     }
-                    if constexpr (kRecord) {
-                        // tiles with masked elements (diagonal, positive, padding: ~1.5 % of all tiles) are always rescanned
-                        // while a row of the warp is still undecided
-                        if (__any_sync(0xffffffffu, band_lo < 3.0e38f)) {
-                            const float tm = cand_rescan<kLoss>(t0, cbase, cbase - vc * h.bg_pad, h.b_glob, h.qscale, rc.diag_col,
-                                                                rc.pos_col, band_lo, band_hi, cand_cnt_row,
-                                                                p.cand + static_cast<size_t>(rb * kBlockM + row_in_block) * kCandMax);
-                            if (tm > band_hi) band_lo = 3.0e38f;
-                        }
-                    }
+                    if constexpr (kRecord) record_candidates(fmaxf(fmaxf(cms[0], cms[1]), fmaxf(cms[2], cms[3])), cms);
                 }
                 if (SIMCLR_PINGPONG && !(kBackward && kPrec != 0) && SIMCLR_TOKEN_CHUNK > 3 && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
                 if constexpr (!kBackward) {
@@ -1925,6 +2120,14 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
 
             // ---- end of segment ----
             if (threadIdx.x == 0 && seg < 2) cta_stamp(p, 1 + 2 * seg);
+            if constexpr (kRecord) {
+                // a pending candidate range of a row that is still undecided now is a real near-tie: publish it
+                if (pending_range >= 0 && band_lo < 3.0e38f) {
+                    uint32_t known_wrong;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(known_wrong) : "r"(cand_wrong_addr) : "memory");
+                    if (known_wrong == 0u) publish_range(pending_range);
+                }
+            }
             if constexpr (!kBackward) {
                 // merge the four warpgroups' partial (max, sum, argmax bookkeeping) through shared memory ...
                 float* mg = smem_merge + (seg & 1) * (kNumSoftmaxWG * kFwdFields * kBlockM);
@@ -1963,6 +2166,24 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                     __stcg(dst + 2 * kBlockM, mp);
                     __stcg(dst + 3 * kBlockM, mf);
                     __stcg(dst + 4 * kBlockM, pm);
+                    if constexpr (kRecord) {
+                        // flush this row's shared-memory candidates of the segment to the global list (one global atomic
+                        // per row that has any) and leave the buffer of this parity clean for segment seg + 2
+                        uint32_t n_c;
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(n_c) : "r"(cand_cnt_addr) : "memory");
+                        if (n_c != 0u) {
+                            const int slot_r = rb * kBlockM + row_in_block;
+                            const uint32_t base_c = atomicAdd(p.cand_cnt + slot_r, n_c);    // may exceed kCandMax: fallback
+                            for (uint32_t i = 0; i < n_c && i < static_cast<uint32_t>(kCandMax); ++i) {
+                                uint32_t col;
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(col) : "r"(cand_list_addr + i * 4) : "memory");
+                                if (base_c + i < static_cast<uint32_t>(kCandMax))
+                                    p.cand[static_cast<size_t>(slot_r) * kCandMax + base_c + i] = static_cast<int>(col);
+                            }
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(cand_cnt_addr), "r"(0u) : "memory");
+                        }
+                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(cand_wrong_addr), "r"(0u) : "memory");
+                    }
                 }
             }
             if (threadIdx.x == 0 && seg < 2) cta_stamp(p, 2 + 2 * seg);

@@ -46,6 +46,17 @@ SIMCLR_DEVICE float softplus_beta_grad(float x) {
 SIMCLR_DEVICE void named_bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// bar.arrive that the compiler cannot move: the 16 registers of the chunk about to be processed pass through the
+// statement as in/out operands, so every use of them (the chunk's arithmetic) stays behind it, and the statement itself
+// stays behind the tcgen05.wait::ld that produced them.  ptxas otherwise floats the arrive to the end of the chunk
+// (observed: the ping-pong token then reaches the other softmax pair a whole chunk late, +12 us per forward kernel).
+SIMCLR_DEVICE void named_bar_arrive_pinned(int id, int nthreads, uint32_t (&r)[16]) {
+    asm volatile("bar.arrive %16, %17;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 : "r"(id), "r"(nthreads)
+                 : "memory");
+}
 SIMCLR_DEVICE void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

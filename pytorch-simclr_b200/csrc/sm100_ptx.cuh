@@ -186,6 +186,12 @@ SIMCLR_DEVICE void tma_reduce_add_2d(const void* tmap, uint32_t smem_src, int32_
                  ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(x), "r"(y)
                  : "memory");
 }
+// 2-D tiled store shared -> global (plain overwrite of the box)
+SIMCLR_DEVICE void tma_store_2d(const void* tmap, uint32_t smem_src, int32_t x, int32_t y) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(x), "r"(y)
+                 : "memory");
+}
 SIMCLR_DEVICE void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all groups of this thread have finished READING their shared-memory source
 SIMCLR_DEVICE void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -301,6 +307,15 @@ SIMCLR_DEVICE void tmem_ld_wait16(uint32_t (&r)[16]) {
                    "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                  :
                  : "memory");
+}
+// four columns; waits for the data (rare paths that want small code rather than a deep load pipeline)
+SIMCLR_DEVICE void tmem_ld4_sync(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+        : "r"(taddr)
+        : "memory");
 }
 SIMCLR_DEVICE void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),

@@ -235,7 +235,7 @@ class PeerBatch:
             float(temperature), None if grad_out is None else grad_out.data_ptr(), operand.data_ptr(), rowvec.data_ptr(),
             stats_local.data_ptr(), stats_global.data_ptr(), loss.data_ptr(), grad1.data_ptr(), grad2.data_ptr(),
             fwd_ws.data_ptr(), fwd_ws_bytes, bwd_ws.data_ptr(), bwd_ws_bytes, self.world, self.rank, tab["operand"],
-            self._mc[gen], tab["colvec"], tab["stats"], self._flags, self.epoch.data_ptr(), tab["zrows"], stream),
+            self._mc[gen], tab["colvec"], tab["stats"], self._flags, self.epoch.data_ptr(), tab["zrows"], 0, stream),
             "simclr_forward_backward_peer")
         self.generation += 1
         return self.generation

@@ -15,7 +15,8 @@ from ._lib import DTYPE_BF16, DTYPE_F32, LOSS_MODIFIED, LOSS_NTXENT, PRECISION_B
 
 __all__ = ["contrastive_forward_backward", "ContrastiveLossFunction", "LOSS_NTXENT", "LOSS_MODIFIED", "pad_rows",
            "pad_dim", "compact_to_padded", "padded_to_compact", "set_precision", "get_precision", "resolve_precision",
-           "set_eager_backward", "get_eager_backward", "run_fused", "run_fused_begin", "run_fused_finish"]
+           "set_eager_backward", "get_eager_backward", "run_fused", "run_fused_begin", "run_fused_finish",
+           "set_deterministic", "get_deterministic"]
 
 BLOCK = 128
 
@@ -33,6 +34,26 @@ _PRECISION = "auto"
 # utils/model_utils.py:115-120) always follows a training forward by its backward, and the accuracy read-back it forces
 # (objective.py:52) otherwise splits the step into two launch sequences with a host round trip in between.
 _EAGER_BACKWARD = True
+
+
+# Run-to-run reproducible gradients (include/simclr_b200.h SIMCLR_FLAG_DETERMINISTIC): None follows
+# torch.are_deterministic_algorithms_enabled() -- the modern form of the reference's cudnn.deterministic switch
+# (pretrain.py:59-61) --, True / False force it.  The deterministic backward is a few percent slower.
+_DETERMINISTIC = None
+
+
+def set_deterministic(flag) -> None:
+    """True / False, or None to follow torch.use_deterministic_algorithms()."""
+    global _DETERMINISTIC
+    _DETERMINISTIC = None if flag is None else bool(flag)
+
+
+def get_deterministic() -> bool:
+    return torch.are_deterministic_algorithms_enabled() if _DETERMINISTIC is None else _DETERMINISTIC
+
+
+def backward_flags() -> int:
+    return _lib.FLAG_DETERMINISTIC if get_deterministic() else 0
 
 
 def set_eager_backward(flag: bool) -> None:
@@ -194,7 +215,7 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
         # accumulation buffer + column vectors), which saves the backward-prepare kernel
         bwd_ws = None
         if prime_backward and gather is None and weight is None:
-            bwd_bytes = lib.simclr_backward_workspace_bytes(loss_kind, b, b, d)
+            bwd_bytes = lib.simclr_backward_workspace_bytes_flags(loss_kind, b, b, d, backward_flags())
             bwd_ws = torch.empty(bwd_bytes, dtype=torch.uint8, device=dev)
         stats_ptr = stats.data_ptr()
         if host_slot is not None and gather is None:
@@ -231,8 +252,8 @@ def run_forward(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature:
 _FUSED_PLAN = {}      # (loss, b, d, precision) -> byte offsets of the scratch carved out of one allocation
 
 
-def _fused_plan(lib, loss_kind: int, b: int, d: int, precision: int):
-    key = (loss_kind, b, d, precision)
+def _fused_plan(lib, loss_kind: int, b: int, d: int, precision: int, flags: int = 0):
+    key = (loss_kind, b, d, precision, flags)
     plan = _FUSED_PLAN.get(key)
     if plan is None:
         bp = pad_rows(b)
@@ -241,8 +262,8 @@ def _fused_plan(lib, loss_kind: int, b: int, d: int, precision: int):
         if not op_bytes:
             raise ValueError("unsupported shape / precision (fp32-grade operands need d <= 128)")
         fwd_bytes = lib.simclr_forward_workspace_bytes(loss_kind, b, b, d)
-        bwd_bytes = lib.simclr_backward_workspace_bytes(loss_kind, b, b, d)
-        off, plan = 0, {}
+        bwd_bytes = lib.simclr_backward_workspace_bytes_flags(loss_kind, b, b, d, flags)
+        off, plan = 0, {"flags": flags}
         for name, n in (("operand", op_bytes), ("rowvec", 4 * 2 * bp * 4), ("stats", 16), ("fwd", fwd_bytes),
                         ("bwd", bwd_bytes)):
             plan[name] = (off, n)
@@ -265,7 +286,7 @@ def run_fused(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature: f
     code = _dtype_code(x1)
     if precision is None:
         precision = resolve_precision(x1, False)
-    plan = _fused_plan(lib, loss_kind, b, d, precision)
+    plan = _fused_plan(lib, loss_kind, b, d, precision, backward_flags())
     with _device_guard(dev):
         stream = torch.cuda.current_stream().cuda_stream
         scratch = torch.empty(plan["total"], dtype=torch.uint8, device=dev)
@@ -288,7 +309,7 @@ def run_fused(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperature: f
                                           float(temperature), precision, _ptr(go), base + plan["operand"][0],
                                           base + plan["rowvec"][0], stats_ptr, loss.data_ptr(), g1.data_ptr(),
                                           g2.data_ptr(), base + plan["fwd"][0], plan["fwd"][1], base + plan["bwd"][0],
-                                          plan["bwd"][1], stream),
+                                          plan["bwd"][1], plan["flags"], stream),
               "simclr_forward_backward")
         if host_slot is not None:
             _hoststats.ring(dev).launched(host_slot)
@@ -310,7 +331,7 @@ def run_fused_begin(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperat
     dev = x1.device
     if precision is None:
         precision = resolve_precision(x1, False)
-    plan = _fused_plan(lib, loss_kind, b, d, precision)
+    plan = _fused_plan(lib, loss_kind, b, d, precision, backward_flags())
     st = _FusedState()
     st.plan, st.loss, st.b, st.d, st.code = plan, loss_kind, b, d, _dtype_code(x1)
     st.normalize, st.temperature, st.precision = int(bool(normalize)), float(temperature), precision
@@ -330,7 +351,7 @@ def run_fused_begin(loss_kind: int, x1: torch.Tensor, x2: torch.Tensor, temperat
                                                 st.temperature, precision, base + plan["operand"][0],
                                                 base + plan["rowvec"][0], stats_ptr, loss.data_ptr(),
                                                 base + plan["fwd"][0], plan["fwd"][1], base + plan["bwd"][0],
-                                                plan["bwd"][1], stream), "simclr_forward_backward_begin")
+                                                plan["bwd"][1], plan["flags"], stream), "simclr_forward_backward_begin")
         if host_slot is not None:
             ring.launched(host_slot)
     return loss, stats, st
@@ -354,7 +375,7 @@ def run_fused_finish(st: "_FusedState", x1: torch.Tensor, x2: torch.Tensor, grad
         check(lib.simclr_forward_backward_finish(st.loss, x1.data_ptr(), x2.data_ptr(), st.b, st.d, st.code, st.normalize,
                                                  st.temperature, st.precision, _ptr(go), base + plan["operand"][0],
                                                  base + plan["rowvec"][0], g1.data_ptr(), g2.data_ptr(),
-                                                 base + plan["bwd"][0], plan["bwd"][1], stream),
+                                                 base + plan["bwd"][0], plan["bwd"][1], plan["flags"], stream),
               "simclr_forward_backward_finish")
     return g1, g2
 
@@ -375,16 +396,19 @@ def run_backward(saved: "_Saved", x1: torch.Tensor, x2: torch.Tensor, grad_out: 
             go = grad_out.to(device=dev, dtype=torch.float32).contiguous()
         ws = getattr(saved, "bwd_ws", None)
         primed = getattr(saved, "primed_colvec", None) if ws is not None else None
+        flags = backward_flags()
+        need = lib.simclr_backward_workspace_bytes_flags(saved.loss, saved.b_local, saved.b_global, saved.d, flags)
+        if ws is not None and ws.numel() < need:
+            ws, primed = None, None       # the switch was flipped between forward and backward: take the unprimed route
         if ws is None:
-            ws = torch.empty(lib.simclr_backward_workspace_bytes(saved.loss, saved.b_local, saved.b_global, saved.d),
-                             dtype=torch.uint8, device=dev)
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
         ws_bytes = ws.numel()
         check(lib.simclr_backward(saved.loss, x1.data_ptr(), x2.data_ptr(), saved.b_local, saved.b_global,
                                   saved.row_offset, saved.d, saved.dtype_code, int(saved.normalize), saved.temperature,
                                   getattr(saved, "precision", PRECISION_BF16), saved.operand_rows.data_ptr(), saved.operand_cols.data_ptr(),
                                   saved.inv_norm.data_ptr(), saved.pos_dot.data_ptr(), saved.lse2_cols.data_ptr(),
                                   _ptr(saved.col_scale), _ptr(go), g1.data_ptr(), g2.data_ptr(), ws.data_ptr(),
-                                  ws_bytes, primed, stream), "simclr_backward")
+                                  ws_bytes, primed, flags, stream), "simclr_backward")
         # the primed state (zeroed accumulation buffer) is consumed: a second backward over a retained graph takes
         # the unprimed route (its backward-prepare kernel zeroes the buffer again)
         saved.primed_colvec = None

@@ -22,8 +22,9 @@ class ContrastiveStep:
     KERNELS_BACKWARD = 2    # tile kernel, finalize
 
     def __init__(self, loss_kind: int, batch: int, dim: int, temperature: float, normalize: bool = True,
-                 dtype: torch.dtype = torch.float32, device="cuda", precision: str = "bf16"):
+                 dtype: torch.dtype = torch.float32, device="cuda", precision: str = "bf16", deterministic: bool = False):
         self.lib = _lib.load()
+        self.flags = _lib.FLAG_DETERMINISTIC if deterministic else 0
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
         self.precision = _lib.PRECISION_SPLIT if precision == "fp32" else _lib.PRECISION_BF16
@@ -45,7 +46,7 @@ class ContrastiveStep:
         self.grad1 = torch.empty_like(self.x1)
         self.grad2 = torch.empty_like(self.x2)
         self.fwd_ws_bytes = self.lib.simclr_forward_workspace_bytes(self.kind, batch, batch, dim)
-        self.bwd_ws_bytes = self.lib.simclr_backward_workspace_bytes(self.kind, batch, batch, dim)
+        self.bwd_ws_bytes = self.lib.simclr_backward_workspace_bytes_flags(self.kind, batch, batch, dim, self.flags)
         if not self.fwd_ws_bytes or not self.bwd_ws_bytes:
             raise ValueError("unsupported shape")
         self.fwd_ws = torch.empty(self.fwd_ws_bytes, dtype=torch.uint8, device=dev)
@@ -88,7 +89,8 @@ class ContrastiveStep:
                                          self.rowvec[1].data_ptr(), self.rowvec[2].data_ptr(), None,
                                          None if grad_out is None else grad_out.data_ptr(), self.grad1.data_ptr(),
                                          self.grad2.data_ptr(), self.bwd_ws.data_ptr(), self.bwd_ws_bytes,
-                                         self.bwd_ws.data_ptr(), st, _lib.STAGE_ALL if stage_mask is None else stage_mask),
+                                         self.bwd_ws.data_ptr(), self.flags, st,
+                                         _lib.STAGE_ALL if stage_mask is None else stage_mask),
               "simclr_backward")
 
     def step(self, grad_out: Optional[torch.Tensor] = None, x1: Optional[torch.Tensor] = None,
@@ -105,7 +107,8 @@ class ContrastiveStep:
                                                None if grad_out is None else grad_out.data_ptr(), self.operand.data_ptr(),
                                                self.rowvec.data_ptr(), self.stats.data_ptr(), self.loss.data_ptr(),
                                                grad1.data_ptr(), grad2.data_ptr(), self.fwd_ws.data_ptr(),
-                                               self.fwd_ws_bytes, self.bwd_ws.data_ptr(), self.bwd_ws_bytes, self._stream()),
+                                               self.fwd_ws_bytes, self.bwd_ws.data_ptr(), self.bwd_ws_bytes, self.flags,
+                                               self._stream()),
               "simclr_forward_backward")
 
     def step_staged(self) -> None:
@@ -164,7 +167,7 @@ class PeerStep:
                                        operand_cols.data_ptr(), self.rowvec[0].data_ptr(), self.rowvec[1].data_ptr(),
                                        None, None, None if grad_out is None else grad_out.data_ptr(),
                                        self.grad1.data_ptr(), self.grad2.data_ptr(), self.bwd_ws.data_ptr(),
-                                       self.bwd_ws_bytes, colvec.data_ptr(), self._stream()), "simclr_backward")
+                                       self.bwd_ws_bytes, colvec.data_ptr(), 0, self._stream()), "simclr_backward")
 
     def step(self, grad_out: Optional[torch.Tensor] = None, x1: Optional[torch.Tensor] = None,
              x2: Optional[torch.Tensor] = None, grad1: Optional[torch.Tensor] = None,

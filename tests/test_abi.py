@@ -52,7 +52,7 @@ def test_diagnostics_live_in_the_tracing_build_only(lib):
 
 
 def test_abi_version_and_error_strings(lib):
-    assert lib.simclr_abi_version() == 11
+    assert lib.simclr_abi_version() == 12
     assert lib.simclr_error_string(0) == b"ok"
     for code in range(-11, 0):
         assert lib.simclr_error_string(code) not in (b"", b"unknown error")
@@ -73,6 +73,9 @@ def test_workspace_sizes(lib):
     assert lib.simclr_forward_workspace_bytes(0, 0, 0, 128) == 0          # bad shape
     assert lib.simclr_forward_workspace_bytes(0, 64, 64, 300) == 0        # unsupported dim
     assert lib.simclr_forward_workspace_bytes(7, 64, 64, 128) == 0        # unknown loss
+    # the deterministic backward keeps one accumulator slot per (CTA, segment)
+    assert lib.simclr_backward_workspace_bytes_flags(0, 4096, 4096, 128, 1) > lib.simclr_backward_workspace_bytes(0, 4096, 4096, 128)
+    assert lib.simclr_backward_workspace_bytes_flags(0, 4096, 4096, 128, 0) == lib.simclr_backward_workspace_bytes(0, 4096, 4096, 128)
     # sharded rows need less accumulator space than the whole batch
     assert lib.simclr_backward_workspace_bytes(0, 512, 4096, 128) < lib.simclr_backward_workspace_bytes(0, 4096, 4096, 128)
 
@@ -95,4 +98,4 @@ def test_argument_validation_without_gpu(lib):
     assert lib.simclr_forward(0, p, p, 4, 4, 0, 8, 0.5, 1, p, None, p, p, p, None, p, 16, None, None, 0, None, None) == -5
     assert lib.simclr_forward(0, p + 4, p, 4, 4, 0, 8, 0.5, 1, p, None, p, p, p, None, p, 1 << 15, None, None, 0, None, None) == -6
     assert lib.simclr_backward(0, p, p, 4, 4, 0, 8, 0, 1, float("nan"), 0, p, p, p, p, p, None, None, p, p, p, 1 << 15,
-                               None, None) == -7
+                               None, 0, None) == -7

@@ -111,10 +111,10 @@ def test_fused_entry_points_reject_bad_arguments_without_a_gpu():
     lib = _lib.load()
     buf = ctypes.create_string_buffer(1 << 12)
     p = (ctypes.addressof(buf) + 255) & ~255
-    assert lib.simclr_forward_backward(0, p, p, 4, 8, 0, 1, 0.5, 0, None, p, None, p, None, p, p, p, 1 << 20, p, 1 << 20, None) == -1
-    assert lib.simclr_forward_backward(0, p, p, 0, 8, 0, 1, 0.5, 0, None, p, p, p, None, p, p, p, 1 << 20, p, 1 << 20, None) == -2
+    assert lib.simclr_forward_backward(0, p, p, 4, 8, 0, 1, 0.5, 0, None, p, None, p, None, p, p, p, 1 << 20, p, 1 << 20, 0, None) == -1
+    assert lib.simclr_forward_backward(0, p, p, 0, 8, 0, 1, 0.5, 0, None, p, p, p, None, p, p, p, 1 << 20, p, 1 << 20, 0, None) == -2
     arr = (ctypes.c_void_p * 2)(p, p)
     assert lib.simclr_forward_backward_peer(0, p, p, 4, 8, 0, 1, 0.5, None, p, p, p, p, None, p, p, p, 1 << 20, p, 1 << 20, 2, 5,
-                                            arr, None, arr, arr, arr, p, None, None) == -12      # rank outside the world
+                                            arr, None, arr, arr, arr, p, None, 0, None) == -12      # rank outside the world
     assert lib.simclr_forward_backward_peer(0, p, p, 4, 8, 0, 1, 0.5, None, p, p, p, p, None, p, p, p, 1 << 20, p, 1 << 20, 2, 0,
-                                            None, None, arr, arr, arr, p, None, None) == -1
+                                            None, None, arr, arr, arr, p, None, 0, None) == -1

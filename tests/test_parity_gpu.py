@@ -36,6 +36,7 @@ def _restore_precision():
     yield
     sb.set_precision("auto")
     sb.set_eager_backward(True)
+    sb.set_deterministic(None)
 
 
 def _mode_for(precision, dtype, d):
@@ -424,3 +425,55 @@ def test_more_near_ties_than_candidate_slots_falls_back_gracefully():
             loss, acc = sb.contrastive_loss(z1.cuda(), z2.cuda(), temperature=0.5)
         assert abs(acc - ref.acc) * 2 * b / 100.0 <= 0.25 * 2 * b
         assert loss.item() == pytest.approx(ref.loss, rel=2e-3)
+
+
+@pytest.mark.parametrize("kind", [0, 1], ids=["ntxent", "modified"])
+@pytest.mark.parametrize("b,d", [(4096, 128), (1000, 100), (2048, 256)])
+def test_deterministic_mode_gives_bit_identical_gradients(kind, b, d):
+    """SIMCLR_FLAG_DETERMINISTIC (the reference's cudnn.deterministic / manual_seed switch, pretrain.py:59-61): per-(CTA,
+    segment) accumulator slots merged in a fixed order.  Repeated runs -- staged calls, the fused step, a CUDA graph
+    replayed under different load -- give torch.equal gradients, and they agree with the default (reduce-add) mode to
+    fp32 round-off."""
+    from pytorch_simclr_b200.runner import ContrastiveStep
+    z1, z2 = oracle.make_embeddings(b, d, seed=3 * b + d, kind="correlated", noise=1.0)
+    det = ContrastiveStep(kind, b, d, 0.5, True, torch.float32, "cuda", "bf16", deterministic=True)
+    ref = ContrastiveStep(kind, b, d, 0.5, True, torch.float32, "cuda", "bf16", deterministic=False)
+    for s in (det, ref):
+        s.x1.copy_(z1)
+        s.x2.copy_(z2)
+    ref.step()
+    torch.cuda.synchronize()
+    outs = []
+    noise = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    for rep in range(6):
+        det.grad1.zero_()
+        det.grad2.zero_()
+        if rep % 2:
+            noise.zero_()                      # perturb timing / cache state between repetitions
+        if rep < 3:
+            det.step()
+        else:
+            det.step_staged()
+        torch.cuda.synchronize()
+        outs.append((det.grad1.clone(), det.grad2.clone(), float(det.loss)))
+    for i, (g1, g2, loss) in enumerate(outs[1:]):
+        assert loss == outs[0][2], (i, loss, outs[0][2])
+        assert torch.equal(g1, outs[0][0]), (i, float((g1 - outs[0][0]).abs().max()), int((g1 != outs[0][0]).sum()))
+        assert torch.equal(g2, outs[0][1]), (i, float((g2 - outs[0][1]).abs().max()), int((g2 != outs[0][1]).sum()))
+    scale = float(ref.grad1.abs().max())
+    assert float((outs[0][0] - ref.grad1).abs().max()) <= 2e-6 * scale
+    assert float((outs[0][1] - ref.grad2).abs().max()) <= 2e-6 * scale
+    # and through the public API under torch.use_deterministic_algorithms
+    sb.set_precision("bf16")
+    sb.set_deterministic(True)
+    fn = sb.contrastive_loss if kind == 0 else sb.modified_contrastive_loss
+    grads = []
+    for rep in range(3):
+        a = z1.cuda().requires_grad_(True)
+        c = z2.cuda().requires_grad_(True)
+        loss, acc = fn(a, c, temperature=0.5)
+        loss.backward()
+        torch.cuda.synchronize()
+        grads.append((a.grad.clone(), c.grad.clone()))
+    assert all(torch.equal(g[0], grads[0][0]) and torch.equal(g[1], grads[0][1]) for g in grads[1:])
+    assert torch.equal(grads[0][0], outs[0][0])

@@ -14,11 +14,17 @@ ap.add_argument("--b", type=int, default=4096)
 ap.add_argument("--d", type=int, default=128)
 ap.add_argument("--loss", type=int, default=0)
 ap.add_argument("--reps", type=int, default=200)
+ap.add_argument("--data", default="iid", choices=["iid", "correlated"])
 args = ap.parse_args()
 step = ContrastiveStep(args.loss, args.b, args.d, 0.5)
 g = torch.Generator().manual_seed(0)
-step.x1.copy_(torch.randn(args.b, args.d, generator=g))
-step.x2.copy_(torch.randn(args.b, args.d, generator=g))
+if args.data == "iid":
+    step.x1.copy_(torch.randn(args.b, args.d, generator=g))
+    step.x2.copy_(torch.randn(args.b, args.d, generator=g))
+else:
+    base = torch.randn(args.b, args.d, generator=g)
+    step.x1.copy_(base + 0.5 * torch.randn(args.b, args.d, generator=g))
+    step.x2.copy_(base + 0.5 * torch.randn(args.b, args.d, generator=g))
 side = torch.cuda.Stream()
 with torch.cuda.stream(side):
     for _ in range(3):
