@@ -283,7 +283,7 @@ __global__ void backward_prepare_kernel(AuxParams a, const float* __restrict__ l
 // Stage 2 epilogue: merge the per-CTA partials of every row, add the exact positive term, produce
 // lse2 / row_loss / stats.  One block per row block, one thread per row.
 // ---------------------------------------------------------------------------------------------
-template <int kLoss>
+template <int kLoss, bool kFused>
 __global__ void __launch_bounds__(kBlockM) forward_finalize_kernel(const TileParams p) {
     __shared__ float red[16];
     __shared__ int flags[4];
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kBlockM) forward_finalize_kernel(const TilePar
     }
     pdl_wait();
     ktrace_begin(p.ktrace, 4);
-    forward_finalize_rowblock<kLoss>(p, rb, tid, ix, w_row, red, flags);
+    forward_finalize_rowblock<kLoss, kFused>(p, rb, tid, ix, w_row, red, flags);
     ktrace_end(p.ktrace, 4);
 }
 
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(kBlockM) forward_finalize_kernel(const TilePar
 // kBwdFinBlocksPerRowBlock blocks of 16 warps per row block: one warp per row.
 // ---------------------------------------------------------------------------------------------
 constexpr int kBwdFinBlocksPerRowBlock = 8;
-template <int D, int kLoss>
+template <int D, int kLoss, bool kDet>
 __global__ void __launch_bounds__(512) backward_finalize_kernel(const TileParams p) {
     static_assert(16 * kBwdFinBlocksPerRowBlock == kBlockM, "one warp per row");
     pdl_launch_dependents();
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(512) backward_finalize_kernel(const TileParams
         pdl_wait();
         ktrace_begin(p.ktrace, 5);
     }
-    backward_finalize_row<D, kLoss>(p, rb, sub * 16 + warp, lane);      // waits for the tile kernel inside
+    backward_finalize_row<D, kLoss, kDet>(p, rb, sub * 16 + warp, lane);      // waits for the tile kernel inside
     if (p.finish_stats && blockIdx.x == gridDim.x - 1 && warp == 15) {
         pdl_wait();
         finish_forward_stats(p, lane);

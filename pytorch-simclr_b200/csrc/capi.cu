@@ -336,10 +336,10 @@ int make_dacc_map(CUtensorMap* map, const void* base, int64_t rows, int64_t d_pa
     return SIMCLR_OK;
 }
 
-template <int D, int kLoss, bool kBackward, bool kConst, int kPrec>
-int launch_tile(const CUtensorMap& rows, const CUtensorMap& cols, const CUtensorMap& dacc, const TileParams& p, int grid,
-                cudaStream_t st) {
-    auto kern = contrastive_tile_kernel<D, kLoss, kBackward, kConst, kPrec>;
+template <int D, int kLoss, bool kBackward, bool kConst, int kPrec, bool kDet>
+int launch_tile_k(const CUtensorMap& rows, const CUtensorMap& cols, const CUtensorMap& dacc, const TileParams& p, int grid,
+                  cudaStream_t st) {
+    auto kern = contrastive_tile_kernel<D, kLoss, kBackward, kConst, kPrec, kDet>;
     static std::once_flag configured[kMaxDevices];
     static cudaError_t configure_rc[kMaxDevices];
     int dev = 0;
@@ -352,6 +352,15 @@ int launch_tile(const CUtensorMap& rows, const CUtensorMap& cols, const CUtensor
     if (configure_rc[dev] != cudaSuccess) return static_cast<int>(configure_rc[dev]);
     return static_cast<int>(launch_pdl(kern, dim3(grid), dim3(kBackward ? kThreadsBackward : kThreadsForward),
                                        SmemLayout<D, kPrec>::kDynamicBytes, st, rows, cols, dacc, p));
+}
+
+template <int D, int kLoss, bool kBackward, bool kConst, int kPrec>
+int launch_tile(const CUtensorMap& rows, const CUtensorMap& cols, const CUtensorMap& dacc, const TileParams& p, int grid,
+                cudaStream_t st) {
+    if constexpr (kBackward) {
+        if (p.deterministic) return launch_tile_k<D, kLoss, true, kConst, kPrec, true>(rows, cols, dacc, p, grid, st);
+    }
+    return launch_tile_k<D, kLoss, kBackward, kConst, kPrec, false>(rows, cols, dacc, p, grid, st);
 }
 
 // kConst = p.const_shift (bounded scores: one exponential per element, no running maximum).  The forward kernel of
@@ -782,8 +791,15 @@ int forward_impl(int loss, const void* operand_rows, const void* operand_cols, i
     }
     cudaError_t e;
     if (!(stages & kStageFwdFin)) return SIMCLR_OK;
-    if (loss == SIMCLR_LOSS_NTXENT) e = launch_pdl(forward_finalize_kernel<kNtXent>, dim3(g.n_row_blocks), dim3(kBlockM), 0, st, p);
-    else e = launch_pdl(forward_finalize_kernel<kModified>, dim3(g.n_row_blocks), dim3(kBlockM), 0, st, p);
+    // (the fused one-GPU step has its own, leaner instantiation: see forward_finalize_rowblock)
+    const bool lean = p.defer_stats != 0 && (p.cand_cnt == nullptr || p.defer_accuracy != 0);
+    if (loss == SIMCLR_LOSS_NTXENT) {
+        e = lean ? launch_pdl(forward_finalize_kernel<kNtXent, true>, dim3(g.n_row_blocks), dim3(kBlockM), 0, st, p)
+                 : launch_pdl(forward_finalize_kernel<kNtXent, false>, dim3(g.n_row_blocks), dim3(kBlockM), 0, st, p);
+    } else {
+        e = lean ? launch_pdl(forward_finalize_kernel<kModified, true>, dim3(g.n_row_blocks), dim3(kBlockM), 0, st, p)
+                 : launch_pdl(forward_finalize_kernel<kModified, false>, dim3(g.n_row_blocks), dim3(kBlockM), 0, st, p);
+    }
     return static_cast<int>(e);
 }
 
@@ -891,8 +907,8 @@ int backward_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t 
     if (!(stages & kStageBwdFin)) return SIMCLR_OK;
 #define SIMCLR_BFIN(DV)                                                                                  \
     case DV:                                                                                             \
-        if (loss == SIMCLR_LOSS_NTXENT) fin_rc = launch_pdl(backward_finalize_kernel<DV, kNtXent>, dim3(g.n_row_blocks * kBwdFinBlocksPerRowBlock), dim3(512), 0, st, p); \
-        else fin_rc = launch_pdl(backward_finalize_kernel<DV, kModified>, dim3(g.n_row_blocks * kBwdFinBlocksPerRowBlock), dim3(512), 0, st, p); \
+        if (loss == SIMCLR_LOSS_NTXENT) fin_rc = deterministic ? launch_pdl(backward_finalize_kernel<DV, kNtXent, true>, dim3(g.n_row_blocks * kBwdFinBlocksPerRowBlock), dim3(512), 0, st, p) : launch_pdl(backward_finalize_kernel<DV, kNtXent, false>, dim3(g.n_row_blocks * kBwdFinBlocksPerRowBlock), dim3(512), 0, st, p); \
+        else fin_rc = deterministic ? launch_pdl(backward_finalize_kernel<DV, kModified, true>, dim3(g.n_row_blocks * kBwdFinBlocksPerRowBlock), dim3(512), 0, st, p) : launch_pdl(backward_finalize_kernel<DV, kModified, false>, dim3(g.n_row_blocks * kBwdFinBlocksPerRowBlock), dim3(512), 0, st, p); \
         break;
     switch (g.d_pad) {
         SIMCLR_BFIN(64)

@@ -970,7 +970,9 @@ __device__ __noinline__ void resolve_ambiguous_rows(const TileParams* pp, int la
     }
 }
 
-template <int kLoss>
+// kFused: the instantiation of the fused one-GPU step (defer_stats and, when candidates are recorded, defer_accuracy): it
+// carries neither the exact re-scoring nor the ticket / last-block code -- this kernel sits between the two tile kernels.
+template <int kLoss, bool kFused>
 SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int tid, const FinIndex& ix, float w_row,
                                              float* red /*smem, 16 floats*/, int* flags /*smem*/) {
     const int blocks_per_view = p.bl_pad / kBlockM;
@@ -978,7 +980,11 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
     const int img = (rb - vr * blocks_per_view) * kBlockM + tid;
     const bool row_ok = img < p.b_loc;
     const int slot = rb * kBlockM + tid;
-    float v_pos = __ldcg(p.pos_dot + slot);
+    const float pos_exact = __ldcg(p.pos_dot + slot);
+    // (issued with the first round of loads: read at the end, it would cost this kernel a second memory round trip --
+    // and the kernel sits between the two tile kernels)
+    const unsigned int n_cand_early = (p.cand_cnt != nullptr && row_ok) ? __ldcg(p.cand_cnt + slot) : 0u;
+    float v_pos = pos_exact;
     if constexpr (kLoss == kModified) v_pos = fmaxf(v_pos * p.qscale, kClampMin);
     else v_pos *= p.k2;               // exact fp32 positive logit in the log2 domain of the MMA scores
     // generic path (several launches, or many small CTAs per row block): visit every contributing partial
@@ -1053,16 +1059,16 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
         if (p.cand_cnt != nullptr) {
             // Exact count: certain unless the best negative lies in the band around the exact positive; then the
             // recorded candidates decide (a row with more than kCandMax of them keeps the tensor-core decision)
-            n_cand = __ldcg(p.cand_cnt + slot);
+            n_cand = n_cand_early;
             float lo, hi;
-            cand_band<kLoss>(p.band, pos_raw_value<kLoss>(__ldcg(p.pos_dot + slot), p.k2, p.qscale), lo, hi);
+            cand_band<kLoss>(p.band, pos_raw_value<kLoss>(pos_exact, p.k2, p.qscale), lo, hi);
             const float best = fmaxf(max_prec, max_foll);
             if (best > hi) hit = 0.f;
             else if (best < lo) hit = 1.f;
             else ambiguous = n_cand <= static_cast<unsigned int>(kCandMax);
         }
     }
-    if (p.cand_cnt != nullptr && p.defer_accuracy) {
+    if (kFused && p.cand_cnt != nullptr) {
         // fused step: list the undecided rows (rare) for the backward tile kernel's idle flush warp; they count as
         // misses here and are added back through amb_hits
         if (ambiguous) {
@@ -1093,7 +1099,7 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
                 }
             }
         }
-    } else if (p.cand_cnt != nullptr) {
+    } else if (!kFused && p.cand_cnt != nullptr) {
         if (n_cand != 0u) p.cand_cnt[slot] = 0u;              // left zero for the next call
         unsigned int todo = __ballot_sync(0xffffffffu, ambiguous);
         const int lane = tid & 31;
@@ -1143,7 +1149,7 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
         p.block_part[rb * 4 + 0] = (red[0] + red[1]) + (red[2] + red[3]);
         p.block_part[rb * 4 + 1] = (red[4] + red[5]) + (red[6] + red[7]);
         p.block_part[rb * 4 + 2] = (red[8] + red[9]) + (red[10] + red[11]);
-        if (p.defer_stats) {
+        if (kFused || p.defer_stats) {
             flags[1] = 0;                 // the backward finalize kernel of this step reduces block_part (finish_stats)
         } else {
             __threadfence();
@@ -1151,7 +1157,7 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
             flags[1] = (prev == static_cast<unsigned int>(p.n_row_blocks) - 1u) ? 1 : 0;
         }
     }
-    if (p.defer_stats) return;
+    if (kFused || p.defer_stats) return;
     named_bar_sync(2, kBlockM);
     if (flags[1] && tid < 32) {
         __threadfence();
@@ -1188,7 +1194,7 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
 // positive-pair term and applies the backward of the row normalisation (NT-Xent: L2, objective.py:26-27; modified:
 // softplus + L1, :70-78).  The two input rows (x_self, x_other: caller inputs, never written by this library) are
 // loaded BEFORE griddepcontrol.wait, i.e. while the tile kernel drains; everything the step produced comes after it.
-template <int D, int kLoss>
+template <int D, int kLoss, bool kDet>
 SIMCLR_DEVICE void backward_finalize_row(const TileParams& p, int rb, int r, int lane) {
     const int blocks_per_view = p.bl_pad / kBlockM;
     const int vr = rb / blocks_per_view;
@@ -1225,7 +1231,7 @@ SIMCLR_DEVICE void backward_finalize_row(const TileParams& p, int rb, int r, int
     const int slot_other = (1 - vr) * p.bl_pad + img;
     const int c_self = vr * p.bg_pad + p.row_off + img;
     const int c_other = (1 - vr) * p.bg_pad + p.row_off + img;
-    if (p.deterministic) {
+    if constexpr (kDet) {
         // add the (CTA, segment) slots of this row block in CTA order: CTA k of the tile kernel owned the tiles
         // [T k / G, T (k + 1) / G); the first contributing CTA may have started in an earlier row block
         const long long grid = p.tile_grid;
@@ -1406,7 +1412,10 @@ struct RingPos {
 // additionally occupies TWO positions whose stages the producer hands (empty) to the softmax warps as staging space
 // for the accumulator flush.  All roles walk the same position sequence, so stage index and parity never need a
 // division and stage / slot / pair / issuer ownership stays aligned (position parity == tile parity).
-template <int D, int kLoss, bool kBackward, bool kConst, int kPrec>
+// kDet (backward): deterministic mode, see TileParams::deterministic -- a template parameter, not a run-time switch: the
+// single-thread issuer loops bound the pipeline by their per-hop latency, and even a predicated-off wait in them costs
+// the default mode more than a microsecond per launch (profiles/r02_notes.md).
+template <int D, int kLoss, bool kBackward, bool kConst, int kPrec, bool kDet = false>
 __global__ void __launch_bounds__(kBackward ? kThreadsBackward : kThreadsForward, 1)
 contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
                         const __grid_constant__ CUtensorMap tmap_dacc, const __grid_constant__ TileParams p) {
@@ -1705,7 +1714,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                     // issuer's) have COMPLETED; the score MMAs of later tiles keep the tensor pipe busy meanwhile.  Tile
                     // idx - 1 used the previous hand-off slot; this warp is that barrier's second waiter and, like the
                     // first, observes every one of its phases (the slot ring is even: a slot always meets the same issuer).
-                    if (p.deterministic && idx > 0) mbar_wait(w_done + 8 * prev_slot.idx, prev_slot.par, 206);
+                    if constexpr (kDet) { if (idx > 0) mbar_wait(w_done + 8 * prev_slot.idx, prev_slot.par, 206); }
                     mbar_wait(w_full + 8 * slot.idx, slot.par, 204);
                     tc_fence_after_sync();
                     if (lane == 0) trace_event(p, 1, idx, 3);
@@ -1733,7 +1742,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 }
             }
             ring.advance();
-            prev_slot = slot;
+            if constexpr (kDet) prev_slot = slot;
             slot.advance();
             if (++buf == NB) buf = 0;
             if (!w.seg_last()) continue;
@@ -1776,7 +1785,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         const int q = (SIMCLR_FLUSH_ALTERNATE && (blockIdx.x & 1)) ? D / 32 - 1 - qq : qq;
                         const int stage = (q / kBoxesPerStage) == 0 ? ring.idx : st1.idx;
                         const uint32_t box = sb_addr + stage * L::kTileBytes + (q % kBoxesPerStage) * kAtomBytes;
-                        if (p.deterministic)      // tmap_dacc describes det_part: this (CTA, segment)'s private slot
+                        if constexpr (kDet)      // tmap_dacc describes det_part: this (CTA, segment)'s private slot
                             tma_store_2d(&tmap_dacc, box, q * 32, (static_cast<int>(blockIdx.x) * p.max_segs + seg) * kBlockM);
                         else
                             tma_reduce_add_2d(&tmap_dacc, box, q * 32, w.rb * kBlockM);
@@ -1881,24 +1890,31 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             // decide (lo = +inf: not recording -- padding rows, rows already known to be wrong, feature switched off)
             float band_lo = 3.0e38f, band_hi = 3.0e38f;
             // this row's slots in the shared-memory candidate buffer of the segment's parity: count | wrong flag | list
-            const uint32_t cand_base = smem_base + L::kOffCand + (seg & 1) * (L::kCandWords * 4);
-            const uint32_t cand_cnt_addr = cand_base + row_in_block * 4;
-            const uint32_t cand_wrong_addr = cand_base + (kBlockM + row_in_block) * 4;
-            const uint32_t cand_list_addr = cand_base + (2 * kBlockM + row_in_block * kCandMax) * 4;
+            // (addresses are recomputed where they are needed -- all of it rare or once per segment -- instead of being
+            // kept in registers across the tile loop: the forward kernel runs at 96 of its 102 registers)
+            auto cand_base = [&]() { return smem_base + L::kOffCand + (seg & 1) * (L::kCandWords * 4); };
+            auto cand_cnt_addr_f = [&]() { return cand_base() + row_in_block * 4; };
+            auto cand_wrong_addr_f = [&]() { return cand_base() + (kBlockM + row_in_block) * 4; };
+            auto cand_list_addr_f = [&]() { return cand_base() + (2 * kBlockM + row_in_block * kCandMax) * 4; };
             int pending_range = -1;          // first global column of this thread's pending candidate range, or -1
             auto publish_range = [&](int first_col) {
                 uint32_t at;
-                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(at) : "r"(cand_cnt_addr) : "memory");
+                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(at) : "r"(cand_cnt_addr_f()) : "memory");
                 if (at < static_cast<uint32_t>(kCandMax))
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(cand_list_addr + at * 4), "r"(first_col) : "memory");
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(cand_list_addr_f() + at * 4), "r"(first_col) : "memory");
 #if SIMCLR_TRACE
                 if (p.ktrace != nullptr) atomicAdd(p.ktrace + 33, 1ull);                       // diagnostics: published ranges
 #endif
             };
+            // The row's exact positive is loaded here and first USED when the first tile of the segment has been processed
+            // (band_pending): consumed at once, the load's latency (~1 us from L2 / HBM) would stall the warp at every
+            // segment start.
+            float pos_exact = 0.f;
+            bool band_pending = false;           // warp-uniform
             if constexpr (kRecord) {
-                if (p.cand_cnt != nullptr && rc.row_ok) {
-                    const int slot_r = rb * kBlockM + row_in_block;
-                    cand_band<kLoss>(p.band, pos_raw_value<kLoss>(__ldcg(p.pos_dot + slot_r), h.k2, h.qscale), band_lo, band_hi);
+                if (p.cand_cnt != nullptr) {
+                    band_pending = true;
+                    if (rc.row_ok) pos_exact = __ldcg(p.pos_dot + rb * kBlockM + row_in_block);
                 }
             }
 
@@ -1948,18 +1964,29 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 // published at all (an immediate TMEM rescan cost ~5000 cycles per event, cold code, with both softmax
                 // pairs waiting for the warp that ran it: +3.4 us per forward launch on random inputs, profiles/r02_notes.md).
                 auto record_candidates = [&](float tile_max, const float (&cmk)[4]) {
+                    if (SIMCLR_CAND_MODE == 3) return;                 // A/B: set-up only, never checked
+                    if (band_pending) {
+                        band_pending = false;
+                        if (rc.row_ok) cand_band<kLoss>(p.band, pos_raw_value<kLoss>(pos_exact, h.k2, h.qscale), band_lo, band_hi);
+                    }
+                    // Branch-free part of the hot path: a negative above the band proves the row wrong (predicated flag
+                    // store, band_lo = +inf).  With unrelated embeddings that is what happens to nearly every row in its
+                    // first tile -- behind a branch it sent every warp through cold code once per segment (~1 us per
+                    // forward launch).  Rows that are not recording have band_hi = 3e38: never true for them.
+                    if (tile_max > band_hi && band_lo < 3.0e38f) {
+                        band_lo = 3.0e38f;
+                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(cand_wrong_addr_f()), "r"(1u) : "memory");
+                    }
                     if (!__any_sync(0xffffffffu, tile_max >= band_lo)) return;
+                    if (SIMCLR_CAND_MODE == 4) { band_lo = 3.0e38f; return; }     // A/B: the vote only
 #if SIMCLR_TRACE
                     if (p.ktrace != nullptr && lane == 0) atomicAdd(p.ktrace + 32, 1ull);     // diagnostics: triggers
 #endif
-                    if (band_lo < 3.0e38f) {
+                    if (tile_max >= band_lo) {
                         uint32_t known_wrong;
-                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(known_wrong) : "r"(cand_wrong_addr) : "memory");
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(known_wrong) : "r"(cand_wrong_addr_f()) : "memory");
                         if (known_wrong != 0u) {
                             band_lo = 3.0e38f;
-                        } else if (tile_max > band_hi) {
-                            band_lo = 3.0e38f;
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(cand_wrong_addr), "r"(1u) : "memory");
                         } else {
                             // every 16-column chunk whose maximum lies in the band (none exceeds it) is a candidate
 #pragma unroll
@@ -1972,6 +1999,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         }
                     }
                 };
+                float cmk[4] = {kNegBig, kNegBig, kNegBig, kNegBig};   // forward: largest valid negative of each 16-column chunk
                 uint32_t ra[kChunk], rb2[kChunk];
                 tmem_ld16(t0, ra);
                 // Ping-pong: the arithmetic of tile `it` starts when the other pair has finished that of tile it-1.
@@ -2013,7 +2041,6 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 } else if (!tile_special) {
                     // Common case: no masked element anywhere in the tile for this warp.  One straight-line block over
                     // the four chunks, so that the tail of chunk k overlaps the head of chunk k+1.
-                    float cmk[4] = {kNegBig, kNegBig, kNegBig, kNegBig};      // forward: maximum of each 16-column chunk
 #if SIMCLR_BWD_DELAY_ST
                     uint32_t wprev[kChunk / 2];           // backward: W of the previous chunk (stored one chunk late)
 #endif
@@ -2052,10 +2079,8 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         const float cm = fmaxf(fmaxf(cmk[0], cmk[1]), fmaxf(cmk[2], cmk[3]));
                         fs.max_prec = fmaxf(fs.max_prec, tile_prec ? cm : kNegBig);
                         fs.max_foll = fmaxf(fs.max_foll, tile_prec ? kNegBig : cm);
-                        if constexpr (kRecord) record_candidates(cm, cmk);
                     }
                 } else {
-                    float cms[4] = {kNegBig, kNegBig, kNegBig, kNegBig};   // largest valid negative of this thread's row per chunk
                     auto process = [&](const uint32_t (&r)[kChunk], int k) {
                         const int cq = cbase + k * kChunk;
                         const int icq = cq - vc * h.bg_pad;
@@ -2063,7 +2088,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         if constexpr (!kBackward) special = special || !warp_rows_ok || (icq + kChunk - 1 >= h.b_glob);
                         if constexpr (!kBackward) {
                             if (special) {
-                                fwd_chunk_special<kLoss, kConst>(h, r, cq, vc, rc, fs, cms[k]);
+                                fwd_chunk_special<kLoss, kConst>(h, r, cq, vc, rc, fs, cmk[k]);
                             } else {
                                 // an unmasked chunk of a tile that overlaps the warp's own images lies entirely before or
                                 // entirely after them: classify it by itself (the tile as a whole straddles the positive)
@@ -2075,7 +2100,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                                 fwd_chunk_fast<kLoss, kConst, kPrec == 0>(h, r, cm, fs);
                                 fs.max_prec = fmaxf(fs.max_prec, prec ? cm : kNegBig);
                                 fs.max_foll = fmaxf(fs.max_foll, prec ? kNegBig : cm);
-                                cms[k] = cm;
+                                cmk[k] = cm;
                             }
                         } else {
                             uint32_t wq[kChunk / 2], unused[kChunk / 2];
@@ -2097,12 +2122,13 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         if (SIMCLR_PINGPONG && k == SIMCLR_TOKEN_CHUNK && it + 1 < n) named_bar_arrive_pinned(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps, cur);
                         process(cur, k);
                     }
-                    if constexpr (kRecord) record_candidates(fmaxf(fmaxf(cms[0], cms[1]), fmaxf(cms[2], cms[3])), cms);
                 }
                 if (SIMCLR_PINGPONG && !(kBackward && kPrec != 0) && SIMCLR_TOKEN_CHUNK > 3 && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
                 if constexpr (!kBackward) {
                     tc_fence_before_sync();
                     mbar_arrive(s_free + 8 * slot);
+                    // (behind the release of the score buffer: the check needs nothing from TMEM)
+                    if constexpr (kRecord) record_candidates(fmaxf(fmaxf(cmk[0], cmk[1]), fmaxf(cmk[2], cmk[3])), cmk);
                 } else {
                     tmem_st_wait();
                     tc_fence_before_sync();
@@ -2124,7 +2150,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 // a pending candidate range of a row that is still undecided now is a real near-tie: publish it
                 if (pending_range >= 0 && band_lo < 3.0e38f) {
                     uint32_t known_wrong;
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(known_wrong) : "r"(cand_wrong_addr) : "memory");
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(known_wrong) : "r"(cand_wrong_addr_f()) : "memory");
                     if (known_wrong == 0u) publish_range(pending_range);
                 }
             }
@@ -2170,19 +2196,19 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         // flush this row's shared-memory candidates of the segment to the global list (one global atomic
                         // per row that has any) and leave the buffer of this parity clean for segment seg + 2
                         uint32_t n_c;
-                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(n_c) : "r"(cand_cnt_addr) : "memory");
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(n_c) : "r"(cand_cnt_addr_f()) : "memory");
                         if (n_c != 0u) {
                             const int slot_r = rb * kBlockM + row_in_block;
                             const uint32_t base_c = atomicAdd(p.cand_cnt + slot_r, n_c);    // may exceed kCandMax: fallback
                             for (uint32_t i = 0; i < n_c && i < static_cast<uint32_t>(kCandMax); ++i) {
                                 uint32_t col;
-                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(col) : "r"(cand_list_addr + i * 4) : "memory");
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(col) : "r"(cand_list_addr_f() + i * 4) : "memory");
                                 if (base_c + i < static_cast<uint32_t>(kCandMax))
                                     p.cand[static_cast<size_t>(slot_r) * kCandMax + base_c + i] = static_cast<int>(col);
                             }
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(cand_cnt_addr), "r"(0u) : "memory");
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(cand_cnt_addr_f()), "r"(0u) : "memory");
                         }
-                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(cand_wrong_addr), "r"(0u) : "memory");
+                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(cand_wrong_addr_f()), "r"(0u) : "memory");
                     }
                 }
             }
