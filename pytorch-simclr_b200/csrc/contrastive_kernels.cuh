@@ -80,6 +80,9 @@ constexpr int kTmemCols = 512;
 #ifndef SIMCLR_TOKEN_CHUNK
 #define SIMCLR_TOKEN_CHUNK 3          // chunk (0..3) before which a pair passes the ping-pong token on; 4 = after the tile
 #endif
+#ifndef SIMCLR_TOKEN_CHUNK_FWD
+#define SIMCLR_TOKEN_CHUNK_FWD SIMCLR_TOKEN_CHUNK      // the forward kernel's own setting
+#endif
 constexpr int kTokenBar0 = 2;         // named barriers 2, 3: ping-pong tokens of the two softmax pairs
 constexpr int kFwdFields = 5;         // per-row partial: sum, run-max, max-preceding, max-following, pos(mma)
 constexpr float kNegBig = -3.0e38f;   // finite stand-in for -inf
@@ -482,6 +485,11 @@ SIMCLR_DEVICE constexpr int poly_pairs_in_round(int pairs, int round) { return r
 #endif
 #ifndef SIMCLR_BWD_DELAY_ST
 #define SIMCLR_BWD_DELAY_ST 0         // 1: store W of chunk k after the arithmetic of chunk k+1 (measured: slower)
+#endif
+#ifndef SIMCLR_BWD_PREFETCH_ROW
+#define SIMCLR_BWD_PREFETCH_ROW 0     // backward: fetch a segment's row entries of the column vectors one segment ahead
+                                      // (measured: +0.4 us per step -- the 80-register backward kernel has no room for
+                                      // two more live values; kept for the record)
 #endif
 #ifndef SIMCLR_TOKEN_FENCE
 #define SIMCLR_TOKEN_FENCE 1          // 1: a basic-block boundary pins the token hand-over in front of its chunk's arithmetic
@@ -1843,6 +1851,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             h.clampc = kClampMin * c0;
         }
         const int b_loc = p.b_loc, row_off = p.row_off;
+        constexpr int kTokenChunk = kBackward ? SIMCLR_TOKEN_CHUNK : SIMCLR_TOKEN_CHUNK_FWD;
         const bool token_fence = p.n_row_blocks != 0;      // always true, unknown to the compiler (see SIMCLR_TOKEN_FENCE)
         // candidates of the exact accuracy count are recorded by the bf16-mode forward kernel (the split mode's scores
         // are fp32-grade already)
@@ -1859,6 +1868,8 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         int idx0 = 0, seg = 0;
         int rb = static_cast<int>(t_begin / nct);
         int j0 = static_cast<int>(t_begin - static_cast<long long>(rb) * nct);
+        float pre_a = 0.f, pre_l2 = 0.f;     // backward: the next segment's row entries of the column vectors
+        bool have_pre = false;
         while (idx0 < n) {
             const int seg_len = min(n - idx0, nct - j0);
             // ---- segment setup ----
@@ -1880,10 +1891,32 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             br.row_a = 0.f;
             br.row_l2 = 0.f;
             if constexpr (kBackward) {
+#if SIMCLR_BWD_PREFETCH_ROW
+                // The row's own column-vector entries are used by the first chunk of the segment: loaded here they would
+                // stall the warp for a memory latency at every segment boundary (the first segment's loads hide under the
+                // pipeline fill).  They are fetched one segment ahead instead.
+                if (have_pre) {
+                    br.row_a = pre_a;
+                    br.row_l2 = pre_l2;
+                } else if (rc.row_ok) {
+                    br.row_a = __ldcg(p.colvec + rc.vr * h.bg_pad + rc.g);
+                    br.row_l2 = __ldcg(p.colvec + 2 * h.bg_pad + rc.vr * h.bg_pad + rc.g);
+                }
+                have_pre = idx0 + seg_len < n;
+                if (have_pre) {
+                    const int vr_n = (rb + 1) / blocks_per_view;
+                    const int img_n = (rb + 1 - vr_n * blocks_per_view) * kBlockM + row_in_block;
+                    const bool ok_n = img_n < b_loc;
+                    const int c_n = vr_n * h.bg_pad + row_off + img_n;
+                    pre_a = ok_n ? __ldcg(p.colvec + c_n) : 0.f;
+                    pre_l2 = ok_n ? __ldcg(p.colvec + 2 * h.bg_pad + c_n) : 0.f;
+                }
+#else
                 if (rc.row_ok) {
                     br.row_a = __ldcg(p.colvec + rc.vr * h.bg_pad + rc.g);
                     br.row_l2 = __ldcg(p.colvec + 2 * h.bg_pad + rc.vr * h.bg_pad + rc.g);
                 }
+#endif
             }
             const int pos_off = kBackward ? 2 * seg : 0;
             // exact accuracy count: the band around this row's exact positive inside which a tensor-core score cannot
@@ -2052,11 +2085,11 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         if (k < 3) tmem_ld16(t0 + (k + 1) * kChunk, nxt);
                         // hand the token over one chunk early: the other pair's first chunk fills the pipes while this
                         // pair drains its last one (covers the bar.arrive -> bar.sync wake-up latency)
-                        if (SIMCLR_PINGPONG && k == SIMCLR_TOKEN_CHUNK && it + 1 < n) named_bar_arrive_pinned(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps, cur);
+                        if (SIMCLR_PINGPONG && k == kTokenChunk && it + 1 < n) named_bar_arrive_pinned(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps, cur);
                         // ptxas floats a bar.arrive (nothing depends on it) to the END of its basic block, i.e. behind the
                         // arithmetic of the chunk it was written in front of -- the other pair then gets the token a chunk
                         // late.  An always-true branch the compiler cannot see through ends the basic block right here.
-                        if (SIMCLR_TOKEN_FENCE && k == SIMCLR_TOKEN_CHUNK && !token_fence) continue;
+                        if (SIMCLR_TOKEN_FENCE && k == kTokenChunk && !token_fence) continue;
                         if constexpr (!kBackward) {
                             fwd_chunk_fast<kLoss, kConst, kPrec == 0>(h, cur, cmk[k], fs);
                         } else if constexpr (kPrec == 0) {
@@ -2119,11 +2152,11 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         uint32_t (&nxt)[kChunk] = (k & 1) ? ra : rb2;
                         tmem_ld_wait16(cur);
                         if (k < 3) tmem_ld16(t0 + (k + 1) * kChunk, nxt);
-                        if (SIMCLR_PINGPONG && k == SIMCLR_TOKEN_CHUNK && it + 1 < n) named_bar_arrive_pinned(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps, cur);
+                        if (SIMCLR_PINGPONG && k == kTokenChunk && it + 1 < n) named_bar_arrive_pinned(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps, cur);
                         process(cur, k);
                     }
                 }
-                if (SIMCLR_PINGPONG && !(kBackward && kPrec != 0) && SIMCLR_TOKEN_CHUNK > 3 && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
+                if (SIMCLR_PINGPONG && !(kBackward && kPrec != 0) && kTokenChunk > 3 && it + 1 < n) named_bar_arrive(kTokenBar0 + (pair ^ 1), 32 * kNumSoftmaxWarps);
                 if constexpr (!kBackward) {
                     tc_fence_before_sync();
                     mbar_arrive(s_free + 8 * slot);
