@@ -77,11 +77,18 @@ def reference_loss(x1, x2, temperature=1.0):
     return loss, acc
 
 
-def time_steps(model, opt, loss_fn, x1, x2, tau, steps, warmup):
+def time_steps(model, opt, loss_fn, x1, x2, tau, steps, warmup, fused_head=False):
     def one():
-        _, z1 = model(x1)                                   # utils/model_utils.py:113
-        _, z2 = model(x2)                                   # :114
-        loss, acc = loss_fn(z1, z2, temperature=tau)        # :115
+        if fused_head:
+            # the projection head up to (not including) its final BatchNorm1d; that module goes into the loss
+            # (pytorch_simclr_b200.bn_contrastive_loss: BatchNorm apply / backward inside the loss kernels)
+            u1 = model.g[:-1](model.f(x1))
+            u2 = model.g[:-1](model.f(x2))
+            loss, acc = loss_fn(u1, u2, model.g[-1], temperature=tau)
+        else:
+            _, z1 = model(x1)                                   # utils/model_utils.py:113
+            _, z2 = model(x2)                                   # :114
+            loss, acc = loss_fn(z1, z2, temperature=tau)        # :115
         loss /= 1                                           # :116 (accum_steps = 1)
         val = loss.item()                                   # :117
         loss.backward()                                     # :120
@@ -127,19 +134,23 @@ def time_loss_only(loss_fn, b, d, tau, steps=30):
 
 def run(name, batch, res, cifar_stem, steps, warmup, tau=0.5, quiet=False):
     from objective import contrastive_loss           # the drop-in module at the repository root
+    from pytorch_simclr_b200 import bn_contrastive_loss
     torch.manual_seed(0)
     out = {"config": name, "batch": batch, "resolution": res, "stem": "cifar 3x3 s1, no maxpool" if cifar_stem else "7x7 s2 + maxpool",
            "temperature": tau, "optimizer": "Adam(lr=1e-3, weight_decay=1e-6)", "data": "synthetic", "dtype": "fp32 (cuDNN TF32 convs: torch default)"}
     g = torch.Generator(device="cuda").manual_seed(1)
     x1 = torch.randn(batch, 3, res, res, device="cuda", generator=g)
     x2 = torch.randn(batch, 3, res, res, device="cuda", generator=g)
-    for label, fn in (("ours", contrastive_loss), ("reference_arithmetic", reference_loss)):
+    for label, fn in (("ours", contrastive_loss), ("ours_fused_head_tail", bn_contrastive_loss),
+                      ("reference_arithmetic", reference_loss)):
         torch.manual_seed(0)
         model = SimCLR(cifar_stem).cuda().train()
         opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-6)
-        ms, val, acc = time_steps(model, opt, fn, x1, x2, tau, steps, warmup)
-        out[label] = {"ms_per_step": ms, "images_per_s": batch / (ms * 1e-3), "last_loss": val, "last_acc": acc,
-                      "loss_only_ms": time_loss_only(fn, batch, 128, tau)}
+        fused = fn is bn_contrastive_loss
+        ms, val, acc = time_steps(model, opt, fn, x1, x2, tau, steps, warmup, fused_head=fused)
+        out[label] = {"ms_per_step": ms, "images_per_s": batch / (ms * 1e-3), "last_loss": val, "last_acc": acc}
+        if not fused:
+            out[label]["loss_only_ms"] = time_loss_only(fn, batch, 128, tau)
         del model, opt
         torch.cuda.empty_cache()
     out["step_ratio_ours_over_reference"] = out["ours"]["ms_per_step"] / out["reference_arithmetic"]["ms_per_step"]

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIMCLR_ABI_VERSION 12
+#define SIMCLR_ABI_VERSION 13
 
 /* loss kinds */
 #define SIMCLR_LOSS_NTXENT 0   /* objective.py:6-55  */
@@ -179,6 +179,45 @@ int simclr_forward_backward_finish(int loss, const void* x_batch1, const void* x
                                    int normalize, float temperature, int precision, const float* grad_out,
                                    const void* operand, const float* rowvec, void* grad1, void* grad2,
                                    void* backward_workspace, size_t backward_workspace_bytes, int flags, void* stream);
+
+/*
+ * Projection-head tail.  The reference produces the embeddings as
+ *     z = BatchNorm1d(out_dim)(Linear(encoder_dim -> out_dim, bias=False)(.))        models/simclr.py:38-39
+ * in two separate forward calls, one per view (utils/model_utils.py:113-114: per-view batch statistics), and passes them
+ * to objective.contrastive_loss.  These entry points take the PRE-BatchNorm activations u1 / u2 instead: the BatchNorm
+ * apply happens in the registers of the prepare kernel (z is never written), and on the way back the finalize kernel's
+ * dL/dz is turned into dL/du, dL/dgamma, dL/dbeta -- loss(BN(u1), BN(u2)) forward and backward with the loss's five kernels
+ * plus one statistics kernel in front and one BatchNorm-backward kernel behind.
+ *   bn_state  f32 [2 views][5][Dpad]: scale = gamma*rstd | shift = beta - mean*scale | mean | rstd | var_unbiased.
+ *             Training: simclr_bn_stats computes it from the batch (biased variance, eps as nn.BatchNorm1d); the caller
+ *             updates the module's running statistics from planes 2 and 4.  Eval: the caller fills scale / shift from the
+ *             running statistics and passes bn_training = 0 (dL/du = scale * dL/dz).
+ *   simclr_bn_t.partial  f32 scratch inside a workspace of simclr_bn_workspace_bytes(b, d) bytes at offset 256 (the first
+ *             256 bytes are simclr_bn_stats' ticket: zero before the first call, left zero).
+ *   grad_gamma / grad_beta  f32 [d], ACCUMULATED into (zero them first), or NULL.
+ * One GPU, unweighted loss; everything else as in simclr_forward_backward_begin / _finish.
+ */
+typedef struct simclr_bn {
+    const float* state;   /* bn_state */
+    float* partial;       /* scratch of the backward: per-CTA column sums of dL/dz and dL/dz * xhat */
+} simclr_bn_t;
+size_t simclr_bn_state_floats(int64_t d);
+size_t simclr_bn_workspace_bytes(int64_t b, int64_t d);
+int simclr_bn_stats(const void* u1, const void* u2, int64_t b, int64_t d, int in_dtype, const float* gamma, const float* beta,
+                    float eps, float* bn_state, void* workspace, size_t workspace_bytes, void* stream);
+int simclr_head_forward(int loss, const void* u1, const void* u2, int64_t b, int64_t d, int in_dtype, int normalize,
+                        float temperature, int precision, const float* bn_state, void* operand, float* rowvec, float* stats,
+                        float* loss_out, void* forward_workspace, size_t forward_workspace_bytes, void* stream);
+int simclr_head_forward_backward_begin(int loss, const void* u1, const void* u2, int64_t b, int64_t d, int in_dtype,
+                                       int normalize, float temperature, int precision, const simclr_bn_t* bn, void* operand,
+                                       float* rowvec, float* stats, float* loss_out, void* forward_workspace,
+                                       size_t forward_workspace_bytes, void* backward_workspace,
+                                       size_t backward_workspace_bytes, int flags, void* stream);
+int simclr_head_forward_backward_finish(int loss, const void* u1, const void* u2, int64_t b, int64_t d, int in_dtype,
+                                        int normalize, float temperature, int precision, const float* grad_out,
+                                        const simclr_bn_t* bn, int bn_training, const void* operand, const float* rowvec,
+                                        void* grad_u1, void* grad_u2, float* grad_gamma, float* grad_beta,
+                                        void* backward_workspace, size_t backward_workspace_bytes, int flags, void* stream);
 
 /*
  * Row-sharded global batch over peer memory (one process per GPU of one NVLink / NVSwitch node; not in the reference,

@@ -7,7 +7,9 @@ from .objective import contrastive_loss, modified_contrastive_loss  # noqa: F401
 from .functional import (ContrastiveLossFunction, contrastive_forward_backward, LOSS_NTXENT,  # noqa: F401
                          LOSS_MODIFIED, set_precision, get_precision, set_eager_backward, get_eager_backward,
                          set_deterministic, get_deterministic)
+from .head import bn_contrastive_loss, bn_modified_contrastive_loss  # noqa: F401
 
 __all__ = ["contrastive_loss", "modified_contrastive_loss", "ContrastiveLossFunction",
            "contrastive_forward_backward", "LOSS_NTXENT", "LOSS_MODIFIED", "set_precision", "get_precision",
-           "set_eager_backward", "get_eager_backward", "set_deterministic", "get_deterministic"]
+           "set_eager_backward", "get_eager_backward", "set_deterministic", "get_deterministic", "bn_contrastive_loss",
+           "bn_modified_contrastive_loss"]

@@ -16,7 +16,7 @@ DTYPE_BF16 = 1
 PRECISION_BF16 = 0
 PRECISION_SPLIT = 1
 FLAG_DETERMINISTIC = 1
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 _lock = threading.Lock()
 _lib = None
@@ -58,6 +58,14 @@ SIGNATURES = {
     "simclr_forward_peer": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp,
                                    _vp, _sz, _vp, _sz, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp]),
     "simclr_peer_barrier": (_int, [_int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "simclr_bn_state_floats": (_sz, [_i64]),
+    "simclr_bn_workspace_bytes": (_sz, [_i64, _i64]),
+    "simclr_bn_stats": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp, _f32, _vp, _vp, _sz, _vp]),
+    "simclr_head_forward": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "simclr_head_forward_backward_begin": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp,
+                                                  _vp, _sz, _vp, _sz, _int, _vp]),
+    "simclr_head_forward_backward_finish": (_int, [_int, _vp, _vp, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _int, _vp, _vp,
+                                                   _vp, _vp, _vp, _vp, _vp, _sz, _int, _vp]),
     "simclr_forward_stages": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp,
                                      _vp, _sz, _vp, _sz, _vp, _vp, _int, _vp, _vp, ctypes.c_uint]),
     "simclr_backward_stages": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp,

@@ -18,6 +18,9 @@ struct AuxParams {
     float qscale;    // (float) b_glob
     float op_scale;  // factor applied to the normalised rows before bf16 rounding (NT-Xent: sqrt(log2(e)/tau), else 1)
     int split;       // 1: also write the residual plane lo = bf16(x - float(bf16(x))) behind the hi plane (fp32-grade mode)
+    // projection-head tail (head_kernels.cuh): BatchNorm state f32 [2][kBnPlanes][d_pad] or nullptr; the rows are then the
+    // PRE-BatchNorm activations and z = u * scale + shift is formed in registers
+    const float* bn_state;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -101,6 +104,17 @@ __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x
         for (int j = threadIdx.x; j < zero_words; j += blockDim.x) zero_ptr[j] = 0u;
     // fused row-sharded step: the epoch of the barrier that the forward tile kernel executes (TileParams::sync_epoch)
     if (bump_epoch != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *bump_epoch += 1u;
+    if (a.bn_state != nullptr) {
+        // BatchNorm apply (the state comes from a kernel of this stream: read behind the wait)
+        const float* st1 = a.bn_state;
+        const float* st2 = a.bn_state + 5 * a.d_pad;
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int k = lane * kPer + u;
+            v1[u] = fmaf(v1[u], __ldg(st1 + k), __ldg(st1 + a.d_pad + k));
+            v2[u] = fmaf(v2[u], __ldg(st2 + k), __ldg(st2 + a.d_pad + k));
+        }
+    }
     if (i >= a.bl_pad) return;
     // candidate counters of the exact accuracy count (forward workspace): zero for both views of this image slot
     if (cand_cnt != nullptr && lane == 0) {
@@ -320,7 +334,29 @@ __global__ void __launch_bounds__(512) backward_finalize_kernel(const TileParams
         pdl_wait();
         ktrace_begin(p.ktrace, 5);
     }
-    backward_finalize_row<D, kLoss, kDet>(p, rb, sub * 16 + warp, lane);      // waits for the tile kernel inside
+    constexpr int kPerLane = D / 32;
+    float dz[kPerLane], dzx[kPerLane];
+#pragma unroll
+    for (int u = 0; u < kPerLane; ++u) dz[u] = dzx[u] = 0.f;
+    backward_finalize_row<D, kLoss, kDet>(p, rb, sub * 16 + warp, lane, dz, dzx);      // waits for the tile kernel inside
+    if (p.bn_partial != nullptr) {
+        // projection-head tail: the column sums BatchNorm's backward needs (sum dz, sum dz * xhat over this CTA's 16 rows),
+        // one partial per CTA -- bn_backward_kernel adds them in CTA order
+        __shared__ float red[16][2][D];
+#pragma unroll
+        for (int u = 0; u < kPerLane; ++u) {
+            red[warp][0][lane * kPerLane + u] = dz[u];
+            red[warp][1][lane * kPerLane + u] = dzx[u];
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < 2 * D; idx += blockDim.x) {
+            const int q = idx / D, k = idx - q * D;
+            float a = 0.f;
+#pragma unroll
+            for (int w = 0; w < 16; ++w) a += red[w][q][k];
+            p.bn_partial[(static_cast<size_t>(blockIdx.x) * 2 + q) * D + k] = a;
+        }
+    }
     if (p.finish_stats && blockIdx.x == gridDim.x - 1 && warp == 15) {
         pdl_wait();
         finish_forward_stats(p, lane);

@@ -9,6 +9,7 @@
 
 #include "../../include/simclr_b200.h"
 #include "aux_kernels.cuh"
+#include "head_kernels.cuh"
 #if SIMCLR_TRACE
 // Diagnostics (timelines, rate probes, primitive self-test) exist only in the tracing build of the library
 // (lib/libsimclr_b200_trace.so, include/simclr_b200_debug.h); the product library carries none of it.
@@ -420,6 +421,7 @@ AuxParams make_aux(const Geometry& g, const Scales& s, int64_t b_local, int64_t 
     a.qscale = s.qscale;
     a.op_scale = s.op_scale;
     a.split = 0;
+    a.bn_state = nullptr;
     return a;
 }
 
@@ -550,7 +552,8 @@ struct FusedSync {
 int prepare_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
                  int normalize, float temperature, int precision, void* operand, float* inv_norm, float* pos_dot,
                  void* forward_workspace, int world, int rank, void* const* operand_global_peers,
-                 void* operand_global_multicast, void* stream, unsigned int* bump_epoch, float* zrows_local) {
+                 void* operand_global_multicast, void* stream, unsigned int* bump_epoch, float* zrows_local,
+                 const float* bn_state = nullptr) {
     if (bad_precision(precision)) return SIMCLR_ERR_BAD_DTYPE;
     if (zrows_local != nullptr && misaligned(zrows_local)) return SIMCLR_ERR_MISALIGNED;
     if (!x_batch1 || !x_batch2 || !operand || !inv_norm || !pos_dot) return SIMCLR_ERR_NULL_POINTER;
@@ -577,6 +580,7 @@ int prepare_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t b
     if (precision == SIMCLR_PRECISION_SPLIT && g.d_pad > 128) return SIMCLR_ERR_UNSUPPORTED_DIM;
     AuxParams a = make_aux(g, s, b_local, b_global, row_offset, d, normalize);
     a.split = precision == SIMCLR_PRECISION_SPLIT ? 1 : 0;
+    a.bn_state = bn_state;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int warps = 8;
     const int blocks = static_cast<int>((g.bl_pad + warps - 1) / warps);
@@ -649,6 +653,7 @@ struct ExactSource {
     const float* inv_norm = nullptr;
     const float* zrows = nullptr;            // [2*Bgpad][Dpad]
     void* const* zrows_peers = nullptr;      // world pointers to [2*Blpad][Dpad]
+    const float* bn_state = nullptr;         // projection-head tail: x1 / x2 are pre-BatchNorm activations
 };
 
 // defer_stats: the backward of the same fused step finishes the loss statistics (simclr_forward_backward)
@@ -706,6 +711,7 @@ int forward_impl(int loss, const void* operand_rows, const void* operand_cols, i
         } else if (exact.x1 && exact.x2 && exact.inv_norm && b_local == b_global) {
             p.x1 = exact.x1;
             p.x2 = exact.x2;
+            p.bn_state = exact.bn_state;
             p.inv_norm = exact.inv_norm;
             p.in_bf16 = exact.in_dtype == SIMCLR_DTYPE_BF16 ? 1 : 0;
             have = true;
@@ -810,7 +816,7 @@ int backward_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t 
                   const float* lse2_cols, const float* col_scale, const float* grad_out, void* grad1, void* grad2,
                   void* workspace, size_t workspace_bytes, const float* primed_colvec, void* stream, void* finish_ws,
                   float* finish_stats, float* finish_loss, const FusedSync* fused = nullptr, unsigned stages = kAllStages,
-                  int flags = 0) {
+                  int flags = 0, const simclr_bn_t* bn = nullptr) {
     if (!x_batch1 || !x_batch2 || !operand_rows || !operand_cols || !inv_norm || !pos_dot || !grad1 || !grad2 || !workspace)
         return SIMCLR_ERR_NULL_POINTER;
     if (!lse2_cols && !primed_colvec) return SIMCLR_ERR_NULL_POINTER;
@@ -857,6 +863,11 @@ int backward_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t 
     p.dacc = w.dacc;
     p.det_part = w.det_part;
     p.deterministic = deterministic ? 1 : 0;
+    if (bn != nullptr) {
+        if (!bn->state || !bn->partial) return SIMCLR_ERR_NULL_POINTER;
+        p.bn_state = bn->state;
+        p.bn_partial = bn->partial;
+    }
     p.x1 = x_batch1;
     p.x2 = x_batch2;
     p.g1 = grad1;
@@ -1002,7 +1013,7 @@ int fused_step_impl(int loss, const void* x_batch1, const void* x_batch2, int64_
                     float temperature, int precision, const float* grad_out, void* operand, float* rowvec, float* stats,
                     float* loss_out, void* grad1, void* grad2, void* forward_workspace, size_t forward_workspace_bytes,
                     void* backward_workspace, size_t backward_workspace_bytes, void* stream, bool begin, bool finish,
-                    int flags) {
+                    int flags, const simclr_bn_t* bn = nullptr) {
     if (!rowvec || !backward_workspace) return SIMCLR_ERR_NULL_POINTER;
     if (begin && !stats) return SIMCLR_ERR_NULL_POINTER;
     const int64_t bp = simclr_pad_rows(b);
@@ -1013,14 +1024,16 @@ int fused_step_impl(int loss, const void* x_batch1, const void* x_batch2, int64_
     float* row_loss = rowvec + 6 * bp;
     int rc;
     if (begin) {
-        rc = simclr_prepare_peer(loss, x_batch1, x_batch2, b, d, in_dtype, normalize, temperature, precision, operand,
-                                 inv_norm, pos_dot, forward_workspace, 0, 0, nullptr, nullptr, nullptr, stream);
+        rc = prepare_impl(loss, x_batch1, x_batch2, b, d, in_dtype, normalize, temperature, precision, operand, inv_norm,
+                          pos_dot, forward_workspace, 0, 0, nullptr, nullptr, stream, nullptr, nullptr,
+                          bn ? bn->state : nullptr);
         if (rc) return rc;
         ExactSource ex;
         ex.x1 = x_batch1;
         ex.x2 = x_batch2;
         ex.in_dtype = in_dtype;
         ex.inv_norm = inv_norm;
+        ex.bn_state = bn ? bn->state : nullptr;
         // The forward primes the backward workspace.  Whole step: the reduction of the loss statistics is left to the
         // backward finalize kernel (five launches, nothing but the column vectors between the two tile kernels).  Split
         // step: the forward finalize kernel completes them, so that the caller can read loss / accuracy while the
@@ -1039,7 +1052,7 @@ int fused_step_impl(int loss, const void* x_batch1, const void* x_batch2, int64_
     return backward_impl(loss, x_batch1, x_batch2, b, b, 0, d, in_dtype, normalize, temperature, precision, operand, operand,
                          inv_norm, pos_dot, nullptr, nullptr, grad_out, g1, g2, backward_workspace,
                          backward_workspace_bytes, static_cast<const float*>(backward_workspace), stream,
-                         (begin && finish) ? forward_workspace : nullptr, stats, loss_out, nullptr, stages, flags);
+                         (begin && finish) ? forward_workspace : nullptr, stats, loss_out, nullptr, stages, flags, bn);
 }
 }  // namespace
 
@@ -1069,6 +1082,111 @@ int simclr_forward_backward_finish(int loss, const void* x_batch1, const void* x
     return fused_step_impl(loss, x_batch1, x_batch2, b, d, in_dtype, normalize, temperature, precision, grad_out,
                            const_cast<void*>(operand), const_cast<float*>(rowvec), nullptr, nullptr, grad1, grad2, nullptr, 0,
                            backward_workspace, backward_workspace_bytes, stream, false, true, flags);
+}
+
+// ---- projection-head tail (include/simclr_b200.h, "Projection-head tail") ----
+size_t simclr_bn_state_floats(int64_t d) {
+    const int64_t dp = simclr_pad_dim(d);
+    return dp == 0 ? 0 : static_cast<size_t>(2) * kBnPlanes * dp;
+}
+
+size_t simclr_bn_workspace_bytes(int64_t b, int64_t d) {
+    const int64_t bp = simclr_pad_rows(b), dp = simclr_pad_dim(d);
+    if (bp == 0 || dp == 0) return 0;
+    const size_t stats_parts = static_cast<size_t>(2) * ((b + kBnRowsPerBlock - 1) / kBnRowsPerBlock) * 2 * dp;   // bn_stats partials
+    const size_t bwd_parts = static_cast<size_t>(2 * bp / 16) * 2 * dp;                                        // finalize CTAs
+    return 256 + sizeof(float) * (stats_parts > bwd_parts ? stats_parts : bwd_parts);
+}
+
+int simclr_bn_stats(const void* u1, const void* u2, int64_t b, int64_t d, int in_dtype, const float* gamma, const float* beta,
+                    float eps, float* bn_state, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!u1 || !u2 || !gamma || !beta || !bn_state || !workspace) return SIMCLR_ERR_NULL_POINTER;
+    if (in_dtype != SIMCLR_DTYPE_F32 && in_dtype != SIMCLR_DTYPE_BF16) return SIMCLR_ERR_BAD_DTYPE;
+    const int64_t dp = simclr_pad_dim(d);
+    if (b < 1 || d < 1) return SIMCLR_ERR_BAD_SHAPE;
+    if (dp == 0) return SIMCLR_ERR_UNSUPPORTED_DIM;
+    if (workspace_bytes < simclr_bn_workspace_bytes(b, d)) return SIMCLR_ERR_WORKSPACE_TOO_SMALL;
+    if (misaligned(workspace) || misaligned(bn_state)) return SIMCLR_ERR_MISALIGNED;
+    int rc = check_device();
+    if (rc) return rc;
+    // the first 256 bytes of the workspace hold the ticket of the last-block reduction: zero on entry (the caller zeroes
+    // the workspace once), left zero
+    unsigned int* ticket = static_cast<unsigned int*>(workspace);
+    float* partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
+    const int blocks = static_cast<int>(2 * ((b + kBnRowsPerBlock - 1) / kBnRowsPerBlock));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    if (in_dtype == SIMCLR_DTYPE_F32)
+        e = launch_pdl(bn_stats_kernel<float>, dim3(blocks), dim3(256), 0, st, static_cast<const float*>(u1),
+                       static_cast<const float*>(u2), static_cast<int>(b), static_cast<int>(d), static_cast<int>(dp), gamma, beta,
+                       eps, bn_state, partial, ticket);
+    else
+        e = launch_pdl(bn_stats_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(u1),
+                       static_cast<const __nv_bfloat16*>(u2), static_cast<int>(b), static_cast<int>(d), static_cast<int>(dp), gamma,
+                       beta, eps, bn_state, partial, ticket);
+    return static_cast<int>(e);
+}
+
+int simclr_head_forward(int loss, const void* u1, const void* u2, int64_t b, int64_t d, int in_dtype, int normalize,
+                        float temperature, int precision, const float* bn_state, void* operand, float* rowvec, float* stats,
+                        float* loss_out, void* forward_workspace, size_t forward_workspace_bytes, void* stream) {
+    if (!rowvec || !stats || !bn_state) return SIMCLR_ERR_NULL_POINTER;
+    const int64_t bp = simclr_pad_rows(b);
+    if (bp == 0) return SIMCLR_ERR_BAD_SHAPE;
+    float* inv_norm = rowvec;
+    float* pos_dot = rowvec + 2 * bp;
+    int rc = prepare_impl(loss, u1, u2, b, d, in_dtype, normalize, temperature, precision, operand, inv_norm, pos_dot,
+                          forward_workspace, 0, 0, nullptr, nullptr, stream, nullptr, nullptr, bn_state);
+    if (rc) return rc;
+    ExactSource ex;
+    ex.x1 = u1;
+    ex.x2 = u2;
+    ex.in_dtype = in_dtype;
+    ex.inv_norm = inv_norm;
+    ex.bn_state = bn_state;
+    return forward_impl(loss, operand, operand, b, b, 0, d, temperature, normalize, precision, pos_dot, nullptr, rowvec + 4 * bp,
+                        rowvec + 6 * bp, stats, loss_out, forward_workspace, forward_workspace_bytes, nullptr, 0, 0, 0, nullptr,
+                        nullptr, nullptr, nullptr, stream, false, nullptr, kAllStages, ex);
+}
+
+int simclr_head_forward_backward_begin(int loss, const void* u1, const void* u2, int64_t b, int64_t d, int in_dtype,
+                                       int normalize, float temperature, int precision, const simclr_bn_t* bn, void* operand,
+                                       float* rowvec, float* stats, float* loss_out, void* forward_workspace,
+                                       size_t forward_workspace_bytes, void* backward_workspace,
+                                       size_t backward_workspace_bytes, int flags, void* stream) {
+    if (!bn) return SIMCLR_ERR_NULL_POINTER;
+    return fused_step_impl(loss, u1, u2, b, d, in_dtype, normalize, temperature, precision, nullptr, operand, rowvec, stats,
+                           loss_out, nullptr, nullptr, forward_workspace, forward_workspace_bytes, backward_workspace,
+                           backward_workspace_bytes, stream, true, false, flags, bn);
+}
+
+int simclr_head_forward_backward_finish(int loss, const void* u1, const void* u2, int64_t b, int64_t d, int in_dtype,
+                                        int normalize, float temperature, int precision, const float* grad_out,
+                                        const simclr_bn_t* bn, int bn_training, const void* operand, const float* rowvec,
+                                        void* grad_u1, void* grad_u2, float* grad_gamma, float* grad_beta,
+                                        void* backward_workspace, size_t backward_workspace_bytes, int flags, void* stream) {
+    if (!bn || !bn->state || !bn->partial) return SIMCLR_ERR_NULL_POINTER;
+    int rc = fused_step_impl(loss, u1, u2, b, d, in_dtype, normalize, temperature, precision, grad_out,
+                             const_cast<void*>(operand), const_cast<float*>(rowvec), nullptr, nullptr, grad_u1, grad_u2, nullptr,
+                             0, backward_workspace, backward_workspace_bytes, stream, false, true, flags, bn);
+    if (rc) return rc;
+    // dL/dz (just written to grad_u1 / grad_u2) -> dL/du, dL/dgamma, dL/dbeta
+    const int64_t dp = simclr_pad_dim(d), bp = simclr_pad_rows(b);
+    const int blocks = static_cast<int>(2 * ((b + kBnRowsPerBlock - 1) / kBnRowsPerBlock));
+    const int parts_per_view = static_cast<int>(bp / 16);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    if (in_dtype == SIMCLR_DTYPE_F32)
+        e = launch_pdl(bn_backward_kernel<float>, dim3(blocks), dim3(256), 0, st, static_cast<const float*>(u1),
+                       static_cast<const float*>(u2), static_cast<float*>(grad_u1), static_cast<float*>(grad_u2),
+                       static_cast<int>(b), static_cast<int>(d), static_cast<int>(dp), bn->state,
+                       static_cast<const float*>(bn->partial), parts_per_view, bn_training, grad_gamma, grad_beta);
+    else
+        e = launch_pdl(bn_backward_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(u1),
+                       static_cast<const __nv_bfloat16*>(u2), static_cast<__nv_bfloat16*>(grad_u1),
+                       static_cast<__nv_bfloat16*>(grad_u2), static_cast<int>(b), static_cast<int>(d), static_cast<int>(dp),
+                       bn->state, static_cast<const float*>(bn->partial), parts_per_view, bn_training, grad_gamma, grad_beta);
+    return static_cast<int>(e);
 }
 
 int simclr_forward_backward_peer(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d,

@@ -166,6 +166,10 @@ struct TileParams {
     // pretrain.py:59-61), for ~2.3x the accumulator traffic.
     const float* det_part;
     int deterministic;
+    // projection-head tail fused into the loss (head_kernels.cuh): x1 / x2 are the PRE-BatchNorm activations;
+    // bn_state f32 [2][5][D] (scale | shift | mean | rstd | var_unbiased per view), bn_partial f32 [finalize CTAs][2][D]
+    const float* bn_state;
+    float* bn_partial;
     const void* x1;            // inputs [b_loc][d]
     const void* x2;
     void* g1;                  // gradients [b_loc][d]
@@ -833,12 +837,14 @@ struct ZRow {
     const float* stash;        // normalised fp32 row (d_pad elements) or nullptr
     const void* x;             // raw input row (d elements of in_dtype) when stash == nullptr
     float mul;                 // 1 / norm (L2 or L1), 1 when the loss was called with normalize = False
+    const float* bn;           // BatchNorm scale | shift of the row's view (projection-head tail) or nullptr
 };
 template <int kLoss>
 SIMCLR_DEVICE ZRow zrow_of(const TileParams& p, int view, int g_img) {
     ZRow z;
     z.x = nullptr;
     z.mul = 1.f;
+    z.bn = nullptr;
     const int d_pad = p.d <= 64 ? 64 : (p.d <= 128 ? 128 : 256);
     if (p.zrows_peers.world > 0) {
         const int owner = g_img / p.b_loc, li = g_img - owner * p.b_loc;
@@ -851,6 +857,7 @@ SIMCLR_DEVICE ZRow zrow_of(const TileParams& p, int view, int g_img) {
         const size_t off = static_cast<size_t>(li) * p.d;
         const char* base = static_cast<const char*>(view == 0 ? p.x1 : p.x2);
         z.x = base + off * (p.in_bf16 ? 2 : 4);
+        if (p.bn_state != nullptr) z.bn = p.bn_state + static_cast<size_t>(view) * 5 * d_pad;
         if (kLoss == kModified || p.normalize) {
             const float inv = __ldcg(p.inv_norm + view * p.bl_pad + li);
             z.mul = inv == kInvNormClamped ? 1.f / kNormEps : inv;
@@ -880,6 +887,12 @@ SIMCLR_DEVICE float4 zrow_vec(const TileParams& p, const ZRow& z, int lane, int 
 #pragma unroll
         for (int u = 0; u < 4; ++u)
             if (k0 + u < p.d) e[u] = load_elem(z.x, static_cast<size_t>(k0 + u), p.in_bf16);
+    }
+    if (z.bn != nullptr) {
+        const int d_pad = p.d <= 64 ? 64 : (p.d <= 128 ? 128 : 256);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (k0 + u < p.d) e[u] = fmaf(e[u], __ldg(z.bn + k0 + u), __ldg(z.bn + d_pad + k0 + u));
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -1203,7 +1216,8 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
 // softplus + L1, :70-78).  The two input rows (x_self, x_other: caller inputs, never written by this library) are
 // loaded BEFORE griddepcontrol.wait, i.e. while the tile kernel drains; everything the step produced comes after it.
 template <int D, int kLoss, bool kDet>
-SIMCLR_DEVICE void backward_finalize_row(const TileParams& p, int rb, int r, int lane) {
+SIMCLR_DEVICE void backward_finalize_row(const TileParams& p, int rb, int r, int lane, float (&dz_out)[D / 32],
+                                         float (&dzx_out)[D / 32]) {
     const int blocks_per_view = p.bl_pad / kBlockM;
     const int vr = rb / blocks_per_view;
     const int img = (rb - vr * blocks_per_view) * kBlockM + r;
@@ -1235,6 +1249,19 @@ SIMCLR_DEVICE void backward_finalize_row(const TileParams& p, int rb, int r, int
         }
     }
     pdl_wait();
+    float xhat[kPerLane];
+    if (p.bn_state != nullptr) {
+        // the inputs are pre-BatchNorm activations: z = u * scale + shift (per view), xhat = (u - mean) * rstd
+        const float* st_s = p.bn_state + static_cast<size_t>(vr) * 5 * D;
+        const float* st_o = p.bn_state + static_cast<size_t>(1 - vr) * 5 * D;
+#pragma unroll
+        for (int u = 0; u < kPerLane; ++u) {
+            const int k = lane * kPerLane + u;
+            xhat[u] = (xs[u] - __ldg(st_s + 2 * D + k)) * __ldg(st_s + 3 * D + k);
+            xs[u] = fmaf(xs[u], __ldg(st_s + k), __ldg(st_s + D + k));
+            xo[u] = fmaf(xo[u], __ldg(st_o + k), __ldg(st_o + D + k));
+        }
+    }
     const int slot_self = rb * kBlockM + r;
     const int slot_other = (1 - vr) * p.bl_pad + img;
     const int c_self = vr * p.bg_pad + p.row_off + img;
@@ -1325,6 +1352,14 @@ SIMCLR_DEVICE void backward_finalize_row(const TileParams& p, int rb, int r, int
             o *= softplus_beta_grad(raw[u]);
         }
         out[u] = o;
+    }
+    if (p.bn_state != nullptr) {
+#pragma unroll
+        for (int u = 0; u < kPerLane; ++u) {
+            const bool in = lane * kPerLane + u < p.d;
+            dz_out[u] = in ? out[u] : 0.f;
+            dzx_out[u] = in ? out[u] * xhat[u] : 0.f;
+        }
     }
     if (vec4) {
         if constexpr (kPerLane == 4)

@@ -52,7 +52,7 @@ def test_diagnostics_live_in_the_tracing_build_only(lib):
 
 
 def test_abi_version_and_error_strings(lib):
-    assert lib.simclr_abi_version() == 12
+    assert lib.simclr_abi_version() == 13
     assert lib.simclr_error_string(0) == b"ok"
     for code in range(-11, 0):
         assert lib.simclr_error_string(code) not in (b"", b"unknown error")
