@@ -277,6 +277,9 @@ int simclr_peer_barrier(int world, int rank, void* const* flag_peers, unsigned i
  * already in flight); the forward finalize kernel bumps the epoch again and the backward tile kernel -- whose operand
  * loads and first score MMAs run ahead of it -- does the same before it loads the peers' column vectors.  The backward
  * finalize kernel adds up the ranks' statistics into stats_global / loss_out (the GLOBAL loss, identical on all ranks).
+ * `epoch_local` is u32 [2] here (both zero-initialised once): the epoch counter and the ticket with which the prepare
+ * kernel's last warp -- the moment this rank's operand push is complete -- publishes the epoch to the peers itself; the
+ * forward finalize kernel's last block does the same for the second barrier, so the tile kernels only wait.
  * Buffers as in the separate calls; operand / colvec / stats *_peers[rank] are this rank's own copies.  Every rank must
  * issue the same sequence of fused steps and barrier calls (they share the flags and the epoch counter).
  */

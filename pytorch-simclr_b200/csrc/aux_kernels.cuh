@@ -62,7 +62,7 @@ __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x
                                __nv_bfloat16* __restrict__ operand, float* __restrict__ inv_norm,
                                float* __restrict__ pos_dot, unsigned int* __restrict__ zero_ptr, int zero_words,
                                unsigned long long* ktrace, PeerTable peers, unsigned int* bump_epoch,
-                               unsigned int* __restrict__ cand_cnt, float* __restrict__ zstash) {
+                               unsigned int* __restrict__ cand_cnt, float* __restrict__ zstash, PeerTable signal_flags) {
     pdl_launch_dependents();
     // The input rows are loaded BEFORE griddepcontrol.wait (they are the caller's tensors: no kernel of this library
     // writes them, and a foreign producer never lets this kernel start early); every store comes after it, because the
@@ -100,6 +100,29 @@ __global__ void prepare_kernel(const T* __restrict__ x1, const T* __restrict__ x
     pdl_wait();
     ktrace_begin(ktrace, 0);
     struct End { unsigned long long* k; __device__ ~End() { ktrace_end(k, 0); } } end_guard{ktrace};
+    // Fused row-sharded step: this rank's side of the barrier behind the operand push is signalled from HERE, by the warp
+    // that finishes last (bump_epoch[1] counts the warps: zero on entry, left zero), instead of by the forward tile kernel
+    // once it has been launched and has reached its first column tile -- the peers see the flag a launch latency earlier.
+    // Runs at every exit of the kernel (exits are warp-uniform).
+    struct Signal {
+        const PeerTable& flags;
+        unsigned int* epoch;
+        __device__ ~Signal() {
+            if (flags.world == 0) return;
+            __threadfence_system();                       // this thread's peer stores are performed
+            __syncwarp();
+            if ((threadIdx.x & 31) != 0) return;
+            const unsigned int warps = gridDim.x * (blockDim.x >> 5);
+            if (atomicAdd(epoch + 1, 1u) != warps - 1u) return;
+            epoch[1] = 0u;
+            __threadfence();
+            const unsigned int target = *reinterpret_cast<volatile unsigned int*>(epoch);
+            for (int r = 0; r < flags.world; ++r) {
+                unsigned int* remote = static_cast<unsigned int*>(flags.ptr[r]) + flags.rank;
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(target) : "memory");
+            }
+        }
+    } signal_guard{signal_flags, bump_epoch};
     if (zero_ptr != nullptr && blockIdx.x == 0)
         for (int j = threadIdx.x; j < zero_words; j += blockDim.x) zero_ptr[j] = 0u;
     // fused row-sharded step: the epoch of the barrier that the forward tile kernel executes (TileParams::sync_epoch)

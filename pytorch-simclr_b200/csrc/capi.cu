@@ -553,7 +553,7 @@ int prepare_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t b
                  int normalize, float temperature, int precision, void* operand, float* inv_norm, float* pos_dot,
                  void* forward_workspace, int world, int rank, void* const* operand_global_peers,
                  void* operand_global_multicast, void* stream, unsigned int* bump_epoch, float* zrows_local,
-                 const float* bn_state = nullptr) {
+                 const float* bn_state = nullptr, void* const* signal_flag_peers = nullptr) {
     if (bad_precision(precision)) return SIMCLR_ERR_BAD_DTYPE;
     if (zrows_local != nullptr && misaligned(zrows_local)) return SIMCLR_ERR_MISALIGNED;
     if (!x_batch1 || !x_batch2 || !operand || !inv_norm || !pos_dot) return SIMCLR_ERR_NULL_POINTER;
@@ -581,13 +581,16 @@ int prepare_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t b
     AuxParams a = make_aux(g, s, b_local, b_global, row_offset, d, normalize);
     a.split = precision == SIMCLR_PRECISION_SPLIT ? 1 : 0;
     a.bn_state = bn_state;
+    PeerTable signal_flags;
+    if ((rc = make_peer_table(signal_flag_peers ? world : 0, rank, signal_flag_peers, &signal_flags))) return rc;
+    if (signal_flags.world > 0 && bump_epoch == nullptr) return SIMCLR_ERR_NULL_POINTER;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int warps = 8;
     const int blocks = static_cast<int>((g.bl_pad + warps - 1) / warps);
     auto* op = static_cast<__nv_bfloat16*>(operand);
     cudaError_t launch_rc = cudaSuccess;
 #define SIMCLR_PREP2(T, LOSS, PER) \
-    launch_rc = launch_pdl(prepare_kernel<T, LOSS, PER>, dim3(blocks), dim3(warps * 32), 0, st, static_cast<const T*>(x_batch1), static_cast<const T*>(x_batch2), a, op, inv_norm, pos_dot, zero_ptr, zero_words, g_ktrace_ptr, peers, bump_epoch, cand_cnt, zrows_local)
+    launch_rc = launch_pdl(prepare_kernel<T, LOSS, PER>, dim3(blocks), dim3(warps * 32), 0, st, static_cast<const T*>(x_batch1), static_cast<const T*>(x_batch2), a, op, inv_norm, pos_dot, zero_ptr, zero_words, g_ktrace_ptr, peers, bump_epoch, cand_cnt, zrows_local, signal_flags)
 #define SIMCLR_PREP(T, LOSS)                          \
     switch (g.d_pad) {                                \
         case 64: SIMCLR_PREP2(T, LOSS, 2); break;     \
@@ -737,6 +740,7 @@ int forward_impl(int loss, const void* operand_rows, const void* operand_cols, i
         if (p.sync_flags.world < 1 || fused->epoch == nullptr) return SIMCLR_ERR_BAD_PEERS;
         p.sync_epoch = fused->epoch;
         p.bump_epoch = fused->epoch;
+        p.sync_presignaled = 1;       // the prepare kernel's last warp published the epoch
     }
     if ((rc = make_peer_table(world, rank, colvec_peers, &p.colvec_peers))) return rc;
     if ((rc = make_peer_table(world, rank, stats_peers, &p.stats_peers))) return rc;
@@ -905,6 +909,7 @@ int backward_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t 
         if (p.sync_flags.world < 1 || fused->epoch == nullptr || fused->stats_all == nullptr || finish_stats == nullptr)
             return SIMCLR_ERR_BAD_PEERS;
         p.sync_epoch = fused->epoch;
+        p.sync_presignaled = 1;       // the forward finalize kernel's last block published the epoch
         p.stats_all = fused->stats_all;
         p.stats_world = fused->world;
         p.stats = finish_stats;
@@ -1217,7 +1222,7 @@ int simclr_forward_backward_peer(int loss, const void* x_batch1, const void* x_b
     int rc = prepare_impl(loss, x_batch1, x_batch2, b_local, d, in_dtype, normalize, temperature, SIMCLR_PRECISION_BF16,
                           operand, inv_norm, pos_dot, forward_workspace, world, rank, operand_global_peers,
                           operand_global_multicast, stream, epoch_local,
-                          zrows_peers ? static_cast<float*>(zrows_peers[rank]) : nullptr);
+                          zrows_peers ? static_cast<float*>(zrows_peers[rank]) : nullptr, nullptr, flag_peers);
     if (rc) return rc;
     ExactSource ex;
     ex.zrows_peers = zrows_peers;

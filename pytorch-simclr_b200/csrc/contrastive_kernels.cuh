@@ -210,6 +210,7 @@ struct TileParams {
     PeerTable sync_flags;
     const unsigned int* sync_epoch;
     unsigned int* bump_epoch;
+    int sync_presignaled;      // the kernel in front of this one has already published the epoch to the peers: wait only
     unsigned long long peer_timeout_ns;   // watchdog of the cross-GPU waits (0 = none)
     // Exact accuracy count (bf16 mode, normalised rows): per-row candidate lists filled by the forward tile kernel and
     // consumed (and reset) by the forward finalize kernel.  nullptr: the count is decided on the tensor-core scores.
@@ -1173,7 +1174,8 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
         if (kFused || p.defer_stats) {
             flags[1] = 0;                 // the backward finalize kernel of this step reduces block_part (finish_stats)
         } else {
-            __threadfence();
+            if (p.colvec_peers.world > 0) __threadfence_system();     // this block's pushes to the peers are performed
+            else __threadfence();
             const unsigned int prev = atomicAdd(p.ticket, 1u);
             flags[1] = (prev == static_cast<unsigned int>(p.n_row_blocks) - 1u) ? 1 : 0;
         }
@@ -1206,7 +1208,18 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
                 dst[2] = s2;
             }
             *p.ticket = 0u;                        // leave the workspace header clean for the next call
-            if (p.bump_epoch != nullptr) *p.bump_epoch += 1u;   // the epoch the backward tile kernel's barrier uses
+            if (p.bump_epoch != nullptr) {
+                // the epoch the backward tile kernel's barrier waits for -- published to the peers right here (every
+                // block of this kernel made its pushes visible before it took its ticket): the peers see it a launch
+                // latency earlier than if the backward tile kernel signalled
+                const unsigned int target = *p.bump_epoch + 1u;
+                *p.bump_epoch = target;
+                __threadfence_system();
+                for (int r = 0; r < p.sync_flags.world; ++r) {
+                    unsigned int* remote = static_cast<unsigned int*>(p.sync_flags.ptr[r]) + p.sync_flags.rank;
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(target) : "memory");
+                }
+            }
         }
     }
 }
@@ -1619,7 +1632,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                     // In-kernel cross-GPU barrier.  Forward: the row-block tile (local rows) is already in flight, the
                     // column tiles are what the peers pushed.  Backward: the operands were complete before this kernel
                     // started (early loads above), the peers' column vectors are what the barrier protects.
-                    peer_sync_thread(p.sync_flags, p.sync_epoch, blockIdx.x == 0, p.peer_timeout_ns);
+                    peer_sync_thread(p.sync_flags, p.sync_epoch, blockIdx.x == 0 && !p.sync_presignaled, p.peer_timeout_ns);
                     synced = true;
                 }
                 const int c0 = tile_col0<kLoss>(p, w.rb / blocks_per_view, w.j);

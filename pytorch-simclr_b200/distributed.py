@@ -187,7 +187,7 @@ class PeerBatch:
         # against 1.422 / 0.7396 / 0.4111 ms without -- the NVLS push is not what limits the step, the second launch's
         # fixed cost is slightly more than the hidden transfer -- hence off by default.
         self.overlap = bool(overlap_local_first)
-        self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.epoch = torch.zeros(4, dtype=torch.int32, device=self.device)      # [0] epoch counter, [1] warp ticket of the fused step's prepare kernel
         self.generation = 0                    # number of forwards issued so far
         self.lib = _lib.load()
 
