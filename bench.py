@@ -460,6 +460,37 @@ def bench_single(args):
     clocks = sampler.stop()
     e2e_default_ms = e2e_ms_per_step(torch, sb, h12, dev, min(args.steps, 50), 3, "auto")
 
+    # the autograd-free form of the same step (one call: contrastive_forward_backward), end to end from pinned host memory
+    sb.set_precision("bf16")
+
+    def e2e_fused_step():
+        x = h12.to(dev, non_blocking=True)
+        loss, stats, g1, g2 = sb.contrastive_forward_backward(LOSS_NTXENT, x[0], x[1], TAU)
+        return stats.tolist()               # loss statistics read back: the step's only synchronisation
+
+    for _ in range(5):
+        e2e_fused_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_fused = min(args.steps, 100)
+    for _ in range(n_fused):
+        e2e_fused_step()
+    torch.cuda.synchronize()
+    e2e_fused_ms = (time.perf_counter() - t0) * 1e3 / n_fused
+    sb.set_precision("auto")
+
+    # deterministic mode (SIMCLR_FLAG_DETERMINISTIC): the same K-step graph protocol
+    step_det = ContrastiveStep(LOSS_NTXENT, b, d, TAU, True, torch.float32, dev, deterministic=True)
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step_det.step(None, *sets[0])
+    torch.cuda.synchronize()
+    n_det = max(3, min(args.steps, 20))
+    g_det = graph_of_steps(torch, step_det, sets, n_det, side)
+    time_graph(torch, g_det)
+    ms_det = time_graph(torch, g_det) / n_det
+    del g_det, step_det
+
     # the fp32-grade arithmetic mode (split bf16 operands) on the same workload: what "auto" picks for fp32 inputs
     step32 = ContrastiveStep(LOSS_NTXENT, b, d, TAU, True, torch.float32, dev, precision="fp32")
     step32.x1.copy_(h1)
@@ -508,6 +539,12 @@ def bench_single(args):
         "e2e_default_precision": {"value": m / (e2e_default_ms * 1e-3), "unit": "views/s", "ms_per_step": e2e_default_ms,
                                   "what": "the same call with the API's default precision ('auto': fp32-grade split "
                                           "operands for float32 inputs with d <= 128)"},
+        "e2e_autograd_free_api": {"value": m / (e2e_fused_ms * 1e-3), "unit": "views/s", "ms_per_step": e2e_fused_ms,
+                                  "what": "contrastive_forward_backward(LOSS_NTXENT, x1, x2, tau) -> (loss, stats, grad1, grad2): "
+                                          "the fused five-kernel step in one call, same H2D copy, loss statistics read back; "
+                                          "no torch.autograd in the loop (precision 'bf16')"},
+        "deterministic_mode": {"ms_per_step": ms_det, "value": m / (ms_det * 1e-3),
+                               "what": "SIMCLR_FLAG_DETERMINISTIC (bit-identical gradients run to run), same back-to-back protocol"},
         "gpu_launches": 5 * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

@@ -18,7 +18,22 @@ import torch
 from . import _hoststats
 from .functional import LOSS_MODIFIED, LOSS_NTXENT, ContrastiveLossFunction
 
-__all__ = ["contrastive_loss", "modified_contrastive_loss"]
+__all__ = ["contrastive_loss", "modified_contrastive_loss", "set_lazy_accuracy", "get_lazy_accuracy"]
+
+# The reference returns the accuracy as a python float (objective.py:52-53 / :96-97), i.e. every call ends with a
+# device -> host read, and its training loop adds a second one (loss.item(), utils/model_utils.py:117).  With
+# set_lazy_accuracy(True) the accuracy comes back as a 0-d device tensor instead and the call enqueues without any host
+# synchronisation (what a CUDA-graph-captured or fully asynchronous training step needs); float(acc) gives the number.
+_LAZY_ACCURACY = False
+
+
+def set_lazy_accuracy(flag: bool) -> None:
+    global _LAZY_ACCURACY
+    _LAZY_ACCURACY = bool(flag)
+
+
+def get_lazy_accuracy() -> bool:
+    return _LAZY_ACCURACY
 
 
 def _as_supported(x: torch.Tensor) -> torch.Tensor:
@@ -34,6 +49,9 @@ def _loss_and_accuracy(x1, x2, kind, temperature, normalize, weight):
     """(loss tensor, accuracy float).  The accuracy forces a device->host read (reference objective.py:52 / :96); for the
     unweighted losses the finalize kernel writes the statistics into pinned host memory and this thread polls it
     (_hoststats.py) instead of paying a stream synchronisation."""
+    if _LAZY_ACCURACY and x1.is_cuda:
+        loss, stats = ContrastiveLossFunction.apply(x1, x2, kind, temperature, normalize, weight, None)
+        return loss, stats[2] * (100.0 / (2 * x1.shape[0]))
     if weight is None and x1.is_cuda and _HOST_STATS:
         ring = _hoststats.ring(x1.device)
         slot = ring.acquire()

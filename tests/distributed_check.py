@@ -105,6 +105,39 @@ for kind, ref_fn, label in ((LOSS_NTXENT, oracle.ntxent_closed_form, "ntxent"), 
         print(f"[rank {rank}/{world}] {label}/fused step {i}: loss {float(ls):.6f} (oracle {ref.loss:.6f}, rel {lrel:.1e}) "
               f"acc {acc:.3f} (oracle {ref.acc:.3f}) grad err {e1:.1e} {e2:.1e} -> {'OK' if good else 'FAIL'}", flush=True)
     del ps
+# ---- DistributedDataParallel training step with the global loss: a small encoder wrapped in DDP, every
+# rank feeds its shard, loss = global_contrastive_loss(..., ddp_scale=True); after backward() the (DDP-averaged) parameter
+# gradients must equal the gradients of the single-process loss over the WHOLE batch (fp64 reference: the same encoder
+# applied to the gathered batch, oracle loss gradients chained through torch autograd) ----
+from torch.nn.parallel import DistributedDataParallel as DDP  # noqa: E402
+
+torch.manual_seed(0)                                              # identical initial weights on every rank
+enc = torch.nn.Sequential(torch.nn.Linear(64, 96), torch.nn.ReLU(), torch.nn.Linear(96, args.d, bias=False)).cuda()
+ddp = DDP(enc, device_ids=[local])
+gen = torch.Generator().manual_seed(5)
+base = torch.randn(args.b, 64, generator=gen)
+v1 = base + 0.3 * torch.randn(args.b, 64, generator=gen)
+v2 = base + 0.3 * torch.randn(args.b, 64, generator=gen)
+off, bl = shard_rows(args.b, world, rank)
+z1 = ddp(v1[off:off + bl].cuda())
+z2 = ddp(v2[off:off + bl].cuda())
+loss, acc = global_contrastive_loss(z1, z2, temperature=args.tau, ddp_scale=True)
+loss.backward()
+torch.cuda.synchronize()
+ref_enc = torch.nn.Sequential(torch.nn.Linear(64, 96), torch.nn.ReLU(), torch.nn.Linear(96, args.d, bias=False)).double()
+ref_enc.load_state_dict({k: v.detach().cpu().double() for k, v in enc.state_dict().items()})
+r1, r2 = ref_enc(v1.double()), ref_enc(v2.double())
+ref = oracle.ntxent_closed_form(r1.detach(), r2.detach(), temperature=args.tau)
+torch.autograd.backward([r1, r2], [torch.from_numpy(ref.grad1), torch.from_numpy(ref.grad2)])
+worst = 0.0
+for (name, p_), q in zip(enc.named_parameters(), ref_enc.parameters()):
+    err = float((p_.grad.detach().cpu().double() - q.grad).abs().max() / q.grad.abs().max())
+    worst = max(worst, err)
+good = worst < 1e-2 and abs(float(loss.detach()) / world - ref.loss) / ref.loss < 2e-3 and round(acc * 2 * args.b / 100.0) == ref.correct
+ok = ok and good
+print(f"[rank {rank}/{world}] DDP step with ddp_scale: loss/world {float(loss.detach()) / world:.6f} (oracle {ref.loss:.6f}) "
+      f"acc {acc:.3f} (oracle {ref.acc:.3f}) worst parameter-gradient error {worst:.1e} -> {'OK' if good else 'FAIL'}", flush=True)
+
 flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()

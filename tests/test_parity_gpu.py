@@ -37,6 +37,7 @@ def _restore_precision():
     sb.set_precision("auto")
     sb.set_eager_backward(True)
     sb.set_deterministic(None)
+    sb.set_lazy_accuracy(False)
 
 
 def _mode_for(precision, dtype, d):
@@ -477,3 +478,47 @@ def test_deterministic_mode_gives_bit_identical_gradients(kind, b, d):
         grads.append((a.grad.clone(), c.grad.clone()))
     assert all(torch.equal(g[0], grads[0][0]) and torch.equal(g[1], grads[0][1]) for g in grads[1:])
     assert torch.equal(grads[0][0], outs[0][0])
+
+
+def test_lazy_accuracy_returns_a_device_tensor_and_allows_graph_capture():
+    """set_lazy_accuracy(True): no host synchronisation inside the call, so forward + loss + backward of the public API
+    can be captured into one CUDA graph (the two .item() syncs of utils/model_utils.py:117 and
+    objective.py:52 are what keeps the reference's step host-bound)."""
+    b, d = 1024, 128
+    z1, z2 = oracle.make_embeddings(b, d, seed=9, kind="correlated", noise=1.0)
+    ref = oracle.ntxent_closed_form(z1, z2, temperature=0.5)
+    sb.set_precision("bf16")
+    sb.set_lazy_accuracy(True)
+    a = z1.cuda().requires_grad_(True)
+    c = z2.cuda().requires_grad_(True)
+    loss, acc = sb.contrastive_loss(a, c, temperature=0.5)
+    assert isinstance(acc, torch.Tensor) and acc.is_cuda and acc.dim() == 0
+    loss.backward()
+    assert float(acc) == ref.acc
+    # whole step under stream capture
+    side = torch.cuda.Stream()
+    xa, xc = z1.cuda(), z2.cuda()
+    ga, gc = torch.zeros_like(xa), torch.zeros_like(xc)
+    out = torch.zeros(2, device="cuda")
+    with torch.cuda.stream(side):
+        for _ in range(2):                                   # warm-up (allocator, library state)
+            p, q = xa.clone().requires_grad_(True), xc.clone().requires_grad_(True)
+            l, ac = sb.contrastive_loss(p, q, temperature=0.5)
+            l.backward()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        p, q = xa.clone().requires_grad_(True), xc.clone().requires_grad_(True)
+        l, ac = sb.contrastive_loss(p, q, temperature=0.5)
+        l.backward()
+        ga.copy_(p.grad)
+        gc.copy_(q.grad)
+        out[0].copy_(l.detach())
+        out[1].copy_(ac)
+    xa.copy_(z2)                                             # new inputs, replay
+    xc.copy_(z1)
+    graph.replay()
+    torch.cuda.synchronize()
+    ref2 = oracle.ntxent_closed_form(z2, z1, temperature=0.5)
+    assert float(out[0]) == pytest.approx(ref2.loss, rel=2e-3) and float(out[1]) == ref2.acc
+    assert _grad_err(ga.cpu().numpy(), ref2.grad1) < 1e-2
