@@ -829,8 +829,9 @@ def bench_multi(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(CONFIG_MULTI),
-            "config_detail": {"parallelism": f"rows/{world}; operands, lse2 and loss statistics pushed over NVLink by the prepare / "
-                                      "finalize kernels (symmetric memory), 2 device-side barriers per step",
+            "config_detail": {"parallelism": f"rows/{world}; operand rows pushed over NVLink by the forward tile kernel itself while it "
+                                      "works on this rank's own columns (two column windows in one launch), lse2 and loss "
+                                      "statistics by the finalize kernels (symmetric memory), 2 device-side barriers per step",
                        "l2": "flushed before every step (256 MiB memset outside the event pair); one event pair = one CUDA "
                              "graph of one step, two graphs (the two buffer generations of the symmetric buffers) replayed "
                              "alternately; per-rank sums, max over ranks",

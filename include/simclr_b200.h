@@ -280,6 +280,15 @@ int simclr_peer_barrier(int world, int rank, void* const* flag_peers, unsigned i
  * `epoch_local` is u32 [2] here (both zero-initialised once): the epoch counter and the ticket with which the prepare
  * kernel's last warp -- the moment this rank's operand push is complete -- publishes the epoch to the peers itself; the
  * forward finalize kernel's last block does the same for the second barrier, so the tile kernels only wait.
+ * Tile-aligned shards (b_local % 128 == 0, at least one tile per SM in this rank's own columns): the forward tile kernel
+ * is ONE launch over TWO column windows and does the operand exchange itself -- window 0, this rank's own columns, is read
+ * from `operand` while the spare warp of every CTA pushes those rows into all ranks' global operand matrices (multimem.st
+ * through the NVSwitch when operand_global_multicast is given) and the warp whose stores are performed last publishes
+ * the epoch; the TMA producers wait for all ranks' flags only in front of window 1, everybody else's columns.  The NVLink
+ * transfer, its drain and the ranks' skew at the start of the step hide under the tiles of window 0 (the prepare kernel
+ * then pushes nothing).  The kernel needs all of its CTAs resident at once (grid = number of SMs, one CTA per SM -- the
+ * GPU must not be shared with another context's long-running kernels); SIMCLR_B200_PEER_WINDOWS=0 restores the
+ * push-in-prepare form.
  * Buffers as in the separate calls; operand / colvec / stats *_peers[rank] are this rank's own copies.  Every rank must
  * issue the same sequence of fused steps and barrier calls (they share the flags and the epoch counter).
  */

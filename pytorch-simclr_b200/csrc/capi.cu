@@ -337,10 +337,10 @@ int make_dacc_map(CUtensorMap* map, const void* base, int64_t rows, int64_t d_pa
     return SIMCLR_OK;
 }
 
-template <int D, int kLoss, bool kBackward, bool kConst, int kPrec, bool kDet>
+template <int D, int kLoss, bool kBackward, bool kConst, int kPrec, bool kDet, bool kWindows = false>
 int launch_tile_k(const CUtensorMap& rows, const CUtensorMap& cols, const CUtensorMap& dacc, const TileParams& p, int grid,
                   cudaStream_t st) {
-    auto kern = contrastive_tile_kernel<D, kLoss, kBackward, kConst, kPrec, kDet>;
+    auto kern = contrastive_tile_kernel<D, kLoss, kBackward, kConst, kPrec, kDet, kWindows>;
     static std::once_flag configured[kMaxDevices];
     static cudaError_t configure_rc[kMaxDevices];
     int dev = 0;
@@ -360,6 +360,10 @@ int launch_tile(const CUtensorMap& rows, const CUtensorMap& cols, const CUtensor
                 cudaStream_t st) {
     if constexpr (kBackward) {
         if (p.deterministic) return launch_tile_k<D, kLoss, true, kConst, kPrec, true>(rows, cols, dacc, p, grid, st);
+    } else if constexpr (kPrec == 0) {
+        // the two-window forward of the row-sharded fused step (bf16 operands only) is its own instantiation: the window
+        // loops cost the one-window kernel a microsecond per launch when they are a run-time switch
+        if (p.n_windows == 2) return launch_tile_k<D, kLoss, false, kConst, 0, false, true>(rows, cols, dacc, p, grid, st);
     }
     return launch_tile_k<D, kLoss, kBackward, kConst, kPrec, false>(rows, cols, dacc, p, grid, st);
 }
@@ -385,7 +389,13 @@ int launch_tile_d(int loss, const CUtensorMap& rows, const CUtensorMap& cols, co
 
 template <bool kBackward>
 int dispatch_tile(int loss, int64_t d_pad, int precision, const CUtensorMap& rows, const CUtensorMap& cols,
-                  const CUtensorMap& dacc, const TileParams& p, int grid, cudaStream_t st) {
+                  const CUtensorMap& dacc, const TileParams& p_in, int grid, cudaStream_t st) {
+    TileParams p = p_in;
+    if (p.n_windows != 2 || kBackward || precision != SIMCLR_PRECISION_BF16) {        // one window: the launch's own column range
+        p.n_windows = 1;
+        p.win0_local = 0;
+        p.win[0] = ColWindow{p.col_start, p.col_cnt, p.n_col_tiles, p.max_segs, p.total_tiles, p.part};
+    }
     if (precision == SIMCLR_PRECISION_SPLIT) {
         switch (d_pad) {
             case 64: return launch_tile_d<64, kBackward, 1>(loss, rows, cols, dacc, p, grid, st);
@@ -547,13 +557,35 @@ struct FusedSync {
     void* const* flag_peers;
     unsigned int* epoch;
     const float* stats_all;
+    // two-window forward (TileParams::n_windows): the tile kernel pushes the operand rows itself
+    bool windows = false;
+    void* const* operand_peers = nullptr;
+    void* operand_multicast = nullptr;
 };
+
+// Can the forward of the fused row-sharded step run as one launch over two column windows (own columns while the operand
+// rows travel, then the peers')?  Needs tile-aligned shards and enough tiles in either window for every CTA.
+// SIMCLR_B200_PEER_WINDOWS=0 switches it off (A/B measurements).
+bool peer_windows_ok(int loss, int64_t b_local, int world) {
+    static const bool enabled = [] {
+        const char* e = std::getenv("SIMCLR_B200_PEER_WINDOWS");
+        return !(e && e[0] == '0');
+    }();
+    if (!enabled || world < 2 || b_local % kBlockM != 0) return false;
+    const long long tpr = b_local / kBlockM;
+    const long long row_blocks = 2 * tpr;
+    const long long views = loss == SIMCLR_LOSS_NTXENT ? 2 : 1;
+    const long long sms = device_info().sm_count;
+    return row_blocks * views * tpr >= sms && row_blocks * views * tpr * (world - 1) >= sms;
+}
 
 int prepare_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t b_local, int64_t d, int in_dtype,
                  int normalize, float temperature, int precision, void* operand, float* inv_norm, float* pos_dot,
                  void* forward_workspace, int world, int rank, void* const* operand_global_peers,
                  void* operand_global_multicast, void* stream, unsigned int* bump_epoch, float* zrows_local,
-                 const float* bn_state = nullptr, void* const* signal_flag_peers = nullptr) {
+                 const float* bn_state = nullptr, void* const* signal_flag_peers = nullptr, int shard_world = 0) {
+    // shard_world > 0: this rank's batch is shard `rank` of `shard_world`, but the kernel pushes nothing (world == 0: the
+    // two-window forward does the push)
     if (bad_precision(precision)) return SIMCLR_ERR_BAD_DTYPE;
     if (zrows_local != nullptr && misaligned(zrows_local)) return SIMCLR_ERR_MISALIGNED;
     if (!x_batch1 || !x_batch2 || !operand || !inv_norm || !pos_dot) return SIMCLR_ERR_NULL_POINTER;
@@ -567,8 +599,10 @@ int prepare_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t b
         if (misaligned(operand_global_multicast)) return SIMCLR_ERR_MISALIGNED;
         peers.mc = operand_global_multicast;
     }
-    const int64_t b_global = peers.world > 0 ? b_local * peers.world : b_local;
-    const int64_t row_offset = peers.world > 0 ? b_local * peers.rank : 0;
+    if (shard_world > 0 && (peers.world > 0 || rank < 0 || rank >= shard_world)) return SIMCLR_ERR_BAD_PEERS;
+    const int geom_world = shard_world > 0 ? shard_world : peers.world;
+    const int64_t b_global = geom_world > 0 ? b_local * geom_world : b_local;
+    const int64_t row_offset = geom_world > 0 ? b_local * (shard_world > 0 ? rank : peers.rank) : 0;
     Geometry g;
     if ((rc = make_geometry(loss, b_local, b_global, row_offset, d, &g))) return rc;
     if (misaligned(operand) || misaligned(forward_workspace)) return SIMCLR_ERR_MISALIGNED;
@@ -740,7 +774,7 @@ int forward_impl(int loss, const void* operand_rows, const void* operand_cols, i
         if (p.sync_flags.world < 1 || fused->epoch == nullptr) return SIMCLR_ERR_BAD_PEERS;
         p.sync_epoch = fused->epoch;
         p.bump_epoch = fused->epoch;
-        p.sync_presignaled = 1;       // the prepare kernel's last warp published the epoch
+        p.sync_presignaled = 1;       // the prepare kernel's last warp published the epoch (windows: this kernel's spare warps)
     }
     if ((rc = make_peer_table(world, rank, colvec_peers, &p.colvec_peers))) return rc;
     if ((rc = make_peer_table(world, rank, stats_peers, &p.stats_peers))) return rc;
@@ -766,7 +800,29 @@ int forward_impl(int loss, const void* operand_rows, const void* operand_cols, i
         // the caller relies on this call to order the operand exchange: do it up front
         if ((rc = simclr_peer_barrier(world, rank, flag_peers, epoch_local, nullptr, nullptr, nullptr, stream))) return rc;
     }
-    if (!overlap) {
+    if (fused != nullptr && fused->windows) {
+        // One launch, two column windows: own columns from the local operand rows while this kernel's spare warps push
+        // those rows to the peers, then everybody else's columns behind the in-kernel wait (TileParams::n_windows).
+        Geometry ga = g, gb = g;
+        set_window(&ga, rank * tpr, tpr);
+        set_window(&gb, ((rank + 1) % world) * tpr, g.tiles_per_view - tpr);
+        if (ga.grid != g.grid || gb.grid != g.grid) return SIMCLR_ERR_BAD_PEERS;       // peer_windows_ok() guarantees it
+        if (static_cast<size_t>(ga.grid) * ga.max_segs * kFwdFields * kBlockM * sizeof(float) > w.part_bytes ||
+            static_cast<size_t>(gb.grid) * gb.max_segs * kFwdFields * kBlockM * sizeof(float) > w.part_bytes)
+            return SIMCLR_ERR_WORKSPACE_TOO_SMALL;
+        p.n_windows = 2;
+        p.win0_local = 1;
+        p.win[0] = ColWindow{ga.col_start, ga.col_cnt, ga.n_col_tiles, ga.max_segs, ga.total_tiles, w.part};
+        p.win[1] = ColWindow{gb.col_start, gb.col_cnt, gb.n_col_tiles, gb.max_segs, gb.total_tiles, w.part2};
+        p.push_src = operand_rows;
+        if ((rc = make_peer_table(world, rank, fused->operand_peers, &p.push_peers))) return rc;
+        p.push_peers.mc = fused->operand_multicast;
+        p.push_ticket = fused->epoch + 1;
+        p.fin_set[0] = PartSet{w.part, ga.total_tiles, ga.n_col_tiles, ga.max_segs, ga.grid};
+        p.fin_set[1] = PartSet{w.part2, gb.total_tiles, gb.n_col_tiles, gb.max_segs, gb.grid};
+        p.n_fin_sets = 2;
+        if ((stages & kStageFwdTile) && (rc = dispatch_tile<false>(loss, g.d_pad, precision, map_rows, map_cols, map_rows, p, g.grid, st))) return rc;
+    } else if (!overlap) {
         p.fin_set[0] = PartSet{w.part, g.total_tiles, g.n_col_tiles, g.max_segs, g.grid};
         p.n_fin_sets = 1;
         if ((stages & kStageFwdTile) && (rc = dispatch_tile<false>(loss, g.d_pad, precision, map_rows, map_cols, map_rows, p, g.grid, st))) return rc;
@@ -1216,13 +1272,20 @@ int simclr_forward_backward_peer(int loss, const void* x_batch1, const void* x_b
     const void* operand_cols = operand_global_peers[rank];
     const float* colvec_local = static_cast<const float*>(colvec_peers[rank]);
     FusedSync fs{world, rank, flag_peers, epoch_local, static_cast<const float*>(stats_peers[rank])};
-    // prepare pushes the operand rows and bumps the epoch; the forward tile kernel signals / waits on it.  The exact fp32
-    // rows for the accuracy candidates stay on the rank that owns them (zrows_peers[rank]); the finalize kernels of the
-    // other ranks read the few rows they need over NVLink
+    if (check_device() == SIMCLR_OK && peer_windows_ok(loss, b_local, world)) {
+        fs.windows = true;
+        fs.operand_peers = operand_global_peers;
+        fs.operand_multicast = operand_global_multicast;
+    }
+    // prepare bumps the epoch and pushes the operand rows, publishing the epoch when its last warp is done -- or, with the
+    // two-window forward, leaves push and signal to the forward tile kernel, which overlaps them with its own columns'
+    // tiles.  The exact fp32 rows for the accuracy candidates stay on the rank that owns them (zrows_peers[rank]); the
+    // finalize kernels of the other ranks read the few rows they need over NVLink
     int rc = prepare_impl(loss, x_batch1, x_batch2, b_local, d, in_dtype, normalize, temperature, SIMCLR_PRECISION_BF16,
-                          operand, inv_norm, pos_dot, forward_workspace, world, rank, operand_global_peers,
-                          operand_global_multicast, stream, epoch_local,
-                          zrows_peers ? static_cast<float*>(zrows_peers[rank]) : nullptr, nullptr, flag_peers);
+                          operand, inv_norm, pos_dot, forward_workspace, fs.windows ? 0 : world, rank,
+                          fs.windows ? nullptr : operand_global_peers, fs.windows ? nullptr : operand_global_multicast, stream,
+                          epoch_local, zrows_peers ? static_cast<float*>(zrows_peers[rank]) : nullptr, nullptr,
+                          fs.windows ? nullptr : flag_peers, fs.windows ? world : 0);
     if (rc) return rc;
     ExactSource ex;
     ex.zrows_peers = zrows_peers;

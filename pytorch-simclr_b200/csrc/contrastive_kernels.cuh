@@ -121,6 +121,13 @@ struct PartSet {
     int n_col_tiles, max_segs, grid;
 };
 
+// One column window of a forward tile-kernel launch (see TileParams::n_windows).
+struct ColWindow {
+    int col_start, col_cnt, n_col_tiles, max_segs;
+    long long total_tiles;
+    float* part;
+};
+
 struct TileParams {
     int b_loc;         // images held by this rank
     int b_glob;        // images in the global batch
@@ -235,6 +242,18 @@ struct TileParams {
     // backward finalize, row-sharded fused step: add up the ranks' statistics [world][4] (fixed order) into stats / loss_out
     const float* stats_all;
     int stats_world;
+    // Forward tile kernel, row-sharded fused step: ONE launch walks TWO column windows.  Window 0 = the columns this rank
+    // produced itself, read from its own operand rows (tmap_rows) -- no peer needed -- while the spare warp of every CTA
+    // pushes this rank's operand rows into all ranks' global operand matrices (push_src -> push_peers) and the warp that
+    // finishes last publishes the epoch; window 1 = everybody else's columns, behind the wait for all ranks' flags.  The
+    // NVLink transfer, its drain and the ranks' skew at the start of the step hide under the tiles of window 0.
+    // n_windows == 1: win[0] repeats n_col_tiles / col_start / ... above (the backward kernel reads only those).
+    int n_windows;
+    int win0_local;
+    ColWindow win[2];
+    const void* push_src;          // this rank's operand rows [2*bl_pad][D] bf16
+    PeerTable push_peers;          // every rank's global operand matrix [2*bg_pad][D] (world == 0: no push)
+    unsigned int* push_ticket;     // counts the CTAs whose push is performed (zero on entry, left zero)
 };
 
 // Waits until *flag (system scope) has reached `target`.  Polls with an exponential __nanosleep back-off (the waiting
@@ -340,17 +359,21 @@ struct SmemLayout {
 
 // First global column of tile j for a row block of view vr.
 template <int kLoss>
-SIMCLR_DEVICE int tile_col0(const TileParams& p, int vr, int j) {
+SIMCLR_DEVICE int tile_col0(int col_start, int col_cnt, int tiles_per_view, int bg_pad, int vr, int j) {
     int v = 0;
     if constexpr (kLoss == kNtXent) {
-        v = j >= p.col_cnt ? 1 : 0;          // NT-Xent rows see both views' windows, view 0 first
-        j -= v * p.col_cnt;
+        v = j >= col_cnt ? 1 : 0;            // NT-Xent rows see both views' windows, view 0 first
+        j -= v * col_cnt;
     } else {
         v = 1 - vr;                           // modified rows see the other view only
     }
-    int idx = p.col_start + j;
-    if (idx >= p.tiles_per_view) idx -= p.tiles_per_view;
-    return v * p.bg_pad + idx * kBlockN;
+    int idx = col_start + j;
+    if (idx >= tiles_per_view) idx -= tiles_per_view;
+    return v * bg_pad + idx * kBlockN;
+}
+template <int kLoss>
+SIMCLR_DEVICE int tile_col0(const TileParams& p, int vr, int j) {
+    return tile_col0<kLoss>(p.col_start, p.col_cnt, p.tiles_per_view, p.bg_pad, vr, j);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1471,7 +1494,8 @@ struct RingPos {
 // kDet (backward): deterministic mode, see TileParams::deterministic -- a template parameter, not a run-time switch: the
 // single-thread issuer loops bound the pipeline by their per-hop latency, and even a predicated-off wait in them costs
 // the default mode more than a microsecond per launch (profiles/r02_notes.md).
-template <int D, int kLoss, bool kBackward, bool kConst, int kPrec, bool kDet = false>
+// kWindows (forward): two column windows in one launch, see TileParams::n_windows -- also its own instantiation.
+template <int D, int kLoss, bool kBackward, bool kConst, int kPrec, bool kDet = false, bool kWindows = false>
 __global__ void __launch_bounds__(kBackward ? kThreadsBackward : kThreadsForward, 1)
 contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_cols,
                         const __grid_constant__ CUtensorMap tmap_dacc, const __grid_constant__ TileParams p) {
@@ -1521,6 +1545,26 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
     const long long t_end = (p.total_tiles * (blockIdx.x + 1)) / gridDim.x;
     const int nct = p.n_col_tiles;
     const int blocks_per_view = p.bl_pad / kBlockM;
+    // column windows (forward only, TileParams::n_windows): every role walks window 0's tile range, then window 1's; the
+    // CTA-wide tile counter (ring positions, hand-off slots, ping-pong parity) and the segment counter run on across them
+    struct WinRange {
+        long long t_begin, t_end;
+        int nct;
+    };
+    constexpr bool kWin = kWindows && !kBackward;
+    constexpr int n_win = kWin ? 2 : 1;
+    auto win_range = [&](int wi) {
+        if constexpr (!kWin) {
+            return WinRange{t_begin, t_end, nct};
+        } else {
+            const long long tt = p.win[wi].total_tiles;
+            return WinRange{(tt * blockIdx.x) / gridDim.x, (tt * (blockIdx.x + 1)) / gridDim.x, p.win[wi].n_col_tiles};
+        }
+    };
+    auto win_col0 = [&](int wi, int vr, int j) {
+        if constexpr (!kWin) return tile_col0<kLoss>(p, vr, j);
+        else return tile_col0<kLoss>(p.win[wi].col_start, p.win[wi].col_cnt, p.tiles_per_view, p.bg_pad, vr, j);
+    };
 
     pdl_launch_dependents();
     if (threadIdx.x == 0) {
@@ -1591,14 +1635,24 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         tma_load_2d(sa_addr + pl * L::kPlaneBytes + ka * kAtomBytes, &tmap_rows, a_full, ka * kAtomK,
                                     pl * 2 * p.bl_pad + rb_ * kBlockM);
             };
-            auto load_cols = [&](int stage, int c0) {
+            auto load_cols = [&](int stage, int c0, bool local) {
                 mbar_arrive_expect_tx(b_full + 8 * stage, L::kTileBytes);
+                // local (window 0 of the row-sharded forward): the tile is this rank's own, read from its operand rows
+                const CUtensorMap* map = &tmap_cols;
+                int y = c0, plane_rows = 2 * p.bg_pad;
+                if constexpr (kWin) {
+                    if (local) {
+                        map = &tmap_rows;
+                        y = c0 >= p.bg_pad ? p.bl_pad + (c0 - p.bg_pad - p.row_off) : c0 - p.row_off;
+                        plane_rows = 2 * p.bl_pad;
+                    }
+                }
 #pragma unroll
                 for (int pl = 0; pl < kPlanes; ++pl)
 #pragma unroll
                     for (int ka = 0; ka < L::kAtoms; ++ka)
-                        tma_load_2d(sb_addr + stage * L::kTileBytes + pl * L::kPlaneBytes + ka * kAtomBytes, &tmap_cols,
-                                    b_full + 8 * stage, ka * kAtomK, pl * 2 * p.bg_pad + c0);
+                        tma_load_2d(sb_addr + stage * L::kTileBytes + pl * L::kPlaneBytes + ka * kAtomBytes, map,
+                                    b_full + 8 * stage, ka * kAtomK, pl * plane_rows + y);
             };
             // Early operand loads (backward, see TileParams::early_operand): the row-block tile and the column tiles of
             // the first positions of the first segment leave before griddepcontrol.wait; their column vectors follow it.
@@ -1606,56 +1660,65 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             if (kBackward && p.early_operand != 0) {
                 for (TileWalker w(t_begin, t_end, nct); w.valid() && early < S; w.next()) {
                     if (early == 0) load_rows(w.rb);
-                    load_cols(early, tile_col0<kLoss>(p, w.rb / blocks_per_view, w.j));
+                    load_cols(early, tile_col0<kLoss>(p, w.rb / blocks_per_view, w.j), false);
                     ++early;
                     if (w.seg_last()) break;
                 }
                 pdl_wait();
             }
-            bool synced = p.sync_flags.world == 0;
+            // two windows: the wait for the peers sits in front of window 1 (window 0 needs nobody)
+            bool synced = p.sync_flags.world == 0 || n_win == 2;
             RingPos<S> ring;
             bool wrapped = false;
             int seg = 0;
-            for (TileWalker w(t_begin, t_end, nct); w.valid(); w.next()) {
-                const int it = w.idx;
-                if (w.seg_first()) {
-                    if (it >= early) {
-                        if (seg > 0) mbar_wait(a_empty, (seg - 1) & 1, 100);
-                        load_rows(w.rb);
+            int base = 0;
+            for (int wi = 0; wi < n_win; ++wi) {
+                const WinRange wr = win_range(wi);
+                const bool local = kWin && wi == 0 && p.win0_local != 0;
+                if (wi == 1 && wr.t_end > wr.t_begin)
+                    peer_sync_thread(p.sync_flags, p.sync_epoch, false, p.peer_timeout_ns);
+                for (TileWalker w(wr.t_begin, wr.t_end, wr.nct); w.valid(); w.next()) {
+                    const int it = base + w.idx;
+                    if (w.seg_first()) {
+                        if (it >= early) {
+                            if (seg > 0) mbar_wait(a_empty, (seg - 1) & 1, 100);
+                            load_rows(w.rb);
+                        }
+                        ++seg;
                     }
-                    ++seg;
-                }
-                trace_event(p, 0, it, 0);
-                if (wrapped) mbar_wait(b_empty + 8 * ring.idx, ring.par ^ 1, 101);   // previous use of the stage released
-                trace_event(p, 0, it, 1);
-                if (!synced) {
-                    // In-kernel cross-GPU barrier.  Forward: the row-block tile (local rows) is already in flight, the
-                    // column tiles are what the peers pushed.  Backward: the operands were complete before this kernel
-                    // started (early loads above), the peers' column vectors are what the barrier protects.
-                    peer_sync_thread(p.sync_flags, p.sync_epoch, blockIdx.x == 0 && !p.sync_presignaled, p.peer_timeout_ns);
-                    synced = true;
-                }
-                const int c0 = tile_col0<kLoss>(p, w.rb / blocks_per_view, w.j);
-                if (it >= early) load_cols(ring.idx, c0);
-                if constexpr (kBackward) {
-                    const uint32_t cv = smem_base + L::kOffCv + ring.idx * (2 * kBlockN * 4);
-                    mbar_arrive_expect_tx(cv_full + 8 * ring.idx, L::kColvecBytes);
-                    bulk_load_1d(cv, p.colvec + c0, kBlockN * 4, cv_full + 8 * ring.idx);
-                    bulk_load_1d(cv + kBlockN * 4, p.colvec + 2 * p.bg_pad + c0, kBlockN * 4, cv_full + 8 * ring.idx);
-                }
-                if (ring.idx == S - 1) wrapped = true;
-                ring.advance();
-                if (kBackward && w.seg_last()) {
-                    // hand two empty stages to the flush warpgroup: staging space of the accumulator flush
+                    trace_event(p, 0, it, 0);
+                    if (wrapped) mbar_wait(b_empty + 8 * ring.idx, ring.par ^ 1, 101);   // previous use of the stage released
+                    trace_event(p, 0, it, 1);
+                    if (!synced) {
+                        // In-kernel cross-GPU barrier.  Forward: the row-block tile (local rows) is already in flight, the
+                        // column tiles are what the peers pushed.  Backward: the operands were complete before this kernel
+                        // started (early loads above), the peers' column vectors are what the barrier protects.
+                        peer_sync_thread(p.sync_flags, p.sync_epoch, blockIdx.x == 0 && !p.sync_presignaled, p.peer_timeout_ns);
+                        synced = true;
+                    }
+                    const int c0 = win_col0(wi, w.rb / blocks_per_view, w.j);
+                    if (it >= early) load_cols(ring.idx, c0, local);
+                    if constexpr (kBackward) {
+                        const uint32_t cv = smem_base + L::kOffCv + ring.idx * (2 * kBlockN * 4);
+                        mbar_arrive_expect_tx(cv_full + 8 * ring.idx, L::kColvecBytes);
+                        bulk_load_1d(cv, p.colvec + c0, kBlockN * 4, cv_full + 8 * ring.idx);
+                        bulk_load_1d(cv + kBlockN * 4, p.colvec + 2 * p.bg_pad + c0, kBlockN * 4, cv_full + 8 * ring.idx);
+                    }
+                    if (ring.idx == S - 1) wrapped = true;
+                    ring.advance();
+                    if (kBackward && w.seg_last()) {
+                        // hand two empty stages to the flush warpgroup: staging space of the accumulator flush
 #pragma unroll 1
-                    for (int k = 0; k < 2; ++k) {
-                        if (wrapped) mbar_wait(b_empty + 8 * ring.idx, ring.par ^ 1, 102);
-                        mbar_arrive(b_full + 8 * ring.idx);
-                        mbar_arrive(cv_full + 8 * ring.idx);      // keeps the phase of cv_full in step with the ring position
-                        if (ring.idx == S - 1) wrapped = true;
-                        ring.advance();
+                        for (int k = 0; k < 2; ++k) {
+                            if (wrapped) mbar_wait(b_empty + 8 * ring.idx, ring.par ^ 1, 102);
+                            mbar_arrive(b_full + 8 * ring.idx);
+                            mbar_arrive(cv_full + 8 * ring.idx);      // keeps the phase of cv_full in step with the ring position
+                            if (ring.idx == S - 1) wrapped = true;
+                            ring.advance();
+                        }
                     }
                 }
+                base += static_cast<int>(wr.t_end - wr.t_begin);
             }
         }
     } else if (warp >= kScoreWarp0 && warp < kScoreWarp0 + kNumIssuers) {
@@ -1670,8 +1733,11 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         RingPos<kSlots> slot, freed;          // freed: slot of tile idx - NB (the buffer's previous tenant)
         int buf = 0;
         int seg_seen = 0;
-        for (TileWalker w(t_begin, t_end, nct); w.valid(); w.next()) {
-            const int idx = w.idx;
+        int base = 0;
+        for (int wi = 0; wi < n_win; ++wi) {
+        const WinRange wr = win_range(wi);
+        for (TileWalker w(wr.t_begin, wr.t_end, wr.nct); w.valid(); w.next()) {
+            const int idx = base + w.idx;
             if (w.seg_first()) {
                 mbar_wait(a_full, seg_seen & 1, 200);      // every issuer observes every phase
                 ++seg_seen;
@@ -1726,6 +1792,8 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                     ring.advance();
                 }
             }
+        }
+        base += static_cast<int>(wr.t_end - wr.t_begin);
         }
     } else if (kBackward && warp >= kGradWarp0 && warp < kFlushWarp0 + 4) {
         // ================================ UMMA issuers: gradient MMAs / flush warpgroup ================================
@@ -1866,7 +1934,47 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             ring.advance();
         }
     } else if (!kBackward && warp == kScoreWarp0 + kNumIssuers) {
-        // ================================ forward: the spare warp primes the backward ================================
+        // ================================ forward: the spare warp ================================
+        // Row-sharded fused step: pushes this CTA's share of the rank's operand rows into every rank's global operand
+        // matrix (one multimem.st per 16 bytes through the NVSwitch, or one store per peer) while the other warps work on
+        // window 0; the warp whose push is performed last publishes the epoch (TileParams::n_windows).
+        if (kWin && p.push_peers.world > 0) {
+            constexpr int kVecPerRow = D * 2 / 16;                  // 16-byte pieces of one bf16 operand row
+            constexpr int kRowsPerIter = kVecPerRow >= 32 ? 1 : 32 / kVecPerRow;
+            const int sub = kVecPerRow >= 32 ? 0 : lane / kVecPerRow;
+            const uint4* src = static_cast<const uint4*>(p.push_src);
+            for (int r = static_cast<int>(blockIdx.x) * kRowsPerIter + sub; r < 2 * p.bl_pad; r += gridDim.x * kRowsPerIter) {
+                const int v = r >= p.bl_pad ? 1 : 0;
+                const int img = r - v * p.bl_pad;
+                if (img >= p.b_loc) continue;
+                const size_t dst_row = static_cast<size_t>(v) * p.bg_pad + p.row_off + img;
+                for (int q = kVecPerRow >= 32 ? lane : lane % kVecPerRow; q < kVecPerRow; q += 32) {
+                    const uint4 val = __ldcg(src + static_cast<size_t>(r) * kVecPerRow + q);
+                    if (p.push_peers.mc != nullptr) {
+                        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(
+                                         static_cast<uint4*>(p.push_peers.mc) + dst_row * kVecPerRow + q),
+                                     "f"(__uint_as_float(val.x)), "f"(__uint_as_float(val.y)), "f"(__uint_as_float(val.z)),
+                                     "f"(__uint_as_float(val.w))
+                                     : "memory");
+                    } else {
+                        for (int t = 0; t < p.push_peers.world; ++t)
+                            static_cast<uint4*>(p.push_peers.ptr[t])[dst_row * kVecPerRow + q] = val;
+                    }
+                }
+            }
+            __threadfence_system();                      // this thread's peer stores are performed
+            __syncwarp();
+            if (lane == 0 && atomicAdd(p.push_ticket, 1u) == gridDim.x - 1) {
+                *p.push_ticket = 0u;
+                __threadfence();
+                const unsigned int target = __ldcg(p.sync_epoch);
+                for (int t = 0; t < p.sync_flags.world; ++t) {
+                    unsigned int* remote = static_cast<unsigned int*>(p.sync_flags.ptr[t]) + p.sync_flags.rank;
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(target) : "memory");
+                }
+            }
+            __syncwarp();
+        }
         if (p.prime_dacc != nullptr) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * 32 + lane; i < p.prime_dacc_vec4;
@@ -1883,7 +1991,11 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         const int row_in_block = quarter * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
         const uint32_t cv_base = smem_base + L::kOffCv;
-        const int n = static_cast<int>(t_end - t_begin);
+        int n = 0;                                            // tiles of this CTA, all windows
+        for (int wi = 0; wi < n_win; ++wi) {
+            const WinRange wr = win_range(wi);
+            n += static_cast<int>(wr.t_end - wr.t_begin);
+        }
         // loop invariants out of the constant bank, once
         Hot h;
         h.k2 = p.k2;
@@ -1913,13 +2025,18 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         // positions), in hand-off slot it % kSlots and TMEM buffer it % NB; the counters below step by two tiles.
         int slot = pair, slot_par = 0;
         int buf = pair % NB;
-        int idx0 = 0, seg = 0;
-        int rb = static_cast<int>(t_begin / nct);
-        int j0 = static_cast<int>(t_begin - static_cast<long long>(rb) * nct);
-        float pre_a = 0.f, pre_l2 = 0.f;     // backward: the next segment's row entries of the column vectors
-        bool have_pre = false;
-        while (idx0 < n) {
-            const int seg_len = min(n - idx0, nct - j0);
+        int seg = 0;
+        int base = 0;                        // tiles of the windows already walked
+        [[maybe_unused]] float pre_a = 0.f, pre_l2 = 0.f;     // backward: the next segment's row entries of the column vectors
+        [[maybe_unused]] bool have_pre = false;
+        for (int wi = 0; wi < n_win; ++wi) {
+        const WinRange wr = win_range(wi);
+        const int n_w = static_cast<int>(wr.t_end - wr.t_begin);
+        int idx0 = 0, seg_w = 0;
+        int rb = static_cast<int>(wr.t_begin / wr.nct);
+        int j0 = static_cast<int>(wr.t_begin - static_cast<long long>(rb) * wr.nct);
+        while (idx0 < n_w) {
+            const int seg_len = min(n_w - idx0, wr.nct - j0);
             // ---- segment setup ----
             RowCtx rc;
             rc.vr = rb / blocks_per_view;                                            // view of this row block
@@ -1950,7 +2067,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                     br.row_a = __ldcg(p.colvec + rc.vr * h.bg_pad + rc.g);
                     br.row_l2 = __ldcg(p.colvec + 2 * h.bg_pad + rc.vr * h.bg_pad + rc.g);
                 }
-                have_pre = idx0 + seg_len < n;
+                have_pre = idx0 + seg_len < n_w;
                 if (have_pre) {
                     const int vr_n = (rb + 1) / blocks_per_view;
                     const int img_n = (rb + 1 - vr_n * blocks_per_view) * kBlockM + row_in_block;
@@ -2000,11 +2117,11 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             }
 
 #pragma unroll 1
-            for (int s = (idx0 ^ pair) & 1; s < seg_len; s += 2) {
-                const int it = idx0 + s;
+            for (int s = ((base + idx0) ^ pair) & 1; s < seg_len; s += 2) {
+                const int it = base + idx0 + s;
                 const int pos = it + pos_off;
                 const int stage = pos & (S - 1), stage_par = (pos >> kLogS) & 1;
-                const int c0 = tile_col0<kLoss>(p, rc.vr, j0 + s);
+                const int c0 = win_col0(wi, rc.vr, j0 + s);
                 const int vc = c0 >= h.bg_pad ? 1 : 0;            // a tile never mixes views
                 const int ic0 = c0 - vc * h.bg_pad;               // image index of the tile's first column
                 // ---- warp-uniform classification (first-argmax rule: does the tile precede the positive in the
@@ -2266,7 +2383,10 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         }
                     }
                     // ... and publish one partial per (CTA, segment) for the finalize kernel
-                    float* dst = p.part + (static_cast<size_t>(blockIdx.x) * p.max_segs + seg) * (kFwdFields * kBlockM) +
+                    // (the partial's slot counts the segments of THIS window: that is how the finalize kernel finds it)
+                    float* dst = (kWin ? p.win[wi].part : p.part) +
+                                 (static_cast<size_t>(blockIdx.x) * (kWin ? p.win[wi].max_segs : p.max_segs) + seg_w) *
+                                     (kFwdFields * kBlockM) +
                                  row_in_block;
                     __stcg(dst + 0 * kBlockM, total);
                     __stcg(dst + 1 * kBlockM, m);
@@ -2296,8 +2416,11 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             if (threadIdx.x == 0 && seg < 2) cta_stamp(p, 2 + 2 * seg);
             idx0 += seg_len;
             ++seg;
+            ++seg_w;
             ++rb;
             j0 = 0;
+        }
+        base += n_w;
         }
     }
 
