@@ -38,6 +38,7 @@
 #pragma once
 
 #include <cstdint>
+#include <type_traits>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -63,9 +64,10 @@ constexpr int kScoreWarp0 = kNumSoftmaxWarps + 1;       // warps 17, 18
 constexpr int kAllocWarp = kScoreWarp0 + 1;             // warp 18 allocates TMEM before it starts issuing
 constexpr int kGradWarp0 = kScoreWarp0 + kNumIssuers;   // warps 19, 20 (backward)
 constexpr int kThreadsForward = 32 * (kNumSoftmaxWarps + 4);                    // 640 (warp 19 idles)
-// One gradient issuer (warp 20) doubles as a flush warp; sharing BOTH (23 warps, 736 threads) compiles and runs but buys
-// no registers: ptxas allocates per warp in units of 512, so 80 registers per thread is the limit down to 22 warps and
-// 96 needs <= 21 warps (which would take the score issuers off the tensor pipe during a flush).
+// One gradient issuer (warp 20) doubles as a flush warp.  Separate warps (25 warps, SIMCLR_BWD_SHARED_FLUSH_WARPS 0) cost
+// registers instead of freeing them: warps are allocated in groups of four, so ptxas budgets 28 warps and caps the kernel
+// at 72 registers (spills reach the softmax loop); sharing BOTH (23 warps) buys none either -- 80 registers per thread is
+// the limit down to 22 warps.  The tile walk is specialised per warp instead (pure issuer / both / pure flusher).
 #ifndef SIMCLR_BWD_SHARED_FLUSH_WARPS
 #define SIMCLR_BWD_SHARED_FLUSH_WARPS 1
 #endif
@@ -1821,13 +1823,19 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             if (warp == kFlushWarp0 + 3 && p.resolve_ambiguous) resolve_ambiguous_rows<kLoss, (D <= 128 ? 1 : 2)>(&p, lane);
         }
 
+        // The tile walk, specialised at compile time for what this warp is: a warp that only issues gets a loop without the
+        // flush's register pressure (the shared loop kept its counters in local memory: LDL / STL in the issuer's per-tile
+        // path, whose latency bounds the pipeline), a warp that only flushes gets one without the issue code.
+        auto walk = [&](auto is_issuer, auto is_flusher) {
+        constexpr bool issuer = decltype(is_issuer)::value;
+        constexpr bool flusher = decltype(is_flusher)::value;
         RingPos<S> ring;
         RingPos<kSlots> slot, prev_slot;      // prev_slot: hand-off slot of tile idx - 1 (deterministic mode)
         int buf = 0;
         int seg = 0;
         for (TileWalker w(t_begin, t_end, nct); w.valid(); w.next()) {
             const int idx = w.idx;
-            if (issuer) {
+            if constexpr (issuer) {
                 // phase 0 of acc_empty = initial zeroing, phase s = flush (and re-zeroing) of segment s-1
                 if (w.seg_first()) mbar_wait(acc_empty, seg & 1, 203);
                 if ((ring.idx & 1) == me) {
@@ -1872,29 +1880,32 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             if (!w.seg_last()) continue;
 
             // ---- end of segment: ring positions ring.idx, ring.idx + 1 are the flush's staging stages ----
-            if (flusher) {
+            if constexpr (flusher) {
                 RingPos<S> st1 = ring;
                 st1.advance();
                 mbar_wait(acc_full, seg & 1, 302);            // every gradient MMA of the segment has completed
                 mbar_wait(b_full + 8 * ring.idx, ring.par, 303);   // the two staging stages are ours
                 mbar_wait(b_full + 8 * st1.idx, st1.par, 304);
                 tc_fence_after_sync();
-                // two 32-column TMEM loads in flight: the load of box q+1 overlaps the shared-memory stores of box q
-                uint32_t ra[32], rb2[32];
-                tmem_ld32(tmem_base + lane_addr + kTmemAcc, ra);
+                // Two 16-column TMEM loads in flight: the load of piece h+1 overlaps the shared-memory stores of piece h.
+                // (16, not 32 columns per load: 64 registers of staging pushed the loop's own counters into local memory.)
+                uint32_t ra[16], rb2[16];
+                tmem_ld16(tmem_base + lane_addr + kTmemAcc, ra);
 #pragma unroll
-                for (int q = 0; q < D / 32; ++q) {
-                    uint32_t (&r)[32] = (q & 1) ? rb2 : ra;
-                    uint32_t (&nxt)[32] = (q & 1) ? ra : rb2;
-                    tmem_ld_wait();
-                    if (q + 1 < D / 32) tmem_ld32(tmem_base + lane_addr + kTmemAcc + (q + 1) * 32, nxt);
-                    tmem_st32_fill(tmem_base + lane_addr + kTmemAcc + q * 32, 0u);     // zero for the next segment
+                for (int h = 0; h < D / 16; ++h) {
+                    uint32_t (&r)[16] = (h & 1) ? rb2 : ra;
+                    uint32_t (&nxt)[16] = (h & 1) ? ra : rb2;
+                    tmem_ld_wait16(r);
+                    if (h + 1 < D / 16) tmem_ld16(tmem_base + lane_addr + kTmemAcc + (h + 1) * 16, nxt);
+                    const int q = h >> 1;                     // 32-column box
+                    if (h & 1) tmem_st32_fill(tmem_base + lane_addr + kTmemAcc + q * 32, 0u);   // zero for the next segment
                     const int stage = (q / kBoxesPerStage) == 0 ? ring.idx : st1.idx;
                     const uint32_t row_addr = sb_addr + stage * L::kTileBytes + (q % kBoxesPerStage) * kAtomBytes +
                                               row_in_block * 128;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        sts_v4(row_addr + ((j ^ (row_in_block & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    for (int j = 0; j < 4; ++j)
+                        sts_v4(row_addr + ((((h & 1) * 4 + j) ^ (row_in_block & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2],
+                               r[4 * j + 3]);
                 }
                 tmem_st_wait();
                 tc_fence_before_sync();
@@ -1933,6 +1944,10 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             ring.advance();
             ring.advance();
         }
+        };
+        if (issuer && flusher) walk(std::true_type{}, std::true_type{});
+        else if (issuer) walk(std::true_type{}, std::false_type{});
+        else walk(std::false_type{}, std::true_type{});
     } else if (!kBackward && warp == kScoreWarp0 + kNumIssuers) {
         // ================================ forward: the spare warp ================================
         // Row-sharded fused step: pushes this CTA's share of the rank's operand rows into every rank's global operand
