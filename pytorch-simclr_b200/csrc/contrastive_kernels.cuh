@@ -1553,7 +1553,8 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         long long t_begin, t_end;
         int nct;
     };
-    constexpr bool kWin = kWindows && !kBackward;
+    constexpr bool kWin = kWindows;
+    static_assert(!(kWindows && kDet), "the deterministic accumulator slots are laid out for one window");
     constexpr int n_win = kWin ? 2 : 1;
     auto win_range = [&](int wi) {
         if constexpr (!kWin) {
@@ -1642,7 +1643,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 // local (window 0 of the row-sharded forward): the tile is this rank's own, read from its operand rows
                 const CUtensorMap* map = &tmap_cols;
                 int y = c0, plane_rows = 2 * p.bg_pad;
-                if constexpr (kWin) {
+                if constexpr (kWin && !kBackward) {
                     if (local) {
                         map = &tmap_rows;
                         y = c0 >= p.bg_pad ? p.bl_pad + (c0 - p.bg_pad - p.row_off) : c0 - p.row_off;
@@ -1660,9 +1661,10 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             // the first positions of the first segment leave before griddepcontrol.wait; their column vectors follow it.
             int early = 0;
             if (kBackward && p.early_operand != 0) {
-                for (TileWalker w(t_begin, t_end, nct); w.valid() && early < S; w.next()) {
+                const WinRange w0 = win_range(0);
+                for (TileWalker w(w0.t_begin, w0.t_end, w0.nct); w.valid() && early < S; w.next()) {
                     if (early == 0) load_rows(w.rb);
-                    load_cols(early, tile_col0<kLoss>(p, w.rb / blocks_per_view, w.j), false);
+                    load_cols(early, win_col0(0, w.rb / blocks_per_view, w.j), false);
                     ++early;
                     if (w.seg_last()) break;
                 }
@@ -1676,7 +1678,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             int base = 0;
             for (int wi = 0; wi < n_win; ++wi) {
                 const WinRange wr = win_range(wi);
-                const bool local = kWin && wi == 0 && p.win0_local != 0;
+                const bool local = kWin && !kBackward && wi == 0 && p.win0_local != 0;
                 if (wi == 1 && wr.t_end > wr.t_begin)
                     peer_sync_thread(p.sync_flags, p.sync_epoch, false, p.peer_timeout_ns);
                 for (TileWalker w(wr.t_begin, wr.t_end, wr.nct); w.valid(); w.next()) {
@@ -1833,8 +1835,11 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         RingPos<kSlots> slot, prev_slot;      // prev_slot: hand-off slot of tile idx - 1 (deterministic mode)
         int buf = 0;
         int seg = 0;
-        for (TileWalker w(t_begin, t_end, nct); w.valid(); w.next()) {
-            const int idx = w.idx;
+        int base = 0;
+        for (int wi = 0; wi < n_win; ++wi) {
+        const WinRange wr = win_range(wi);
+        for (TileWalker w(wr.t_begin, wr.t_end, wr.nct); w.valid(); w.next()) {
+            const int idx = base + w.idx;
             if constexpr (issuer) {
                 // phase 0 of acc_empty = initial zeroing, phase s = flush (and re-zeroing) of segment s-1
                 if (w.seg_first()) mbar_wait(acc_empty, seg & 1, 203);
@@ -1932,7 +1937,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
 #if SIMCLR_FLUSH_WAIT_READ
                     bulk_wait_group_read0();
 #else
-                    if (idx == w.n - 1) bulk_wait_group0();
+                    if (wi == n_win - 1 && w.idx == w.n - 1) bulk_wait_group0();
                     else bulk_wait_group_read0();
 #endif
                     mbar_arrive(b_empty + 8 * ring.idx);
@@ -1944,6 +1949,8 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             ring.advance();
             ring.advance();
         }
+        base += static_cast<int>(wr.t_end - wr.t_begin);
+        }
         };
         if (issuer && flusher) walk(std::true_type{}, std::true_type{});
         else if (issuer) walk(std::true_type{}, std::false_type{});
@@ -1953,7 +1960,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         // Row-sharded fused step: pushes this CTA's share of the rank's operand rows into every rank's global operand
         // matrix (one multimem.st per 16 bytes through the NVSwitch, or one store per peer) while the other warps work on
         // window 0; the warp whose push is performed last publishes the epoch (TileParams::n_windows).
-        if (kWin && p.push_peers.world > 0) {
+        if (kWin && !kBackward && p.push_peers.world > 0) {
             constexpr int kVecPerRow = D * 2 / 16;                  // 16-byte pieces of one bf16 operand row
             constexpr int kRowsPerIter = kVecPerRow >= 32 ? 1 : 32 / kVecPerRow;
             const int sub = kVecPerRow >= 32 ? 0 : lane / kVecPerRow;
