@@ -338,6 +338,13 @@ __global__ void __launch_bounds__(kBlockM) forward_finalize_kernel(const TilePar
     pdl_wait();
     ktrace_begin(p.ktrace, 4);
     forward_finalize_rowblock<kLoss, kFused>(p, rb, tid, ix, w_row, red, flags);
+    if (kFused && p.amb_done != nullptr) {
+        // the list of rows for the exact re-scoring is complete when every block has counted itself: the blocks of the
+        // backward finalize kernel that work it off start ahead of their grid dependency and wait for this count instead
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(p.amb_done, 1u);
+    }
     ktrace_end(p.ktrace, 4);
 }
 
@@ -350,9 +357,47 @@ template <int D, int kLoss, bool kDet>
 __global__ void __launch_bounds__(512) backward_finalize_kernel(const TileParams p) {
     static_assert(16 * kBwdFinBlocksPerRowBlock == kBlockM, "one warp per row");
     pdl_launch_dependents();
-    const int rb = blockIdx.x / kBwdFinBlocksPerRowBlock;
-    const int sub = blockIdx.x % kBwdFinBlocksPerRowBlock;
+    // The first kResolveBlocks blocks (fused one-GPU step, TileParams::resolve_ambiguous) re-score the rows the forward
+    // finalize kernel listed; the others are the regular blocks, eight per row block.
+    const int n_extra = p.resolve_ambiguous ? kResolveBlocks : 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (static_cast<int>(blockIdx.x) < n_extra) {
+        // Nothing here depends on the backward tile kernel: the list, the candidates and the inputs come from the forward
+        // finalize kernel, two launches upstream, so these blocks work while the tile kernel's last CTAs drain (they become
+        // resident as soon as the first tile CTAs exit).  Programmatic launch does not order them behind that kernel,
+        // though -- on a small problem they can start while it is still running: they wait until all of its blocks have
+        // counted themselves (amb_done; those blocks were resident before any block of this kernel could be).  The block
+        // that finishes last reduces the loss statistics (behind the grid dependency, like the regular path).
+        __shared__ int last;
+        if (threadIdx.x == 0) {
+            unsigned int seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.amb_done) : "memory");
+                if (seen >= static_cast<unsigned int>(p.n_row_blocks)) break;
+                __nanosleep(100);
+            } while (true);
+        }
+        __syncthreads();
+        if (__ldcg(p.amb_cnt) == 0u) return;               // nothing listed (the usual case): the regular path finishes
+        resolve_ambiguous_rows<kLoss, (D <= 128 ? 1 : 2)>(p, static_cast<int>(blockIdx.x) * 16 + warp, kResolveBlocks * 16, lane);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            last = atomicAdd(p.amb_ticket, 1u) == static_cast<unsigned int>(kResolveBlocks) - 1u ? 1 : 0;
+            if (last) *p.amb_ticket = 0u;
+        }
+        __syncthreads();
+        if (last && warp == 0) {
+            __threadfence();
+            pdl_wait();
+            finish_forward_stats(p, lane);
+        }
+        return;
+    }
+    const int block = static_cast<int>(blockIdx.x) - n_extra;
+    const int rb = block / kBwdFinBlocksPerRowBlock;
+    const int sub = block % kBwdFinBlocksPerRowBlock;
+    const int n_regular = p.n_row_blocks * kBwdFinBlocksPerRowBlock;
     if (p.ktrace != nullptr && threadIdx.x == 0) {
         pdl_wait();
         ktrace_begin(p.ktrace, 5);
@@ -377,12 +422,13 @@ __global__ void __launch_bounds__(512) backward_finalize_kernel(const TileParams
             float a = 0.f;
 #pragma unroll
             for (int w = 0; w < 16; ++w) a += red[w][q][k];
-            p.bn_partial[(static_cast<size_t>(blockIdx.x) * 2 + q) * D + k] = a;
+            p.bn_partial[(static_cast<size_t>(block) * 2 + q) * D + k] = a;
         }
     }
-    if (p.finish_stats && blockIdx.x == gridDim.x - 1 && warp == 15) {
+    if (p.finish_stats && block == n_regular - 1 && warp == 15) {
         pdl_wait();
-        finish_forward_stats(p, lane);
+        // (rows listed for the exact re-scoring: the extra blocks finish the statistics when they are through)
+        if (!(p.resolve_ambiguous && __ldcg(p.amb_cnt) != 0u)) finish_forward_stats(p, lane);
     }
     ktrace_end(p.ktrace, 5);
 }

@@ -762,11 +762,11 @@ int forward_impl(int loss, const void* operand_rows, const void* operand_cols, i
             p.cand = w.cand;
             p.band = (loss == SIMCLR_LOSS_NTXENT ? s.k2 : 1.0f) * kBandRel;
             if (defer_stats && fused == nullptr && p.x1 != nullptr) {
-                // fused one-GPU step: the exact re-scoring is left to the backward tile kernel (header words 1, 2 of the
+                // fused one-GPU step: the exact re-scoring is left to the backward tile kernel (header words 1 - 3 of the
                 // workspace: zeroed by the prepare kernel with the ticket)
                 p.defer_accuracy = 1;
                 p.amb_cnt = w.ticket + 1;
-                p.amb_hits = w.ticket + 2;
+                p.amb_done = w.ticket + 3;
                 p.amb_list = w.amb_list;
             }
         }
@@ -958,7 +958,8 @@ int backward_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t 
             // the forward finalize kernel of this fused step listed the rows it could not decide (forward_impl)
             p.resolve_ambiguous = 1;
             p.amb_cnt = fw.ticket + 1;
-            p.amb_hits = fw.ticket + 2;
+            p.amb_ticket = fw.ticket + 2;
+            p.amb_done = fw.ticket + 3;
             p.amb_list = fw.amb_list;
             p.cand_cnt = fw.cand_cnt;
             p.cand = fw.cand;
@@ -981,10 +982,12 @@ int backward_impl(int loss, const void* x_batch1, const void* x_batch2, int64_t 
         return rc;
     cudaError_t fin_rc = cudaSuccess;
     if (!(stages & kStageBwdFin)) return SIMCLR_OK;
+    // (+ the blocks that re-score the rows the forward finalize kernel listed, see resolve_ambiguous_rows)
+    const int fin_blocks = g.n_row_blocks * kBwdFinBlocksPerRowBlock + (p.resolve_ambiguous ? kResolveBlocks : 0);
 #define SIMCLR_BFIN(DV)                                                                                  \
     case DV:                                                                                             \
-        if (loss == SIMCLR_LOSS_NTXENT) fin_rc = deterministic ? launch_pdl(backward_finalize_kernel<DV, kNtXent, true>, dim3(g.n_row_blocks * kBwdFinBlocksPerRowBlock), dim3(512), 0, st, p) : launch_pdl(backward_finalize_kernel<DV, kNtXent, false>, dim3(g.n_row_blocks * kBwdFinBlocksPerRowBlock), dim3(512), 0, st, p); \
-        else fin_rc = deterministic ? launch_pdl(backward_finalize_kernel<DV, kModified, true>, dim3(g.n_row_blocks * kBwdFinBlocksPerRowBlock), dim3(512), 0, st, p) : launch_pdl(backward_finalize_kernel<DV, kModified, false>, dim3(g.n_row_blocks * kBwdFinBlocksPerRowBlock), dim3(512), 0, st, p); \
+        if (loss == SIMCLR_LOSS_NTXENT) fin_rc = deterministic ? launch_pdl(backward_finalize_kernel<DV, kNtXent, true>, dim3(fin_blocks), dim3(512), 0, st, p) : launch_pdl(backward_finalize_kernel<DV, kNtXent, false>, dim3(fin_blocks), dim3(512), 0, st, p); \
+        else fin_rc = deterministic ? launch_pdl(backward_finalize_kernel<DV, kModified, true>, dim3(fin_blocks), dim3(512), 0, st, p) : launch_pdl(backward_finalize_kernel<DV, kModified, false>, dim3(fin_blocks), dim3(512), 0, st, p); \
         break;
     switch (g.d_pad) {
         SIMCLR_BFIN(64)

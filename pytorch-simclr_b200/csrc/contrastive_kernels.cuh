@@ -233,12 +233,14 @@ struct TileParams {
     const float* zrows;
     PeerTable zrows_peers;
     // Fused one-GPU step: the forward finalize kernel only LISTS the rows that need the exact re-scoring (amb_cnt /
-    // amb_list, defer_accuracy) and an otherwise idle flush warp of the backward tile kernel works the list off while the
-    // tile pipeline runs (resolve_ambiguous), adding the rows it confirms to amb_hits; the backward finalize kernel adds
-    // that to the count.  Nothing of the exact arithmetic then sits between the two tile kernels.
+    // amb_list, defer_accuracy); extra blocks of the backward finalize kernel work the list off (resolve_ambiguous, see
+    // resolve_ambiguous_rows), marking the entries of the rows that lose their positive, and the last of them to finish
+    // (amb_ticket) adds the unmarked ones to the count.  Nothing of the exact arithmetic then sits between the two tile
+    // kernels or inside them.
     unsigned int* amb_cnt;     // [1] zero on entry (workspace header)
-    unsigned int* amb_hits;    // [1] zero on entry (workspace header)
-    int* amb_list;             // [2*bl_pad] row slots
+    unsigned int* amb_ticket;  // [1] zero on entry, left zero (workspace header)
+    unsigned int* amb_done;    // [1] zero on entry: forward finalize blocks that have finished listing (workspace header)
+    int* amb_list;             // [2*bl_pad] row slots (-1 - slot: re-scored and lost)
     int defer_accuracy;
     int resolve_ambiguous;
     // backward finalize, row-sharded fused step: add up the ranks' statistics [world][4] (fixed order) into stats / loss_out
@@ -950,8 +952,10 @@ SIMCLR_DEVICE float reference_logit(const TileParams& p, float s) {
 // Does the row (view vr, global image g) keep its positive as FIRST argmax among the columns of its recorded candidate
 // chunks (list[i] = first global column of a kCandRange-column chunk)?  Whole warp.  All columns of a chunk are in
 // flight at once: a chunk costs one memory latency.
+// (u_begin, u_count: the columns [u_begin, u_begin + u_count) of every chunk only; whole chunks by default)
 template <int kLoss, int kVecs, int kRound = kCandRange>
-SIMCLR_DEVICE bool exact_first_argmax_v(const TileParams& p, int vr, int g, const int* list, int n, int lane) {
+SIMCLR_DEVICE bool exact_first_argmax_v(const TileParams& p, int vr, int g, const int* list, int n, int lane, int u_begin = 0,
+                                        int u_count = kCandRange) {
     static_assert(kCandRange % kRound == 0, "a chunk is re-scored in whole rounds");
     const ZRow row = zrow_of<kLoss>(p, vr, g), pos = zrow_of<kLoss>(p, 1 - vr, g);
     float4 zr[kVecs], zp[kVecs];
@@ -965,7 +969,7 @@ SIMCLR_DEVICE bool exact_first_argmax_v(const TileParams& p, int vr, int g, cons
     for (int i = 0; i < n && ok; ++i) {
         const int first = __ldcg(list + i);
         const int vc = first >= p.bg_pad ? 1 : 0;            // a chunk never mixes views
-        for (int u0 = 0; u0 < kCandRange && ok; u0 += kRound) {
+        for (int u0 = u_begin; u0 < u_begin + u_count && ok; u0 += kRound) {
             const int ic0 = first + u0 - vc * p.bg_pad;
             float4 zc[kRound][kVecs];
 #pragma unroll
@@ -997,23 +1001,49 @@ SIMCLR_DEVICE bool exact_first_argmax(const TileParams& p, int vr, int g, const 
                       : exact_first_argmax_v<kLoss, 2>(p, vr, g, list, n, lane);
 }
 
-// One warp of the backward tile kernel (fused one-GPU step): work off this CTA's share of the rows the forward finalize
-// kernel listed as undecided.  Not inlined: its registers must not count against the tile kernel's roles.
+// Fused one-GPU step: the rows whose accuracy decision the forward finalize kernel left open (amb_list, usually none, a
+// few per step on unrelated inputs) are re-scored exactly by kResolveBlocks extra blocks of the BACKWARD FINALIZE kernel,
+// one warp per candidate COLUMN (row, positive and column re-derived from the inputs: ~700 instructions behind a handful
+// of dependent loads), `worker` of `n_workers` warps.  The list is walked in batches of 32 entries -- lane l holds entry
+// base + l and its number of chunks -- and the batch's columns are dealt round-robin.  A column that beats the positive
+// marks the row's list entry (slot -> -1 - slot: the same value whoever writes it); finish_forward_stats counts the
+// unmarked entries.  (First built into an idle flush warp of the backward tile kernel: under that kernel's load one
+// 16-column chunk of the modified loss took 46 us of the warp, which the CTA's first accumulator flush then waited
+// for -- two listed rows cost the 2N = 8192 step +17 us with a warm L2 and +45 us with a cold one.)
+constexpr int kResolveBlocks = 16;
 template <int kLoss, int kVecs>
-__device__ __noinline__ void resolve_ambiguous_rows(const TileParams* pp, int lane) {
-    const TileParams& p = *pp;
+SIMCLR_DEVICE void resolve_ambiguous_rows(const TileParams& p, int worker, int n_workers, int lane) {
     const unsigned int n = __ldcg(p.amb_cnt);
-    for (unsigned int i = blockIdx.x; i < n; i += gridDim.x) {
-        const int slot = __ldcg(p.amb_list + i);
-        const int vr = slot >= p.bl_pad ? 1 : 0;
-        const int g = p.row_off + slot - vr * p.bl_pad;
-        const int n_c = static_cast<int>(__ldcg(p.cand_cnt + slot));
-        // rounds of 8 / 4 columns: the routine lives in an 80-register kernel
-        const bool ok = exact_first_argmax_v<kLoss, kVecs, 8 / kVecs>(p, vr, g, p.cand + static_cast<size_t>(slot) * kCandMax, n_c, lane);
-        if (lane == 0) {
-            p.cand_cnt[slot] = 0u;                            // left zero for the next call
-            if (ok) atomicAdd(p.amb_hits, 1u);
+    int next = worker;                         // this warp's next item, counted from the start of the current batch
+    for (unsigned int base = 0; base < n; base += 32) {
+        const unsigned int i = base + lane;
+        // (an entry another warp has already marked still counts its chunks: every warp must see the same enumeration)
+        const int entry = i < n ? __ldcg(p.amb_list + i) : 0;
+        const int slot = entry >= 0 ? entry : -1 - entry;
+        int n_c = 0;
+        if (i < n) n_c = min(static_cast<int>(__ldcg(p.cand_cnt + slot)), kCandMax);
+        int incl = n_c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
+        const int excl = incl - n_c;
+        const int items = __shfl_sync(0xffffffffu, incl, 31) * kCandRange;
+        int jj = next;
+        for (; jj < items; jj += n_workers) {
+            const int ci = jj / kCandRange, u = jj - ci * kCandRange;
+            const unsigned int owner = __ballot_sync(0xffffffffu, excl <= ci && ci < excl + n_c);
+            const int src = __ffs(owner) - 1;
+            const int slot_s = __shfl_sync(0xffffffffu, slot, src);
+            const int c = ci - __shfl_sync(0xffffffffu, excl, src);
+            const int vr = slot_s >= p.bl_pad ? 1 : 0;
+            const int g = p.row_off + slot_s - vr * p.bl_pad;
+            const bool ok = exact_first_argmax_v<kLoss, kVecs, 1>(p, vr, g, p.cand + static_cast<size_t>(slot_s) * kCandMax + c, 1,
+                                                                  lane, u, 1);
+            if (!ok && lane == 0) p.amb_list[base + src] = -1 - slot_s;
+        }
+        next = jj - items;
     }
 }
 
@@ -1117,7 +1147,7 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
     }
     if (kFused && p.cand_cnt != nullptr) {
         // fused step: list the undecided rows (rare) for the backward tile kernel's idle flush warp; they count as
-        // misses here and are added back through amb_hits
+        // misses here and are added back by the backward finalize kernel
         if (ambiguous) {
             p.amb_list[atomicAdd(p.amb_cnt, 1u)] = slot;
             hit = 0.f;
@@ -1433,8 +1463,18 @@ SIMCLR_DEVICE void finish_forward_stats(const TileParams& p, int lane) {
         s0 = warp_sum(s0);
         s1 = warp_sum(s1);
         s2 = warp_sum(s2);
-        // rows the backward tile kernel re-scored exactly and confirmed (fused step, see TileParams::amb_hits)
-        if (p.amb_hits != nullptr) s2 += static_cast<float>(__ldcg(p.amb_hits));
+        // rows the backward tile kernel re-scored exactly (fused step, see resolve_ambiguous_rows): an unmarked list entry
+        // is a confirmed hit; the rows' candidate counters are left zero for the next call
+        if (p.amb_cnt != nullptr && p.resolve_ambiguous) {
+            const unsigned int n_amb = __ldcg(p.amb_cnt);
+            float confirmed = 0.f;
+            for (unsigned int i = lane; i < n_amb; i += 32) {
+                const int entry = __ldcg(p.amb_list + i);
+                confirmed += entry >= 0 ? 1.f : 0.f;
+                p.cand_cnt[entry >= 0 ? entry : -1 - entry] = 0u;
+            }
+            s2 += warp_sum(confirmed);
+        }
     }
     if (lane == 0) {
         p.stats[0] = s0;
@@ -1820,9 +1860,6 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             tmem_st_wait();
             tc_fence_before_sync();
             mbar_arrive(acc_empty);
-            // the last flush warp now has nothing to do until the first segment ends: it re-scores the rows whose
-            // accuracy decision the forward finalize kernel left open (fused step; usually none) under the tile pipeline
-            if (warp == kFlushWarp0 + 3 && p.resolve_ambiguous) resolve_ambiguous_rows<kLoss, (D <= 128 ? 1 : 2)>(&p, lane);
         }
 
         // The tile walk, specialised at compile time for what this warp is: a warp that only issues gets a loop without the
