@@ -20,7 +20,8 @@ LIB_PATH = os.path.join(LIB_DIR, "libsimclr_b200.so")
 TRACE_LIB_PATH = os.path.join(LIB_DIR, "libsimclr_b200_trace.so")      # the same library with the debug stamps compiled in
 STAMP = LIB_PATH + ".stamp"
 SOURCES = ["capi.cu"]
-DEPS = ["capi.cu", "contrastive_kernels.cuh", "aux_kernels.cuh", "selftest.cuh", "probes.cuh", "sm100_ptx.cuh", "row_math.cuh",
+DEPS = ["capi.cu", "contrastive_kernels.cuh", "aux_kernels.cuh", "head_kernels.cuh", "selftest.cuh", "probes.cuh", "sm100_ptx.cuh",
+        "row_math.cuh",
         os.path.join("..", "..", "include", "simclr_b200.h"), os.path.join("..", "..", "include", "simclr_b200_debug.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]

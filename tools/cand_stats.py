@@ -47,5 +47,4 @@ for kind, label in ((0, "ntxent"), (1, "modified")):
             torch.cuda.synchronize()
         alone_us = e0.elapsed_time(e1) * 1e3 / 20
         print(f"{label:8s} {data:10s}: first-level triggers {int(t[32]):8d}  rescans {int(t[33]):8d}  rows in band {int(t[34]):8d}  cycles in rescans {int(t[35]):9d} (inside routine {int(t[36])}, in {int(t[38])} TMEM loads {int(t[37])})  "
-              f"| resolve: longest routine {int(t[40])} ns, longest re-scoring {int(t[41])} ns, items {int(t[42])} | "
               f"(warp-tiles: {64 * 64 * 16 // (1 if kind == 0 else 2)}; fwd tile {int(t[3]) - int(t[2])} ns, alone {alone_us:.1f} us) acc rows {float(step.stats[2]):.0f}")

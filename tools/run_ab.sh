@@ -1,3 +1,5 @@
+# GPU box: same-box A/B of two builds of the library (lib/libsimclr_b200_prev.so against the current one), twice each.
+#   gpurun --timeout 900 -- bash tools/run_ab.sh
 cd $GRAFT_REPO_ROOT
 for i in 1 2; do
 for v in prev cur; do

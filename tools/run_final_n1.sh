@@ -1,3 +1,5 @@
+# GPU box: the -m gpu tests, the default bench line, the reference arm and smoke() (outputs under gpurun_out/r02b_*).
+#   gpurun --timeout 2400 -- bash tools/run_final_n1.sh
 cd $GRAFT_REPO_ROOT
 timeout 900 python -m pytest tests/ -x -q -m gpu > gpurun_out/r02b_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02b_pytest_gpu.log
 timeout 600 python bench.py > gpurun_out/r02b_bench_n1.json 2> gpurun_out/r02b_bench_n1.err; echo "bench rc=$?"

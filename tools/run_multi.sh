@@ -1,3 +1,5 @@
+# GPU box, N = $1 GPUs: tests/distributed_check.py and the bench line (short cross-GPU watchdog).
+#   gpurun --gpus N --timeout 1200 -- bash tools/run_multi.sh N
 export SIMCLR_B200_PEER_TIMEOUT_S=20
 cd $GRAFT_REPO_ROOT
 N=$1

@@ -1,3 +1,7 @@
+# GPU box: ncu launch list + ncu --set full captures of tools/profile_step.py (each after a plain run of the same command),
+# exported as CSV (the .ncu-rep files stay in /tmp: gpurun_out is limited to 64 MiB); then, here:
+#   python tools/ncu_summary.py gpurun_out/r02b_ncu_full_tile_kernels.csv gpurun_out/r02b_ncu_full_rowwise_kernels.csv --out profiles/r02b_ncu_summary.md
+#   gpurun --timeout 1500 -- bash tools/run_ncu.sh
 cd $GRAFT_REPO_ROOT
 CMD="python tools/profile_step.py --steps 3"
 $CMD > gpurun_out/r02b_profile_step_plain.log 2>&1 &&
