@@ -232,6 +232,22 @@ def timed_replays(torch, graph, flush, n, warm):
     return sum(ms) / n, min(ms)
 
 
+def replay_times(torch, graph, flush, n, warm):
+    """The individual CUDA-event times (ms) of n graph replays, L2 flushed before each."""
+    for _ in range(warm):
+        flush.zero_()
+        graph.replay()
+    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+    torch.cuda.synchronize()
+    for a, b in pairs:
+        flush.zero_()
+        a.record()
+        graph.replay()
+        b.record()
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in pairs]
+
+
 def graph_of_steps(torch, step, sets, n, side, first=0):
     """One CUDA graph holding n fused steps; step i reads / writes input set (first + i) mod len(sets)."""
     g = torch.cuda.CUDAGraph()
@@ -329,7 +345,9 @@ def time_one_step_config(torch, kind, b, d, tau, precision, dtype, side, flush, 
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph, stream=side):
         step.step()
-    ms, _ = timed_replays(torch, graph, flush, n, 2)
+    # median of the replays (the configurations are measured one after another behind the 2N = 65536 base, i.e. across
+    # power-state changes of the GPU: single slow replays moved the mean of the first ones by 20 %)
+    ms = sorted(replay_times(torch, graph, flush, n, 3))[n // 2]
     loss = float(step.loss)
     del graph, step
     return ms, loss
@@ -358,7 +376,7 @@ def extra_configs(torch, side, flush, peak, budget_s=150.0):
                 tf = algorithmic_flops(m, d) / (ms * 1e-3) / 1e12
                 sweep.append({"2N": m, "d": d, "tau": tau, "ms_per_step": round(ms, 5),
                               "Mviews_per_s": round(m / ms / 1e3, 3), "frac_of_peak": round(tf / peak, 4)})
-    out["configs[4] loss sweep (NT-Xent fwd+bwd, bf16 mode, one step per event pair, L2 flushed)"] = sweep
+    out["configs[4] loss sweep (NT-Xent fwd+bwd, bf16 mode, one step per event pair, L2 flushed, median)"] = sweep
     # configs[1] and the first half of configs[4]: pretrain steps with the loss swapped in
     sys.path.insert(0, os.path.join(REPO, "bench"))
     try:
