@@ -181,6 +181,38 @@ def cpu_reference_arm(steps, warmup, b=B_SINGLE, d=DIM):
     return 2 * b / dt, dt * 1e3, cores, kind
 
 
+def cpu_reference_one_thread(b=B_SINGLE, d=DIM):
+    """The same call on ONE host thread: one warm-up, two timed calls."""
+    import torch
+    fn, _ = reference_loss_fn()
+    cores = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        gen = torch.Generator().manual_seed(0)
+        z1, z2 = torch.randn(b, d, generator=gen), torch.randn(b, d, generator=gen)
+        ts = []
+        for i in range(3):
+            t0 = time.perf_counter()
+            a, c = z1.clone().requires_grad_(True), z2.clone().requires_grad_(True)
+            loss, _acc = fn(a, c, temperature=TAU)
+            loss.backward()
+            ts.append(time.perf_counter() - t0)
+        return min(ts[1:]) * 1e3
+    finally:
+        torch.set_num_threads(cores)
+
+
+def cpu_model_name() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_reference_rows(steps, warmup, b_global=B_GLOBAL, d=DIM, rows=1024):
     """Bounded sample of the 2N = 65536 workload on the host cores: NT-Xent forward+backward (reference arithmetic,
     fp32 torch CPU: normalise, similarity block, self-mask, cross-entropy, autograd) for `rows` view-1 rows against all
@@ -538,6 +570,7 @@ def bench_single(args):
     achieved = bwd_flops / (ms_bwd_tile * 1e-3) / 1e12
     traffic, traffic_src = measured_traffic("backward_tile")
     cpu_value, cpu_ms, cores, cpu_kind = cpu_reference_arm(steps=8, warmup=2)
+    cpu_ms_1t = cpu_reference_one_thread()
     line = {
         "metric": METRIC, "value": m / (ms_step * 1e-3), "unit": "views/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -590,7 +623,9 @@ def bench_single(args):
                               "ms_per_step because programmatic dependent launch overlaps prologues and tails in the step",
         "cpu_baseline": {"value": cpu_value, "unit": "views/s", "cores": cores, "kind": cpu_kind,
                          "sample": "8 fwd+bwd calls of the same workload (2N=8192, d=128, fp32) after 2 warm-ups",
-                         "ms_per_step": cpu_ms},
+                         "ms_per_step": cpu_ms, "cpu_model": cpu_model_name(),
+                         "one_thread": {"ms_per_step": cpu_ms_1t, "value": m / (cpu_ms_1t * 1e-3),
+                                        "sample": "the same call on 1 thread, best of 2 after a warm-up"}},
         "precision_modes": {"bf16 (this line)": {"ms_per_step": ms_step, "contract": "loss 2e-3, gradients 1e-2"},
                             "fp32-grade (split bf16 operands)": {"ms_per_step": ms_fp32, "value": m / (ms_fp32 * 1e-3),
                                                                  "contract": "loss 1e-5, gradients 1e-4"},
@@ -947,7 +982,8 @@ def main():
             "scaling": "strong" if multi else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config,
             "config_detail": {"arithmetic": "fp32, torch CPU, all host threads"},
-            "cpu_baseline": {"value": value, "unit": "views/s", "cores": cores, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "views/s", "cores": cores, "kind": kind, "sample": sample,
+                             "cpu_model": cpu_model_name()},
             "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return

@@ -118,3 +118,47 @@ def test_fused_entry_points_reject_bad_arguments_without_a_gpu():
                                             arr, None, arr, arr, arr, p, None, 0, None) == -12      # rank outside the world
     assert lib.simclr_forward_backward_peer(0, p, p, 4, 8, 0, 1, 0.5, None, p, p, p, p, None, p, p, p, 1 << 20, p, 1 << 20, 2, 0,
                                             None, None, arr, arr, arr, p, None, 0, None) == -1
+
+
+def test_deterministic_and_lazy_accuracy_switches():
+    from pytorch_simclr_b200 import _lib
+    assert sb.get_deterministic() is False and F.backward_flags() == 0
+    sb.set_deterministic(True)
+    try:
+        assert sb.get_deterministic() is True and F.backward_flags() == _lib.FLAG_DETERMINISTIC
+        lib = _lib.load()
+        # the deterministic backward keeps one accumulator slot per (CTA, segment): a larger workspace, sized by the library
+        assert lib.simclr_backward_workspace_bytes_flags(0, 4096, 4096, 128, _lib.FLAG_DETERMINISTIC) > \
+            lib.simclr_backward_workspace_bytes(0, 4096, 4096, 128)
+        assert F._fused_plan(lib, 0, 4096, 128, _lib.PRECISION_BF16, _lib.FLAG_DETERMINISTIC)["bwd"][1] == \
+            lib.simclr_backward_workspace_bytes_flags(0, 4096, 4096, 128, _lib.FLAG_DETERMINISTIC)
+    finally:
+        sb.set_deterministic(False)
+    assert sb.get_lazy_accuracy() is False
+    sb.set_lazy_accuracy(True)
+    assert sb.get_lazy_accuracy() is True
+    sb.set_lazy_accuracy(False)
+
+
+def test_peer_transport_refuses_what_it_cannot_compute():
+    """ADVICE (round 1): transport='peer' must not silently drop per-row weights or the fp32-grade mode."""
+    from pytorch_simclr_b200 import distributed as D
+    z = torch.randn(8, 16)
+    with pytest.raises(ValueError, match="per-row weights"):
+        D.global_contrastive_loss(z, z, weight=torch.ones(16), transport="peer")
+    with pytest.raises(ValueError, match="CUDA"):
+        D.global_contrastive_loss(z, z, transport="peer")
+    with pytest.raises(ValueError, match="transport must be"):
+        D.global_contrastive_loss(z, z, transport="smoke-signals")
+    assert "ddp_scale" in inspect.signature(D.global_contrastive_loss).parameters
+    assert "ddp_scale" in inspect.signature(D.global_modified_contrastive_loss).parameters
+
+
+def test_head_tail_argument_checks_without_a_gpu():
+    u = torch.randn(8, 16)
+    with pytest.raises(TypeError, match="BatchNorm1d"):
+        sb.bn_contrastive_loss(u, u, torch.nn.LayerNorm(16))
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        sb.bn_contrastive_loss(u, u, torch.nn.BatchNorm1d(16))
+    lib = __import__("pytorch_simclr_b200._lib", fromlist=["load"]).load()
+    assert lib.simclr_bn_state_floats(128) == 2 * 5 * 128 and lib.simclr_bn_workspace_bytes(4096, 128) > 256
