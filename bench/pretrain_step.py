@@ -10,7 +10,8 @@ two separate forwards (per-view BatchNorm statistics), loss, `loss /= accum_step
 (lr 1e-3, weight decay 1e-6, pretrain.py:80).  Synthetic inputs.  Timed with CUDA events around whole steps, once with
 `objective.contrastive_loss` of this repository (the drop-in) and once with the reference's loss arithmetic restated
 in eager torch ops (objective.py:23-53); the loss alone (forward + backward on detached embeddings) is timed next to
-them.  One JSON line per configuration.  The loss is ~0.01 % of the step's FLOPs: the point of this
+them; further arms: the projection head's last BatchNorm fused into the loss, the whole step captured in a CUDA graph
+(accuracy left on the device), and the eager step under bf16 autocast + channels_last.  One JSON line per configuration.  The loss is ~0.01 % of the step's FLOPs: the point of this
 harness is that swapping it in changes nothing else and removes the loss's share of the step.
 """
 import argparse
@@ -111,6 +112,85 @@ def time_steps(model, opt, loss_fn, x1, x2, tau, steps, warmup, fused_head=False
     return ms[len(ms) // 2], val, acc
 
 
+def time_graph_captured(model, loss_fn, x1, x2, tau, steps, warmup):
+    """The same step captured ONCE in a CUDA graph and replayed: two forwards, the drop-in loss with the
+    accuracy left on the device (`set_lazy_accuracy`: no host synchronisation inside the step), backward, capturable Adam.
+    The loss value and the accuracy are read after the replay -- the reference's `loss.item()` (:117) moves behind the step."""
+    import pytorch_simclr_b200 as sb
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-6, capturable=True)
+    sb.set_lazy_accuracy(True)
+    try:
+        def one():
+            _, z1 = model(x1)
+            _, z2 = model(x2)
+            loss, acc = loss_fn(z1, z2, temperature=tau)
+            loss.backward()
+            opt.step()
+            return loss, acc
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(3, warmup)):
+                opt.zero_grad(set_to_none=True)
+                one()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            loss, acc = one()
+        for _ in range(2):
+            graph.replay()
+        ms = []
+        for _ in range(steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            graph.replay()
+            val = loss.item()
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        ms.sort()
+        return ms[len(ms) // 2], val, float(acc)
+    finally:
+        sb.set_lazy_accuracy(False)
+
+
+def time_autocast_steps(model, opt, loss_fn, x1, x2, tau, steps, warmup):
+    """The eager step with bf16 autocast and channels_last activations (what a user would switch on for a B200); the
+    embeddings reach the loss as bf16 tensors, i.e. on its bf16-input path."""
+    model = model.to(memory_format=torch.channels_last)
+    x1 = x1.contiguous(memory_format=torch.channels_last)
+    x2 = x2.contiguous(memory_format=torch.channels_last)
+
+    def one():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            _, z1 = model(x1)
+            _, z2 = model(x2)
+        loss, acc = loss_fn(z1, z2, temperature=tau)
+        val = loss.item()
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        return val, acc
+
+    for _ in range(warmup):
+        one()
+    ms = []
+    for _ in range(steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        val, acc = one()
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    ms.sort()
+    return ms[len(ms) // 2], val, acc
+
+
 def time_loss_only(loss_fn, b, d, tau, steps=30):
     g = torch.Generator(device="cuda").manual_seed(3)
     z1 = torch.randn(b, d, device="cuda", generator=g)
@@ -152,6 +232,23 @@ def run(name, batch, res, cifar_stem, steps, warmup, tau=0.5, quiet=False):
         if not fused:
             out[label]["loss_only_ms"] = time_loss_only(fn, batch, 128, tau)
         del model, opt
+        torch.cuda.empty_cache()
+    # the same step without host synchronisation, captured in a CUDA graph; and with bf16 autocast
+    for label in ("ours_graph_captured", "ours_bf16_autocast_channels_last", "reference_arithmetic_bf16_autocast_channels_last"):
+        try:
+            torch.manual_seed(0)
+            model = SimCLR(cifar_stem).cuda().train()
+            if label == "ours_graph_captured":
+                ms, val, acc = time_graph_captured(model, contrastive_loss, x1, x2, tau, steps, warmup)
+            else:
+                opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-6)
+                fn = contrastive_loss if label.startswith("ours") else (lambda a, c, temperature: reference_loss(a.float(), c.float(), temperature))
+                ms, val, acc = time_autocast_steps(model, opt, fn, x1, x2, tau, steps, warmup)
+                del opt
+            out[label] = {"ms_per_step": ms, "images_per_s": batch / (ms * 1e-3), "last_loss": val, "last_acc": acc}
+            del model
+        except Exception as e:                                  # an arm that cannot run must not take the others down
+            out[label] = {"skipped": f"{type(e).__name__}: {e}"}
         torch.cuda.empty_cache()
     out["step_ratio_ours_over_reference"] = out["ours"]["ms_per_step"] / out["reference_arithmetic"]["ms_per_step"]
     if not quiet:
