@@ -515,14 +515,6 @@ SIMCLR_DEVICE constexpr int poly_pairs_in_round(int pairs, int round) { return r
 #ifndef SIMCLR_FLUSH_ALTERNATE
 #define SIMCLR_FLUSH_ALTERNATE 1
 #endif
-#ifndef SIMCLR_BWD_DELAY_ST
-#define SIMCLR_BWD_DELAY_ST 0         // 1: store W of chunk k after the arithmetic of chunk k+1 (measured: slower)
-#endif
-#ifndef SIMCLR_BWD_PREFETCH_ROW
-#define SIMCLR_BWD_PREFETCH_ROW 0     // backward: fetch a segment's row entries of the column vectors one segment ahead
-                                      // (measured: +0.4 us per step -- the 80-register backward kernel has no room for
-                                      // two more live values; kept for the record)
-#endif
 #ifndef SIMCLR_TOKEN_FENCE
 #define SIMCLR_TOKEN_FENCE 1          // 1: a basic-block boundary pins the token hand-over in front of its chunk's arithmetic
 #endif
@@ -2086,8 +2078,6 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
         int buf = pair % NB;
         int seg = 0;
         int base = 0;                        // tiles of the windows already walked
-        [[maybe_unused]] float pre_a = 0.f, pre_l2 = 0.f;     // backward: the next segment's row entries of the column vectors
-        [[maybe_unused]] bool have_pre = false;
         for (int wi = 0; wi < n_win; ++wi) {
         const WinRange wr = win_range(wi);
         const int n_w = static_cast<int>(wr.t_end - wr.t_begin);
@@ -2115,32 +2105,10 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
             br.row_a = 0.f;
             br.row_l2 = 0.f;
             if constexpr (kBackward) {
-#if SIMCLR_BWD_PREFETCH_ROW
-                // The row's own column-vector entries are used by the first chunk of the segment: loaded here they would
-                // stall the warp for a memory latency at every segment boundary (the first segment's loads hide under the
-                // pipeline fill).  They are fetched one segment ahead instead.
-                if (have_pre) {
-                    br.row_a = pre_a;
-                    br.row_l2 = pre_l2;
-                } else if (rc.row_ok) {
-                    br.row_a = __ldcg(p.colvec + rc.vr * h.bg_pad + rc.g);
-                    br.row_l2 = __ldcg(p.colvec + 2 * h.bg_pad + rc.vr * h.bg_pad + rc.g);
-                }
-                have_pre = idx0 + seg_len < n_w;
-                if (have_pre) {
-                    const int vr_n = (rb + 1) / blocks_per_view;
-                    const int img_n = (rb + 1 - vr_n * blocks_per_view) * kBlockM + row_in_block;
-                    const bool ok_n = img_n < b_loc;
-                    const int c_n = vr_n * h.bg_pad + row_off + img_n;
-                    pre_a = ok_n ? __ldcg(p.colvec + c_n) : 0.f;
-                    pre_l2 = ok_n ? __ldcg(p.colvec + 2 * h.bg_pad + c_n) : 0.f;
-                }
-#else
                 if (rc.row_ok) {
                     br.row_a = __ldcg(p.colvec + rc.vr * h.bg_pad + rc.g);
                     br.row_l2 = __ldcg(p.colvec + 2 * h.bg_pad + rc.vr * h.bg_pad + rc.g);
                 }
-#endif
             }
             const int pos_off = kBackward ? 2 * seg : 0;
             // exact accuracy count: the band around this row's exact positive inside which a tensor-core score cannot
@@ -2298,9 +2266,6 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                 } else if (!tile_special) {
                     // Common case: no masked element anywhere in the tile for this warp.  One straight-line block over
                     // the four chunks, so that the tail of chunk k overlaps the head of chunk k+1.
-#if SIMCLR_BWD_DELAY_ST
-                    uint32_t wprev[kChunk / 2];           // backward: W of the previous chunk (stored one chunk late)
-#endif
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         uint32_t (&cur)[kChunk] = (k & 1) ? rb2 : ra;
@@ -2319,17 +2284,7 @@ contrastive_tile_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
                         } else if constexpr (kPrec == 0) {
                             uint32_t wq[kChunk / 2], unused[kChunk / 2];
                             bwd_chunk<kLoss, kConst, false>(h, cur, cv_tile + k * kChunk * 4, 0, rc, br, wq, unused);
-#if SIMCLR_BWD_DELAY_ST
-                            // The store of chunk k-1 follows the arithmetic of chunk k in program order, so that the
-                            // exponentials of chunk k need not queue behind the pack / store tail of chunk k-1
-                            // (tcgen05 instructions are scheduling fences for each other, plain arithmetic is not).
-                            if (k > 0) tmem_st8(t0 + (k - 1) * (kChunk / 2), wprev);
-#pragma unroll
-                            for (int i = 0; i < kChunk / 2; ++i) wprev[i] = wq[i];
-                            if (k == 3) tmem_st8(t0 + 3 * (kChunk / 2), wprev);
-#else
                             tmem_st8(t0 + k * (kChunk / 2), wq);
-#endif
                         }
                     }
                     if constexpr (!kBackward) {
