@@ -419,8 +419,10 @@ def extra_configs(torch, side, flush, peak, budget_s=150.0):
                 out[key] = {"skipped": "time budget of the default bench run spent; run bench/pretrain_step.py"}
                 continue
             res = pretrain_step.run(key, args[0], args[1], args[2], steps=5, warmup=3, quiet=True)
-            out[key] = {k: res[k] for k in ("ours", "ours_fused_head_tail", "reference_arithmetic",
-                                            "step_ratio_ours_over_reference", "dtype")}
+            out[key] = {k: res[k] for k in ("ours", "ours_fused_head_tail", "reference_arithmetic", "ours_graph_captured",
+                                            "ours_bf16_autocast_channels_last",
+                                            "reference_arithmetic_bf16_autocast_channels_last",
+                                            "step_ratio_ours_over_reference", "dtype") if k in res}
     except Exception as e:      # torchvision missing or out of memory: report, do not fail the headline
         out["pretrain steps"] = {"skipped": f"{type(e).__name__}: {e}"}
     out["seconds"] = round(time.perf_counter() - t_start, 1)
