@@ -9,6 +9,7 @@ from __future__ import annotations
 import argparse
 import hashlib
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -37,11 +38,17 @@ def _nvcc() -> str:
     return found
 
 
+_COMMENT = re.compile(rb"//[^\n]*|/\*.*?\*/", re.S)
+
+
 def _digest() -> str:
+    """Stamp of the library: the compiler flags and the sources with comments and blank space removed, so that a comment
+    edit does not orphan the profiles that are keyed to the stamp (profiles/ncu_traffic.json).  A "//" inside a string
+    literal is stripped as well -- harmless for a digest."""
     h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
     for dep in DEPS:
         with open(os.path.join(CSRC, dep), "rb") as f:
-            h.update(f.read())
+            h.update(b" ".join(_COMMENT.sub(b"", f.read()).split()))
     return h.hexdigest()
 
 

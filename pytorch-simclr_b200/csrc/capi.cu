@@ -219,7 +219,7 @@ struct FwdWorkspace {
     unsigned int* ticket;
     unsigned int* cand_cnt;   // [2*bl_pad] candidate counters of the exact accuracy count (zero between calls)
     int* cand;                // [2*bl_pad][kCandMax]
-    int* amb_list;            // [2*bl_pad] rows whose accuracy decision is left to the backward tile kernel (fused step)
+    int* amb_list;            // [2*bl_pad] rows whose accuracy decision is left to the backward finalize kernel (fused step)
     float* part;
     float* part2;      // partials of the second launch of the overlapped row-sharded forward
     float* block_part;
@@ -762,7 +762,7 @@ int forward_impl(int loss, const void* operand_rows, const void* operand_cols, i
             p.cand = w.cand;
             p.band = (loss == SIMCLR_LOSS_NTXENT ? s.k2 : 1.0f) * kBandRel;
             if (defer_stats && fused == nullptr && p.x1 != nullptr) {
-                // fused one-GPU step: the exact re-scoring is left to the backward tile kernel (header words 1 - 3 of the
+                // fused one-GPU step: the exact re-scoring is left to the backward finalize kernel (header words 1 - 3 of the
                 // workspace: zeroed by the prepare kernel with the ticket)
                 p.defer_accuracy = 1;
                 p.amb_cnt = w.ticket + 1;

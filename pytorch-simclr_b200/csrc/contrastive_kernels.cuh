@@ -18,7 +18,7 @@
 //              tile and used as the A operand of a second tcgen05.mma:  dacc[r,:] += W[r,:] * op[c,:]
 // The 2N x 2N matrix never exists outside one 128 x 128 TMEM tile.
 //
-// Warp roles (forward 640 threads, backward 672; 1 CTA / SM, each CTA owns a contiguous range of (row block, column tile)):
+// Warp roles (forward 640 threads, backward 768; 1 CTA / SM, each CTA owns a contiguous range of (row block, column tile)):
 //   warps 0-15  four softmax warpgroups = two pairs.  CTA tile `it` lives in TMEM score buffer it % NB
 //               (NB = 4 forward, (512 - D) / 128 backward) and is consumed by pair it % 2, each warpgroup of the
 //               pair taking 64 of the 128 columns; a pair therefore always has a second buffer being filled by
@@ -26,6 +26,8 @@
 //   warp 16     TMA producer (row-block tile once per segment, column tiles through an mbarrier ring)
 //   warps 17,18 UMMA issuers for the score tiles (one elected lane each; warp 18 also owns the TMEM allocation)
 //   warps 19,20 backward only: UMMA issuers for the gradient MMAs
+//   warp 19     forward only, spare: zeroes the backward's accumulation buffer; row-sharded fused step: pushes this CTA's
+//               share of the rank's operand rows to all ranks and publishes the barrier epoch (TileParams::n_windows)
 //   warps 20-23 backward only: flush warpgroup (one warp per TMEM lane quarter; warp 20 doubles as an issuer): at the
 //               end of a segment it drains the gradient accumulator TMEM -> 128B-swizzled fp32 boxes in two ring stages
 //               the producer hands over -> TMA reduce-add into dacc, and re-zeroes the accumulator.  The softmax
@@ -213,7 +215,8 @@ struct TileParams {
     int defer_stats;
     int finish_stats;
     // Row-sharded batch, fused step (simclr_forward_backward_peer): the cross-GPU barrier in front of this launch is
-    // executed INSIDE it -- CTA 0 signals, the TMA producer of every CTA waits before it touches what the peers pushed
+    // executed INSIDE it -- the kernel in front has published this rank's epoch (sync_presignaled; else CTA 0 signals), the
+    // TMA producer of every CTA waits before it touches what the peers pushed
     // (sync_flags.world > 0).  *sync_epoch is the value to signal / wait for; the preceding kernel of the stream bumped it
     // (bump_epoch of the prepare / forward finalize kernel).  No barrier kernel, no collective call.
     PeerTable sync_flags;
@@ -1138,7 +1141,7 @@ SIMCLR_DEVICE void forward_finalize_rowblock(const TileParams& p, int rb, int ti
         }
     }
     if (kFused && p.cand_cnt != nullptr) {
-        // fused step: list the undecided rows (rare) for the backward tile kernel's idle flush warp; they count as
+        // fused step: list the undecided rows (rare) for the extra blocks of the backward finalize kernel; they count as
         // misses here and are added back by the backward finalize kernel
         if (ambiguous) {
             p.amb_list[atomicAdd(p.amb_cnt, 1u)] = slot;
@@ -1455,7 +1458,7 @@ SIMCLR_DEVICE void finish_forward_stats(const TileParams& p, int lane) {
         s0 = warp_sum(s0);
         s1 = warp_sum(s1);
         s2 = warp_sum(s2);
-        // rows the backward tile kernel re-scored exactly (fused step, see resolve_ambiguous_rows): an unmarked list entry
+        // rows this kernel's extra blocks re-scored exactly (fused step, see resolve_ambiguous_rows): an unmarked list entry
         // is a confirmed hit; the rows' candidate counters are left zero for the next call
         if (p.amb_cnt != nullptr && p.resolve_ambiguous) {
             const unsigned int n_amb = __ldcg(p.amb_cnt);
