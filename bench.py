@@ -694,6 +694,9 @@ def bench_multi(args):
     torch.cuda.set_device(dev)
     # NCCL chatter goes to stderr (main() redirects descriptor 1), so a caller's NCCL_DEBUG=INFO stays usable
     os.environ.setdefault("NCCL_DEBUG", "WARN")
+    # a benchmark's ranks run in lock step: a cross-GPU wait of minutes (the library's default watchdog is sized for
+    # training jobs) would only be a rank that died -- fail after two minutes instead of ten
+    os.environ.setdefault("SIMCLR_B200_PEER_TIMEOUT_S", "120")
     dist.init_process_group("nccl", device_id=dev)
     b, d, m = B_GLOBAL, DIM, 2 * B_GLOBAL
     row_off, bl = shard_rows(b, world, rank)

@@ -27,6 +27,7 @@ ap.add_argument("--dim", dest="d", type=int, default=128)
 ap.add_argument("--tau", type=float, default=0.5)
 args = ap.parse_args()
 
+os.environ.setdefault("SIMCLR_B200_PEER_TIMEOUT_S", "120")      # a test's ranks run in lock step: do not wait ten minutes for a dead one
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 local = int(os.environ.get("LOCAL_RANK", rank))
 torch.cuda.set_device(local)
