@@ -162,3 +162,22 @@ def test_head_tail_argument_checks_without_a_gpu():
         sb.bn_contrastive_loss(u, u, torch.nn.BatchNorm1d(16))
     lib = __import__("pytorch_simclr_b200._lib", fromlist=["load"]).load()
     assert lib.simclr_bn_state_floats(128) == 2 * 5 * 128 and lib.simclr_bn_workspace_bytes(4096, 128) > 256
+
+
+def test_library_stamp_ignores_comments_but_not_code(tmp_path, monkeypatch):
+    """pytorch-simclr_b200/build.py: profiles are keyed to the stamp; a comment edit must not orphan them."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_build_for_test", os.path.join(root, "pytorch-simclr_b200", "build.py"))
+    build = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(build)
+    monkeypatch.setattr(build, "CSRC", str(tmp_path))
+    monkeypatch.setattr(build, "DEPS", ["k.cu"])
+    src = tmp_path / "k.cu"
+    src.write_text("// a kernel\n__global__ void k(int* p) { *p = 1; /* one */ }\n")
+    first = build._digest()
+    src.write_text("// the same kernel, other words\n\n__global__ void k(int* p) {\n    *p = 1;   /* still one */\n}\n")
+    assert build._digest() == first
+    src.write_text("// a kernel\n__global__ void k(int* p) { *p = 2; /* one */ }\n")
+    assert build._digest() != first
