@@ -119,3 +119,29 @@ def test_size_independent_properties():
     perm = np.random.default_rng(0).permutation(64)
     permuted = oracle.ntxent_closed_form(z1[perm], z2[perm], temperature=0.5)
     assert base.loss == pytest.approx(permuted.loss, rel=1e-12)         # consistent relabelling
+
+
+def test_row_sample_checker_matches_the_closed_form():
+    """bench.py's multi-GPU parity block relies on oracle.ntxent_row_sample_check (the only form that fits 2N = 65536):
+    pinned here against ntxent_closed_form, which is pinned against the reference's own outputs above."""
+    for seed, kind, b, d, tau in ((3, "iid", 96, 64, 0.5), (4, "correlated", 200, 128, 0.1)):
+        z1, z2 = oracle.make_embeddings(b, d, seed=seed, kind=kind)
+        full = oracle.ntxent_closed_form(z1, z2, temperature=tau, grad_output=0.25)
+        rows = np.array([0, 1, b - 1, b, b + 7, 2 * b - 1])
+        loss, correct, grads = oracle.ntxent_row_sample_check(z1, z2, tau, rows, grad_output=0.25, block=64)
+        assert loss == pytest.approx(full.loss, rel=1e-12)
+        assert correct == full.correct
+        ref = np.concatenate((full.grad1, full.grad2))[rows]
+        assert np.allclose(np.asarray(grads), ref, rtol=1e-9, atol=1e-14)
+
+
+def test_row_sample_checker_counts_exact_ties_like_the_reference():
+    """first-argmax rule (objective.py:51): a duplicate of the positive that PRECEDES it in the reference's column order
+    takes the hit away, one that follows does not."""
+    z1, z2 = oracle.make_embeddings(32, 16, seed=8)
+    z1, z2 = z1.clone(), z2.clone()
+    z2[20] = z2[3]          # row 3 of view 1: positive is column (view 2, 3); the copy at (view 2, 20) FOLLOWS it
+    z2[1] = z2[9]           # row 9 of view 1: the copy at (view 2, 1) PRECEDES its positive (view 2, 9)
+    full = oracle.ntxent_closed_form(z1, z2, temperature=0.5)
+    _, correct, _ = oracle.ntxent_row_sample_check(z1, z2, 0.5, np.array([0]))
+    assert correct == full.correct
