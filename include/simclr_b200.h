@@ -113,10 +113,12 @@ int simclr_prepare(int loss, const void* x_batch1, const void* x_batch2, int64_t
  * lets the NT-Xent kernel use a constant softmax shift instead of a running maximum.
  * Accuracy count (stats[2], objective.py:51-53 / :95-97: first argmax == positive): with bf16 operands a tensor-core score
  * is only known to within 2^-8 of the largest possible score, so rows whose best negative lies within that band of the
- * exact positive are decided by re-scoring the (at most 8) negatives inside the band in exact fp32 -- which needs the
- * exact rows: `x_batch1` / `x_batch2` / `in_dtype` / `inv_norm` as given to / produced by simclr_prepare (one GPU,
- * b_local == b_global; or zrows_* of simclr_forward_peer).  All NULL, normalize == 0, or more than 8 negatives inside the
- * band of a row: that row is decided on the tensor-core scores (exact ties between identical rows stay exact either way).
+ * exact positive are decided by re-scoring, in exact fp32 and in the reference's own logit expression, the columns of the
+ * (at most 8) recorded 16-column chunks whose maximum lies inside the band -- which needs the exact rows: `x_batch1` /
+ * `x_batch2` / `in_dtype` / `inv_norm` as given to / produced by simclr_prepare (one GPU, b_local == b_global; or zrows_* of
+ * simclr_forward_peer).  All NULL, normalize == 0 for NT-Xent, or more than 8 such chunks for one row: that row is decided
+ * on the tensor-core scores (exact ties between identical rows stay exact either way).  In the fused one-GPU step
+ * (simclr_forward_backward) the re-scoring runs in spare blocks of the backward finalize kernel.
  */
 int simclr_forward(int loss, const void* operand_rows, const void* operand_cols, int64_t b_local, int64_t b_global,
                    int64_t row_offset, int64_t d, float temperature, int normalize, const float* pos_dot,
